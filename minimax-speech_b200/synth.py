@@ -1,0 +1,190 @@
+"""Deterministic synthetic weights and inputs for the hot path.
+
+The reference ships no checkpoints and its constructors are not
+available on the GPU box, so weights are generated here with the *same key schema
+and shapes* as the reference ``state_dict``s from a seed,
+using numpy's PCG64 stream (stable across machines for one numpy version).
+
+``init="reference"`` follows the reference initialisers' distributions
+(speech/cosyvoice/flow/decoder.py:196-208: kaiming-normal conv/linear weights, zero
+biases, unit LayerNorm; dac-vae/model.py:17-104 + torch defaults: weight-norm'd
+convs keep torch's default kaiming-uniform ``weight_v`` with ``weight_g=|v|``, zero
+bias, Snake alpha ~ xavier-normal).  ``init="test"`` additionally randomises
+biases, LayerNorm affine parameters and ``weight_g`` so that parity tests exercise
+every term of the arithmetic.
+"""
+import math
+import zlib
+
+import numpy as np
+import torch
+
+ESTIMATOR_CFG = dict(in_channels=320, out_channels=80, channels=256, n_blocks=4, num_mid_blocks=12,
+                     num_heads=8, head_dim=64, static_chunk_size=50)  # speech/config.yaml:105-116
+DAC_CFG = dict(latent_dim=80, decoder_dim=1536, decoder_rates=(5, 4, 4, 3, 2), d_out=1,
+               sample_rate=24000)  # dac-vae/configs/configx2.yml
+CFG_RATE = 0.7  # speech/config.yaml:99
+NOISE_FRAMES = 50 * 300  # flow_matching.py:321
+
+
+def _rng(seed, name):
+    return np.random.default_rng([seed, zlib.crc32(name.encode())])
+
+
+def _normal(seed, name, shape, std, mean=0.0):
+    a = _rng(seed, name).standard_normal(int(np.prod(shape)), dtype=np.float32).reshape(shape)
+    return torch.from_numpy(a * np.float32(std) + np.float32(mean))
+
+
+def _uniform(seed, name, shape, bound):
+    a = _rng(seed, name).random(int(np.prod(shape)), dtype=np.float32).reshape(shape)
+    return torch.from_numpy((a * 2 - 1) * np.float32(bound))
+
+
+def estimator_state_dict(seed=1986, init="reference", in_channels=320, out_channels=80, channels=256,
+                         n_blocks=4, num_mid_blocks=12, num_heads=8, head_dim=64, **_):
+    """Keys/shapes of ``CausalConditionalDecoder.state_dict()`` for ``channels=[C]``."""
+    C, inner, temb = channels, num_heads * head_dim, channels * 4
+    test = init == "test"
+    sd = {}
+
+    def lin(name, out_f, in_f, bias=True, k=None):
+        shape = (out_f, in_f) if k is None else (out_f, in_f, k)
+        fan_in = in_f * (k or 1)
+        sd[name + ".weight"] = _normal(seed, name + ".weight", shape, math.sqrt(2.0 / fan_in))
+        if bias:
+            sd[name + ".bias"] = (_normal(seed, name + ".bias", (out_f,), 0.1) if test
+                                  else torch.zeros(out_f))
+
+    def ln(name, n):
+        sd[name + ".weight"] = (_normal(seed, name + ".weight", (n,), 0.1, 1.0) if test else torch.ones(n))
+        sd[name + ".bias"] = (_normal(seed, name + ".bias", (n,), 0.1) if test else torch.zeros(n))
+
+    def resnet(p, cin):
+        lin(p + ".mlp.1", C, temb)
+        lin(p + ".block1.block.0", C, cin, k=3)
+        ln(p + ".block1.block.2", C)
+        lin(p + ".block2.block.0", C, C, k=3)
+        ln(p + ".block2.block.2", C)
+        lin(p + ".res_conv", C, cin, k=1)
+
+    def tblock(p):
+        ln(p + ".norm1", C)
+        for n in ("to_q", "to_k", "to_v"):
+            lin(p + ".attn1." + n, inner, C, bias=False)
+        lin(p + ".attn1.to_out.0", C, inner)
+        ln(p + ".norm3", C)
+        lin(p + ".ff.net.0.proj", 4 * C, C)
+        lin(p + ".ff.net.2", C, 4 * C)
+
+    lin("time_mlp.linear_1", temb, in_channels)
+    lin("time_mlp.linear_2", temb, temb)
+    resnet("down_blocks.0.0", in_channels)
+    for j in range(n_blocks):
+        tblock(f"down_blocks.0.1.{j}")
+    lin("down_blocks.0.2", C, C, k=3)
+    for i in range(num_mid_blocks):
+        resnet(f"mid_blocks.{i}.0", C)
+        for j in range(n_blocks):
+            tblock(f"mid_blocks.{i}.1.{j}")
+    resnet("up_blocks.0.0", 2 * C)
+    for j in range(n_blocks):
+        tblock(f"up_blocks.0.1.{j}")
+    lin("up_blocks.0.2", C, C, k=3)
+    lin("final_block.block.0", C, C, k=3)
+    ln("final_block.block.2", C)
+    lin("final_proj", out_channels, C, k=1)
+    return sd
+
+
+def dac_decoder_state_dict(seed=0, init="reference", latent_dim=80, decoder_dim=1536,
+                           decoder_rates=(5, 4, 4, 3, 2), d_out=1, **_):
+    """Keys/shapes of the ``decoder.*`` + ``de_conv_pre.*`` part of ``DACVAE.state_dict()``."""
+    test = init == "test"
+    sd = {}
+
+    def wn(name, w_shape, fan_in, n_bias, transpose=False):
+        v = _uniform(seed, name + ".weight_v", w_shape, 1.0 / math.sqrt(fan_in))
+        g = v.reshape(w_shape[0], -1).norm(dim=1).reshape(w_shape[0], 1, 1)
+        if test:
+            g = g * _uniform(seed, name + ".weight_g", (w_shape[0], 1, 1), 0.3).add(1.0)
+        sd[name + ".bias"] = (_uniform(seed, name + ".bias", (n_bias,), 1.0 / math.sqrt(fan_in)) if test
+                              else torch.zeros(n_bias))
+        sd[name + ".weight_g"] = g
+        sd[name + ".weight_v"] = v
+
+    def snake(name, c):
+        sd[name + ".alpha"] = _normal(seed, name + ".alpha", (1, c, 1), math.sqrt(2.0 / (c + 1)))
+
+    def conv(name, cout, cin, k):  # WNConv1d shadow adds the trailing ".0" (dac-vae/model.py:509-514)
+        wn(name + ".0", (cout, cin, k), cin * k, cout)
+
+    conv("decoder.model.0", decoder_dim, latent_dim, 7)
+    c = decoder_dim
+    for i, s in enumerate(decoder_rates):
+        p = f"decoder.model.{i + 1}.block"
+        snake(p + ".0", c)
+        # ConvTranspose1d weight is [Cin, Cout, k]; torch's fan_in for it is Cout*k
+        wn(p + ".1", (c, c // 2, 2 * s), (c // 2) * 2 * s, c // 2)
+        c //= 2
+        for j in range(3):
+            q = f"{p}.{j + 2}.block"
+            snake(q + ".0", c)
+            conv(q + ".1", c, c, 7)
+            snake(q + ".2", c)
+            conv(q + ".3", c, c, 1)
+    n = len(decoder_rates)
+    snake(f"decoder.model.{n + 1}", c)
+    conv(f"decoder.model.{n + 2}", d_out, c, 7)
+    conv("de_conv_pre", latent_dim, latent_dim, 1)
+    return sd
+
+
+def fixed_noise(frames=NOISE_FRAMES, channels=80):
+    """``CausalConditionalCFM.rand_noise`` (flow_matching.py:320-321): seed-0 torch randn.
+    Does not disturb the caller's global RNG state (the reference does)."""
+    g = torch.Generator().manual_seed(0)
+    return torch.randn([1, channels, NOISE_FRAMES], generator=g)[:, :, :frames]
+
+
+def utterance_inputs(index, frames, channels=80):
+    """Synthetic (mu, spks, cond) for utterance ``index``."""
+    mu = _normal(1234 + index, "mu", (1, channels, frames), 1.0)
+    spks = _normal(1234 + index, "spks", (1, channels), 1.0)
+    cond = torch.zeros(1, channels, frames)
+    p = min(150, frames // 5)
+    cond[:, :, :p] = _normal(1234 + index, "cond", (1, channels, p), 1.0)
+    return mu, spks, cond
+
+
+def batch_inputs(lengths, channels=80, first_index=0):
+    """Right-padded batch: mu[B,80,T], mask[B,1,T], spks[B,80], cond[B,80,T]."""
+    B, T = len(lengths), max(lengths)
+    mu = torch.zeros(B, channels, T)
+    cond = torch.zeros(B, channels, T)
+    spks = torch.zeros(B, channels)
+    mask = torch.zeros(B, 1, T)
+    for i, n in enumerate(lengths):
+        m, s, c = utterance_inputs(first_index + i, n, channels)
+        mu[i, :, :n], spks[i], cond[i, :, :n], mask[i, :, :n] = m[0], s[0], c[0], 1.0
+    return mu, mask, spks, cond
+
+
+def dac_latents(index, frames, channels=80):
+    return _normal(4321 + index, "z", (1, channels, frames), 1.0)
+
+
+def mixed_lengths(n=256, lo_s=2, hi_s=30, frame_rate=50, seed=0):
+    """BASELINE config 5: ``n`` utterance lengths, uniform in whole seconds."""
+    import random
+    r = random.Random(seed)
+    return [frame_rate * r.randint(lo_s, hi_s) for _ in range(n)]
+
+
+def checksum(sd):
+    """Order-independent fingerprint of a state dict (guards golden fixtures)."""
+    tot = 0.0
+    for k in sorted(sd):
+        v = sd[k].double()
+        tot += float(v.sum()) + 0.5 * float(v.abs().sum())
+    return tot

@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(imported from /root/reference through oracle/ref_import.py) with the deterministic synthetic
+weights of minimax-speech_b200/synth.py loaded into the reference modules.
+
+Run in the build container only:   python -m oracle.gen_golden
+The fixtures hold inputs' seeds + reference outputs (small); weights are regenerated from
+their seed wherever the fixtures are consumed, guarded by a checksum.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import as R  # noqa: E402
+import minimax_speech_b200.synth as synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+EST_SEED, DAC_SEED = 7, 11
+
+
+def est_inputs(lengths, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, T = len(lengths), max(lengths)
+    x = torch.randn(B, 80, T, generator=g)
+    mu = torch.randn(B, 80, T, generator=g)
+    cond = torch.randn(B, 80, T, generator=g)
+    spks = torch.randn(B, 80, generator=g)
+    t = torch.rand(B, generator=g)
+    mask = torch.zeros(B, 1, T)
+    for b, n in enumerate(lengths):
+        mask[b, :, :n] = 1
+    return x, mask, mu, t, spks, cond
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    with torch.inference_mode():
+        # ---- estimator / CFM ----
+        sd = synth.estimator_state_dict(EST_SEED, init="test")
+        cfm = R.build_reference_flow()
+        cfm.estimator.load_state_dict(sd, strict=True)
+        est = cfm.estimator
+        out = {"weights_seed": EST_SEED, "weights_checksum": synth.checksum(sd)}
+        for name, lengths, seed, streaming in [("a", [64, 64], 100, False), ("b", [130, 77], 101, False),
+                                               ("c", [130, 77], 102, True)]:
+            x, mask, mu, t, spks, cond = est_inputs(lengths, seed)
+            y = est(x, mask, mu, t, spks, cond, streaming=streaming)
+            out[f"est_{name}_lengths"] = np.array(lengths)
+            out[f"est_{name}_seed"] = seed
+            out[f"est_{name}_streaming"] = streaming
+            out[f"est_{name}_y"] = y.numpy()
+            print("estimator", name, y.shape, float(y.abs().mean()))
+        # whole solve, literal reference call (B=1 each: flow_matching.py:97-110 is batch-1 only)
+        for name, lengths, n_steps, streaming in [("a", [96], 4, False), ("b", [80, 50], 3, False),
+                                                  ("c", [120], 2, True)]:
+            mu, mask, spks, cond = synth.batch_inputs(lengths, first_index=50)
+            ys = []
+            for b, n in enumerate(lengths):
+                y, _ = cfm(mu=mu[b:b + 1, :, :n].clone(), mask=mask[b:b + 1, :, :n], n_timesteps=n_steps,
+                           temperature=1.0, spks=spks[b:b + 1], cond=cond[b:b + 1, :, :n], streaming=streaming)
+                yp = torch.zeros(1, 80, max(lengths))
+                yp[:, :, :n] = y
+                ys.append(yp)
+            y = torch.cat(ys, 0)
+            out[f"cfm_{name}_lengths"] = np.array(lengths)
+            out[f"cfm_{name}_steps"] = n_steps
+            out[f"cfm_{name}_streaming"] = streaming
+            out[f"cfm_{name}_y"] = y.numpy()
+            print("cfm", name, y.shape, float(y.abs().mean()))
+        out["rand_noise_probe"] = cfm.rand_noise[0, :2, :8].numpy()
+        np.savez_compressed(os.path.join(OUT, "flow_golden.npz"), **out)
+
+        # ---- DAC-VAE decode ----
+        sd = synth.dac_decoder_state_dict(DAC_SEED, init="test")
+        dac = R.build_reference_dac()
+        missing, unexpected = dac.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith(("encoder.", "en_conv_post.")) for k in missing), (missing[:5], unexpected)
+        out = {"weights_seed": DAC_SEED, "weights_checksum": synth.checksum(sd)}
+        for name, frames, idx in [("a", 24, 0), ("b", 7, 1), ("c", 1, 2)]:
+            z = synth.dac_latents(idx, frames)
+            y = dac.decode(z)
+            out[f"dac_{name}_frames"] = frames
+            out[f"dac_{name}_index"] = idx
+            out[f"dac_{name}_y"] = y.numpy()
+            print("dac", name, y.shape, float(y.abs().max()))
+        np.savez_compressed(os.path.join(OUT, "dac_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

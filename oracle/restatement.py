@@ -1,0 +1,270 @@
+"""TEST INFRASTRUCTURE -- the CPU oracle for the hot path.  Not product code: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference
+arm may import this module.
+
+A functional fp32 restatement (plain torch CPU tensor ops on ``state_dict`` entries,
+no ``nn.Module``) of the reference's algorithm for
+
+  * ``CausalConditionalDecoder.forward``        speech/cosyvoice/flow/decoder.py:405-496
+  * ``ConditionalCFM.solve_euler`` + CFG         speech/cosyvoice/flow/flow_matching.py:74-126
+  * ``CausalConditionalCFM.forward``             speech/cosyvoice/flow/flow_matching.py:323-348
+  * ``DACVAE.decode``                            dac-vae/model.py:485-488 (+ :107-143, :237-379)
+
+Parity status: the reference holds NO golden vectors / tests for this path
+(SURVEY.md §4, §8c).  This restatement is therefore pinned against outputs of the
+reference itself, imported unmodified through ``oracle/ref_import.py`` in the build
+container, with weights from ``minimax-speech_b200/synth.py`` loaded into the
+reference modules (``oracle/gen_golden.py`` -> ``tests/golden/*.npz``,
+``tests/test_oracle_golden.py``).  The third-party ``diffusers==0.29.0`` attention /
+GELU arithmetic is restated from its published algorithm (see ref_import.py).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------
+# Estimator (CausalConditionalDecoder with channels=[C])
+# --------------------------------------------------------------------------------------
+
+
+def sinusoidal_pos_emb(t, dim=320, scale=1000.0):
+    """matcha/models/components/decoder.py:14-29."""
+    half = dim // 2
+    f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    e = scale * t.float().unsqueeze(1) * f.unsqueeze(0)
+    return torch.cat([e.sin(), e.cos()], dim=-1)
+
+
+def time_mlp(sd, t, in_channels=320):
+    """decoder.py:422-423 -> TimestepEmbedding (matcha decoder.py:73-117): Linear, SiLU, Linear."""
+    e = sinusoidal_pos_emb(t, in_channels).to(t.dtype)
+    h = F.linear(e, sd["time_mlp.linear_1.weight"], sd["time_mlp.linear_1.bias"])
+    h = F.silu(h)
+    return F.linear(h, sd["time_mlp.linear_2.weight"], sd["time_mlp.linear_2.bias"])
+
+
+def causal_conv(x, w, b):
+    """decoder.py:59-62: left-pad k-1 zeros, no right context."""
+    return F.conv1d(F.pad(x, (w.shape[-1] - 1, 0)), w, b)
+
+
+def causal_block(sd, p, x, mask):
+    """CausalBlock1D decoder.py:65-78: conv3 -> LayerNorm over channels -> Mish, masked."""
+    h = causal_conv(x * mask, sd[p + ".block.0.weight"], sd[p + ".block.0.bias"])
+    h = F.layer_norm(h.transpose(1, 2), (h.shape[1],), sd[p + ".block.2.weight"], sd[p + ".block.2.bias"], 1e-5)
+    h = F.mish(h.transpose(1, 2))
+    return h * mask
+
+
+def resnet_block(sd, p, x, mask, temb):
+    """ResnetBlock1D.forward matcha decoder.py:56-61 with causal blocks."""
+    h = causal_block(sd, p + ".block1", x, mask)
+    h = h + F.linear(F.mish(temb), sd[p + ".mlp.1.weight"], sd[p + ".mlp.1.bias"]).unsqueeze(-1)
+    h = causal_block(sd, p + ".block2", h, mask)
+    return h + F.conv1d(x * mask, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
+
+
+def attention_bias(mask, streaming, chunk):
+    """add_optional_chunk_mask mask.py:161-236 + mask_to_bias common.py:160-168.
+    mask [B,1,T] (0/1) -> additive bias [B,T,T]."""
+    m = mask.bool()
+    B, _, T = m.shape
+    if streaming and chunk > 0:
+        pos = torch.arange(T)
+        block_end = (torch.div(pos, chunk, rounding_mode="trunc") + 1) * chunk  # mask.py:154-157
+        cm = pos.unsqueeze(0) < block_end.unsqueeze(1)
+        m = m & cm.unsqueeze(0)
+    else:
+        m = m.repeat(1, T, 1)
+    dead = m.sum(dim=-1) == 0  # mask.py:233-235
+    m = m.clone()
+    m[dead] = True
+    return (1.0 - m.float()) * -1.0e10
+
+
+def transformer_block(sd, p, u, bias, heads):
+    """BasicTransformerBlock.forward transformer.py:243-316 (self-attn + FF, pre-LN)."""
+    B, T, C = u.shape
+    n = F.layer_norm(u, (C,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], 1e-5)
+    q = F.linear(n, sd[p + ".attn1.to_q.weight"])
+    k = F.linear(n, sd[p + ".attn1.to_k.weight"])
+    v = F.linear(n, sd[p + ".attn1.to_v.weight"])
+    hd = q.shape[-1] // heads
+    q = q.view(B, T, heads, hd).transpose(1, 2)
+    k = k.view(B, T, heads, hd).transpose(1, 2)
+    v = v.view(B, T, heads, hd).transpose(1, 2)
+    s = torch.matmul(q, k.transpose(-1, -2)) * (hd ** -0.5) + bias.unsqueeze(1)
+    o = torch.matmul(torch.softmax(s, dim=-1), v)
+    o = o.transpose(1, 2).reshape(B, T, heads * hd)
+    u = u + F.linear(o, sd[p + ".attn1.to_out.0.weight"], sd[p + ".attn1.to_out.0.bias"])
+    n = F.layer_norm(u, (C,), sd[p + ".norm3.weight"], sd[p + ".norm3.bias"], 1e-5)
+    h = F.gelu(F.linear(n, sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"]))  # exact erf
+    return u + F.linear(h, sd[p + ".ff.net.2.weight"], sd[p + ".ff.net.2.bias"])
+
+
+def _count(sd, fmt):
+    n = 0
+    while (fmt.format(n)) in sd:
+        n += 1
+    return n
+
+
+def estimator_forward(sd, x, mask, mu, t, spks, cond, streaming=False, heads=8, chunk=50, taps=None):
+    """CausalConditionalDecoder.forward decoder.py:405-496 for channels=[C].
+    x,mu,cond [R,80,T]; mask [R,1,T]; t [R]; spks [R,80] -> [R,80,T].
+    ``taps`` (optional dict) receives named intermediates for kernel-level tests."""
+    n_blocks = _count(sd, "down_blocks.0.1.{}.norm1.weight")
+    n_mid = _count(sd, "mid_blocks.{}.0.mlp.1.weight")
+    temb = time_mlp(sd, t, sd["time_mlp.linear_1.weight"].shape[1])
+    T = x.shape[-1]
+    h = torch.cat([x, mu, spks.unsqueeze(-1).expand(-1, -1, T), cond], dim=1)  # decoder.py:427-433
+    bias = attention_bias(mask, streaming, chunk)
+
+    def group(h, prefix):
+        h = resnet_block(sd, prefix + ".0", h, mask, temb)
+        if taps is not None:
+            taps[prefix + ".0"] = h
+        u = h.transpose(1, 2)
+        for j in range(n_blocks):
+            u = transformer_block(sd, f"{prefix}.1.{j}", u, bias, heads)
+            if taps is not None:
+                taps[f"{prefix}.1.{j}"] = u
+        return u.transpose(1, 2)
+
+    h = group(h, "down_blocks.0")
+    skip = h
+    h = causal_conv(h * mask, sd["down_blocks.0.2.weight"], sd["down_blocks.0.2.bias"])
+    for i in range(n_mid):
+        h = group(h, f"mid_blocks.{i}")
+    h = torch.cat([h, skip], dim=1)
+    h = group(h, "up_blocks.0")
+    h = causal_conv(h * mask, sd["up_blocks.0.2.weight"], sd["up_blocks.0.2.bias"])
+    h = causal_block(sd, "final_block", h, mask)
+    out = F.conv1d(h * mask, sd["final_proj.weight"], sd["final_proj.bias"])
+    return out * mask
+
+
+# --------------------------------------------------------------------------------------
+# CFM Euler solve with classifier-free guidance
+# --------------------------------------------------------------------------------------
+
+
+def cosine_t_span(n_timesteps, dtype=torch.float32):
+    """flow_matching.py:345-347."""
+    t = torch.linspace(0, 1, n_timesteps + 1, dtype=dtype)
+    return 1 - torch.cos(t * 0.5 * torch.pi)
+
+
+def solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate=0.7, streaming=False, heads=8, chunk=50):
+    """ConditionalCFM.solve_euler flow_matching.py:74-126, generalised to B>=1 with the
+    reference's per-utterance semantics (the reference hard-codes B=1): row b of
+    the conditional half sees (mu,spks,cond)[b]; the unconditional half sees zeros."""
+    x = z.clone()
+    B = x.shape[0]
+    t, dt = t_span[0], t_span[1] - t_span[0]
+    zeros3, zeros2 = torch.zeros_like(mu), torch.zeros_like(spks)
+    for step in range(1, len(t_span)):
+        xin = torch.cat([x, x], 0)
+        v = estimator_forward(sd, xin, torch.cat([mask, mask], 0), torch.cat([mu, zeros3], 0),
+                              t.reshape(1).expand(2 * B), torch.cat([spks, zeros2], 0),
+                              torch.cat([cond, zeros3], 0), streaming, heads, chunk)
+        v = (1.0 + cfg_rate) * v[:B] - cfg_rate * v[B:]  # :118-119
+        x = x + dt * v
+        t = t + dt
+        if step < len(t_span) - 1:
+            dt = t_span[step + 1] - t
+    return x.float()
+
+
+def cfm_forward(sd, noise, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False,
+                cfg_rate=0.7, heads=8, chunk=50):
+    """CausalConditionalCFM.forward flow_matching.py:323-348.  ``noise`` = rand_noise [1,80,>=T]."""
+    z = noise[:, :, :mu.shape[2]].to(mu.dtype).expand(mu.shape[0], -1, -1) * temperature
+    t_span = cosine_t_span(n_timesteps, mu.dtype)
+    return solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate, streaming, heads, chunk)
+
+
+# --------------------------------------------------------------------------------------
+# DAC-VAE decoder
+# --------------------------------------------------------------------------------------
+
+
+def wn_weight(sd, p):
+    """torch.nn.utils.weight_norm (dim=0): w = g * v / ||v||, norm over all dims but 0
+    (dim 0 is Cin for ConvTranspose1d) -- layers.py:9-14."""
+    v, g = sd[p + ".weight_v"], sd[p + ".weight_g"]
+    return v * (g / v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1))
+
+
+def snake(x, alpha):
+    """layers.py:18-24."""
+    return x + (alpha + 1e-9).reciprocal() * torch.sin(alpha * x).pow(2)
+
+
+def wn_conv_lrelu(sd, p, x, dilation=1, padding=0):
+    """Generator Conv1d = Sequential(weight_norm(Conv1d), LeakyReLU(0.1)) -- the shadowing
+    WNConv1d at dac-vae/model.py:509-514."""
+    return F.leaky_relu(F.conv1d(x, wn_weight(sd, p + ".0"), sd[p + ".0.bias"], dilation=dilation,
+                                 padding=padding), 0.1)
+
+
+def residual_unit(sd, p, x, dilation):
+    """ResidualUnit model.py:107-143."""
+    y = snake(x, sd[p + ".block.0.alpha"])
+    y = wn_conv_lrelu(sd, p + ".block.1", y, dilation, 3 * dilation)
+    y = snake(y, sd[p + ".block.2.alpha"])
+    y = wn_conv_lrelu(sd, p + ".block.3", y)
+    return x + y
+
+
+def dac_decode(sd, z, taps=None):
+    """DACVAE.decode model.py:485-488: de_conv_pre -> Decoder (model.py:326-379). z [B,80,L]."""
+    rates = []
+    while f"decoder.model.{len(rates) + 1}.block.1.weight_v" in sd:
+        w = sd[f"decoder.model.{len(rates) + 1}.block.1.weight_v"]
+        rates.append(w.shape[-1] // 2)
+    x = wn_conv_lrelu(sd, "de_conv_pre", z)
+    x = wn_conv_lrelu(sd, "decoder.model.0", x, 1, 3)
+    for i, s in enumerate(rates):
+        p = f"decoder.model.{i + 1}.block"
+        x = snake(x, sd[p + ".0.alpha"])
+        x = F.conv_transpose1d(x, wn_weight(sd, p + ".1"), sd[p + ".1.bias"], stride=s,
+                               padding=math.ceil(s / 2), output_padding=s % 2)  # model.py:255-262
+        for j, d in enumerate((1, 3, 9)):
+            x = residual_unit(sd, f"{p}.{j + 2}", x, d)
+        if taps is not None:
+            taps[f"stage{i + 1}"] = x
+    n = len(rates)
+    x = snake(x, sd[f"decoder.model.{n + 1}.alpha"])
+    x = wn_conv_lrelu(sd, f"decoder.model.{n + 2}", x, 1, 3)
+    return torch.tanh(x)
+
+
+def dac_decode_varlen(sd, z, lengths):
+    """Per-utterance semantics for a right-padded batch: utterance b is decoded alone at its own
+    length (this is what a loop over the reference's ``decode`` gives); padding is zero."""
+    hop = 1
+    k = 1
+    while f"decoder.model.{k}.block.1.weight_v" in sd:
+        hop *= sd[f"decoder.model.{k}.block.1.weight_v"].shape[-1] // 2
+        k += 1
+    out = torch.zeros(z.shape[0], 1, z.shape[2] * hop)
+    for b, n in enumerate(lengths):
+        out[b, :, :n * hop] = dac_decode(sd, z[b:b + 1, :, :n])[0]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Parity metrics
+# --------------------------------------------------------------------------------------
+
+
+def rel_l2(y, ref):
+    y, ref = y.double(), ref.double()
+    return float((y - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def snr_db(y, ref):
+    y, ref = y.double(), ref.double()
+    return float(10.0 * torch.log10(ref.pow(2).sum() / (ref - y).pow(2).sum().clamp_min(1e-30)))

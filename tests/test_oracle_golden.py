@@ -1,0 +1,84 @@
+"""Pins oracle/restatement.py against outputs of the unmodified reference (tests/golden/*.npz,
+made by oracle/gen_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import minimax_speech_b200.synth as synth
+from oracle import restatement as O
+from oracle.gen_golden import est_inputs
+
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+@pytest.fixture(scope="module")
+def flow(golden_dir):
+    g = np.load(os.path.join(golden_dir, "flow_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"])), \
+        "synthetic weights differ from the ones the goldens were made with"
+    return g, sd
+
+
+@pytest.fixture(scope="module")
+def dac(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dac_golden.npz"))
+    sd = synth.dac_decoder_state_dict(int(g["weights_seed"]), init="test")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    return g, sd
+
+
+def test_fixed_noise_matches_reference(flow):
+    g, _ = flow
+    n = synth.fixed_noise(64)
+    assert np.allclose(n[0, :2, :8].numpy(), g["rand_noise_probe"], atol=0, rtol=0)
+    assert abs(float(n[0, 0, 0]) - (-1.12584)) < 1e-4  # SURVEY.md §8c determinism anchor
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_estimator_matches_reference(flow, case):
+    g, sd = flow
+    x, mask, mu, t, spks, cond = est_inputs(list(g[f"est_{case}_lengths"]), int(g[f"est_{case}_seed"]))
+    with torch.inference_mode():
+        y = O.estimator_forward(sd, x, mask, mu, t, spks, cond, streaming=bool(g[f"est_{case}_streaming"]))
+    ref = torch.from_numpy(g[f"est_{case}_y"])
+    assert O.rel_l2(y, ref) < 2e-5
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_cfm_solve_matches_reference(flow, case):
+    g, sd = flow
+    lengths = [int(v) for v in g[f"cfm_{case}_lengths"]]
+    mu, mask, spks, cond = synth.batch_inputs(lengths, first_index=50)
+    with torch.inference_mode():
+        y = O.cfm_forward(sd, synth.fixed_noise(), mu, mask, int(g[f"cfm_{case}_steps"]), 1.0, spks, cond,
+                          streaming=bool(g[f"cfm_{case}_streaming"]))
+    y = y * mask  # reference per-utterance outputs are zero-padded in the fixture
+    ref = torch.from_numpy(g[f"cfm_{case}_y"])
+    for b, n in enumerate(lengths):
+        assert O.rel_l2(y[b, :, :n], ref[b, :, :n]) < 5e-5
+    assert float((y * (1 - mask)).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_dac_decode_matches_reference(dac, case):
+    g, sd = dac
+    z = synth.dac_latents(int(g[f"dac_{case}_index"]), int(g[f"dac_{case}_frames"]))
+    with torch.inference_mode():
+        y = O.dac_decode(sd, z)
+    ref = torch.from_numpy(g[f"dac_{case}_y"])
+    assert y.shape == ref.shape
+    assert O.snr_db(y, ref) > 100.0
+
+
+def test_dac_varlen_is_per_utterance(dac):
+    _, sd = dac
+    z = torch.cat([synth.dac_latents(5, 6), torch.zeros(1, 80, 6)], 0)
+    z[1, :, :3] = synth.dac_latents(6, 3)[0]
+    with torch.inference_mode():
+        y = O.dac_decode_varlen(sd, z, [6, 3])
+        y1 = O.dac_decode(sd, z[1:2, :, :3])
+    assert torch.equal(y[1, :, :1440], y1[0])
+    assert float(y[1, :, 1440:].abs().max()) == 0.0
