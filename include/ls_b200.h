@@ -1,0 +1,130 @@
+/* ls_b200.h -- C ABI of the B200-native CFM-solve + DAC-VAE-decode hot path.
+ *
+ * Plain C: opaque handles, raw pointers, sizes, a CUDA stream passed as void*; no torch types.
+ * Every entry point returns LS_OK (0) or a negative LS_ERR_* code and never throws; the message of
+ * the last failure on the calling thread is available from ls_last_error().
+ *
+ * Reference interfaces these entry points replace (paths relative to the reference repo):
+ *   ls_flow_estimator_forward  <- ConditionalCFM.forward_estimator, the nn.Module / TensorRT seam with
+ *                                 inputs x, mask, mu, t, spks, cond -> estimator_out
+ *                                 (speech/cosyvoice/flow/flow_matching.py:128-155;
+ *                                  speech/cosyvoice/bin/export_onnx.py:84-85 names the tensors)
+ *   ls_flow_solve              <- CausalConditionalCFM.forward + ConditionalCFM.solve_euler
+ *                                 (speech/cosyvoice/flow/flow_matching.py:323-348, 74-126)
+ *   ls_dac_decode              <- DACVAE.decode (dac-vae/model.py:485-488)
+ *   ls_flow_create / ls_dac_create take the reference state_dict unchanged (key schema: SURVEY.md
+ *                                 Appendix A/B); weight-norm folding and layout packing happen inside.
+ *
+ * Tensor layouts at the boundary are the reference's: float32, NCT contiguous
+ * (x/mu/cond [rows,80,T], mask [rows,1,T], spks [rows,80], t [rows], latents z [B,80,L],
+ * waveform [B,1,L*hop]).  Unless stated otherwise pointers are DEVICE pointers valid on `stream`.
+ * Calls on one handle must be serialised by the caller (one handle per stream/thread, like one
+ * TensorRT execution context); different handles are independent.
+ */
+#ifndef LS_B200_H
+#define LS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS_OK 0
+#define LS_ERR_INVALID (-1)     /* bad argument / shape */
+#define LS_ERR_CUDA (-2)        /* CUDA runtime or driver failure */
+#define LS_ERR_WEIGHTS (-3)     /* missing / mis-shaped state_dict entry */
+#define LS_ERR_UNSUPPORTED (-4) /* configuration outside what the kernels cover */
+
+#define LS_ABI_VERSION 1
+
+/* One state_dict entry: host float32, C-contiguous. */
+typedef struct ls_tensor {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} ls_tensor;
+
+typedef struct ls_flow ls_flow;
+typedef struct ls_dac ls_dac;
+
+int32_t ls_abi_version(void);
+const char* ls_last_error(void);
+/* Reports SM count and compute capability; LS_ERR_UNSUPPORTED unless the device is sm_100. */
+int32_t ls_device_check(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- flow: CausalConditionalDecoder estimator + Euler/CFG solve ---- */
+int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);
+void ls_flow_destroy(ls_flow* h);
+
+/* One estimator evaluation.  rows = batch rows as the reference passes them (2 for CFG at B=1).
+ * out may alias x (the TensorRT path binds the output to x's buffer, flow_matching.py:136-152). */
+int32_t ls_flow_estimator_forward(ls_flow* h, const float* x, const float* mask, const float* mu, const float* t,
+                                  const float* spks, const float* cond, float* out, int32_t rows, int32_t T,
+                                  int32_t streaming, void* stream);
+
+/* Whole n_timesteps Euler solve with classifier-free guidance, B >= 1 utterances with per-utterance
+ * semantics (equal to B reference calls at batch 1).  noise: [80][noise_stride] rows of the fixed-noise
+ * buffer (CausalConditionalCFM.rand_noise); t_span_host: n_timesteps+1 HOST floats (the schedule the
+ * caller computed exactly as the reference does).  out: [B,80,T], zero where mask == 0. */
+int32_t ls_flow_solve(ls_flow* h, const float* mu, const float* mask, const float* spks, const float* cond,
+                      const float* noise, int64_t noise_stride, const float* t_span_host, int32_t n_timesteps,
+                      float temperature, float cfg_rate, int32_t streaming, float* out, int32_t B, int32_t T,
+                      void* stream);
+
+/* ---- DAC-VAE decoder ---- */
+int32_t ls_dac_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_dac** out);
+void ls_dac_destroy(ls_dac* h);
+int32_t ls_dac_hop_length(const ls_dac* h);
+/* z [B,80,L] -> wav [B,1,L*hop].  lengths (DEVICE int32 [B], may be NULL): valid latent frames per item;
+ * each item is decoded as if alone at its own length, the rest of its row is zero. */
+int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* wav, int32_t B, int32_t L,
+                      void* stream);
+
+/* ---- end to end with HOST buffers (pinned or pageable): H2D copies, solve, decode, D2H copy, and a
+ * stream synchronise all happen inside the call.  wav_host: [B,1,T*hop]. */
+int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,
+                           const float* spks_host, const float* cond_host, const float* noise_dev,
+                           int64_t noise_stride, const float* t_span_host, int32_t n_timesteps, float temperature,
+                           float cfg_rate, float* wav_host, int32_t B, int32_t T, void* stream);
+
+/* Number of kernel launches issued by this library since load (all handles, all threads). */
+int64_t ls_launch_count(void);
+
+/* ---- kernel-level hooks used by the parity tests (tests/test_kernels_gpu.py) ---- */
+typedef struct ls_conv_gemm_desc {
+  const void* a0; /* bf16 [B][T_in][a0_C] */
+  const void* a1; /* optional second K source (channel concat), bf16 [B][T_in][a1_C] */
+  const void* w;  /* bf16 [taps*N][K], K = a0_C + a1_C */
+  int32_t a0_C, a1_C, T_in, K;
+  int32_t B, M, N, block_n, taps, dil, pad;
+  const int32_t* lengths;
+  int32_t m_len_mul, m_len_add, skip_halo;
+  int32_t chan_mod;
+  const float* bias;
+  int32_t act; /* 0 none, 1 leaky-relu(0.1), 2 gelu(erf), 3 layernorm+mish, 4 leaky-relu then tanh */
+  const float* ln_g;
+  const float* ln_b;
+  const float* temb;
+  int64_t temb_bstride;
+  const void* addend;
+  int32_t addend_dtype; /* 1 f32, 2 bf16 */
+  void* out0;
+  int32_t out0_dtype; /* 0 none, 1 f32, 2 bf16 */
+  void* out1;
+  int32_t out1_mode; /* 0 none, 1 layernorm, 2 copy, 3 snake */
+  const float* p1_a;
+  const float* p1_b;
+  int32_t n_store;
+  int64_t out_ld, out_shift, out_bstride, out_alloc, out_valid_mul;
+} ls_conv_gemm_desc;
+int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream);
+/* qkv bf16 [B][T][3*H*64] -> out bf16 [B][T][H*64] */
+int32_t ls_test_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H,
+                          int32_t chunk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_B200_H */

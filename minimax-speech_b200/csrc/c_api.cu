@@ -1,0 +1,215 @@
+// extern "C" surface declared in include/ls_b200.h.
+#include <atomic>
+#include <cstdarg>
+#include <mutex>
+
+#include "dac_engine.h"
+#include "engine_common.h"
+#include "flow_engine.h"
+
+namespace ls {
+
+std::atomic<long long> g_launch_count{0};
+
+static thread_local std::string t_error;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+const char* get_error() { return t_error.c_str(); }
+
+template <typename F>
+static int32_t guarded(F&& f) {
+  try {
+    f();
+    return LS_OK;
+  } catch (const EngineError& e) {
+    set_error("%s", e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_error("%s", e.what());
+    return LS_ERR_INVALID;
+  } catch (...) {
+    set_error("unknown failure");
+    return LS_ERR_INVALID;
+  }
+}
+
+}  // namespace ls
+
+struct ls_flow {
+  std::unique_ptr<ls::FlowEngine> eng;
+  // staging for ls_synthesize_host
+  float* stage = nullptr;
+  size_t stage_bytes = 0;
+};
+struct ls_dac {
+  std::unique_ptr<ls::DacEngine> eng;
+};
+
+extern "C" {
+
+int32_t ls_abi_version(void) { return LS_ABI_VERSION; }
+const char* ls_last_error(void) { return ls::get_error(); }
+int64_t ls_launch_count(void) { return ls::g_launch_count.load(); }
+
+int32_t ls_device_check(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  return ls::guarded([&] {
+    cudaDeviceProp prop;
+    LS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    ls::require(prop.major == 10, "device is not sm_100 (B200)", LS_ERR_UNSUPPORTED);
+  });
+}
+
+int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_flow_create: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_flow>();
+    h->eng = std::make_unique<ls::FlowEngine>(w, device);
+    *out = h.release();
+  });
+}
+void ls_flow_destroy(ls_flow* h) {
+  if (!h) return;
+  if (h->stage) cudaFree(h->stage);
+  delete h;
+}
+
+int32_t ls_flow_estimator_forward(ls_flow* h, const float* x, const float* mask, const float* mu, const float* t,
+                                  const float* spks, const float* cond, float* out, int32_t rows, int32_t T,
+                                  int32_t streaming, void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && x && mask && mu && t && spks && cond && out, "ls_flow_estimator_forward: null argument");
+    h->eng->estimator_forward(x, mask, mu, t, spks, cond, out, rows, T, streaming != 0, (cudaStream_t)stream);
+  });
+}
+
+int32_t ls_flow_solve(ls_flow* h, const float* mu, const float* mask, const float* spks, const float* cond,
+                      const float* noise, int64_t noise_stride, const float* t_span_host, int32_t n_timesteps,
+                      float temperature, float cfg_rate, int32_t streaming, float* out, int32_t B, int32_t T,
+                      void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && mu && mask && spks && cond && noise && t_span_host && out, "ls_flow_solve: null argument");
+    h->eng->solve(mu, mask, spks, cond, noise, noise_stride, t_span_host, n_timesteps, temperature, cfg_rate,
+                  streaming != 0, out, B, T, (cudaStream_t)stream);
+  });
+}
+
+int32_t ls_dac_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_dac** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_dac_create: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_dac>();
+    h->eng = std::make_unique<ls::DacEngine>(w, device);
+    *out = h.release();
+  });
+}
+void ls_dac_destroy(ls_dac* h) { delete h; }
+int32_t ls_dac_hop_length(const ls_dac* h) { return h ? h->eng->hop() : 0; }
+
+int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* wav, int32_t B, int32_t L,
+                      void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && z && wav, "ls_dac_decode: null argument");
+    h->eng->decode(z, lengths, wav, B, L, (cudaStream_t)stream);
+  });
+}
+
+int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,
+                           const float* spks_host, const float* cond_host, const float* noise_dev,
+                           int64_t noise_stride, const float* t_span_host, int32_t n_timesteps, float temperature,
+                           float cfg_rate, float* wav_host, int32_t B, int32_t T, void* stream) {
+  return ls::guarded([&] {
+    ls::require(flow && dac && mu_host && mask_host && spks_host && cond_host && noise_dev && wav_host,
+                "ls_synthesize_host: null argument");
+    ls::require(B > 0 && T > 0, "B and T must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int F = flow->eng->feat();
+    const int hop = dac->eng->hop();
+    const size_t n_mu = (size_t)B * F * T, n_mask = (size_t)B * T, n_spk = (size_t)B * F;
+    const size_t n_wav = (size_t)B * T * hop;
+    // staging layout: mu | cond | latent | mask | spks | lengths(int) | wav
+    const size_t need = (3 * n_mu + n_mask + n_spk + (size_t)B + n_wav) * sizeof(float) + 7 * 256;
+    LS_CUDA(cudaSetDevice(flow->eng->device()));
+    if (need > flow->stage_bytes) {
+      LS_CUDA(cudaStreamSynchronize(s));
+      if (flow->stage) cudaFree(flow->stage);
+      flow->stage = nullptr;
+      LS_CUDA(cudaMalloc(&flow->stage, need));
+      flow->stage_bytes = need;
+    }
+    auto al = [](size_t n) { return (n + 63) & ~size_t(63); };
+    float* d_mu = flow->stage;
+    float* d_cond = d_mu + al(n_mu);
+    float* d_lat = d_cond + al(n_mu);
+    float* d_mask = d_lat + al(n_mu);
+    float* d_spk = d_mask + al(n_mask);
+    int32_t* d_len = reinterpret_cast<int32_t*>(d_spk + al(n_spk));
+    float* d_wav = reinterpret_cast<float*>(d_len) + al((size_t)B);
+    LS_CUDA(cudaMemcpyAsync(d_mu, mu_host, n_mu * 4, cudaMemcpyHostToDevice, s));
+    LS_CUDA(cudaMemcpyAsync(d_cond, cond_host, n_mu * 4, cudaMemcpyHostToDevice, s));
+    LS_CUDA(cudaMemcpyAsync(d_mask, mask_host, n_mask * 4, cudaMemcpyHostToDevice, s));
+    LS_CUDA(cudaMemcpyAsync(d_spk, spks_host, n_spk * 4, cudaMemcpyHostToDevice, s));
+    flow->eng->solve(d_mu, d_mask, d_spk, d_cond, noise_dev, noise_stride, t_span_host, n_timesteps, temperature,
+                     cfg_rate, false, d_lat, B, T, s);
+    LS_CUDA(ls::launch_mask_to_lengths(d_mask, d_len, B, T, 1, s));
+    dac->eng->decode(d_lat, d_len, d_wav, B, T, s);
+    LS_CUDA(cudaMemcpyAsync(wav_host, d_wav, n_wav * 4, cudaMemcpyDeviceToHost, s));
+    LS_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream) {
+  return ls::guarded([&] {
+    ls::require(d && d->a0 && d->w, "ls_test_conv_gemm: null argument");
+    int dev = 0, sms = 0;
+    LS_CUDA(cudaGetDevice(&dev));
+    LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUtensorMap a0, a1, w;
+    ls::require(ls::make_act_map(&a0, d->a0, d->a0_C, d->T_in, d->B, d->a0_C, (long long)d->T_in * d->a0_C, 128),
+                "tensor map a0", LS_ERR_CUDA);
+    if (d->a1)
+      ls::require(ls::make_act_map(&a1, d->a1, d->a1_C, d->T_in, d->B, d->a1_C, (long long)d->T_in * d->a1_C, 128),
+                  "tensor map a1", LS_ERR_CUDA);
+    else
+      a1 = a0;
+    ls::require(ls::make_weight_map(&w, d->w, d->K, d->taps * d->N, d->block_n), "tensor map w", LS_ERR_CUDA);
+    ls::ConvGemmParams p{};
+    p.B = d->B, p.M = d->M, p.N = d->N, p.block_n = d->block_n, p.taps = d->taps, p.dil = d->dil, p.pad = d->pad;
+    p.kb_per_tap = (d->K + 63) / 64;
+    p.kb_split = d->a1 ? d->a0_C / 64 : p.kb_per_tap;
+    p.lengths = d->lengths, p.m_len_mul = d->m_len_mul, p.m_len_add = d->m_len_add, p.skip_halo = d->skip_halo;
+    p.chan_mod = d->chan_mod, p.bias = d->bias, p.act = d->act, p.ln_g = d->ln_g, p.ln_b = d->ln_b;
+    p.temb = d->temb, p.temb_bstride = d->temb_bstride, p.addend = d->addend, p.addend_dtype = d->addend_dtype;
+    p.out0 = d->out0, p.out0_dtype = d->out0_dtype, p.out1 = d->out1, p.out1_mode = d->out1_mode;
+    p.p1_a = d->p1_a, p.p1_b = d->p1_b, p.n_store = d->n_store;
+    p.out_ld = d->out_ld, p.out_shift = d->out_shift, p.out_bstride = d->out_bstride, p.out_alloc = d->out_alloc;
+    p.out_valid_mul = d->out_valid_mul;
+    LS_CUDA(ls::launch_conv_gemm(a0, a1, w, p, sms, (cudaStream_t)stream));
+  });
+}
+
+int32_t ls_test_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H,
+                          int32_t chunk, void* stream) {
+  return ls::guarded([&] {
+    ls::require(qkv && out, "ls_test_attention: null argument");
+    CUtensorMap m;
+    ls::require(ls::make_act_map(&m, qkv, 3 * H * 64, T, B, 3 * H * 64, (long long)T * 3 * H * 64, 128),
+                "tensor map qkv", LS_ERR_CUDA);
+    ls::AttnParams ap{};
+    ap.B = B, ap.T = T, ap.H = H, ap.lengths = lengths, ap.chunk = chunk;
+    ap.scale_log2e = 0.125f * 1.4426950408889634f;
+    ap.out = reinterpret_cast<__nv_bfloat16*>(out);
+    LS_CUDA(ls::launch_attention(m, ap, (cudaStream_t)stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Kernel-level interface shared by the engines (flow_engine.cu / dac_engine.cu) and the C-ABI test hooks.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace ls {
+
+extern std::atomic<long long> g_launch_count;  // kernels launched by this library
+inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4 };
+enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 };
+enum Out1Mode : int { OUT1_NONE = 0, OUT1_LN = 1, OUT1_COPY = 2, OUT1_SNAKE = 3 };
+
+// Implicit-GEMM 1-D convolution on time-major activations:
+//   D[b, t, n] = sum_tap sum_c A[b, t + tap*dil - pad, c] * W[tap][n][c]        (rows outside [0,T_in) read as 0)
+// followed by a fused, row-local epilogue (see conv_gemm.cu).  Linear layers are taps=1.
+struct ConvGemmParams {
+  // iteration space
+  int B;              // batch items (utterance x CFG half)
+  int M;              // output rows per batch item in this launch's iteration space
+  int N;              // total output columns (multiple of block_n)
+  int block_n;        // tile width: multiple of 16, <= 256
+  int taps, dil, pad;
+  int kb_per_tap;     // 64-wide K blocks per tap (over both A sources)
+  int kb_split;       // K blocks [0,kb_split) come from A source 0, the rest from A source 1
+  const int* lengths; // [B] valid length units per batch item (device), or nullptr = everything valid
+  int m_len_mul, m_len_add;  // rows that matter: lengths[b]*m_len_mul + m_len_add (+ skip_halo before tiles are skipped)
+  int skip_halo;
+  // epilogue
+  int chan_mod;       // per-channel vectors are indexed with (n % chan_mod)
+  const float* bias;  // [chan_mod] or nullptr
+  int act;
+  const float* ln_g;  // ACT_LN_MISH: LayerNorm affine over the N(=block_n) columns, eps 1e-5
+  const float* ln_b;
+  const float* temb;  // optional [.. , N] vector added after the activation; row b uses temb + b*temb_bstride
+  long long temb_bstride;
+  const void* addend; // optional residual, same flat indexing as out0
+  int addend_dtype;   // OUT_F32 / OUT_BF16
+  // outputs: flat element index inside batch item = row*out_ld + n + out_shift; stored if in [0, valid),
+  // zero-filled if in [valid, alloc), dropped otherwise.  valid = lengths ? lengths[b]*out_valid_mul : alloc.
+  void* out0;
+  int out0_dtype;
+  void* out1;         // always bf16
+  int out1_mode;
+  const float* p1_a;  // OUT1_LN: gamma | OUT1_SNAKE: alpha
+  const float* p1_b;  // OUT1_LN: beta  | OUT1_SNAKE: 1/(alpha+1e-9)
+  int n_store;        // only columns n < n_store are stored (N padding)
+  long long out_ld, out_shift, out_bstride, out_alloc, out_valid_mul;
+};
+
+// Tensor maps are created on the host (tma_host.cpp helpers) and passed by value.
+cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+
+// Flash attention forward over a packed [B][T][3*H*64] bf16 QKV tensor (Q | K | V column blocks).
+struct AttnParams {
+  int B, T, H;
+  const int* lengths;   // [B] valid keys per batch item or nullptr (= T)
+  int chunk;            // >0: block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
+  float scale_log2e;    // softmax scale * log2(e)
+  __nv_bfloat16* out;   // [B][T][H*64]
+};
+cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);
+
+// ---- bandwidth kernels (elementwise.cu) ----
+// NCT fp32 [B][C][T] -> time-major bf16 dst[b][t][c_off + c], dst row stride ld; rows >= len zeroed.
+cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,
+                            int ld, int c_off, const int* lengths, cudaStream_t s);
+// broadcast a per-batch vector [B][C] over time into dst[b][t][c_off + c]
+cudaError_t launch_pack_bcast(const float* src, __nv_bfloat16* dst, int B, int C, int T, int ld, int c_off,
+                              const int* lengths, cudaStream_t s);
+// zero dst[b][t][c_off .. c_off+C)
+cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, int c_off, cudaStream_t s);
+// x_state[b][t][c] = noise[c][t] * temperature (noise row stride noise_ld); also writes bf16 copies into
+// xin rows b and B+b (channel offset 0).
+cudaError_t launch_init_state(const float* noise, int noise_ld, float temperature, float* x_state,
+                              __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s);
+// CFG combine + Euler update (flow_matching.py:118-120): x += dt*((1+w) v[b] - w v[B+b]); refresh bf16 copies.
+cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin, int B, int C, int T, int ld,
+                             float dt, float cfg_rate, cudaStream_t s);
+// time-major fp32 [B][T][C] -> NCT fp32 [B][C][T], rows >= len zeroed
+cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T, const int* lengths, cudaStream_t s);
+// lengths[b] = number of non-zero entries of mask[b][0][:]
+cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s);
+// timestep conditioning for nt time values: sinusoidal embedding -> MLP -> per-resnet projections
+struct TimeEmbedParams {
+  const float* t;        // [nt] device
+  const float* freqs;    // [in_dim/2]
+  const float* w1; const float* b1;   // [hid][in_dim]
+  const float* w2; const float* b2;   // [hid][hid]
+  const float* wr; const float* br;   // [n_res][out_dim][hid], [n_res][out_dim]
+  float* out;            // [nt][n_res][out_dim]
+  int nt, in_dim, hid, n_res, out_dim;
+};
+cudaError_t launch_time_embed(const TimeEmbedParams& p, cudaStream_t s);
+
+// ---- host helpers (tma_host.cu) ----
+// bf16 activation [B][T][C] viewed through 64 x rows x 1 boxes with 128B swizzle (OOB -> zero)
+bool make_act_map(CUtensorMap* map, const void* base, int C, int T, int B, long long row_stride_elems,
+                  long long batch_stride_elems, int box_rows);
+// bf16 weight matrix [rows][K] with 64 x box_rows boxes
+bool make_weight_map(CUtensorMap* map, const void* base, int K, int rows, int box_rows);
+
+}  // namespace ls

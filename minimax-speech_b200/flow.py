@@ -1,0 +1,197 @@
+"""Drop-in replacements for the reference's flow-matching decoder classes.
+
+Same constructor / ``forward`` signatures, same ``state_dict`` key schema (reference checkpoints load
+with ``load_state_dict`` unchanged) as
+
+  * ``cosyvoice.flow.decoder.CausalConditionalDecoder``      speech/cosyvoice/flow/decoder.py:294-496
+  * ``cosyvoice.flow.flow_matching.ConditionalCFM``           speech/cosyvoice/flow/flow_matching.py:21-155
+  * ``cosyvoice.flow.flow_matching.CausalConditionalCFM``     speech/cosyvoice/flow/flow_matching.py:317-348
+
+so ``speech/config.yaml:89,105`` can name these classes instead (``!new:minimax_speech_b200.flow....``).
+All arithmetic runs in the CUDA library behind include/ls_b200.h; these modules only hold parameters,
+validate arguments and marshal pointers.  Inference only: ``compute_loss*`` (training) is out of scope.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import native, synth
+
+
+class _Holder(nn.Module):
+    """Parameter container addressed by the reference's dotted state_dict names."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder")
+
+
+def _register_tree(root, state_dict):
+    for name, value in state_dict.items():
+        mod = root
+        *path, leaf = name.split(".")
+        for part in path:
+            if not hasattr(mod, part):
+                mod.add_module(part, _Holder())
+            mod = getattr(mod, part)
+        mod.register_parameter(leaf, nn.Parameter(value.clone(), requires_grad=False))
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def _as_f32(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _check_prefix_mask(mask):
+    """The kernels take per-utterance lengths; the reference always builds prefix masks
+    (``~make_pad_mask(len)``, flow.py:478,493)."""
+    m = mask != 0
+    if bool((m[..., 1:] & ~m[..., :-1]).any()):
+        raise ValueError("mask must be a prefix (right-padding) mask")
+
+
+class CausalConditionalDecoder(nn.Module):
+    """Estimator.  ``forward(x, mask, mu, t, spks, cond, streaming)`` -> ``[rows, out_channels, T]``."""
+
+    def __init__(self, in_channels=320, out_channels=80, channels=(256,), dropout=0.0, attention_head_dim=64,
+                 n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn="gelu", static_chunk_size=50,
+                 num_decoding_left_chunks=-1, weight_seed=1986):
+        super().__init__()
+        channels = tuple(channels)
+        if channels != (256,) or attention_head_dim != 64 or act_fn != "gelu" or in_channels != 4 * out_channels:
+            raise NotImplementedError("B200 estimator covers config.yaml's CausalConditionalDecoder: "
+                                      "channels=[256], head_dim 64, act_fn gelu, in_channels = 4*out_channels")
+        if static_chunk_size != 50 or num_decoding_left_chunks != -1:
+            raise NotImplementedError("streaming mask: static_chunk_size=50 with all left chunks")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.static_chunk_size, self.num_decoding_left_chunks = static_chunk_size, num_decoding_left_chunks
+        _register_tree(self, synth.estimator_state_dict(
+            weight_seed, "reference", in_channels=in_channels, out_channels=out_channels, channels=256,
+            n_blocks=n_blocks, num_mid_blocks=num_mid_blocks, num_heads=num_heads, head_dim=attention_head_dim))
+        self._handle = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+
+    def invalidate(self):
+        self._handle = None
+
+    def handle(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
+        if self._handle is None or self._handle.device != device:
+            self._handle = native.FlowHandle(self.state_dict(), device)
+        return self._handle
+
+    @torch.inference_mode()
+    def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
+        dev = x.device
+        rows, _, T = x.shape
+        spks = torch.zeros(rows, self.out_channels, device=dev) if spks is None else spks
+        cond = torch.zeros_like(x) if cond is None else cond
+        _check_prefix_mask(mask)
+        t = t.reshape(-1).expand(rows) if t.numel() == 1 else t
+        out = self.handle(dev).estimator_forward(_as_f32(x, dev), _as_f32(mask, dev), _as_f32(mu, dev),
+                                                 _as_f32(t, dev), _as_f32(spks, dev), _as_f32(cond, dev), streaming)
+        return out.to(x.dtype)
+
+
+class ConditionalCFM(nn.Module):
+    def __init__(self, in_channels, cfm_params, n_spks=1, spk_emb_dim=64, estimator=None):
+        super().__init__()
+        self.n_feats, self.n_spks, self.spk_emb_dim = in_channels, n_spks, spk_emb_dim
+        self.solver = _get(cfm_params, "solver", "euler")
+        self.sigma_min = _get(cfm_params, "sigma_min", 1e-4)
+        self.t_scheduler = _get(cfm_params, "t_scheduler", "cosine")
+        self.training_cfg_rate = _get(cfm_params, "training_cfg_rate", 0.2)
+        self.inference_cfg_rate = _get(cfm_params, "inference_cfg_rate", 0.7)
+        self.estimator = estimator
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _t_span(self, n_timesteps):
+        t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)  # schedule kept in fp32
+        if self.t_scheduler == "cosine":
+            t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
+        return t_span
+
+    def _solve(self, z, t_span, mu, mask, spks, cond, streaming=False):
+        """z: [1 or B, 80, >=T] noise rows (row stride may exceed T)."""
+        dev = mu.device
+        B, F, T = mu.shape
+        _check_prefix_mask(mask)
+        if z.shape[0] != 1:
+            raise NotImplementedError("per-utterance noise: pass z with a single leading row shared by the batch")
+        spks = torch.zeros(B, F, device=dev) if spks is None else spks
+        cond = torch.zeros_like(mu) if cond is None else cond
+        h = self.estimator.handle(dev)
+        return h.solve(_as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev), _as_f32(cond, dev), z[0],
+                       t_span.numpy(), 1.0, self.inference_cfg_rate, streaming)
+
+    # -- reference surface --------------------------------------------------------------------
+    @torch.inference_mode()
+    def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, prompt_len=0,
+                cache=None, noise=None):
+        """flow_matching.py:39-72.  ``noise`` (optional, [1,80,T]) injects the initial sample for parity;
+        by default it is drawn with torch.randn like the reference."""
+        if mu.shape[0] != 1:
+            raise ValueError("the prompt/overlap cache path is defined for batch 1 (flow.py:453)")
+        cache = torch.zeros(1, mu.shape[1], 0, 2) if cache is None else cache
+        z = (torch.randn_like(mu) if noise is None else noise.to(mu.device, mu.dtype)) * temperature
+        z = _as_f32(z, mu.device)
+        cache_size = cache.shape[2]
+        if cache_size != 0:
+            z[:, :, :cache_size] = cache[:, :, :, 0].to(z)
+            mu[:, :, :cache_size] = cache[:, :, :, 1].to(mu)  # in place, like the reference (:62-64)
+        z_cache = torch.concat([z[:, :, :prompt_len], z[:, :, -34:]], dim=2)
+        mu_cache = torch.concat([mu[:, :, :prompt_len], mu[:, :, -34:]], dim=2)
+        cache = torch.stack([z_cache, mu_cache.to(z_cache)], dim=-1)
+        return self._solve(z, self._t_span(n_timesteps), mu, mask, spks, cond), cache
+
+    def solve_euler(self, x, t_span, mu, mask, spks, cond, streaming=False):
+        """flow_matching.py:74-126; ``x`` is the initial noise."""
+        return self._solve(_as_f32(x, mu.device), t_span.detach().float().cpu(), mu, mask, spks, cond, streaming)
+
+    def forward_estimator(self, x, mask, mu, t, spks, cond, streaming=False):
+        """flow_matching.py:128-155 (nn.Module branch)."""
+        return self.estimator(x, mask, mu, t, spks, cond, streaming=streaming)
+
+    def compute_loss(self, *a, **k):
+        raise NotImplementedError("training losses are out of scope of the B200 hot path (SURVEY.md section 8)")
+
+    compute_loss_contrastive = compute_loss
+
+
+class CausalConditionalCFM(ConditionalCFM):
+    def __init__(self, in_channels, cfm_params, n_spks=1, spk_emb_dim=64, estimator=None):
+        super().__init__(in_channels, cfm_params, n_spks, spk_emb_dim, estimator)
+        # flow_matching.py:320-321 draws seed-0 noise (and reseeds the global RNGs as a side effect, which
+        # this implementation deliberately does not do)
+        self.rand_noise = synth.fixed_noise()
+        self._noise_dev = {}
+
+    def _noise_on(self, device):
+        key = str(device)
+        if key not in self._noise_dev:
+            self._noise_dev[key] = self.rand_noise.to(device=device, dtype=torch.float32).contiguous()
+        return self._noise_dev[key]
+
+    @torch.inference_mode()
+    def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False):
+        """flow_matching.py:323-348 -> ``(latent [B,80,T] fp32, None)``; B >= 1 (per-utterance semantics)."""
+        dev = mu.device
+        B, F, T = mu.shape
+        if T > self.rand_noise.shape[2]:
+            raise ValueError(f"T={T} exceeds the fixed-noise buffer ({self.rand_noise.shape[2]} frames)")
+        _check_prefix_mask(mask)
+        spks = torch.zeros(B, F, device=dev) if spks is None else spks
+        cond = torch.zeros_like(mu) if cond is None else cond
+        h = self.estimator.handle(dev)
+        out = h.solve(_as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev), _as_f32(cond, dev),
+                      self._noise_on(dev)[0], self._t_span(n_timesteps).numpy(), temperature,
+                      self.inference_cfg_rate, streaming)
+        return out, None

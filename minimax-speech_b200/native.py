@@ -1,0 +1,200 @@
+"""ctypes binding of include/ls_b200.h.  There is no fallback: if the CUDA library cannot be loaded
+(or built with nvcc) every entry point raises."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import build as _build
+
+LS_OK = 0
+ACT_NONE, ACT_LRELU, ACT_GELU, ACT_LN_MISH, ACT_LRELU_TANH = range(5)
+OUT_NONE, OUT_F32, OUT_BF16 = range(3)
+OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
+
+EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_destroy",
+           "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
+           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_test_conv_gemm", "ls_test_attention"]
+
+
+class LsTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class ConvGemmDesc(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("w", C.c_void_p),
+        ("a0_C", C.c_int32), ("a1_C", C.c_int32), ("T_in", C.c_int32), ("K", C.c_int32),
+        ("B", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("block_n", C.c_int32),
+        ("taps", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
+        ("lengths", C.c_void_p),
+        ("m_len_mul", C.c_int32), ("m_len_add", C.c_int32), ("skip_halo", C.c_int32),
+        ("chan_mod", C.c_int32),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+        ("temb", C.c_void_p), ("temb_bstride", C.c_int64),
+        ("addend", C.c_void_p), ("addend_dtype", C.c_int32),
+        ("out0", C.c_void_p), ("out0_dtype", C.c_int32),
+        ("out1", C.c_void_p), ("out1_mode", C.c_int32),
+        ("p1_a", C.c_void_p), ("p1_b", C.c_void_p),
+        ("n_store", C.c_int32),
+        ("out_ld", C.c_int64), ("out_shift", C.c_int64), ("out_bstride", C.c_int64), ("out_alloc", C.c_int64),
+        ("out_valid_mul", C.c_int64),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the .so is missing or stale and nvcc is present)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
+        try:
+            lib = C.CDLL(path)
+        except OSError as e:
+            raise RuntimeError(f"cannot load {path}: {e}.  The hot path has no CPU or PyTorch fallback; "
+                               "build it with `python minimax-speech_b200/build.py`.") from e
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        lib.ls_abi_version.restype = i32
+        lib.ls_last_error.restype = C.c_char_p
+        lib.ls_launch_count.restype = i64
+        lib.ls_device_check.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        lib.ls_flow_create.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_flow_destroy.argtypes = [vp]
+        lib.ls_flow_destroy.restype = None
+        lib.ls_flow_estimator_forward.argtypes = [vp] * 8 + [i32, i32, i32, vp]
+        lib.ls_flow_solve.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, i32, vp, i32, i32, vp]
+        lib.ls_dac_create.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_dac_destroy.argtypes = [vp]
+        lib.ls_dac_destroy.restype = None
+        lib.ls_dac_hop_length.argtypes = [vp]
+        lib.ls_dac_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+        lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
+        lib.ls_test_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), vp]
+        lib.ls_test_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if fn.restype is C.c_int:
+                fn.restype = i32
+        _lib = lib
+        return lib
+
+
+def check(code, what):
+    if code != LS_OK:
+        msg = load().ls_last_error()
+        raise RuntimeError(f"{what} failed (code {code}): {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(load().ls_launch_count())
+
+
+def current_stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def tensor_table(state_dict):
+    """state_dict (any device/dtype) -> (ctypes array of LsTensor, keep-alive list) over host fp32 copies."""
+    keep, arr = [], (LsTensor * len(state_dict))()
+    for i, (k, v) in enumerate(state_dict.items()):
+        a = np.ascontiguousarray(v.detach().to("cpu", torch.float32).numpy())
+        name = k.encode()
+        keep.append((a, name))
+        arr[i].name = name
+        arr[i].data = a.ctypes.data
+        arr[i].ndim = a.ndim
+        if a.ndim > 4:
+            raise ValueError(f"{k}: more than 4 dims")
+        for d in range(a.ndim):
+            arr[i].shape[d] = a.shape[d]
+    return arr, keep
+
+
+class FlowHandle:
+    """Owns an ls_flow*: the packed estimator weights + workspace on one device."""
+
+    def __init__(self, state_dict, device):
+        lib = load()
+        self.device = torch.device(device)
+        arr, keep = tensor_table(state_dict)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ls_flow_create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_flow_create")
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ls_flow_destroy(h)
+
+    def estimator_forward(self, x, mask, mu, t, spks, cond, streaming=False, out=None):
+        rows, _, T = x.shape
+        out = torch.empty_like(x) if out is None else out
+        check(load().ls_flow_estimator_forward(self._h, ptr(x), ptr(mask), ptr(mu), ptr(t), ptr(spks), ptr(cond),
+                                               ptr(out), rows, T, int(bool(streaming)),
+                                               current_stream_ptr(self.device)), "ls_flow_estimator_forward")
+        return out
+
+    def solve(self, mu, mask, spks, cond, noise, t_span, temperature, cfg_rate, streaming=False):
+        B, F, T = mu.shape
+        out = torch.empty(B, F, T, device=mu.device, dtype=torch.float32)
+        ts = np.ascontiguousarray(t_span, dtype=np.float32)
+        check(load().ls_flow_solve(self._h, ptr(mu), ptr(mask), ptr(spks), ptr(cond), ptr(noise),
+                                   noise.stride(-2), C.c_void_p(ts.ctypes.data), len(ts) - 1, float(temperature),
+                                   float(cfg_rate), int(bool(streaming)), ptr(out), B, T,
+                                   current_stream_ptr(self.device)), "ls_flow_solve")
+        return out
+
+
+class DacHandle:
+    def __init__(self, state_dict, device):
+        lib = load()
+        self.device = torch.device(device)
+        arr, keep = tensor_table(state_dict)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ls_dac_create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_dac_create")
+        self._h = h
+        self.hop_length = int(lib.ls_dac_hop_length(h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ls_dac_destroy(h)
+
+    def decode(self, z, lengths=None):
+        B, _, L = z.shape
+        wav = torch.empty(B, 1, L * self.hop_length, device=z.device, dtype=torch.float32)
+        check(load().ls_dac_decode(self._h, ptr(z), ptr(lengths), ptr(wav), B, L,
+                                   current_stream_ptr(self.device)), "ls_dac_decode")
+        return wav
+
+
+def synthesize_host(flow, dac, mu, mask, spks, cond, noise_dev, t_span, temperature, cfg_rate, wav_out):
+    """End-to-end call on HOST tensors (pinned preferred): copies, solve, decode and read-back inside."""
+    B, _, T = mu.shape
+    ts = np.ascontiguousarray(t_span, dtype=np.float32)
+    check(load().ls_synthesize_host(flow._h, dac._h, ptr(mu), ptr(mask), ptr(spks), ptr(cond), ptr(noise_dev),
+                                    noise_dev.stride(-2), C.c_void_p(ts.ctypes.data), len(ts) - 1,
+                                    float(temperature), float(cfg_rate), ptr(wav_out), B, T,
+                                    current_stream_ptr(flow.device)), "ls_synthesize_host")
+    return wav_out

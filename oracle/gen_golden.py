@@ -90,6 +90,14 @@ def main():
             print("dac", name, y.shape, float(y.abs().max()))
         np.savez_compressed(os.path.join(OUT, "dac_golden.npz"), **out)
 
+        # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
+        import json
+        keys = {"estimator": {k: list(v.shape) for k, v in est.state_dict().items()},
+                "dac_decoder": {k: list(v.shape) for k, v in dac.state_dict().items()
+                                if k.startswith(("decoder.", "de_conv_pre."))}}
+        with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
+            json.dump(keys, f, indent=0, sort_keys=True)
+
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,154 @@
+"""Parity proper (B200): the drop-in modules, called like the reference's, against the CPU oracle and the
+golden outputs of the unmodified reference.  Tolerances are north_star's: latent rel-L2 <= 1e-2 (bf16 mode),
+waveform SNR >= 30 dB."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import minimax_speech_b200.synth as synth  # noqa: E402
+from minimax_speech_b200.dac import DACVAEDecoder  # noqa: E402
+from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder  # noqa: E402
+from oracle import restatement as O  # noqa: E402
+from oracle.gen_golden import est_inputs  # noqa: E402
+
+DEV = torch.device("cuda:0")
+LATENT_TOL = 1e-2
+SNR_MIN_DB = 30.0
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+@pytest.fixture(scope="module")
+def flow(golden_dir):
+    g = np.load(os.path.join(golden_dir, "flow_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    est = CausalConditionalDecoder()
+    est.load_state_dict(sd)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    return g, sd, cfm
+
+
+@pytest.fixture(scope="module")
+def dac(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dac_golden.npz"))
+    sd = synth.dac_decoder_state_dict(int(g["weights_seed"]), init="test")
+    dec = DACVAEDecoder()
+    dec.load_state_dict(sd)
+    return g, sd, dec
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_estimator_vs_reference_golden(flow, case):
+    g, sd, cfm = flow
+    lengths = [int(v) for v in g[f"est_{case}_lengths"]]
+    x, mask, mu, t, spks, cond = est_inputs(lengths, int(g[f"est_{case}_seed"]))
+    y = cfm.forward_estimator(x.to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV), spks.to(DEV), cond.to(DEV),
+                              streaming=bool(g[f"est_{case}_streaming"])).cpu()
+    ref = torch.from_numpy(g[f"est_{case}_y"])
+    for b, n in enumerate(lengths):
+        e = O.rel_l2(y[b, :, :n], ref[b, :, :n])
+        print(f"estimator {case}[{b}] rel-L2 {e:.3e}")
+        assert e < 1.6e-2  # single call; SURVEY section 6: reference bf16 autocast itself sits at 1.6e-2
+        assert float(y[b, :, n:].abs().max() if n < y.shape[2] else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_cfm_solve_vs_reference_golden(flow, case):
+    g, sd, cfm = flow
+    lengths = [int(v) for v in g[f"cfm_{case}_lengths"]]
+    mu, mask, spks, cond = synth.batch_inputs(lengths, first_index=50)
+    y, none = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=int(g[f"cfm_{case}_steps"]), temperature=1.0,
+                  spks=spks.to(DEV), cond=cond.to(DEV), streaming=bool(g[f"cfm_{case}_streaming"]))
+    assert none is None and y.dtype == torch.float32 and y.shape == mu.shape
+    y = y.cpu()
+    ref = torch.from_numpy(g[f"cfm_{case}_y"])
+    for b, n in enumerate(lengths):
+        e = O.rel_l2(y[b, :, :n], ref[b, :, :n])
+        print(f"cfm {case}[{b}] rel-L2 {e:.3e}")
+        assert e < LATENT_TOL
+        assert float(y[b, :, n:].abs().max() if n < y.shape[2] else 0.0) == 0.0
+
+
+def test_cfm_10_step_full_config_vs_oracle(flow):
+    """BASELINE config-1 shape at reduced length (oracle time): 10 steps, CFG, one utterance."""
+    g, sd, cfm = flow
+    mu, mask, spks, cond = synth.batch_inputs([150], first_index=7)
+    y, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=10, spks=spks.to(DEV), cond=cond.to(DEV))
+    with torch.inference_mode():
+        ref = O.cfm_forward(sd, synth.fixed_noise(), mu, mask, 10, 1.0, spks, cond)
+    e = O.rel_l2(y.cpu(), ref)
+    print(f"cfm 10-step rel-L2 {e:.3e}")
+    assert e < LATENT_TOL
+
+
+def test_batched_equals_per_utterance(flow):
+    """Size-independent property: a padded mixed-length batch equals one call per utterance."""
+    g, sd, cfm = flow
+    lengths = [200, 131, 64, 17]
+    mu, mask, spks, cond = synth.batch_inputs(lengths, first_index=20)
+    yb, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=3, spks=spks.to(DEV), cond=cond.to(DEV))
+    for b, n in enumerate(lengths):
+        y1, _ = cfm(mu=mu[b:b + 1, :, :n].to(DEV), mask=mask[b:b + 1, :, :n].to(DEV), n_timesteps=3,
+                    spks=spks[b:b + 1].to(DEV), cond=cond[b:b + 1, :, :n].to(DEV))
+        e = O.rel_l2(yb[b, :, :n].cpu(), y1[0].cpu())
+        assert e < 1e-5, (b, e)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_dac_decode_vs_reference_golden(dac, case):
+    g, sd, dec = dac
+    z = synth.dac_latents(int(g[f"dac_{case}_index"]), int(g[f"dac_{case}_frames"]))
+    y = dec.decode(z.to(DEV)).cpu()
+    ref = torch.from_numpy(g[f"dac_{case}_y"])
+    assert y.shape == ref.shape
+    s = O.snr_db(y, ref)
+    print(f"dac {case} SNR {s:.1f} dB")
+    assert s > SNR_MIN_DB
+
+
+def test_dac_decode_long_vs_oracle(dac):
+    g, sd, dec = dac
+    z = synth.dac_latents(3, 150)
+    y = dec.decode(z.to(DEV)).cpu()
+    with torch.inference_mode():
+        ref = O.dac_decode(sd, z)
+    s = O.snr_db(y, ref)
+    print(f"dac 3 s SNR {s:.1f} dB")
+    assert s > SNR_MIN_DB
+    assert float(y.abs().max()) <= 1.0
+
+
+def test_dac_varlen_batch_equals_per_utterance(dac):
+    g, sd, dec = dac
+    lengths = [60, 33, 5]
+    z = torch.zeros(3, 80, 60)
+    for b, n in enumerate(lengths):
+        z[b, :, :n] = synth.dac_latents(10 + b, n)[0]
+    y = dec.decode(z.to(DEV), torch.tensor(lengths)).cpu()
+    hop = dec.hop_length
+    for b, n in enumerate(lengths):
+        y1 = dec.decode(z[b:b + 1, :, :n].to(DEV)).cpu()
+        s = O.snr_db(y[b, :, :n * hop], y1[0])
+        assert s > 60.0, (b, s)
+        assert float(y[b, :, n * hop:].abs().max() if n < 60 else 0.0) == 0.0
+
+
+def test_end_to_end_latents_to_waveform(flow, dac):
+    """flow latents -> DAC waveform, both ours vs both oracle (reported separately from decoder-only)."""
+    g, sd, cfm = flow
+    _, dsd, dec = dac
+    mu, mask, spks, cond = synth.batch_inputs([100], first_index=3)
+    lat, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=10, spks=spks.to(DEV), cond=cond.to(DEV))
+    wav = dec.decode(lat).cpu()
+    with torch.inference_mode():
+        lat_ref = O.cfm_forward(sd, synth.fixed_noise(), mu, mask, 10, 1.0, spks, cond)
+        wav_ref = O.dac_decode(dsd, lat_ref)
+    print(f"e2e latent rel-L2 {O.rel_l2(lat.cpu(), lat_ref):.3e}  waveform SNR {O.snr_db(wav, wav_ref):.1f} dB")
+    assert O.rel_l2(lat.cpu(), lat_ref) < LATENT_TOL
