@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Headline benchmark: seconds of 24 kHz audio synthesised per second (BASELINE.json metric) on the
+configuration the metric is quoted on -- configs[1]: 16 x 10 s utterances per GPU, 10-step Euler + CFG through
+the CausalConditionalDecoder estimator, then DAC-VAE decode, bf16 tensor-core operands with fp32 accumulation.
+
+  python bench.py --gpus N --steps K --warmup W                 (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W  (the reference algorithm on the host CPU cores)
+
+One JSON line on stdout (rank 0).  A step = one pass of the whole hot path over one batch of synthetic inputs.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "audio-sec synthesized/sec (24 kHz)"
+UNIT = "audio-s/s"
+FRAME_RATE = 50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0, help="utterance length")
+    ap.add_argument("--n-timesteps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def config_of(a):
+    return {"workload": f"configs[1]: flow (CausalConditionalDecoder, {a.n_timesteps}-step Euler + CFG) + DAC-VAE "
+                        f"decode, {a.batch} x {a.seconds:g} s utterances per GPU, 24 kHz",
+            "utterances_per_gpu": a.batch, "utterance_seconds": a.seconds, "n_timesteps": a.n_timesteps,
+            "cfg_rate": 0.7, "latent_rate_hz": FRAME_RATE, "sharding": "utterances per rank, no data-path collective; "
+            "one waveform gather", "l2": "256 MiB scratch write between steps (inside the timed region); the "
+            "per-step working set (> 1 GB activations + 212 MB weights) also exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ CPU / reference arm
+def oracle_sample(seconds, n_timesteps, esd, dsd):
+    """One utterance through the CPU oracle (fp32, all host threads): the reference algorithm's CPU path."""
+    import minimax_speech_b200.synth as synth
+    from oracle import restatement as O
+    T = int(round(seconds * FRAME_RATE))
+    mu, mask, spks, cond = synth.batch_inputs([T])
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        lat = O.cfm_forward(esd, synth.fixed_noise(), mu, mask, n_timesteps, 1.0, spks, cond)
+        wav = O.dac_decode(dsd, lat)
+    dt = time.perf_counter() - t0
+    return dt, float(wav.abs().max())
+
+
+def cpu_baseline(a, esd, dsd):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle_sample(0.32, 1, esd, dsd)  # thread-pool / allocator warm-up
+    dt, _ = oracle_sample(a.seconds, a.n_timesteps, esd, dsd)
+    return {"value": a.seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 of {a.batch} utterances ({a.seconds:g} s, {a.n_timesteps} steps CFG + DAC decode), "
+                      f"oracle/restatement.py fp32 torch-CPU, {torch.get_num_threads()} threads, {dt:.2f} s"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import minimax_speech_b200.synth as synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    esd = synth.estimator_state_dict(1986, "reference")
+    dsd = synth.dac_decoder_state_dict(0, "reference")
+    oracle_sample(0.32, 1, esd, dsd)
+    seconds = a.seconds
+    probe, _ = oracle_sample(seconds, a.n_timesteps, esd, dsd)
+    note = ""
+    if probe * (a.steps + a.warmup) > 240.0 and seconds > 2.0:
+        seconds, note = 2.0, " (sample shortened to 2 s utterances to bound the run)"
+    for _ in range(max(a.warmup - 1, 0)):
+        oracle_sample(seconds, a.n_timesteps, esd, dsd)
+    times = [oracle_sample(seconds, a.n_timesteps, esd, dsd)[0] for _ in range(a.steps)]
+    total = sum(times)
+    value = seconds * a.steps / total
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"each step = 1 utterance ({seconds:g} s, {a.n_timesteps} steps CFG + DAC decode) of the "
+                    f"{a.batch}-utterance batch, oracle/restatement.py (restatement of the reference's PyTorch "
+                    f"CPU path; the reference itself is Python and is not on this box), fp32, {cores} threads{note}"}
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": 1000.0 * total / a.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": config_of(a), "impl": "reference", "cpu_baseline": cb,
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out = self.p.communicate()[0]
+        sm, mx, pw, reasons = [], 0, [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), pw.append(float(f[2]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c, w in zip(sm, pw) if w > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(a):
+    import torch.distributed as dist
+    import minimax_speech_b200.native as native
+    import minimax_speech_b200.synth as synth
+    from minimax_speech_b200.dac import DACVAEDecoder
+    from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder
+    from minimax_speech_b200.pipeline import Synthesizer, gather_waveforms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+
+    esd = synth.estimator_state_dict(1986, "reference")
+    dsd = synth.dac_decoder_state_dict(0, "reference")
+    est = CausalConditionalDecoder()
+    est.load_state_dict(esd)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    dac = DACVAEDecoder()
+    dac.load_state_dict(dsd)
+    syn = Synthesizer(cfm, dac)
+
+    T = int(round(a.seconds * FRAME_RATE))
+    B = a.batch
+    lengths = [T] * B
+    ids = list(range(rank * B, rank * B + B))
+    mu_h, mask_h, spks_h, cond_h = [t.pin_memory() for t in synth.batch_inputs(lengths, first_index=rank * B)]
+    mu, mask, spks, cond = [t.to(dev) for t in (mu_h, mask_h, spks_h, cond_h)]
+    n_samples = [T * dac.hop_length] * B
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        scratch.zero_()  # L2 flush
+        wav = syn(mu, mask, spks, cond, n_timesteps=a.n_timesteps)
+        if world > 1:
+            return gather_waveforms(wav, n_samples, ids, dst=0)
+        return wav
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sync_all()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = step()
+    e1.record()
+    sync_all()
+    launches = native.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    audio_per_step = world * B * a.seconds
+    value = audio_per_step * a.steps / (ms / 1000.0)
+
+    # ---- end to end through the host-buffer C-ABI call (H2D of inputs + D2H of the waveform inside) ----
+    wav_h = torch.empty(B, 1, T * dac.hop_length, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        syn.synthesize_host(mu_h, mask_h, spks_h, cond_h, a.n_timesteps, wav_out=wav_h, device=dev)
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        scratch.zero_()
+        syn.synthesize_host(mu_h, mask_h, spks_h, cond_h, a.n_timesteps, wav_out=wav_h, device=dev)
+    e1.record()
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    ems = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    ems = float(ems.item())
+    clock_rec = clocks.stop() if clocks else None
+    h2d = sum(t.numel() * 4 for t in (mu_h, mask_h, spks_h, cond_h))
+    d2h = wav_h.numel() * 4
+    e2e = {"value": audio_per_step * a.steps / (ems / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ems / a.steps, "wall_ms_per_step_rank0": wall_ms / a.steps,
+           "api": "Synthesizer.synthesize_host -> ls_synthesize_host (pinned host buffers)"}
+
+    # ---- per-kernel device time (CUDA events around every launch, separate pass) -> roofline ----
+    roofline, kernels = None, None
+    if rank == 0 and not a.no_profile:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained")
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+        if not peak_tf:
+            peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        peak_bw = peaks.get("hbm_gbs") or 6650.0
+        native.profile_begin()
+        for _ in range(a.steps):
+            syn(mu, mask, spks, cond, n_timesteps=a.n_timesteps)
+        prof = native.profile_end()
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        kernels = {}
+        for k, v in prof.items():
+            if not v["launches"]:
+                continue
+            sec = v["ms"] / 1000.0
+            kernels[k] = {"launches_per_step": v["launches"] / a.steps, "ms_per_step": v["ms"] / a.steps,
+                          "share_of_kernel_time": v["ms"] / tot,
+                          "tflops": v["flops"] / sec / 1e12 if sec else None,
+                          "gbs": v["bytes"] / sec / 1e9 if sec else None}
+        dom = max(("conv_gemm_estimator", "attention", "conv_gemm_dac"), key=lambda k: prof[k]["ms"])
+        ach = prof[dom]["flops"] / (prof[dom]["ms"] / 1000.0) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except (OSError, ValueError):
+            pass
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                    "flops_per_launch": prof[dom]["flops"] / prof[dom]["launches"],
+                    "avg_launch_us": 1000.0 * prof[dom]["ms"] / prof[dom]["launches"],
+                    "hbm_peak_gbs": peak_bw}
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb = cpu_baseline(a, esd, dsd)
+
+    if rank == 0:
+        rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+               "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_of(a),
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_rec, "roofline": roofline,
+               "kernels": kernels, "cpu_baseline": cb, "audio_seconds_per_step": audio_per_step}
+        print(json.dumps(rec))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

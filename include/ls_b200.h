@@ -92,6 +92,18 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
 /* Number of kernel launches issued by this library since load (all handles, all threads). */
 int64_t ls_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline figures: between ls_profile_begin() and ls_profile_end() every launch
+ * is bracketed by CUDA events on its stream.  ls_profile_end synchronises the device and fills 4 entries:
+ * 0 conv_gemm (estimator), 1 attention, 2 conv_gemm (DAC decoder), 3 bandwidth kernels. */
+typedef struct ls_profile_entry {
+  int64_t launches;
+  double ms;    /* summed device time of the launches */
+  double flops; /* algorithmic FLOPs of the launches (2*M*N*K, unpadded K) */
+  double bytes; /* algorithmic bytes (operands read once + outputs written once) */
+} ls_profile_entry;
+int32_t ls_profile_begin(void);
+int32_t ls_profile_end(ls_profile_entry* out4);
+
 /* ---- kernel-level hooks used by the parity tests (tests/test_kernels_gpu.py) ---- */
 typedef struct ls_conv_gemm_desc {
   const void* a0; /* bf16 [B][T_in][a0_C] */

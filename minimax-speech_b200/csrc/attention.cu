@@ -6,12 +6,13 @@
 // the key-padding mask is a per-utterance key bound, the streaming block-causal mask (chunk 50) a per-row bound.
 //
 // One CTA = 128 query rows of one (batch row, head).  S = Q K^T and O_j = P V run on tcgen05 with fp32
-// accumulators in TMEM; the 4 softmax warps own one query row per thread (online softmax, no shuffles), write
-// P as bf16 into a 128B-swizzled K-major smem tile and keep the running output in registers.  Two CTAs share an
-// SM so one CTA's MMAs overlap the other's softmax.
+// accumulators in TMEM; 8 softmax warps (two threads per query row, 64 keys each, row max / sum exchanged through
+// smem) run the online softmax, write P as bf16 into a 128B-swizzled K-major smem tile and keep the running
+// output in registers.  Two CTAs share an SM so one CTA's MMAs overlap the other's softmax.
 #include <cmath>
 
 #include "kernels.h"
+#include "profiler.h"
 #include "ptx.cuh"
 
 namespace ls {
@@ -21,9 +22,15 @@ constexpr int kQ = 128;
 constexpr int kKV = 128;
 constexpr int kD = 64;
 constexpr int kTile = kQ * kD * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kAttnThreads = 160;
-constexpr int kAttnSmem = 6 * kTile + 1024 + 128;  // Q, K x2, V, P x2 (+ align slack + barriers)
+constexpr int kSoftmaxWarps = 8;                   // warp w: TMEM lane quarter w%4, key half w/4
+constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
+constexpr int kAttnThreads = kSoftmaxThreads + 32;  // + control warp
+constexpr int kAttnSmem = 6 * kTile + 1024 + 128 + 3 * 1024;  // Q, K x2, V, P x2, align slack, barriers, exchange
 constexpr int kAttnTmemCols = 256;                 // S: cols [0,128)   O_j: cols [128,192)
+
+__device__ __forceinline__ void softmax_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory");
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ AttnParams p) {
@@ -51,10 +58,12 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   uint64_t* bar_p = bars + 5;
   uint64_t* bar_o = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  float* s_max = reinterpret_cast<float*>(bars + 16);  // [2 parity][2 half][128]
+  float* s_sum = s_max + 2 * 2 * kQ;                   // [2 half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if (lane == 0) {
       prefetch_tmap(&mapQKV);
       mbar_init(bar_q, 1);
@@ -62,7 +71,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       mbar_init(&bar_k[1], 1);
       mbar_init(bar_v, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
+      mbar_init(bar_p, kSoftmaxThreads);
       mbar_init(bar_o, 1);
       fence_barrier_init();
     }
@@ -77,7 +86,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if (lane == 0) {
       // ------------------------------------------------ control thread: TMA loads + MMA issue
       const int inner = p.H * kD;
@@ -131,60 +140,78 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------ softmax warps: thread = query row
-    const int r = warp * 32 + lane;
+    // ------------------------------------------------ softmax warps: 2 threads per query row (64 keys each)
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int r = quarter * 32 + lane;
     const int qi = q0 + r;
     int limit = len;
     if (p.chunk > 0) limit = min(len, (qi / p.chunk + 1) * p.chunk);
     const float c = p.scale_log2e;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_s + lane_addr + (uint32_t)(half * 64);
+    const uint32_t o_addr = tmem_o + lane_addr + (uint32_t)(half * 32);
     float m = -INFINITY, l = 0.f;
-    float o[kD];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    uint8_t* prow = sP + half * kTile + r * 128;  // this thread's 64 keys = one 128-byte swizzled row
     const int sw = r & 7;
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      const int nvalid = limit - j * kKV;
+      const int nvalid = limit - j * kKV - half * 64;  // valid keys among this thread's 64
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t s[32];
-        tmem_ld32(tmem_s + lane_addr + cc * 32, s);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t s[32];
+        tmem_ld32(s_addr + cc * 32, s);
+        tmem_ld_wait();
+        if (nvalid >= 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
+        }
       }
+      float* xm = s_max + (j & 1) * 2 * kQ;
+      xm[half * kQ + r] = mx;
+      softmax_barrier();
+      mx = fmaxf(mx, xm[(half ^ 1) * kQ + r]);
       const float m_new = fmaxf(m, mx * c);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2_approx(m - m_use);
       float rowsum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t s[32];
-        tmem_ld32(tmem_s + lane_addr + cc * 32, s);
+        tmem_ld32(s_addr + cc * 32, s);
         tmem_ld_wait();
         float pv[32];
+        if (nvalid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m_use));
-          pv[i] = cc * 32 + i < nvalid ? e : 0.f;
-          rowsum += pv[i];
+          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m_use));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m_use));
+            pv[i] = cc * 32 + i < nvalid ? e : 0.f;
+          }
         }
-        uint8_t* pk = prow + (cc >> 1) * kTile;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
           uint4 v;
-          v.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
-          v.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
-          v.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
-          v.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
-          const int ch = (cc & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(pk + ((ch ^ sw) << 4)) = v;
+          v.x = pack_bf16x2(pv[8 * q4 + 0], pv[8 * q4 + 1]);
+          v.y = pack_bf16x2(pv[8 * q4 + 2], pv[8 * q4 + 3]);
+          v.z = pack_bf16x2(pv[8 * q4 + 4], pv[8 * q4 + 5]);
+          v.w = pack_bf16x2(pv[8 * q4 + 6], pv[8 * q4 + 7]);
+          const int ch = cc * 4 + q4;
+          *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = v;
         }
       }
       l = fmaf(l, alpha, rowsum);
@@ -195,20 +222,22 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
 
       mbar_wait(bar_o, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      {
         uint32_t s[32];
-        tmem_ld32(tmem_o + lane_addr + cc * 32, s);
+        tmem_ld32(o_addr, s);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[cc * 32 + i] = fmaf(o[cc * 32 + i], alpha, __uint_as_float(s[i]));
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(s[i]));
       }
     }
+    s_sum[half * kQ + r] = l;
+    softmax_barrier();
+    l += s_sum[(half ^ 1) * kQ + r];
     if (qi < p.T) {
       const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = p.out + ((long long)b * p.T + qi) * (p.H * kD) + h * kD;
+      __nv_bfloat16* dst = p.out + ((long long)b * p.T + qi) * (p.H * kD) + h * kD + half * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 v;
         v.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
         v.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
@@ -221,7 +250,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kAttnTmemCols);
   }
@@ -238,6 +267,8 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
   }
   if (p.B <= 0 || p.T <= 0) return cudaSuccess;
   dim3 grid((p.T + kQ - 1) / kQ, p.H, p.B);
+  const double bh = (double)p.B * p.H;
+  ProfScope prof(stream, PK_ATTENTION, 4.0 * bh * p.T * (double)p.T * kD, bh * p.T * kD * 2.0 * 4.0);
   attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(mapQKV, p);
   count_launch();
   return cudaGetLastError();

@@ -6,6 +6,7 @@
 #include "dac_engine.h"
 #include "engine_common.h"
 #include "flow_engine.h"
+#include "profiler.h"
 
 namespace ls {
 
@@ -167,6 +168,20 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
   });
 }
 
+int32_t ls_profile_begin(void) {
+  ls::prof_begin();
+  return LS_OK;
+}
+int32_t ls_profile_end(ls_profile_entry* out4) {
+  return ls::guarded([&] {
+    ls::require(out4 != nullptr, "ls_profile_end: null argument");
+    long long n[ls::PK_COUNT];
+    double ms[ls::PK_COUNT], fl[ls::PK_COUNT], by[ls::PK_COUNT];
+    ls::prof_end(n, ms, fl, by);
+    for (int k = 0; k < ls::PK_COUNT; ++k) out4[k] = ls_profile_entry{n[k], ms[k], fl[k], by[k]};
+  });
+}
+
 int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream) {
   return ls::guarded([&] {
     ls::require(d && d->a0 && d->w, "ls_test_conv_gemm: null argument");
@@ -193,6 +208,7 @@ int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream) {
     p.p1_a = d->p1_a, p.p1_b = d->p1_b, p.n_store = d->n_store;
     p.out_ld = d->out_ld, p.out_shift = d->out_shift, p.out_bstride = d->out_bstride, p.out_alloc = d->out_alloc;
     p.out_valid_mul = d->out_valid_mul;
+    p.k_true = d->K, p.tag = 0;
     LS_CUDA(ls::launch_conv_gemm(a0, a1, w, p, sms, (cudaStream_t)stream));
   });
 }

@@ -11,12 +11,14 @@
 // copy of the result for the next GEMM).
 //
 // Structure: persistent CTAs (one per SM), warp-specialised:
-//   warp 0  TMA producer  (A: 128 rows x 64 ch box per tap via a 3-D map, OOB rows -> 0 = conv zero padding;
+//   warp 0  TMEM allocator, then TMA producer  (A: 128 rows x 64 ch box per tap via a 3-D map, OOB rows -> 0 = conv zero padding;
 //                          B: block_n x 64 weight box), multi-stage mbarrier ring
 //   warp 1  tcgen05.mma issuer (one lane), fp32 accumulators in TMEM, double buffered
-//   warp 2  TMEM allocator
-//   warps 4-7 epilogue: thread = output row, tcgen05.ld 16 columns at a time
+//   warps 2-17 epilogue (512 threads): warp w owns TMEM lanes 32*(w%4).. (= 32 output rows) and every 4th
+//              16-column chunk; accumulators are pulled into registers in one burst and the TMEM stage is
+//              released immediately, LayerNorm statistics are combined across the 4 column groups through smem
 #include "kernels.h"
+#include "profiler.h"
 #include "ptx.cuh"
 
 namespace ls {
@@ -24,10 +26,14 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 2;
+constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 6;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
+constexpr int kSmemBudget = 206 * 1024;             // for the operand ring
 
 struct TileCoord {
   int b, mt, nt;
@@ -48,46 +54,38 @@ __device__ __forceinline__ bool tile_skipped(const ConvGemmParams& p, const Tile
   return (long long)c.mt * kBlockM >= need;
 }
 
-// Stores 16 consecutive values u[0..15] of this thread's row starting at column n (n % 16 == 0).
-// flat = row_flat + n is the element index inside the batch item.
-struct RowStore {
+// 16 consecutive output columns of one row.  state: 2 store values, 1 store zeros, 0 drop.
+struct ChunkStore {
   long long valid, alloc;
   int n_store;
   bool row_in;
-
-  __device__ __forceinline__ int group_state(long long flat, int len) const {  // 2 store, 1 zero, 0 drop
+  __device__ __forceinline__ int state(long long flat, int width = 16) const {
     if (!row_in || flat < 0) return 0;
-    if (flat + len <= valid) return 2;
-    if (flat + len <= alloc) return 1;
+    if (flat + width <= valid) return 2;
+    if (flat + width <= alloc) return 1;
     return 0;
   }
   __device__ __forceinline__ void f32(float* base, long long flat, int n, const float (&u)[16]) const {
-    if (n_store - n >= 16 || ((n_store - n) & 3) == 0) {
+    const int st = state(flat, min(16, n_store - n));
+    if (st == 0 || n >= n_store) return;
+    if (n + 16 <= n_store) {
+      float4* d = reinterpret_cast<float4*>(base + flat);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (n + 4 * g >= n_store) break;
-        const int st = group_state(flat + 4 * g, 4);
-        if (st == 0) continue;
-        float4 v = st == 2 ? make_float4(u[4 * g], u[4 * g + 1], u[4 * g + 2], u[4 * g + 3])
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(base + flat + 4 * g) = v;
-      }
+      for (int g = 0; g < 4; ++g)
+        d[g] = st == 2 ? make_float4(u[4 * g], u[4 * g + 1], u[4 * g + 2], u[4 * g + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (n + i >= n_store) break;
-        const int st = group_state(flat + i, 1);
-        if (st) base[flat + i] = st == 2 ? u[i] : 0.f;
-      }
+      for (int i = 0; i < 16; ++i)
+        if (n + i < n_store) base[flat + i] = st == 2 ? u[i] : 0.f;
     }
   }
   __device__ __forceinline__ void bf16(__nv_bfloat16* base, long long flat, int n, const float (&u)[16]) const {
-    if (n_store - n >= 16 || ((n_store - n) & 7) == 0) {
+    const int st = state(flat, min(16, n_store - n));
+    if (st == 0 || n >= n_store) return;
+    if (n + 16 <= n_store) {
+      uint4* d = reinterpret_cast<uint4*>(base + flat);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        if (n + 8 * g >= n_store) break;
-        const int st = group_state(flat + 8 * g, 8);
-        if (st == 0) continue;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (st == 2) {
           v.x = pack_bf16x2(u[8 * g + 0], u[8 * g + 1]);
@@ -95,15 +93,12 @@ struct RowStore {
           v.z = pack_bf16x2(u[8 * g + 4], u[8 * g + 5]);
           v.w = pack_bf16x2(u[8 * g + 6], u[8 * g + 7]);
         }
-        *reinterpret_cast<uint4*>(base + flat + 8 * g) = v;
+        d[g] = v;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (n + i >= n_store) break;
-        const int st = group_state(flat + i, 1);
-        if (st) base[flat + i] = __float2bfloat16(st == 2 ? u[i] : 0.f);
-      }
+      for (int i = 0; i < 16; ++i)
+        if (n + i < n_store) base[flat + i] = __float2bfloat16(st == 2 ? u[i] : 0.f);
     }
   }
 };
@@ -114,6 +109,35 @@ __device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(p) + g);
     v[4 * g] = t.x, v[4 * g + 1] = t.y, v[4 * g + 2] = t.z, v[4 * g + 3] = t.w;
   }
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// LayerNorm statistics of a 256-wide row whose 4 x 64 column quarters live in 4 threads (one per column
+// group): per-thread (mean, M2), combined with the parallel-variance formula through shared memory.
+__device__ __forceinline__ void row_stats(const float (&v)[4][16], float2* red, int g, int row, float& mean,
+                                          float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[j][i];
+  const float lm = s * (1.0f / 64.0f);
+  float m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[j][i] - lm;
+      m2 = fmaf(d, d, m2);
+    }
+  red[g * kBlockM + row] = make_float2(lm, m2);
+  epi_barrier();
+  const float2 a = red[row], b = red[kBlockM + row], c = red[2 * kBlockM + row], d = red[3 * kBlockM + row];
+  mean = 0.25f * (a.x + b.x + c.x + d.x);
+  const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
+  const float M2 = a.y + b.y + c.y + d.y + 64.0f * (da * da + db * db + dc * dc + dd * dd);
+  rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -130,6 +154,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float2* red_base = reinterpret_cast<float2*>(bars + 32);  // 256 B after the barriers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,11 +175,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], kEpiThreads);
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
+    __syncwarp();
     tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     tmem_relinquish();
   }
@@ -220,20 +246,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (thread = output row)
-    const int ew = warp - 4;
-    const int row = ew * 32 + lane;
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read (warp id % 4)
+    const int g = (warp - kFirstEpiWarp) >> 2;  // column group: owns 16-column chunks g, g+4, g+8, g+12
+    const int row = q * 32 + lane;
+    const int n_chunks = p.block_n >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t parity = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
-      if (tile_skipped(p, tc)) continue;
       const int t = tc.mt * kBlockM + row;
       const int n0 = tc.nt * p.block_n;
-      RowStore st;
+      ChunkStore st;
       st.alloc = p.out_alloc;
-      st.valid = p.lengths ? min((long long)p.lengths[tc.b] * p.out_valid_mul, p.out_alloc) : p.out_alloc;
       st.n_store = p.n_store;
       st.row_in = t < p.M;
       const long long row_flat = (long long)t * p.out_ld + p.out_shift;
@@ -241,164 +268,219 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       float* out0f = reinterpret_cast<float*>(p.out0) + boff;
       __nv_bfloat16* out0h = reinterpret_cast<__nv_bfloat16*>(p.out0) + boff;
       __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + boff;
+
+      if (tile_skipped(p, tc)) {
+        if (p.zero_skipped) {  // keep "everything past the valid length is zero" true for final outputs
+          st.valid = 0;
+          float zero[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) zero[i] = 0.f;
+          for (int c = g; c < n_chunks; c += 4) {
+            const int n = n0 + c * 16;
+            if (p.out0_dtype == OUT_F32) st.f32(out0f, row_flat + n, n, zero);
+            else if (p.out0_dtype == OUT_BF16) st.bf16(out0h, row_flat + n, n, zero);
+            if (p.out1_mode != OUT1_NONE) st.bf16(out1, row_flat + n, n, zero);
+          }
+        }
+        continue;
+      }
+      st.valid = p.lengths ? min((long long)p.lengths[tc.b] * p.out_valid_mul, p.out_alloc) : p.out_alloc;
       const float* addf = reinterpret_cast<const float*>(p.addend) + boff;
       const __nv_bfloat16* addh = reinterpret_cast<const __nv_bfloat16*>(p.addend) + boff;
       const float* temb = p.temb ? p.temb + (long long)tc.b * p.temb_bstride : nullptr;
+      float2* red = red_base + parity * (2 * 4 * kBlockM);
+      parity ^= 1;
 
+      // ---- accumulators -> registers in one burst, then hand the TMEM stage back to the MMA warp
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_stride);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      float v[4][16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (g + 4 * j < n_chunks) tmem_ld16(taddr + (uint32_t)((g + 4 * j) * 16), reinterpret_cast<uint32_t(&)[16]>(v[j]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
 
-      // v = acc + bias, then the cheap activations
-      auto pre = [&](int c, float (&v)[16]) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int ch0 = (n0 + c) % p.chan_mod;
-        if (p.bias) {
-          float bv[16];
-          load16(p.bias + ch0, bv);
+      // ---- bias + pointwise activation, in place
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
-        } else {
+      for (int j = 0; j < 4; ++j) {
+        if (g + 4 * j < n_chunks) {
+          const int ch0 = (n0 + (g + 4 * j) * 16) % p.chan_mod;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        }
-        if (p.act == ACT_LRELU || p.act == ACT_LRELU_TANH) {
+          for (int g4 = 0; g4 < 4; ++g4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + g4);
+            float* x = &v[j][4 * g4];
+            x[0] += bv.x, x[1] += bv.y, x[2] += bv.z, x[3] += bv.w;
+            if (p.act == ACT_LRELU || p.act == ACT_LRELU_TANH) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.1f * v[i];
-          if (p.act == ACT_LRELU_TANH) {
+              for (int i = 0; i < 4; ++i) x[i] = x[i] > 0.f ? x[i] : 0.1f * x[i];
+              if (p.act == ACT_LRELU_TANH) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
-          }
-        } else if (p.act == ACT_GELU) {
+                for (int i = 0; i < 4; ++i) x[i] = tanhf(x[i]);
+              }
+            } else if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-        }
-      };
-
-      float mean = 0.f, rstd = 0.f;
-      if (p.act == ACT_LN_MISH) {  // LayerNorm statistics over the full row (block_n == N)
-        float s = 0.f, ss = 0.f, shift = 0.f;
-        for (int c = 0; c < p.block_n; c += 16) {
-          float v[16];
-          pre(c, v);
-          if (c == 0) shift = v[0];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float d = v[i] - shift;
-            s += d;
-            ss = fmaf(d, d, ss);
+              for (int i = 0; i < 4; ++i) x[i] = gelu_erf(x[i]);
+            }
           }
         }
-        const float inv_n = 1.0f / (float)p.block_n;
-        const float md = s * inv_n;
-        mean = shift + md;
-        rstd = rsqrtf(fmaxf(ss * inv_n - md * md, 0.f) + 1e-5f);
       }
 
-      float s1 = 0.f, ss1 = 0.f, shift1 = 0.f;  // statistics of u for OUT1_LN
-      for (int c = 0; c < p.block_n; c += 16) {
-        float u[16];
-        pre(c, u);
-        const int n = n0 + c;
-        const int ch0 = n % p.chan_mod;
-        if (p.act == ACT_LN_MISH) {
-          float g[16], bb[16];
-          load16(p.ln_g + ch0, g);
-          load16(p.ln_b + ch0, bb);
+      if (p.act == ACT_LN_MISH) {  // LayerNorm over the 256-wide row, then Mish
+        float mean, rstd;
+        row_stats(v, red, g, row, mean, rstd);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = mish_f(fmaf((u[i] - mean) * rstd, g[i], bb[i]));
-        }
-        if (temb) {
-          float tv[16];
-          load16(temb + n, tv);
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] += tv[i];
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + (g + 4 * j) * 16) + g4);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + (g + 4 * j) * 16) + g4);
+            float* x = &v[j][4 * g4];
+            x[0] = mish_f(fmaf((x[0] - mean) * rstd, gm.x, bt.x));
+            x[1] = mish_f(fmaf((x[1] - mean) * rstd, gm.y, bt.y));
+            x[2] = mish_f(fmaf((x[2] - mean) * rstd, gm.z, bt.z));
+            x[3] = mish_f(fmaf((x[3] - mean) * rstd, gm.w, bt.w));
+          }
         }
-        const long long flat = row_flat + n;
-        if (p.addend && st.row_in && flat >= 0 && flat + 16 <= st.valid) {
-          if (p.addend_dtype == OUT_F32) {
+      }
+
+      // ---- time-embedding add, residual add, primary store, copy / snake secondary store
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (g + 4 * j < n_chunks) {
+          const int n = n0 + (g + 4 * j) * 16;
+          const long long flat = row_flat + n;
+          const bool partial = n + 16 > p.n_store;  // only the padded final conv (n_store = 1)
+          const int stt = st.state(flat, partial ? max(p.n_store - n, 1) : 16);
+          if (temb) {
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 a = *reinterpret_cast<const float4*>(addf + flat + 4 * g4);
-              u[4 * g4] += a.x, u[4 * g4 + 1] += a.y, u[4 * g4 + 2] += a.z, u[4 * g4 + 3] += a.w;
+              const float4 tv = __ldg(reinterpret_cast<const float4*>(temb + n) + g4);
+              float* x = &v[j][4 * g4];
+              x[0] += tv.x, x[1] += tv.y, x[2] += tv.z, x[3] += tv.w;
             }
-          } else {
+          }
+          if (p.addend && stt == 2) {
+            if (p.addend_dtype == OUT_F32) {
 #pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-              const uint4 a = *reinterpret_cast<const uint4*>(addh + flat + 8 * g8);
-              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+              for (int g4 = 0; g4 < 4; ++g4) {
+                const float4 a = *reinterpret_cast<const float4*>(addf + flat + 4 * g4);
+                float* x = &v[j][4 * g4];
+                x[0] += a.x, x[1] += a.y, x[2] += a.z, x[3] += a.w;
+              }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                u[8 * g8 + 2 * j] += __low2float(h2);
-                u[8 * g8 + 2 * j + 1] += __high2float(h2);
+              for (int g8 = 0; g8 < 2; ++g8) {
+                const uint4 a = *reinterpret_cast<const uint4*>(addh + flat + 8 * g8);
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                  v[j][8 * g8 + 2 * k] += __low2float(h2);
+                  v[j][8 * g8 + 2 * k + 1] += __high2float(h2);
+                }
+              }
+            }
+          }
+          if (stt != 0 && n < p.n_store) {
+            if (partial) {  // scalar tail
+              for (int i = 0; i < 16 && n + i < p.n_store; ++i) {
+                const float x = stt == 2 ? v[j][i] : 0.f;
+                if (p.out0_dtype == OUT_F32) out0f[flat + i] = x;
+                else if (p.out0_dtype == OUT_BF16) out0h[flat + i] = __float2bfloat16(x);
+                if (p.out1_mode == OUT1_COPY) out1[flat + i] = __float2bfloat16(x);
+              }
+            } else {
+              if (p.out0_dtype == OUT_F32) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  const float* x = &v[j][4 * g4];
+                  reinterpret_cast<float4*>(out0f + flat)[g4] =
+                      stt == 2 ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              } else if (p.out0_dtype == OUT_BF16) {
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  const float* x = &v[j][8 * g8];
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (stt == 2)
+                    o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                   pack_bf16x2(x[6], x[7]));
+                  reinterpret_cast<uint4*>(out0h + flat)[g8] = o;
+                }
+              }
+              if (p.out1_mode == OUT1_COPY) {
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  const float* x = &v[j][8 * g8];
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (stt == 2)
+                    o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                   pack_bf16x2(x[6], x[7]));
+                  reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
+                }
+              } else if (p.out1_mode == OUT1_SNAKE) {
+                const int ch0 = n % p.chan_mod;
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  const float* x = &v[j][8 * g8];
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (stt == 2) {
+                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + 2 * g8);
+                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + 2 * g8 + 1);
+                    const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + 2 * g8);
+                    const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + 2 * g8 + 1);
+                    o.x = pack_bf16x2(snake_f(x[0], a0.x, i0.x), snake_f(x[1], a0.y, i0.y));
+                    o.y = pack_bf16x2(snake_f(x[2], a0.z, i0.z), snake_f(x[3], a0.w, i0.w));
+                    o.z = pack_bf16x2(snake_f(x[4], a1.x, i1.x), snake_f(x[5], a1.y, i1.y));
+                    o.w = pack_bf16x2(snake_f(x[6], a1.z, i1.z), snake_f(x[7], a1.w, i1.w));
+                  }
+                  reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
+                }
               }
             }
           }
         }
-        if (p.out0_dtype == OUT_F32)
-          st.f32(out0f, flat, n, u);
-        else if (p.out0_dtype == OUT_BF16)
-          st.bf16(out0h, flat, n, u);
-        if (p.out1_mode == OUT1_LN) {
-          if (c == 0) shift1 = u[0];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float d = u[i] - shift1;
-            s1 += d;
-            ss1 = fmaf(d, d, ss1);
-          }
-        } else if (p.out1_mode == OUT1_COPY) {
-          st.bf16(out1, flat, n, u);
-        } else if (p.out1_mode == OUT1_SNAKE) {
-          float al[16], ia[16];
-          load16(p.p1_a + ch0, al);
-          load16(p.p1_b + ch0, ia);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = snake_f(u[i], al[i], ia[i]);
-          st.bf16(out1, flat, n, u);
-        }
       }
-      // TMEM accumulator fully consumed: hand it back to the MMA warp before the LN write-out
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
 
-      if (p.out1_mode == OUT1_LN) {  // second output = LayerNorm(u) in bf16; u re-read from this thread's own row
-        const float inv_n = 1.0f / (float)p.block_n;
-        const float md = s1 * inv_n;
-        const float mean1 = shift1 + md;
-        const float rstd1 = rsqrtf(fmaxf(ss1 * inv_n - md * md, 0.f) + 1e-5f);
-        for (int c = 0; c < p.block_n; c += 16) {
-          const int n = n0 + c;
+      if (p.out1_mode == OUT1_LN) {  // second output = LayerNorm(u), bf16 operand of the next GEMM
+        float mean, rstd;
+        row_stats(v, red + 4 * kBlockM, g, row, mean, rstd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + (g + 4 * j) * 16;
           const long long flat = row_flat + n;
-          float u[16], g[16], bb[16];
-          if (st.row_in && flat >= 0 && flat + 16 <= st.valid) {
+          const int stt = st.state(flat);
+          if (stt == 0) continue;
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 a = *reinterpret_cast<const float4*>(out0f + flat + 4 * g4);
-              u[4 * g4] = a.x, u[4 * g4 + 1] = a.y, u[4 * g4 + 2] = a.z, u[4 * g4 + 3] = a.w;
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const float* x = &v[j][8 * g8];
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (stt == 2) {
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.p1_a + (g + 4 * j) * 16) + 2 * g8);
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.p1_a + (g + 4 * j) * 16) + 2 * g8 + 1);
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.p1_b + (g + 4 * j) * 16) + 2 * g8);
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.p1_b + (g + 4 * j) * 16) + 2 * g8 + 1);
+              o.x = pack_bf16x2(fmaf((x[0] - mean) * rstd, a0.x, b0.x), fmaf((x[1] - mean) * rstd, a0.y, b0.y));
+              o.y = pack_bf16x2(fmaf((x[2] - mean) * rstd, a0.z, b0.z), fmaf((x[3] - mean) * rstd, a0.w, b0.w));
+              o.z = pack_bf16x2(fmaf((x[4] - mean) * rstd, a1.x, b1.x), fmaf((x[5] - mean) * rstd, a1.y, b1.y));
+              o.w = pack_bf16x2(fmaf((x[6] - mean) * rstd, a1.z, b1.z), fmaf((x[7] - mean) * rstd, a1.w, b1.w));
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) u[i] = 0.f;
+            reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
           }
-          load16(p.p1_a + n % p.chan_mod, g);
-          load16(p.p1_b + n % p.chan_mod, bb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = fmaf((u[i] - mean1) * rstd1, g[i], bb[i]);
-          st.bf16(out1, flat, n, u);
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
   }
@@ -424,7 +506,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   if (stages < 2) return cudaErrorInvalidValue;
   const int acc_stride = pow2_at_least(p.block_n, 32);
   const int tmem_cols = 2 * acc_stride;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + kRedBytes;
   // tmem_cols == 512 must never share an SM with a second CTA of this kernel (alloc would spin):
   if (tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   static bool attr_done = false;
@@ -437,6 +519,13 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   const long long total = (long long)p.B * m_tiles * (p.N / p.block_n);
   if (total <= 0) return cudaSuccess;
   const int grid = (int)(total < num_sms ? total : num_sms);
+  const double kt = p.k_true > 0 ? p.k_true : p.kb_per_tap * kBlockK;
+  const double rows = (double)p.B * p.M;
+  const double out_b = (p.out0_dtype == OUT_F32 ? 4.0 : p.out0_dtype == OUT_BF16 ? 2.0 : 0.0) +
+                       (p.out1_mode != OUT1_NONE ? 2.0 : 0.0) +
+                       (p.addend ? (p.addend_dtype == OUT_F32 ? 4.0 : 2.0) : 0.0);
+  ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
+                 rows * kt * 2.0 + (double)p.taps * p.N * kt * 2.0 + rows * (p.n_store < p.N ? p.n_store : p.N) * out_b);
   conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(mapA0, mapA1, mapW, p, stages, tmem_cols, acc_stride);
   count_launch();
   return cudaGetLastError();

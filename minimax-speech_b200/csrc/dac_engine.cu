@@ -243,6 +243,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       p.out_ld = w.N, p.out_shift = 0, p.out_bstride = rows * w.N, p.out_alloc = rows * w.N;
       p.out_valid_mul = (long long)rate * w.N;
     }
+    p.k_true = w.K, p.tag = 1;
     LS_CUDA(launch_conv_gemm(a, a, w.map, p, num_sms_, s));
   };
 
@@ -281,6 +282,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       p.n_store = st.up.N;
       p.out_ld = st.up.N, p.out_shift = -(long long)padT * st.cout;
       p.out_bstride = rows * st.cout, p.out_alloc = rows * st.cout, p.out_valid_mul = (long long)rate * st.cout;
+      p.k_true = st.cin, p.tag = 1;
       LS_CUDA(launch_conv_gemm(pl.sA[i], pl.sA[i], st.up.map, p, num_sms_, s));
     }
     static const int dils[3] = {1, 3, 9};
@@ -308,7 +310,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
   {  // final Snake (applied) -> conv7 -> LeakyReLU -> tanh, mono fp32 waveform
     ConvGemmParams p{};
     p.act = ACT_LRELU_TANH, p.out0 = wav, p.out0_dtype = OUT_F32;
-    p.chan_mod = 16, p.n_store = 1;
+    p.chan_mod = 16, p.n_store = 1, p.zero_skipped = 1;
     p.out_ld = 1, p.out_shift = 0, p.out_bstride = rows, p.out_alloc = rows, p.out_valid_mul = rate;
     conv(pl.sA[stages_.size()], final_, rows, rate, 1, p);
   }

@@ -2,6 +2,7 @@
 // flow/decoder.py:427-433), timestep conditioning (matcha decoder.py:14-29,73-117 + ResnetBlock1D.mlp :49),
 // CFG combine + Euler update (flow_matching.py:118-120) and the NCT <-> time-major boundary transposes.
 #include "kernels.h"
+#include "profiler.h"
 #include "ptx.cuh"
 
 namespace ls {
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(1024) time_embed_kernel(const TimeEmbedParams 
 
 cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,
                             int ld, int c_off, const int* lengths, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   pack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, src_bstride, ld, c_off, lengths);
   count_launch();
@@ -187,12 +189,14 @@ cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, 
 }
 cudaError_t launch_pack_bcast(const float* src, __nv_bfloat16* dst, int B, int C, int T, int ld, int c_off,
                               const int* lengths, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   dim3 grid((unsigned)(((long long)T * C + 255) / 256), B);
   pack_bcast_kernel<<<grid, 256, 0, s>>>(src, dst, C, T, ld, c_off, lengths);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, int c_off, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   dim3 grid((unsigned)(((long long)T * C + 255) / 256), B);
   pack_zero_kernel<<<grid, 256, 0, s>>>(dst, C, T, ld, c_off);
   count_launch();
@@ -200,6 +204,7 @@ cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, in
 }
 cudaError_t launch_init_state(const float* noise, int noise_ld, float temperature, float* x_state,
                               __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   init_state_kernel<<<grid, block, 0, s>>>(noise, noise_ld, temperature, x_state, xin, B, C, T, ld, lengths);
   count_launch();
@@ -207,6 +212,7 @@ cudaError_t launch_init_state(const float* noise, int noise_ld, float temperatur
 }
 cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin, int B, int C, int T, int ld,
                              float dt, float cfg_rate, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   const long long n4 = (long long)B * T * C / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
@@ -216,17 +222,20 @@ cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin,
   return cudaGetLastError();
 }
 cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T, const int* lengths, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   unpack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, lengths);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   mask_to_lengths_kernel<<<B, 256, 0, s>>>(mask, lengths, B, T, dup);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_time_embed(const TimeEmbedParams& p, cudaStream_t s) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   if (p.nt <= 0) return cudaSuccess;
   const size_t smem = (size_t)(p.in_dim + 2 * p.hid) * sizeof(float);
   time_embed_kernel<<<p.nt, 1024, smem, s>>>(p);

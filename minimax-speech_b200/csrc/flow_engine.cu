@@ -265,6 +265,7 @@ struct Epi {
   int out1_mode = OUT1_NONE;
   const float* p1_a = nullptr;
   const float* p1_b = nullptr;
+  int zero_skipped = 0;
 };
 }  // namespace
 
@@ -287,6 +288,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
     p.p1_a = e.p1_a, p.p1_b = e.p1_b, p.n_store = w.N;
     p.out_ld = w.N, p.out_shift = 0, p.out_bstride = (long long)T * w.N, p.out_alloc = (long long)T * w.N;
     p.out_valid_mul = w.N;
+    p.k_true = w.K, p.tag = 0, p.zero_skipped = e.zero_skipped;
     LS_CUDA(launch_conv_gemm(a0, a1 ? *a1 : a0, w.map, p, num_sms_, s));
   };
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
@@ -380,7 +382,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   }
   {  // final_proj (decoder.py:495-496) -> v fp32 [B2][T][80], masked
     Epi e;
-    e.out0 = ws<void>(o_v_), e.out0_dtype = OUT_F32;
+    e.out0 = ws<void>(o_v_), e.out0_dtype = OUT_F32, e.zero_skipped = 1;
     gemm(pl.hB, nullptr, 0, final_proj_, e);
   }
   (void)inner;

@@ -30,6 +30,7 @@ struct ConvGemmParams {
   const int* lengths; // [B] valid length units per batch item (device), or nullptr = everything valid
   int m_len_mul, m_len_add;  // rows that matter: lengths[b]*m_len_mul + m_len_add (+ skip_halo before tiles are skipped)
   int skip_halo;
+  int zero_skipped;   // 1: skipped tiles still zero-fill their outputs
   // epilogue
   int chan_mod;       // per-channel vectors are indexed with (n % chan_mod)
   const float* bias;  // [chan_mod] or nullptr
@@ -50,6 +51,8 @@ struct ConvGemmParams {
   const float* p1_b;  // OUT1_LN: beta  | OUT1_SNAKE: 1/(alpha+1e-9)
   int n_store;        // only columns n < n_store are stored (N padding)
   long long out_ld, out_shift, out_bstride, out_alloc, out_valid_mul;
+  // accounting only (profiler): true K per tap and which engine launched it (0 flow, 1 DAC)
+  int k_true, tag;
 };
 
 // Tensor maps are created on the host (tma_host.cpp helpers) and passed by value.

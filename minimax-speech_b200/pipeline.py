@@ -1,0 +1,87 @@
+"""Flow -> DAC-VAE glue (the reference never wires the two together: SURVEY.md section 0) and the
+utterance sharding used at N > 1 GPUs (one utterance group per rank, one gather of waveforms at the end,
+mirroring dac-vae/extract_dac_latents.py:146-150's contiguous per-rank slices)."""
+import numpy as np
+import torch
+
+from . import native
+
+
+class Synthesizer:
+    """latents = cfm(mu, mask, n_timesteps, spks=, cond=)[0];  wav = dac.decode(latents)."""
+
+    def __init__(self, cfm, dac):
+        self.cfm, self.dac = cfm, dac
+
+    @torch.inference_mode()
+    def __call__(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, streaming=False):
+        lat, _ = self.cfm(mu=mu, mask=mask, n_timesteps=n_timesteps, temperature=temperature, spks=spks, cond=cond,
+                          streaming=streaming)
+        lengths = mask[:, 0, :].ne(0).sum(-1).to(torch.int32)
+        return self.dac.decode(lat, lengths)
+
+    @torch.inference_mode()
+    def synthesize_host(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, wav_out=None, device=None):
+        """Host tensors in, host waveform out; host<->device copies happen inside the C call."""
+        device = torch.device(device or "cuda:%d" % torch.cuda.current_device())
+        B, _, T = mu.shape
+        if wav_out is None:
+            wav_out = torch.empty(B, 1, T * self.dac.hop_length, dtype=torch.float32).pin_memory()
+        flow_h = self.cfm.estimator.handle(device)
+        dac_h = self.dac.handle(device)
+        return native.synthesize_host(flow_h, dac_h, mu, mask, spks, cond, self.cfm._noise_on(device)[0],
+                                      self.cfm._t_span(n_timesteps).numpy(), temperature,
+                                      self.cfm.inference_cfg_rate, wav_out)
+
+
+def utterance_cost(frames):
+    """Relative cost model of one utterance: linear + attention FLOPs per step."""
+    return frames * (132.2e6 + 114688.0 * frames)
+
+
+def shard_utterances(lengths, world_size):
+    """Length-balanced assignment (greedy longest-first); returns per-rank lists of utterance indices."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    loads = [0.0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: loads[k])
+        shards[r].append(i)
+        loads[r] += utterance_cost(lengths[i])
+    return [sorted(s) for s in shards]
+
+
+def gather_waveforms(wav, n_samples, index, dst=0, group=None):
+    """Variable-length gather to ``dst``: every rank contributes ``wav [b,1,S_r]`` with per-item valid sample
+    counts ``n_samples`` and global utterance ids ``index``.  Returns {utterance id: 1-D tensor} on ``dst``.
+    One collective for the payload (padded all_gather over NCCL/NVLink, or gloo on CPU) plus a tiny metadata one."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = wav.device
+    meta = torch.tensor([wav.shape[0], wav.shape[-1]], device=dev, dtype=torch.int64)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    bmax = int(max(m[0] for m in metas))
+    smax = int(max(m[1] for m in metas))
+    pad = torch.zeros(bmax, smax + 2, device=dev, dtype=torch.float32)
+    b = wav.shape[0]
+    pad[:b, :wav.shape[-1]] = wav[:, 0, :]
+    pad[:b, smax] = torch.as_tensor(n_samples, device=dev, dtype=torch.float32)
+    pad[:b, smax + 1] = torch.as_tensor(index, device=dev, dtype=torch.float32)
+    out = torch.empty(world, bmax, smax + 2, device=dev, dtype=torch.float32) if rank == dst else None
+    if dist.get_backend(group) == "nccl":
+        dist.gather(pad, list(out.unbind(0)) if rank == dst else None, dst=dst, group=group)
+    else:
+        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst, group=group)
+        if rank == dst:
+            out = torch.stack(bufs)
+    if rank != dst:
+        return None
+    res = {}
+    for r in range(world):
+        for i in range(int(metas[r][0])):
+            n = int(out[r, i, smax])
+            res[int(out[r, i, smax + 1])] = out[r, i, :n]
+    return res
