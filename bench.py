@@ -269,7 +269,7 @@ def run_b200(a):
                           "share_of_kernel_time": v["ms"] / tot,
                           "tflops": v["flops"] / sec / 1e12 if sec else None,
                           "gbs": v["bytes"] / sec / 1e9 if sec else None}
-        dom = max(("conv_gemm_estimator", "attention", "conv_gemm_dac"), key=lambda k: prof[k]["ms"])
+        dom = max(("conv_gemm_estimator", "attention", "conv_gemm_dac", "tblock_estimator"), key=lambda k: prof[k]["ms"])
         ach = prof[dom]["flops"] / (prof[dom]["ms"] / 1000.0) / 1e12
         traffic = None
         try:

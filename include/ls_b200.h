@@ -93,8 +93,10 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
 int64_t ls_launch_count(void);
 
 /* Per-kernel timing for bench.py's roofline figures: between ls_profile_begin() and ls_profile_end() every launch
- * is bracketed by CUDA events on its stream.  ls_profile_end synchronises the device and fills 4 entries:
- * 0 conv_gemm (estimator), 1 attention, 2 conv_gemm (DAC decoder), 3 bandwidth kernels. */
+ * is bracketed by CUDA events on its stream.  ls_profile_end synchronises the device and fills LS_PROFILE_KINDS
+ * entries: 0 conv_gemm (estimator), 1 attention, 2 conv_gemm (DAC decoder), 3 bandwidth kernels,
+ * 4 fused transformer-block kernel (estimator). */
+#define LS_PROFILE_KINDS 5
 typedef struct ls_profile_entry {
   int64_t launches;
   double ms;    /* summed device time of the launches */
@@ -102,7 +104,7 @@ typedef struct ls_profile_entry {
   double bytes; /* algorithmic bytes (operands read once + outputs written once) */
 } ls_profile_entry;
 int32_t ls_profile_begin(void);
-int32_t ls_profile_end(ls_profile_entry* out4);
+int32_t ls_profile_end(ls_profile_entry* out, int32_t n_entries);
 
 /* ---- kernel-level hooks used by the parity tests (tests/test_kernels_gpu.py) ---- */
 typedef struct ls_conv_gemm_desc {
@@ -135,6 +137,13 @@ int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream);
 /* qkv bf16 [B][T][3*H*64] -> out bf16 [B][T][H*64] */
 int32_t ls_test_attention(const void* qkv, void* out, const int32_t* lengths, int32_t B, int32_t T, int32_t H,
                           int32_t chunk, void* stream);
+
+/* Fused transformer-block tail (tblock.cu): att bf16 [R][512], u fp32 [R][256] (updated in place when
+ * tail_mode == 0), bf16 weights wo [256][512], w1 [1024][256], w2 [256][1024], wqkv [1536][256], vec = 2560 floats
+ * (bo, g3, be3, b1, b2, g1n, be1n).  tail_mode 0 -> qkv_out bf16 [R][1536]; 1 -> tail_out bf16 [R][256]. */
+int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1, const void* w2, const void* wqkv,
+                       const float* vec, void* qkv_out, void* tail_out, const int32_t* lengths, int32_t R, int32_t T,
+                       int32_t tail_mode, void* stream);
 
 #ifdef __cplusplus
 }

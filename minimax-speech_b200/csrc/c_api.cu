@@ -172,9 +172,9 @@ int32_t ls_profile_begin(void) {
   ls::prof_begin();
   return LS_OK;
 }
-int32_t ls_profile_end(ls_profile_entry* out4) {
+int32_t ls_profile_end(ls_profile_entry* out4, int32_t n_entries) {
   return ls::guarded([&] {
-    ls::require(out4 != nullptr, "ls_profile_end: null argument");
+    ls::require(out4 != nullptr && n_entries == ls::PK_COUNT, "ls_profile_end: need LS_PROFILE_KINDS entries");
     long long n[ls::PK_COUNT];
     double ms[ls::PK_COUNT], fl[ls::PK_COUNT], by[ls::PK_COUNT];
     ls::prof_end(n, ms, fl, by);
@@ -225,6 +225,27 @@ int32_t ls_test_attention(const void* qkv, void* out, const int32_t* lengths, in
     ap.scale_log2e = 0.125f * 1.4426950408889634f;
     ap.out = reinterpret_cast<__nv_bfloat16*>(out);
     LS_CUDA(ls::launch_attention(m, ap, (cudaStream_t)stream));
+  });
+}
+
+int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1, const void* w2, const void* wqkv,
+                       const float* vec, void* qkv_out, void* tail_out, const int32_t* lengths, int32_t R, int32_t T,
+                       int32_t tail_mode, void* stream) {
+  return ls::guarded([&] {
+    ls::require(att && u && wo && w1 && w2 && wqkv && vec, "ls_test_tblock: null argument");
+    int dev = 0, sms = 0;
+    LS_CUDA(cudaGetDevice(&dev));
+    LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUtensorMap ma, mo, m1, m2, mq;
+    ls::require(ls::make_act_map(&ma, att, 512, R, 1, 512, (long long)R * 512, 128), "tensor map att", LS_ERR_CUDA);
+    ls::require(ls::make_weight_map(&mo, wo, 512, 256, 128) && ls::make_weight_map(&m1, w1, 256, 1024, 128) &&
+                    ls::make_weight_map(&m2, w2, 1024, 256, 128) && ls::make_weight_map(&mq, wqkv, 256, 1536, 128),
+                "tensor map weights", LS_ERR_CUDA);
+    ls::TBlockParams p{};
+    p.R = R, p.T = T, p.lengths = lengths, p.u = u, p.vec = vec;
+    p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv_out), p.tail = reinterpret_cast<__nv_bfloat16*>(tail_out);
+    p.tail_mode = tail_mode;
+    LS_CUDA(ls::launch_tblock(ma, mo, m1, m2, mq, p, sms, (cudaStream_t)stream));
   });
 }
 

@@ -63,6 +63,9 @@ struct FlowEngine::ResnetW {
 struct FlowEngine::TBlockW {
   PackedLinear qkv, out, ff1, ff2;
   size_t n1g, n1b, n3g, n3b;
+  // fused transformer-block kernel (tblock.cu): per-block vector pack + weight maps with 128-row boxes
+  size_t vec = 0;
+  CUtensorMap m_out, m_ff1, m_ff2, m_qkv;
 };
 struct FlowEngine::GroupW {
   ResnetW res;
@@ -71,6 +74,7 @@ struct FlowEngine::GroupW {
 
 struct FlowEngine::Plan {
   CUtensorMap xin, hA, hB, skip, nrm, qkv, att, ff;
+  CUtensorMap att_flat;  // [B2*T][512] view of the attention output for the fused block kernel
 };
 
 FlowEngine::~FlowEngine() {
@@ -170,7 +174,38 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
       std::memcpy(arena_.host(br_) + (size_t)r * C_ * 4, w.get(p + ".mlp.1.bias", {C_}).data, (size_t)C_ * 4);
     }
   }
+  // fused transformer-block kernel: bo | norm3 | ff bias 1 | ff bias 2 | norm1 of the NEXT block of the group
+  fused_blocks_ = C_ == 256 && inner == 512;
+  if (fused_blocks_) {
+    for (auto& g : groups_)
+      for (size_t j = 0; j < g.tb.size(); ++j) {
+        TBlockW& t = g.tb[j];
+        t.vec = arena_.reserve(TBLOCK_VEC_FLOATS * 4);
+        auto put = [&](int off, size_t src_off, int n) {
+          std::memcpy(arena_.host(t.vec) + (size_t)off * 4, arena_.host(src_off), (size_t)n * 4);
+        };
+        put(0, t.out.bias_off, 256);
+        put(256, t.n3g, 256);
+        put(512, t.n3b, 256);
+        put(768, t.ff1.bias_off, 1024);
+        put(1792, t.ff2.bias_off, 256);
+        if (j + 1 < g.tb.size()) {
+          put(2048, g.tb[j + 1].n1g, 256);
+          put(2304, g.tb[j + 1].n1b, 256);
+        }
+      }
+  }
   arena_.upload();
+  if (fused_blocks_) {
+    for (auto& g : groups_)
+      for (auto& t : g.tb) {
+        require(make_weight_map(&t.m_out, arena_.ptr<uint8_t>(t.out.w_off), 512, 256, 128) &&
+                    make_weight_map(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, 128) &&
+                    make_weight_map(&t.m_ff2, arena_.ptr<uint8_t>(t.ff2.w_off), 1024, 256, 128) &&
+                    make_weight_map(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, 128),
+                "cuTensorMapEncodeTiled failed for a fused-block weight matrix", LS_ERR_CUDA);
+      }
+  }
   for (auto& g : groups_) {
     finalize_linear(arena_, g.res.conv1);
     finalize_linear(arena_, g.res.conv2);
@@ -245,6 +280,8 @@ const FlowEngine::Plan& FlowEngine::plan_for(int B2, int T) {
   mk(&pl->qkv, o_qkv_, 3 * inner);
   mk(&pl->att, o_att_, inner);
   mk(&pl->ff, o_ff_, 4 * C_);
+  require(make_act_map(&pl->att_flat, ws_base_ + o_att_, inner, B2 * T, 1, inner, (long long)B2 * T * inner, 128),
+          "cuTensorMapEncodeTiled failed for the attention output", LS_ERR_CUDA);
   const Plan& ref = *pl;
   plans_[key] = std::move(pl);
   return ref;
@@ -319,6 +356,33 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       e.out0 = u, e.out0_dtype = OUT_F32;
       e.out1 = ws<void>(o_nrm_), e.out1_mode = OUT1_LN, e.p1_a = f32(g.tb[0].n1g), e.p1_b = f32(g.tb[0].n1b);
       gemm(pl.hA, nullptr, 0, g.res.conv2, e);
+    }
+    auto attention = [&]() {
+      AttnParams ap{};
+      ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
+      ap.scale_log2e = 0.125f * 1.4426950408889634f;
+      ap.out = ws<__nv_bfloat16>(o_att_);
+      LS_CUDA(launch_attention(pl.qkv, ap, s));
+    };
+    if (fused_blocks_) {
+      // QKV of the first block from the resnet's LayerNorm output; every later QKV comes out of the fused kernel
+      {
+        Epi e;
+        e.out1 = ws<void>(o_qkv_), e.out1_mode = OUT1_COPY;
+        gemm(pl.nrm, nullptr, 0, g.tb[0].qkv, e);
+      }
+      for (int j = 0; j < n_blocks_; ++j) {
+        const TBlockW& t = g.tb[j];
+        attention();
+        const bool last = j + 1 == n_blocks_;
+        TBlockParams tp{};
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.u = u, tp.vec = arena_.ptr<float>(t.vec);
+        tp.qkv = ws<__nv_bfloat16>(o_qkv_), tp.tail = reinterpret_cast<__nv_bfloat16*>(tail);
+        tp.tail_mode = last ? 1 : 0;
+        LS_CUDA(launch_tblock(pl.att_flat, t.m_out, t.m_ff1, t.m_ff2, last ? t.m_qkv : g.tb[j + 1].m_qkv, tp,
+                              num_sms_, s));
+      }
+      return;
     }
     for (int j = 0; j < n_blocks_; ++j) {
       const TBlockW& t = g.tb[j];

@@ -33,6 +33,7 @@ class FlowEngine {
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
 
   int device_ = 0, num_sms_ = 148;
+  bool fused_blocks_ = false;
   int C_ = 256, in_ch_ = 320, feat_ = 80, heads_ = 8, hid_ = 1024, n_blocks_ = 4, n_mid_ = 12, chunk_ = 50;
   Arena arena_;
   std::vector<GroupW> groups_;

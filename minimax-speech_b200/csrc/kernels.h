@@ -69,6 +69,25 @@ struct AttnParams {
 };
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);
 
+// Fused row-local tail of a transformer block (tblock.cu): out-proj + residual + LayerNorm + FF1 + GELU + FF2 +
+// residual, then either the next block's LayerNorm + QKV projection (tail_mode 0) or a masked bf16 copy of the
+// residual stream (tail_mode 1).  Fixed estimator geometry: C = 256, 8 heads x 64, FF = 1024.
+#define TBLOCK_VEC_FLOATS 2560
+struct TBlockParams {
+  int R;               // rows = batch rows x T (time-major, flattened)
+  int T;               // rows per batch row (only used with lengths)
+  const int* lengths;  // [R / T] valid frames per batch row, or nullptr
+  float* u;            // [R][256] fp32 residual stream, updated in place (tail_mode 0) / read only (tail_mode 1)
+  const float* vec;    // device, TBLOCK_VEC_FLOATS: bo[256] g3[256] be3[256] b1[1024] b2[256] g1n[256] be1n[256]
+  __nv_bfloat16* qkv;  // tail_mode 0: [R][1536] = next block's Q | K | V
+  __nv_bfloat16* tail; // tail_mode 1: [R][256] = u'' (zero on padded rows)
+  int tail_mode;
+};
+// mapAtt: bf16 [R][512] activation map (make_act_map with T = R, B = 1); weight maps with 128-row boxes.
+cudaError_t launch_tblock(const CUtensorMap& mapAtt, const CUtensorMap& mapWo, const CUtensorMap& mapW1,
+                          const CUtensorMap& mapW2, const CUtensorMap& mapWqkv, const TBlockParams& p, int num_sms,
+                          cudaStream_t stream);
+
 // ---- bandwidth kernels (elementwise.cu) ----
 // NCT fp32 [B][C][T] -> time-major bf16 dst[b][t][c_off + c], dst row stride ld; rows >= len zeroed.
 cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,

@@ -4,7 +4,7 @@
 
 namespace ls {
 
-enum ProfKind : int { PK_CONV_FLOW = 0, PK_ATTENTION = 1, PK_CONV_DAC = 2, PK_ELEMENTWISE = 3, PK_COUNT = 4 };
+enum ProfKind : int { PK_CONV_FLOW = 0, PK_ATTENTION = 1, PK_CONV_DAC = 2, PK_ELEMENTWISE = 3, PK_TBLOCK = 4, PK_COUNT = 5 };
 
 bool prof_enabled();
 void prof_begin();

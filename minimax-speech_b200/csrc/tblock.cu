@@ -1,0 +1,569 @@
+// Fused transformer-block tail for the estimator, sm_100a: everything of a BasicTransformerBlock that is
+// row-local, in ONE kernel per 128-row tile, chained through TMEM / shared memory instead of HBM:
+//
+//   u'   = att . Wo^T + bo + u                 attn1.to_out.0 + residual    matcha transformer.py:266-277
+//   n3   = LayerNorm(u'; norm3)                                              transformer.py:303
+//   h    = GELU_erf(n3 . W1^T + b1)            ff.net.0 (diffusers GELU)     transformer.py:109-110,131-134
+//   u''  = u' + h . W2^T + b2                  ff.net.2 + residual           transformer.py:313-314
+//   tail 0:  n1 = LayerNorm(u''; next block's norm1);  qkv = n1 . Wqkv^T     transformer.py:243-271 (next block)
+//   tail 1:  masked bf16 copy of u'' (input of the conv that follows the block group, decoder.py:452-455)
+//
+// `att` is the flash kernel's output (bf16 [R][512]); `u` the fp32 residual stream (read once, written once).
+// The 1024-wide FF intermediate and both LayerNorm outputs never leave the SM.
+//
+// Structure (one CTA per SM, persistent over tiles, 10 warps):
+//   warp 0      TMA producer: streams the att tile and every weight tile (128 rows x 64 K, 16 KB, 128B swizzle)
+//               through a 5-slot mbarrier ring in exactly the order the MMA warp consumes them
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane); M=128 x N=128 x K=16 bf16 MMAs, fp32 accumulate
+//   warps 2-9   epilogue: warp w owns TMEM lanes 32*(w%4).. (= 32 rows) and column half (w-2)/4
+// TMEM (512 columns): D = [0,256) holds u' then u''; H0/H1 = [256,384) / [384,512) double-buffer the 128-wide
+// FF1 chunks (and later the 128-wide QKV chunks).  FF2 accumulates straight onto u' in D (the epilogue writes
+// u' back with tcgen05.st), so the residual add costs nothing.
+// Shared memory: A3 (64 KB) = LayerNorm output as the K-major A operand of FF1 / QKV; AH (2 x 32 KB) = GELU
+// output chunks as the A operand of FF2; ring (80 KB); per-block vectors (10 KB).
+#include "kernels.h"
+#include "profiler.h"
+#include "ptx.cuh"
+
+namespace ls {
+namespace {
+
+constexpr int kC = 256, kInner = 512, kFF = 1024, kQKV = 1536;
+constexpr int kTileM = 128;
+constexpr int kSlotBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
+constexpr int kSlots = 5;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 2;
+constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
+
+constexpr int kOffA3 = 0;
+constexpr int kOffAH = 4 * kSlotBytes;
+constexpr int kOffRing = kOffAH + 4 * kSlotBytes;
+constexpr int kOffVec = kOffRing + kSlots * kSlotBytes;
+constexpr int kOffRed = kOffVec + TBLOCK_VEC_FLOATS * 4;
+constexpr int kOffBars = kOffRed + 2 * 2 * kTileM * 8;  // [buffer][half][row] float2
+constexpr int kSmemBytes = kOffBars + 256 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "tblock shared memory budget");
+
+// offsets (floats) inside the per-block vector pack
+constexpr int V_BO = 0, V_G3 = 256, V_BE3 = 512, V_B1 = 768, V_B2 = 1792, V_G1N = 2048, V_BE1N = 2304;
+static_assert(V_BE1N + 256 == TBLOCK_VEC_FLOATS, "vector pack layout");
+
+constexpr uint32_t kTmemD = 0, kTmemH = 256;
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// true if every row of the tile is padding (t >= lengths[b])
+__device__ __forceinline__ bool tile_all_padding(const TBlockParams& p, int row0) {
+  if (p.lengths == nullptr) return false;
+  const int last = min(row0 + kTileM, p.R) - 1;
+  for (int b = row0 / p.T; b <= last / p.T; ++b) {
+    const int t_start = max(row0, b * p.T) - b * p.T;
+    if (t_start < p.lengths[b]) return false;
+  }
+  return true;
+}
+
+struct RowStats {
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  // merge a 32-value chunk (Chan's parallel update); exact two-pass statistics inside the chunk
+  __device__ __forceinline__ void add32(const float (&x)[32]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += x[i];
+    const float cm = s * (1.0f / 32.0f);
+    float cm2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float d = x[i] - cm;
+      cm2 = fmaf(d, d, cm2);
+    }
+    const float nn = n + 32.0f;
+    const float delta = cm - mean;
+    mean += delta * (32.0f / nn);
+    m2 += cm2 + delta * delta * (n * 32.0f / nn);
+    n = nn;
+  }
+};
+
+// combine the two 128-column halves of a row through shared memory -> (mean, rstd) of the 256-wide row
+__device__ __forceinline__ void combine_halves(const RowStats& st, float2* red, int hf, int row, float& mean,
+                                               float& rstd) {
+  red[hf * kTileM + row] = make_float2(st.mean, st.m2);
+  epi_barrier();
+  const float2 o = red[(hf ^ 1) * kTileM + row];
+  mean = 0.5f * (st.mean + o.x);
+  const float d = o.x - st.mean;
+  const float m2 = st.m2 + o.y + d * d * 64.0f;
+  rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+}
+
+// 32 values -> bf16 -> 4 x 16 B chunks (chunk0 .. chunk0+3) of one 128-byte swizzled smem row
+__device__ __forceinline__ void store_row_chunks(uint8_t* row_base, int sw, int chunk0, const float (&y)[32]) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint4 v;
+    v.x = pack_bf16x2(y[8 * q4 + 0], y[8 * q4 + 1]);
+    v.y = pack_bf16x2(y[8 * q4 + 2], y[8 * q4 + 3]);
+    v.z = pack_bf16x2(y[8 * q4 + 4], y[8 * q4 + 5]);
+    v.w = pack_bf16x2(y[8 * q4 + 6], y[8 * q4 + 7]);
+    *reinterpret_cast<uint4*>(row_base + (((chunk0 + q4) ^ sw) << 4)) = v;
+  }
+}
+
+__device__ __forceinline__ void store_global_bf16x32(__nv_bfloat16* dst, const float (&y)[32]) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint4 v;
+    v.x = pack_bf16x2(y[8 * q4 + 0], y[8 * q4 + 1]);
+    v.y = pack_bf16x2(y[8 * q4 + 2], y[8 * q4 + 3]);
+    v.z = pack_bf16x2(y[8 * q4 + 4], y[8 * q4 + 5]);
+    v.w = pack_bf16x2(y[8 * q4 + 6], y[8 * q4 + 7]);
+    reinterpret_cast<uint4*>(dst)[q4] = v;
+  }
+}
+
+// y[i] = (x[i] - mean) * rstd * g[i] + b[i] with g, b read from shared memory (warp-uniform addresses)
+__device__ __forceinline__ void normalize32(const float (&x)[32], float mean, float rstd, const float* g,
+                                            const float* b, float (&y)[32]) {
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[g4];
+    const float4 bv = reinterpret_cast<const float4*>(b)[g4];
+    y[4 * g4 + 0] = fmaf((x[4 * g4 + 0] - mean) * rstd, gv.x, bv.x);
+    y[4 * g4 + 1] = fmaf((x[4 * g4 + 1] - mean) * rstd, gv.y, bv.y);
+    y[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean) * rstd, gv.z, bv.z);
+    y[4 * g4 + 3] = fmaf((x[4 * g4 + 3] - mean) * rstd, gv.w, bv.w);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant__ CUtensorMap mapWo,
+              const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+              const __grid_constant__ CUtensorMap mapWqkv, const __grid_constant__ TBlockParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA3 = smem + kOffA3;
+  uint8_t* sAH = smem + kOffAH;
+  uint8_t* sRing = smem + kOffRing;
+  float* sVec = reinterpret_cast<float*>(smem + kOffVec);
+  float2* sRed = reinterpret_cast<float2*>(smem + kOffRed);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* full = bars;             // [kSlots]  TMA -> MMA
+  uint64_t* empty = bars + kSlots;   // [kSlots]  MMA -> TMA
+  uint64_t* d_full = bars + 2 * kSlots;  // MMA -> epilogue: D holds out-proj / FF2 result
+  uint64_t* a3_ready = d_full + 1;   // epilogue -> MMA: A3 written (and D read / rewritten)
+  uint64_t* h_full = a3_ready + 1;   // [2] MMA -> epilogue: H[i] holds an FF1 / QKV chunk
+  uint64_t* ah_ready = h_full + 2;   // [2] epilogue -> MMA: H[i] drained (and AH[i] written in the FF phase)
+  uint64_t* ah_free = ah_ready + 2;  // [2] MMA -> epilogue: FF2 MMAs that read AH[i] have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ah_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.R + kTileM - 1) / kTileM;
+  const bool do_qkv = p.tail_mode == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapAtt);
+    prefetch_tmap(&mapWo);
+    prefetch_tmap(&mapW1);
+    prefetch_tmap(&mapW2);
+    prefetch_tmap(&mapWqkv);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(a3_ready, kEpiThreads);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&ah_ready[i], kEpiThreads);
+      mbar_init(&ah_free[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp >= kFirstEpiWarp) {
+    for (int i = threadIdx.x - kFirstEpiWarp * 32; i < TBLOCK_VEC_FLOATS; i += kEpiThreads) sVec[i] = __ldg(p.vec + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* m, int c0, int c1, bool act) {
+        mbar_wait(&empty[slot], phase ^ 1);
+        uint8_t* dst = sRing + slot * kSlotBytes;
+        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+        if (act) tma_load_3d(dst, m, &full[slot], c0, c1, 0);
+        else tma_load_2d(dst, m, &full[slot], c0, c1);
+        if (++slot == kSlots) slot = 0, phase ^= 1;
+      };
+      auto ff1 = [&](int c) {
+        for (int kb = 0; kb < kC / 64; ++kb) load(&mapW1, kb * 64, c * 128, false);
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileM;
+        if (tile_all_padding(p, row0)) continue;
+        for (int kb = 0; kb < kInner / 64; ++kb) {
+          load(&mapAtt, kb * 64, row0, true);
+          load(&mapWo, kb * 64, 0, false);
+          load(&mapWo, kb * 64, 128, false);
+        }
+        ff1(0);
+        ff1(1);
+        for (int c = 0; c < kFF / 128; ++c) {
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            load(&mapW2, c * 128 + kb2 * 64, 0, false);
+            load(&mapW2, c * 128 + kb2 * 64, 128, false);
+          }
+          if (c + 2 < kFF / 128) ff1(c + 2);
+        }
+        if (do_qkv)
+          for (int c = 0; c < kQKV / 128; ++c)
+            for (int kb = 0; kb < kC / 64; ++kb) load(&mapWqkv, kb * 64, c * 128, false);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, 128, false, false);
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t a3_cnt = 0;
+      uint32_t fills0 = 0, fills1 = 0;      // fills issued into H[i]
+      uint32_t drained0 = 0, drained1 = 0;  // fills of H[i] known to be consumed by the epilogue
+      // wait for the ring slot `ahead` positions after the current one; returns its descriptor
+      auto slot_desc = [&](int ahead) -> uint64_t {
+        int s = slot + ahead;
+        uint32_t ph = phase;
+        if (s >= kSlots) s -= kSlots, ph ^= 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        return make_smem_desc_sw128(smem_u32(sRing + s * kSlotBytes));
+      };
+      auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
+        for (int j = 0; j < n; ++j) {
+          umma_commit(&empty[slot]);
+          if (++slot == kSlots) slot = 0, phase ^= 1;
+        }
+      };
+      auto wait_drained = [&](int i) {  // the epilogue has finished with the latest fill of H[i]
+        const uint32_t f = i ? fills1 : fills0;
+        if ((i ? drained1 : drained0) < f) {
+          mbar_wait(&ah_ready[i], (f - 1) & 1);
+          tc_fence_after();
+          if (i) drained1 = f;
+          else drained0 = f;
+        }
+      };
+      // H[i] = A3 (128 x 256, K-major in smem) . Wchunk^T, weights from 4 ring slots
+      auto gemm_from_a3 = [&](int i) {
+        wait_drained(i);
+        const uint32_t d = tmem_base + kTmemH + (uint32_t)i * 128;
+        for (int kb = 0; kb < kC / 64; ++kb) {
+          const uint64_t bdesc = slot_desc(0);
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA3 + kb * kSlotBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          release(1);
+        }
+        umma_commit(&h_full[i]);
+        if (i) fills1 += 1;
+        else fills0 += 1;
+      };
+      const uint32_t dD = tmem_base + kTmemD;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileM;
+        if (tile_all_padding(p, row0)) continue;
+        // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
+        for (int kb = 0; kb < kInner / 64; ++kb) {
+          const uint64_t adesc = slot_desc(0);
+          const uint64_t b0 = slot_desc(1);
+          const uint64_t b1 = slot_desc(2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16(dD, adesc + 2 * k, b0 + 2 * k, idesc, acc);
+            umma_bf16(dD + 128, adesc + 2 * k, b1 + 2 * k, idesc, acc);
+          }
+          release(3);
+        }
+        umma_commit(d_full);
+        // ---- FF: H[c&1] = n3 . W1[c]^T ; D += gelu(H[c&1]) . W2[:, c]^T
+        mbar_wait(a3_ready, a3_cnt & 1);  // n3 in A3, u' written back to D
+        a3_cnt += 1;
+        tc_fence_after();
+        gemm_from_a3(0);
+        gemm_from_a3(1);
+        for (int c = 0; c < kFF / 128; ++c) {
+          const int i = c & 1;
+          wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
+            const uint64_t b0 = slot_desc(0);
+            const uint64_t b1 = slot_desc(1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(dD, adesc + 2 * k, b0 + 2 * k, idesc, 1u);
+              umma_bf16(dD + 128, adesc + 2 * k, b1 + 2 * k, idesc, 1u);
+            }
+            release(2);
+          }
+          umma_commit(&ah_free[i]);
+          if (c + 2 < kFF / 128) gemm_from_a3(i);
+        }
+        umma_commit(d_full);
+        // ---- tail: D drained by the epilogue (and, tail 0, next block's LayerNorm written to A3)
+        mbar_wait(a3_ready, a3_cnt & 1);
+        a3_cnt += 1;
+        tc_fence_after();
+        if (do_qkv)
+          for (int c = 0; c < kQKV / 128; ++c) gemm_from_a3(c & 1);
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int hf = (warp - kFirstEpiWarp) >> 2;  // column half
+    const int row = q * 32 + lane;
+    const int sw = row & 7;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t d_cnt = 0;
+    uint32_t h_cnt0 = 0, h_cnt1 = 0;    // H[i] fills consumed
+    uint32_t ah_cnt0 = 0, ah_cnt1 = 0;  // AH[i] writes done
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = tile * kTileM;
+      if (tile_all_padding(p, row0)) continue;
+      const int grow = row0 + row;
+      const bool in_range = grow < p.R;
+      bool valid = in_range;
+      if (in_range && p.lengths) {
+        const int b = grow / p.T;
+        valid = grow - b * p.T < p.lengths[b];
+      }
+      float* urow = p.u + (size_t)(in_range ? grow : 0) * kC + hf * 128;
+
+      // ------------------------------------------------ out-proj epilogue: u' = D + bo + u ; n3 = LN(u')
+      {
+        float4 ub[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) ub[g] = in_range ? __ldcs(reinterpret_cast<const float4*>(urow) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(d_full, d_cnt & 1);
+        d_cnt += 1;
+        tc_fence_after();
+        RowStats st;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = hf * 128 + ch * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemD + col, d);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[g];
+            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + bo.x + ub[g].x;
+            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + bo.y + ub[g].y;
+            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + bo.z + ub[g].z;
+            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + bo.w + ub[g].w;
+          }
+          if (ch < 3) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              ub[g] = in_range ? __ldcs(reinterpret_cast<const float4*>(urow + (ch + 1) * 32) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          st.add32(x);
+          tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x));
+        }
+        tmem_st_wait();
+        float mean, rstd;
+        combine_halves(st, sRed, hf, row, mean, rstd);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = hf * 128 + ch * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemD + col, d);
+          tmem_ld_wait();
+          float y[32];
+          normalize32(reinterpret_cast<const float(&)[32]>(d), mean, rstd, sVec + V_G3 + col, sVec + V_BE3 + col, y);
+          store_row_chunks(sA3 + (col >> 6) * kSlotBytes + row * 128, sw, (ch & 1) * 4, y);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(a3_ready);
+      }
+
+      // ------------------------------------------------ FF1 chunks: AH[i] = gelu(H[i] + b1)
+      for (int c = 0; c < kFF / 128; ++c) {
+        const int i = c & 1;
+        mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
+        if (i) h_cnt1 += 1;
+        else h_cnt0 += 1;
+        tc_fence_after();
+        float y[2][32];
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int col = hf * 64 + sub * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemH + i * 128 + col, d);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b1 = reinterpret_cast<const float4*>(sVec + V_B1 + c * 128 + col)[g];
+            y[sub][4 * g + 0] = gelu_erf(__uint_as_float(d[4 * g + 0]) + b1.x);
+            y[sub][4 * g + 1] = gelu_erf(__uint_as_float(d[4 * g + 1]) + b1.y);
+            y[sub][4 * g + 2] = gelu_erf(__uint_as_float(d[4 * g + 2]) + b1.z);
+            y[sub][4 * g + 3] = gelu_erf(__uint_as_float(d[4 * g + 3]) + b1.w);
+          }
+        }
+        const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
+        if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
+        if (i) ah_cnt1 += 1;
+        else ah_cnt0 += 1;
+        uint8_t* dst = sAH + i * 2 * kSlotBytes + hf * kSlotBytes + row * 128;
+        store_row_chunks(dst, sw, 0, y[0]);
+        store_row_chunks(dst, sw, 4, y[1]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&ah_ready[i]);
+      }
+
+      // ------------------------------------------------ FF2 epilogue: u'' = D + b2
+      mbar_wait(d_full, d_cnt & 1);
+      d_cnt += 1;
+      tc_fence_after();
+      if (!do_qkv) {
+        __nv_bfloat16* trow_out = p.tail + (size_t)(in_range ? grow : 0) * kC + hf * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = hf * 128 + ch * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemD + col, d);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
+            x[4 * g + 0] = valid ? __uint_as_float(d[4 * g + 0]) + b2.x : 0.f;
+            x[4 * g + 1] = valid ? __uint_as_float(d[4 * g + 1]) + b2.y : 0.f;
+            x[4 * g + 2] = valid ? __uint_as_float(d[4 * g + 2]) + b2.z : 0.f;
+            x[4 * g + 3] = valid ? __uint_as_float(d[4 * g + 3]) + b2.w : 0.f;
+          }
+          if (in_range) store_global_bf16x32(trow_out + ch * 32, x);
+        }
+        tc_fence_before();
+        mbar_arrive(a3_ready);
+      } else {
+        RowStats st;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = hf * 128 + ch * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemD + col, d);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
+            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + b2.x;
+            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + b2.y;
+            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + b2.z;
+            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + b2.w;
+          }
+          if (in_range) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              __stcs(reinterpret_cast<float4*>(urow + ch * 32) + g, make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]));
+          }
+          st.add32(x);
+        }
+        float mean, rstd;
+        combine_halves(st, sRed + 2 * kTileM, hf, row, mean, rstd);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = hf * 128 + ch * 32;
+          uint32_t d[32];
+          tmem_ld32(trow + kTmemD + col, d);
+          tmem_ld_wait();
+          float x[32], y[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
+            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + b2.x;
+            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + b2.y;
+            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + b2.z;
+            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + b2.w;
+          }
+          normalize32(x, mean, rstd, sVec + V_G1N + col, sVec + V_BE1N + col, y);
+          store_row_chunks(sA3 + (col >> 6) * kSlotBytes + row * 128, sw, (ch & 1) * 4, y);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(a3_ready);
+
+        // -------------------------------------------- QKV chunks of the next block -> global bf16
+        __nv_bfloat16* qrow = p.qkv + (size_t)(in_range ? grow : 0) * kQKV + hf * 64;
+        for (int c = 0; c < kQKV / 128; ++c) {
+          const int i = c & 1;
+          mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
+          if (i) h_cnt1 += 1;
+          else h_cnt0 += 1;
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t d[32];
+            tmem_ld32(trow + kTmemH + i * 128 + hf * 64 + sub * 32, d);
+            tmem_ld_wait();
+            if (in_range) store_global_bf16x32(qrow + c * 128 + sub * 32, reinterpret_cast<const float(&)[32]>(d));
+          }
+          tc_fence_before();
+          mbar_arrive(&ah_ready[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_tblock(const CUtensorMap& mapAtt, const CUtensorMap& mapWo, const CUtensorMap& mapW1,
+                          const CUtensorMap& mapW2, const CUtensorMap& mapWqkv, const TBlockParams& p, int num_sms,
+                          cudaStream_t stream) {
+  if (p.R <= 0 || p.T <= 0 || p.u == nullptr || p.vec == nullptr) return cudaErrorInvalidValue;
+  if (p.tail_mode == 0 ? p.qkv == nullptr : p.tail == nullptr) return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int n_tiles = (p.R + kTileM - 1) / kTileM;
+  const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  const double rows = (double)p.R;
+  const double macs = (double)kInner * kC + 2.0 * kC * kFF + (p.tail_mode == 0 ? (double)kC * kQKV : 0.0);
+  const double bytes = rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0)) + macs * 2.0;
+  ProfScope prof(stream, PK_TBLOCK, 2.0 * rows * macs, bytes);
+  tblock_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mapAtt, mapWo, mapW1, mapW2, mapWqkv, p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace ls

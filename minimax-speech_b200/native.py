@@ -16,7 +16,7 @@ OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
-           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention"]
+           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
 
 
 class LsTensor(C.Structure):
@@ -50,7 +50,7 @@ class ProfileEntry(C.Structure):
     _fields_ = [("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
-PROFILE_KINDS = ["conv_gemm_estimator", "attention", "conv_gemm_dac", "bandwidth"]
+PROFILE_KINDS = ["conv_gemm_estimator", "attention", "conv_gemm_dac", "bandwidth", "tblock_estimator"]
 
 _lib = None
 _lock = threading.Lock()
@@ -90,7 +90,8 @@ def load():
         lib.ls_dac_hop_length.argtypes = [vp]
         lib.ls_dac_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
-        lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry)]
+        lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
+        lib.ls_test_tblock.argtypes = [vp] * 10 + [i32, i32, i32, vp]
         lib.ls_test_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), vp]
         lib.ls_test_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
         for name in EXPORTS:
@@ -112,8 +113,8 @@ def profile_begin():
 
 
 def profile_end():
-    arr = (ProfileEntry * 4)()
-    check(load().ls_profile_end(arr), "ls_profile_end")
+    arr = (ProfileEntry * len(PROFILE_KINDS))()
+    check(load().ls_profile_end(arr, len(PROFILE_KINDS)), "ls_profile_end")
     return {k: dict(launches=int(e.launches), ms=float(e.ms), flops=float(e.flops), bytes=float(e.bytes))
             for k, e in zip(PROFILE_KINDS, arr)}
 

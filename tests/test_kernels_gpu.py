@@ -258,3 +258,77 @@ def test_attention(T, lengths, chunk):
     for b, n in enumerate(lengths):
         e = rel(out[b, :n].float(), ref[b, :n])
         assert e < 1e-2, (b, e)
+
+
+# ------------------------------------------------------------------------------------------ fused transformer block
+def _tblock_operands(R, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rn = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(DEV)
+    att = bf16(rn(R, 512))
+    u = rn(R, 256, scale=2.0) + 0.5
+    wo = bf16(rn(256, 512, scale=512 ** -0.5))
+    w1 = bf16(rn(1024, 256, scale=256 ** -0.5))
+    w2 = bf16(rn(256, 1024, scale=1024 ** -0.5))
+    wqkv = bf16(rn(1536, 256, scale=256 ** -0.5))
+    vec = torch.cat([rn(256, scale=0.1), 1 + rn(256, scale=0.1), rn(256, scale=0.1), rn(1024, scale=0.2),
+                     rn(256, scale=0.1), 1 + rn(256, scale=0.1), rn(256, scale=0.1)]).contiguous()
+    return att, u, wo, w1, w2, wqkv, vec
+
+
+def _tblock_ref(att, u, wo, w1, w2, wqkv, vec):
+    bo, g3, be3, b1, b2, g1n, be1n = torch.split(vec, [256, 256, 256, 1024, 256, 256, 256])
+    u1 = att.float() @ wo.float().T + bo + u
+    n3 = bf16(F.layer_norm(u1, (256,), g3, be3, 1e-5)).float()
+    h = bf16(F.gelu(n3 @ w1.float().T + b1)).float()
+    u2 = u1 + h @ w2.float().T + b2
+    n1 = bf16(F.layer_norm(u2, (256,), g1n, be1n, 1e-5)).float()
+    return u2, n1 @ wqkv.float().T
+
+
+def _tblock(att, u, wo, w1, w2, wqkv, vec, tail_mode, lengths=None, T=None):
+    R = att.shape[0]
+    qkv = torch.full((R, 1536), float("nan"), device=DEV, dtype=torch.bfloat16) if tail_mode == 0 else None
+    tail = torch.full((R, 256), float("nan"), device=DEV, dtype=torch.bfloat16) if tail_mode == 1 else None
+    native.check(native.load().ls_test_tblock(native.ptr(att), native.ptr(u), native.ptr(wo), native.ptr(w1),
+                                              native.ptr(w2), native.ptr(wqkv), native.ptr(vec), native.ptr(qkv),
+                                              native.ptr(tail), native.ptr(lengths), R, T or R, tail_mode,
+                                              native.current_stream_ptr(DEV)), "ls_test_tblock")
+    torch.cuda.synchronize()
+    return qkv, tail
+
+
+@pytest.mark.parametrize("R", [128, 300, 128 * 151 + 17])
+def test_tblock_qkv_tail(R):
+    ops = _tblock_operands(R, 5 + R)
+    u_ref, qkv_ref = _tblock_ref(*ops)
+    u = ops[1].clone()
+    qkv, _ = _tblock(ops[0], u, *ops[2:], tail_mode=0)
+    assert rel(u, u_ref) < 2e-3, rel(u, u_ref)       # bf16 rounding of the FF intermediate on both sides
+    assert rel(qkv.float(), qkv_ref) < 6e-3, rel(qkv.float(), qkv_ref)
+
+
+def test_tblock_masked_copy_tail_and_tile_skip():
+    T, lens = 200, [200, 70, 0, 131]
+    R = T * len(lens)
+    ops = _tblock_operands(R, 77)
+    u_ref, _ = _tblock_ref(*ops)
+    u = ops[1].clone()
+    lengths = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    _, tail = _tblock(ops[0], u, *ops[2:], tail_mode=1, lengths=lengths, T=T)
+    assert torch.equal(u, ops[1])  # tail_mode 1 leaves the residual stream alone
+    tail = tail.float().view(len(lens), T, 256)
+    u_ref = u_ref.view(len(lens), T, 256)
+    for b, n in enumerate(lens):
+        if n:
+            assert rel(tail[b, :n], u_ref[b, :n]) < 4e-3
+        # padded rows are zero, except inside tiles that are padding only (skipped: left untouched = NaN fill)
+        pad = tail[b, n:]
+        assert bool(((pad == 0) | pad.isnan()).all())
+    rows = torch.arange(R, device=DEV).view(len(lens), T)
+    for b, n in enumerate(lens):  # a padded row inside a tile that also holds valid rows must be exactly zero
+        for t in range(n, T):
+            r = int(rows[b, t])
+            tile0 = (r // 128) * 128
+            has_valid = any((rr // T) < len(lens) and (rr % T) < lens[rr // T] for rr in range(tile0, min(tile0 + 128, R)))
+            if has_valid:
+                assert float(tail[b, t].abs().max()) == 0.0
