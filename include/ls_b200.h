@@ -106,6 +106,10 @@ typedef struct ls_profile_entry {
 int32_t ls_profile_begin(void);
 int32_t ls_profile_end(ls_profile_entry* out, int32_t n_entries);
 
+/* Development aid: kernels that support it write clock64 timelines ([grid][64] int64) into this device buffer
+ * while it is set (NULL clears it).  Not used by any product path. */
+int32_t ls_debug_set_buffer(void* dev_ptr, int64_t bytes);
+
 /* ---- kernel-level hooks used by the parity tests (tests/test_kernels_gpu.py) ---- */
 typedef struct ls_conv_gemm_desc {
   const void* a0; /* bf16 [B][T_in][a0_C] */

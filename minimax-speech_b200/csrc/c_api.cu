@@ -11,6 +11,8 @@
 namespace ls {
 
 std::atomic<long long> g_launch_count{0};
+long long* g_debug_buffer = nullptr;
+long long g_debug_bytes = 0;
 
 static thread_local std::string t_error;
 void set_error(const char* fmt, ...) {
@@ -168,6 +170,12 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
   });
 }
 
+int32_t ls_debug_set_buffer(void* dev_ptr, int64_t bytes) {
+  ls::g_debug_buffer = reinterpret_cast<long long*>(dev_ptr);
+  ls::g_debug_bytes = dev_ptr ? bytes : 0;
+  return LS_OK;
+}
+
 int32_t ls_profile_begin(void) {
   ls::prof_begin();
   return LS_OK;
@@ -236,16 +244,23 @@ int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1
     int dev = 0, sms = 0;
     LS_CUDA(cudaGetDevice(&dev));
     LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CUtensorMap ma, mo, m1, m2, mq;
-    ls::require(ls::make_act_map(&ma, att, 512, R, 1, 512, (long long)R * 512, 128), "tensor map att", LS_ERR_CUDA);
-    ls::require(ls::make_weight_map(&mo, wo, 512, 256, 128) && ls::make_weight_map(&m1, w1, 256, 1024, 128) &&
-                    ls::make_weight_map(&m2, w2, 1024, 256, 128) && ls::make_weight_map(&mq, wqkv, 256, 1536, 128),
+    ls::require(tail_mode == 0 ? qkv_out != nullptr : tail_out != nullptr, "ls_test_tblock: missing output");
+    ls::TBlockMaps m;
+    ls::require(ls::make_tile_map(&m.att, att, 2, 512, R, 128) && ls::make_tile_map(&m.u, u, 4, 256, R, 128),
+                "tensor map att / u", LS_ERR_CUDA);
+    ls::require(ls::make_weight_map(&m.wo, wo, 512, 256, TBLOCK_WBOX_ROWS) &&
+                    ls::make_weight_map(&m.w1, w1, 256, 1024, TBLOCK_WBOX_ROWS) &&
+                    ls::make_weight_map(&m.w2, w2, 1024, 256, TBLOCK_WBOX_ROWS) &&
+                    ls::make_weight_map(&m.wqkv, wqkv, 256, 1536, TBLOCK_WBOX_ROWS),
                 "tensor map weights", LS_ERR_CUDA);
+    m.qkv_out = m.att, m.tail_out = m.att;
+    if (tail_mode == 0)
+      ls::require(ls::make_tile_map(&m.qkv_out, qkv_out, 2, 1536, R, 128), "tensor map qkv", LS_ERR_CUDA);
+    else
+      ls::require(ls::make_tile_map(&m.tail_out, tail_out, 2, 256, R, 128), "tensor map tail", LS_ERR_CUDA);
     ls::TBlockParams p{};
-    p.R = R, p.T = T, p.lengths = lengths, p.u = u, p.vec = vec;
-    p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv_out), p.tail = reinterpret_cast<__nv_bfloat16*>(tail_out);
-    p.tail_mode = tail_mode;
-    LS_CUDA(ls::launch_tblock(ma, mo, m1, m2, mq, p, sms, (cudaStream_t)stream));
+    p.R = R, p.T = T, p.lengths = lengths, p.vec = vec, p.tail_mode = tail_mode;
+    LS_CUDA(ls::launch_tblock(m, p, sms, (cudaStream_t)stream));
   });
 }
 

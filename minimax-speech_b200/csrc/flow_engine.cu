@@ -74,7 +74,8 @@ struct FlowEngine::GroupW {
 
 struct FlowEngine::Plan {
   CUtensorMap xin, hA, hB, skip, nrm, qkv, att, ff;
-  CUtensorMap att_flat;  // [B2*T][512] view of the attention output for the fused block kernel
+  // flattened [B2*T][C] views for the fused block kernel (TMA loads and stores)
+  CUtensorMap att_flat, u_flat, qkv_flat, tail_skip, tail_hB;
 };
 
 FlowEngine::~FlowEngine() {
@@ -199,10 +200,10 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
   if (fused_blocks_) {
     for (auto& g : groups_)
       for (auto& t : g.tb) {
-        require(make_weight_map(&t.m_out, arena_.ptr<uint8_t>(t.out.w_off), 512, 256, 128) &&
-                    make_weight_map(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, 128) &&
-                    make_weight_map(&t.m_ff2, arena_.ptr<uint8_t>(t.ff2.w_off), 1024, 256, 128) &&
-                    make_weight_map(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, 128),
+        require(make_weight_map(&t.m_out, arena_.ptr<uint8_t>(t.out.w_off), 512, 256, TBLOCK_WBOX_ROWS) &&
+                    make_weight_map(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, TBLOCK_WBOX_ROWS) &&
+                    make_weight_map(&t.m_ff2, arena_.ptr<uint8_t>(t.ff2.w_off), 1024, 256, TBLOCK_WBOX_ROWS) &&
+                    make_weight_map(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, TBLOCK_WBOX_ROWS),
                 "cuTensorMapEncodeTiled failed for a fused-block weight matrix", LS_ERR_CUDA);
       }
   }
@@ -280,8 +281,13 @@ const FlowEngine::Plan& FlowEngine::plan_for(int B2, int T) {
   mk(&pl->qkv, o_qkv_, 3 * inner);
   mk(&pl->att, o_att_, inner);
   mk(&pl->ff, o_ff_, 4 * C_);
-  require(make_act_map(&pl->att_flat, ws_base_ + o_att_, inner, B2 * T, 1, inner, (long long)B2 * T * inner, 128),
-          "cuTensorMapEncodeTiled failed for the attention output", LS_ERR_CUDA);
+  const long long R = (long long)B2 * T;
+  require(make_tile_map(&pl->att_flat, ws_base_ + o_att_, 2, inner, R, 128) &&
+              make_tile_map(&pl->u_flat, ws_base_ + o_u_, 4, C_, R, 128) &&
+              make_tile_map(&pl->qkv_flat, ws_base_ + o_qkv_, 2, 3 * inner, R, 128) &&
+              make_tile_map(&pl->tail_skip, ws_base_ + o_skip_, 2, C_, R, 128) &&
+              make_tile_map(&pl->tail_hB, ws_base_ + o_hB_, 2, C_, R, 128),
+          "cuTensorMapEncodeTiled failed for a fused-block activation view", LS_ERR_CUDA);
   const Plan& ref = *pl;
   plans_[key] = std::move(pl);
   return ref;
@@ -376,11 +382,13 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         attention();
         const bool last = j + 1 == n_blocks_;
         TBlockParams tp{};
-        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.u = u, tp.vec = arena_.ptr<float>(t.vec);
-        tp.qkv = ws<__nv_bfloat16>(o_qkv_), tp.tail = reinterpret_cast<__nv_bfloat16*>(tail);
-        tp.tail_mode = last ? 1 : 0;
-        LS_CUDA(launch_tblock(pl.att_flat, t.m_out, t.m_ff1, t.m_ff2, last ? t.m_qkv : g.tb[j + 1].m_qkv, tp,
-                              num_sms_, s));
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(t.vec), tp.tail_mode = last ? 1 : 0;
+        TBlockMaps tm;
+        tm.att = pl.att_flat, tm.wo = t.m_out, tm.w1 = t.m_ff1, tm.w2 = t.m_ff2;
+        tm.wqkv = last ? t.m_qkv : g.tb[j + 1].m_qkv;
+        tm.u = pl.u_flat, tm.qkv_out = pl.qkv_flat;
+        tm.tail_out = tail == ws<void>(o_skip_) ? pl.tail_skip : pl.tail_hB;
+        LS_CUDA(launch_tblock(tm, tp, num_sms_, s));
       }
       return;
     }

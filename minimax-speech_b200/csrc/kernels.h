@@ -9,6 +9,8 @@
 namespace ls {
 
 extern std::atomic<long long> g_launch_count;  // kernels launched by this library
+extern long long* g_debug_buffer;              // device buffer for kernel timelines (development aid), or nullptr
+extern long long g_debug_bytes;
 inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4 };
@@ -73,20 +75,25 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
 // residual, then either the next block's LayerNorm + QKV projection (tail_mode 0) or a masked bf16 copy of the
 // residual stream (tail_mode 1).  Fixed estimator geometry: C = 256, 8 heads x 64, FF = 1024.
 #define TBLOCK_VEC_FLOATS 2560
+#define TBLOCK_CLUSTER 2                           /* CTAs per cluster sharing every weight box by TMA multicast */
+#define TBLOCK_WBOX_ROWS (128 / TBLOCK_CLUSTER)    /* box rows of the weight tensor maps */
 struct TBlockParams {
   int R;               // rows = batch rows x T (time-major, flattened)
   int T;               // rows per batch row (only used with lengths)
   const int* lengths;  // [R / T] valid frames per batch row, or nullptr
-  float* u;            // [R][256] fp32 residual stream, updated in place (tail_mode 0) / read only (tail_mode 1)
   const float* vec;    // device, TBLOCK_VEC_FLOATS: bo[256] g3[256] be3[256] b1[1024] b2[256] g1n[256] be1n[256]
-  __nv_bfloat16* qkv;  // tail_mode 0: [R][1536] = next block's Q | K | V
-  __nv_bfloat16* tail; // tail_mode 1: [R][256] = u'' (zero on padded rows)
-  int tail_mode;
+  int tail_mode;       // 0: u updated in place + next block's QKV written; 1: masked bf16 copy of u'' written
+  long long* timeline; // development aid (ls_debug_set_buffer): [grid][64] clock64 stamps of the first tile, or nullptr
 };
-// mapAtt: bf16 [R][512] activation map (make_act_map with T = R, B = 1); weight maps with 128-row boxes.
-cudaError_t launch_tblock(const CUtensorMap& mapAtt, const CUtensorMap& mapWo, const CUtensorMap& mapW1,
-                          const CUtensorMap& mapW2, const CUtensorMap& mapWqkv, const TBlockParams& p, int num_sms,
-                          cudaStream_t stream);
+// Every global tensor is reached through TMA (loads and stores), 128-row boxes, 128-byte swizzle:
+struct TBlockMaps {
+  CUtensorMap att;       // bf16 [R][512]  attention output              (make_tile_map, box 64 x 128)
+  CUtensorMap wo, w1, w2, wqkv;  // bf16 weights [N][K], K contiguous     (make_weight_map, box 64 x TBLOCK_WBOX_ROWS)
+  CUtensorMap u;         // fp32 [R][256]  residual stream, in/out        (box 32 x 128)
+  CUtensorMap qkv_out;   // bf16 [R][1536] next block's Q | K | V          (box 64 x 128)   tail_mode 0
+  CUtensorMap tail_out;  // bf16 [R][256]  u'' masked                      (box 64 x 128)   tail_mode 1
+};
+cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream);
 
 // ---- bandwidth kernels (elementwise.cu) ----
 // NCT fp32 [B][C][T] -> time-major bf16 dst[b][t][c_off + c], dst row stride ld; rows >= len zeroed.
@@ -126,5 +133,8 @@ bool make_act_map(CUtensorMap* map, const void* base, int C, int T, int B, long 
                   long long batch_stride_elems, int box_rows);
 // bf16 weight matrix [rows][K] with 64 x box_rows boxes
 bool make_weight_map(CUtensorMap* map, const void* base, int K, int rows, int box_rows);
+// row-major [rows][cols] matrix of bf16 (elem_bytes 2) or fp32 (4) with (128 B / elem_bytes) x box_rows boxes,
+// 128-byte swizzle; usable for TMA loads (OOB rows read as zero) and TMA stores (OOB rows dropped)
+bool make_tile_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, int box_rows);
 
 }  // namespace ls

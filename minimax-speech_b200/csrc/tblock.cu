@@ -32,6 +32,10 @@ constexpr int kC = 256, kInner = 512, kFF = 1024, kQKV = 1536;
 constexpr int kTileM = 128;
 constexpr int kSlotBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
 constexpr int kSlots = 5;
+constexpr int kCS = TBLOCK_CLUSTER;          // CTAs per cluster: each loads 1/kCS of every weight box and multicasts it
+constexpr int kPartRows = 128 / kCS;         // weight rows per CTA per box
+constexpr int kPartBytes = kPartRows * 128;
+constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstEpiWarp = 2;
@@ -112,18 +116,6 @@ __device__ __forceinline__ void store_row_chunks(uint8_t* row_base, int sw, int 
   }
 }
 
-__device__ __forceinline__ void store_global_bf16x32(__nv_bfloat16* dst, const float (&y)[32]) {
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    uint4 v;
-    v.x = pack_bf16x2(y[8 * q4 + 0], y[8 * q4 + 1]);
-    v.y = pack_bf16x2(y[8 * q4 + 2], y[8 * q4 + 3]);
-    v.z = pack_bf16x2(y[8 * q4 + 4], y[8 * q4 + 5]);
-    v.w = pack_bf16x2(y[8 * q4 + 6], y[8 * q4 + 7]);
-    reinterpret_cast<uint4*>(dst)[q4] = v;
-  }
-}
-
 // y[i] = (x[i] - mean) * rstd * g[i] + b[i] with g, b read from shared memory (warp-uniform addresses)
 __device__ __forceinline__ void normalize32(const float (&x)[32], float mean, float rstd, const float* g,
                                             const float* b, float (&y)[32]) {
@@ -141,7 +133,9 @@ __device__ __forceinline__ void normalize32(const float (&x)[32], float mean, fl
 __global__ void __launch_bounds__(kThreads, 1)
 tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant__ CUtensorMap mapWo,
               const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
-              const __grid_constant__ CUtensorMap mapWqkv, const __grid_constant__ TBlockParams p) {
+              const __grid_constant__ CUtensorMap mapWqkv, const __grid_constant__ CUtensorMap mapU,
+              const __grid_constant__ CUtensorMap mapQkvOut, const __grid_constant__ CUtensorMap mapTail,
+              const __grid_constant__ TBlockParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA3 = smem + kOffA3;
@@ -157,12 +151,29 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint64_t* h_full = a3_ready + 1;   // [2] MMA -> epilogue: H[i] holds an FF1 / QKV chunk
   uint64_t* ah_ready = h_full + 2;   // [2] epilogue -> MMA: H[i] drained (and AH[i] written in the FF phase)
   uint64_t* ah_free = ah_ready + 2;  // [2] MMA -> epilogue: FF2 MMAs that read AH[i] have retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ah_free + 2);
+  uint64_t* u_full = ah_free + 2;    // [2] TMA -> epilogue: staging pair i holds a chunk of the u tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.R + kTileM - 1) / kTileM;
   const bool do_qkv = p.tail_mode == 0;
+  // Clusters of kCS CTAs walk the tiles together (tile = group*kCS + rank): all of them stream the same weight
+  // sequence, so each CTA fetches 1/kCS of every weight box from L2 and multicasts it to the whole cluster.  A group
+  // past the end of the tensor (rows >= R) is a phantom tile: TMA reads zeros and drops the stores.
+  const int rank = kCS > 1 ? (int)cluster_ctarank() : 0;
+  const int n_groups = (n_tiles + kCS - 1) / kCS;
+  const int group0 = blockIdx.x / kCS, group_step = gridDim.x / kCS;
+  auto group_skipped = [&](int g) {
+    for (int r = 0; r < kCS; ++r)
+      if (!tile_all_padding(p, (g * kCS + r) * kTileM)) return false;
+    return true;
+  };
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 64 : nullptr;
+#define TL(i)                         \
+  do {                                \
+    if (tl) tl[(i)] = clock64();      \
+  } while (0)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapAtt);
@@ -170,9 +181,12 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     prefetch_tmap(&mapW1);
     prefetch_tmap(&mapW2);
     prefetch_tmap(&mapWqkv);
+    prefetch_tmap(&mapU);
+    prefetch_tmap(&mapQkvOut);
+    prefetch_tmap(&mapTail);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], kCS);  // released by the MMA warp of every CTA of the cluster
     }
     mbar_init(d_full, 1);
     mbar_init(a3_ready, kEpiThreads);
@@ -180,6 +194,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       mbar_init(&h_full[i], 1);
       mbar_init(&ah_ready[i], kEpiThreads);
       mbar_init(&ah_free[i], 1);
+      mbar_init(&u_full[i], 1);
     }
     fence_barrier_init();
   }
@@ -193,6 +208,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (kCS > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -201,37 +217,45 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      auto load = [&](const CUtensorMap* m, int c0, int c1, bool act) {
+      // weight box (128 rows x 64 K): this CTA fetches rows [rank*kPartRows, +kPartRows) for the whole cluster
+      auto load = [&](const CUtensorMap* m, int c0, int c1) {
         mbar_wait(&empty[slot], phase ^ 1);
         uint8_t* dst = sRing + slot * kSlotBytes;
         mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-        if (act) tma_load_3d(dst, m, &full[slot], c0, c1, 0);
+        if (kCS > 1) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
         else tma_load_2d(dst, m, &full[slot], c0, c1);
         if (++slot == kSlots) slot = 0, phase ^= 1;
       };
-      auto ff1 = [&](int c) {
-        for (int kb = 0; kb < kC / 64; ++kb) load(&mapW1, kb * 64, c * 128, false);
+      auto load_rows = [&](const CUtensorMap* m, int c0, int c1) {  // this CTA's own activation rows
+        mbar_wait(&empty[slot], phase ^ 1);
+        uint8_t* dst = sRing + slot * kSlotBytes;
+        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+        tma_load_2d(dst, m, &full[slot], c0, c1);
+        if (++slot == kSlots) slot = 0, phase ^= 1;
       };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = tile * kTileM;
-        if (tile_all_padding(p, row0)) continue;
+      auto ff1 = [&](int c) {
+        for (int kb = 0; kb < kC / 64; ++kb) load(&mapW1, kb * 64, c * 128);
+      };
+      for (int g = group0; g < n_groups; g += group_step) {
+        const int row0 = (g * kCS + rank) * kTileM;
+        if (group_skipped(g)) continue;
         for (int kb = 0; kb < kInner / 64; ++kb) {
-          load(&mapAtt, kb * 64, row0, true);
-          load(&mapWo, kb * 64, 0, false);
-          load(&mapWo, kb * 64, 128, false);
+          load_rows(&mapAtt, kb * 64, row0);
+          load(&mapWo, kb * 64, 0);
+          load(&mapWo, kb * 64, 128);
         }
         ff1(0);
         ff1(1);
         for (int c = 0; c < kFF / 128; ++c) {
           for (int kb2 = 0; kb2 < 2; ++kb2) {
-            load(&mapW2, c * 128 + kb2 * 64, 0, false);
-            load(&mapW2, c * 128 + kb2 * 64, 128, false);
+            load(&mapW2, c * 128 + kb2 * 64, 0);
+            load(&mapW2, c * 128 + kb2 * 64, 128);
           }
           if (c + 2 < kFF / 128) ff1(c + 2);
         }
         if (do_qkv)
           for (int c = 0; c < kQKV / 128; ++c)
-            for (int kb = 0; kb < kC / 64; ++kb) load(&mapWqkv, kb * 64, c * 128, false);
+            for (int kb = 0; kb < kC / 64; ++kb) load(&mapWqkv, kb * 64, c * 128);
       }
     }
   } else if (warp == 1) {
@@ -254,7 +278,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       };
       auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
         for (int j = 0; j < n; ++j) {
-          umma_commit(&empty[slot]);
+          if (kCS > 1) umma_commit_mc(&empty[slot], kCtaMask);
+          else umma_commit(&empty[slot]);
           if (++slot == kSlots) slot = 0, phase ^= 1;
         }
       };
@@ -283,14 +308,16 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         else fills0 += 1;
       };
       const uint32_t dD = tmem_base + kTmemD;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = tile * kTileM;
-        if (tile_all_padding(p, row0)) continue;
+      TL(0);
+      for (int g = group0; g < n_groups; g += group_step) {
+        if (group_skipped(g)) continue;
+        if (g != group0) tl = nullptr;
         // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
         for (int kb = 0; kb < kInner / 64; ++kb) {
           const uint64_t adesc = slot_desc(0);
           const uint64_t b0 = slot_desc(1);
           const uint64_t b1 = slot_desc(2);
+          if (kb == 0) TL(1);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
@@ -300,15 +327,18 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           release(3);
         }
         umma_commit(d_full);
+        TL(2);
         // ---- FF: H[c&1] = n3 . W1[c]^T ; D += gelu(H[c&1]) . W2[:, c]^T
         mbar_wait(a3_ready, a3_cnt & 1);  // n3 in A3, u' written back to D
         a3_cnt += 1;
         tc_fence_after();
+        TL(3);
         gemm_from_a3(0);
         gemm_from_a3(1);
         for (int c = 0; c < kFF / 128; ++c) {
           const int i = c & 1;
           wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
+          TL(4 + c);
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
             const uint64_t b0 = slot_desc(0);
@@ -324,12 +354,18 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (c + 2 < kFF / 128) gemm_from_a3(i);
         }
         umma_commit(d_full);
+        TL(12);
         // ---- tail: D drained by the epilogue (and, tail 0, next block's LayerNorm written to A3)
         mbar_wait(a3_ready, a3_cnt & 1);
         a3_cnt += 1;
         tc_fence_after();
+        TL(13);
         if (do_qkv)
-          for (int c = 0; c < kQKV / 128; ++c) gemm_from_a3(c & 1);
+          for (int c = 0; c < kQKV / 128; ++c) {
+            gemm_from_a3(c & 1);
+            TL(14 + c);
+          }
+        TL(26);
       }
     }
   } else {
@@ -338,53 +374,75 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     const int hf = (warp - kFirstEpiWarp) >> 2;  // column half
     const int row = q * 32 + lane;
     const int sw = row & 7;
+    const bool leader = threadIdx.x == kFirstEpiWarp * 32;  // issues the TMA loads / stores of the staging boxes
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // Outside the FF phase the AH region is free: 4 staging boxes of 16 KB (128 rows x 128 B, 128B swizzle) through
+    // which u is loaded and u'' / qkv / tail are stored with TMA, so every global access is a full-line burst.
+    uint8_t* stage = sAH;
     uint32_t d_cnt = 0;
     uint32_t h_cnt0 = 0, h_cnt1 = 0;    // H[i] fills consumed
     uint32_t ah_cnt0 = 0, ah_cnt1 = 0;  // AH[i] writes done
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row0 = tile * kTileM;
-      if (tile_all_padding(p, row0)) continue;
+    uint32_t uf_cnt0 = 0, uf_cnt1 = 0;  // u_full[i] phases consumed
+    auto load_u = [&](int ch, int row0) {  // leader: both column halves of 32-column chunk ch -> staging pair ch&1
+      const int b = ch & 1;
+      mbar_arrive_expect_tx(&u_full[b], 2 * kSlotBytes);
+      tma_load_2d(stage + (b * 2 + 0) * kSlotBytes, &mapU, &u_full[b], ch * 32, row0);
+      tma_load_2d(stage + (b * 2 + 1) * kSlotBytes, &mapU, &u_full[b], 128 + ch * 32, row0);
+    };
+    for (int g = group0; g < n_groups; g += group_step) {
+      const int row0 = (g * kCS + rank) * kTileM;
+      if (group_skipped(g)) continue;
       const int grow = row0 + row;
-      const bool in_range = grow < p.R;
-      bool valid = in_range;
-      if (in_range && p.lengths) {
+      bool valid = grow < p.R;
+      if (valid && p.lengths) {
         const int b = grow / p.T;
         valid = grow - b * p.T < p.lengths[b];
       }
-      float* urow = p.u + (size_t)(in_range ? grow : 0) * kC + hf * 128;
+      long long* tle = (leader && g == group0) ? tl : nullptr;
+#define TLE(i)                        \
+  do {                                \
+    if (tle) tle[(i)] = clock64();    \
+  } while (0)
+      if (leader) {
+        bulk_wait_read<0>();  // the previous tile's stores have left the staging boxes
+        load_u(0, row0);
+        load_u(1, row0);
+      }
 
       // ------------------------------------------------ out-proj epilogue: u' = D + bo + u ; n3 = LN(u')
       {
-        float4 ub[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) ub[g] = in_range ? __ldcs(reinterpret_cast<const float4*>(urow) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(d_full, d_cnt & 1);
         d_cnt += 1;
         tc_fence_after();
+        TLE(32);
         RowStats st;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int col = hf * 128 + ch * 32;
+          const int b = ch & 1;
+          mbar_wait(&u_full[b], (b ? uf_cnt1 : uf_cnt0) & 1);
+          if (b) uf_cnt1 += 1;
+          else uf_cnt0 += 1;
+          const uint8_t* urow = stage + (b * 2 + hf) * kSlotBytes + row * 128;
           uint32_t d[32];
           tmem_ld32(trow + kTmemD + col, d);
           tmem_ld_wait();
           float x[32];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
+            const float4 uv = *reinterpret_cast<const float4*>(urow + ((g ^ sw) << 4));
             const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[g];
-            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + bo.x + ub[g].x;
-            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + bo.y + ub[g].y;
-            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + bo.z + ub[g].z;
-            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + bo.w + ub[g].w;
-          }
-          if (ch < 3) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              ub[g] = in_range ? __ldcs(reinterpret_cast<const float4*>(urow + (ch + 1) * 32) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + bo.x + uv.x;
+            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + bo.y + uv.y;
+            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + bo.z + uv.z;
+            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + bo.w + uv.w;
           }
           st.add32(x);
           tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x));
+          if (ch < 2) {  // staging pair b has been read by everyone: refill it with chunk ch+2
+            epi_barrier();
+            if (leader) load_u(ch + 2, row0);
+          }
         }
         tmem_st_wait();
         float mean, rstd;
@@ -402,6 +460,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(a3_ready);
+        TLE(33);
       }
 
       // ------------------------------------------------ FF1 chunks: AH[i] = gelu(H[i] + b1)
@@ -411,6 +470,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         if (i) h_cnt1 += 1;
         else h_cnt0 += 1;
         tc_fence_after();
+        if (c == 4) TLE(56);
         float y[2][32];
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -427,24 +487,29 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             y[sub][4 * g + 3] = gelu_erf(__uint_as_float(d[4 * g + 3]) + b1.w);
           }
         }
+        if (c == 4) TLE(57);
         const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
         if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
         if (i) ah_cnt1 += 1;
         else ah_cnt0 += 1;
+        if (c == 4) TLE(58);
         uint8_t* dst = sAH + i * 2 * kSlotBytes + hf * kSlotBytes + row * 128;
         store_row_chunks(dst, sw, 0, y[0]);
         store_row_chunks(dst, sw, 4, y[1]);
+        if (c == 4) TLE(59);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&ah_ready[i]);
+        TLE(34 + c);
       }
 
       // ------------------------------------------------ FF2 epilogue: u'' = D + b2
       mbar_wait(d_full, d_cnt & 1);
       d_cnt += 1;
       tc_fence_after();
+      TLE(42);
       if (!do_qkv) {
-        __nv_bfloat16* trow_out = p.tail + (size_t)(in_range ? grow : 0) * kC + hf * 128;
+        // masked bf16 copy of u'' -> 4 staging boxes (column quarter = hf*2 + ch/2) -> TMA store
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int col = hf * 128 + ch * 32;
@@ -460,15 +525,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             x[4 * g + 2] = valid ? __uint_as_float(d[4 * g + 2]) + b2.z : 0.f;
             x[4 * g + 3] = valid ? __uint_as_float(d[4 * g + 3]) + b2.w : 0.f;
           }
-          if (in_range) store_global_bf16x32(trow_out + ch * 32, x);
+          store_row_chunks(stage + (hf * 2 + (ch >> 1)) * kSlotBytes + row * 128, sw, (ch & 1) * 4, x);
         }
+        fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(a3_ready);
+        epi_barrier();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tma_store_2d(&mapTail, stage + k * kSlotBytes, k * 64, row0);
+          bulk_commit();
+        }
       } else {
         RowStats st;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int col = hf * 128 + ch * 32;
+          const int b = ch & 1;
           uint32_t d[32];
           tmem_ld32(trow + kTmemD + col, d);
           tmem_ld_wait();
@@ -481,12 +554,22 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + b2.z;
             x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + b2.w;
           }
-          if (in_range) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              __stcs(reinterpret_cast<float4*>(urow + ch * 32) + g, make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]));
-          }
           st.add32(x);
+          if (ch >= 2) {  // the store of chunk ch-2 must have left staging pair b
+            if (leader) bulk_wait_read<1>();
+            epi_barrier();
+          }
+          uint8_t* dst = stage + (b * 2 + hf) * kSlotBytes + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(dst + ((g ^ sw) << 4)) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+          fence_proxy_async_smem();
+          epi_barrier();
+          if (leader) {
+            tma_store_2d(&mapU, stage + (b * 2 + 0) * kSlotBytes, ch * 32, row0);
+            tma_store_2d(&mapU, stage + (b * 2 + 1) * kSlotBytes, 128 + ch * 32, row0);
+            bulk_commit();
+          }
         }
         float mean, rstd;
         combine_halves(st, sRed + 2 * kTileM, hf, row, mean, rstd);
@@ -511,31 +594,47 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(a3_ready);
+        TLE(43);
 
-        // -------------------------------------------- QKV chunks of the next block -> global bf16
-        __nv_bfloat16* qrow = p.qkv + (size_t)(in_range ? grow : 0) * kQKV + hf * 64;
+        // -------------------------------------------- QKV chunks of the next block -> staging -> TMA store
         for (int c = 0; c < kQKV / 128; ++c) {
           const int i = c & 1;
           mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
           if (i) h_cnt1 += 1;
           else h_cnt0 += 1;
           tc_fence_after();
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            uint32_t d[32];
-            tmem_ld32(trow + kTmemH + i * 128 + hf * 64 + sub * 32, d);
-            tmem_ld_wait();
-            if (in_range) store_global_bf16x32(qrow + c * 128 + sub * 32, reinterpret_cast<const float(&)[32]>(d));
-          }
+          if (c == 6) TLE(60);
+          uint32_t d0[32], d1[32];
+          tmem_ld32(trow + kTmemH + i * 128 + hf * 64, d0);
+          tmem_ld32(trow + kTmemH + i * 128 + hf * 64 + 32, d1);
+          tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(&ah_ready[i]);
+          mbar_arrive(&ah_ready[i]);  // H[i] is drained: the MMA warp may refill it
+          if (c == 6) TLE(61);
+          if (leader) bulk_wait_read<1>();  // the store issued two chunks ago has left staging pair i
+          epi_barrier();
+          if (c == 6) TLE(62);
+          uint8_t* dst = stage + (i * 2 + hf) * kSlotBytes + row * 128;
+          store_row_chunks(dst, sw, 0, reinterpret_cast<const float(&)[32]>(d0));
+          store_row_chunks(dst, sw, 4, reinterpret_cast<const float(&)[32]>(d1));
+          fence_proxy_async_smem();
+          epi_barrier();
+          if (c == 6) TLE(63);
+          if (leader) {
+            tma_store_2d(&mapQkvOut, stage + (i * 2 + 0) * kSlotBytes, c * 128, row0);
+            tma_store_2d(&mapQkvOut, stage + (i * 2 + 1) * kSlotBytes, c * 128 + 64, row0);
+            bulk_commit();
+          }
+          TLE(44 + c);
         }
       }
     }
+    if (leader) bulk_wait<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kCS > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -544,11 +643,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
 
 }  // namespace
 
-cudaError_t launch_tblock(const CUtensorMap& mapAtt, const CUtensorMap& mapWo, const CUtensorMap& mapW1,
-                          const CUtensorMap& mapW2, const CUtensorMap& mapWqkv, const TBlockParams& p, int num_sms,
-                          cudaStream_t stream) {
-  if (p.R <= 0 || p.T <= 0 || p.u == nullptr || p.vec == nullptr) return cudaErrorInvalidValue;
-  if (p.tail_mode == 0 ? p.qkv == nullptr : p.tail == nullptr) return cudaErrorInvalidValue;
+cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream) {
+  if (p.R <= 0 || p.T <= 0 || p.vec == nullptr) return cudaErrorInvalidValue;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(tblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -556,14 +652,38 @@ cudaError_t launch_tblock(const CUtensorMap& mapAtt, const CUtensorMap& mapWo, c
     attr_done = true;
   }
   const int n_tiles = (p.R + kTileM - 1) / kTileM;
-  const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  const int n_groups = (n_tiles + kCS - 1) / kCS;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    max_clusters = num_sms / kCS;
+    if (kCS > 1) {  // clusters are placed inside one GPC: ask how many fit at once
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms / kCS * kCS), qc.blockDim = dim3(kThreads), qc.dynamicSmemBytes = kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = kCS, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa, qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tblock_kernel, &qc) == cudaSuccess && n > 0 && n < max_clusters)
+        max_clusters = n;
+    }
+  }
+  const int grid = (n_groups < max_clusters ? n_groups : max_clusters) * kCS;
   const double rows = (double)p.R;
   const double macs = (double)kInner * kC + 2.0 * kC * kFF + (p.tail_mode == 0 ? (double)kC * kQKV : 0.0);
   const double bytes = rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0)) + macs * 2.0;
+  TBlockParams pp = p;
+  pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 64 * 8) ? g_debug_buffer : nullptr;
   ProfScope prof(stream, PK_TBLOCK, 2.0 * rows * macs, bytes);
-  tblock_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mapAtt, mapWo, mapW1, mapW2, mapWqkv, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmemBytes, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tblock_kernel, m.att, m.wo, m.w1, m.w2, m.wqkv, m.u, m.qkv_out, m.tail_out, pp);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace ls

@@ -16,7 +16,7 @@ OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
-           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
+           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
 
 
 class LsTensor(C.Structure):
@@ -90,6 +90,7 @@ def load():
         lib.ls_dac_hop_length.argtypes = [vp]
         lib.ls_dac_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
+        lib.ls_debug_set_buffer.argtypes = [vp, i64]
         lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
         lib.ls_test_tblock.argtypes = [vp] * 10 + [i32, i32, i32, vp]
         lib.ls_test_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), vp]
