@@ -36,7 +36,7 @@ constexpr int kCS = TBLOCK_CLUSTER;          // CTAs per cluster: each loads 1/k
 constexpr int kPartRows = 128 / kCS;         // weight rows per CTA per box
 constexpr int kPartBytes = kPartRows * 128;
 constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstEpiWarp = 2;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
@@ -46,7 +46,7 @@ constexpr int kOffAH = 4 * kSlotBytes;
 constexpr int kOffRing = kOffAH + 4 * kSlotBytes;
 constexpr int kOffVec = kOffRing + kSlots * kSlotBytes;
 constexpr int kOffRed = kOffVec + TBLOCK_VEC_FLOATS * 4;
-constexpr int kOffBars = kOffRed + 2 * 2 * kTileM * 8;  // [buffer][half][row] float2
+constexpr int kOffBars = kOffRed + 4 * kTileM * 8;  // [column group][row] float2
 constexpr int kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "tblock shared memory budget");
 
@@ -91,15 +91,15 @@ struct RowStats {
   }
 };
 
-// combine the two 128-column halves of a row through shared memory -> (mean, rstd) of the 256-wide row
-__device__ __forceinline__ void combine_halves(const RowStats& st, float2* red, int hf, int row, float& mean,
+// combine the four 64-column groups of a row through shared memory -> (mean, rstd) of the 256-wide row
+__device__ __forceinline__ void combine_groups(const RowStats& st, float2* red, int cg, int row, float& mean,
                                                float& rstd) {
-  red[hf * kTileM + row] = make_float2(st.mean, st.m2);
+  red[cg * kTileM + row] = make_float2(st.mean, st.m2);
   epi_barrier();
-  const float2 o = red[(hf ^ 1) * kTileM + row];
-  mean = 0.5f * (st.mean + o.x);
-  const float d = o.x - st.mean;
-  const float m2 = st.m2 + o.y + d * d * 64.0f;
+  const float2 a = red[row], b = red[kTileM + row], c = red[2 * kTileM + row], d = red[3 * kTileM + row];
+  mean = 0.25f * (a.x + b.x + c.x + d.x);
+  const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
+  const float m2 = a.y + b.y + c.y + d.y + 64.0f * (da * da + db * db + dc * dc + dd * dd);
   rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
 }
 
@@ -116,17 +116,17 @@ __device__ __forceinline__ void store_row_chunks(uint8_t* row_base, int sw, int 
   }
 }
 
-// y[i] = (x[i] - mean) * rstd * g[i] + b[i] with g, b read from shared memory (warp-uniform addresses)
-__device__ __forceinline__ void normalize32(const float (&x)[32], float mean, float rstd, const float* g,
+// y[i] = (x[i] * rstd + nmr) * g[i] + b[i]  (nmr = -mean * rstd), g / b read from shared memory (warp-uniform)
+__device__ __forceinline__ void normalize32(const float (&x)[32], float rstd, float nmr, const float* g,
                                             const float* b, float (&y)[32]) {
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
     const float4 gv = reinterpret_cast<const float4*>(g)[g4];
     const float4 bv = reinterpret_cast<const float4*>(b)[g4];
-    y[4 * g4 + 0] = fmaf((x[4 * g4 + 0] - mean) * rstd, gv.x, bv.x);
-    y[4 * g4 + 1] = fmaf((x[4 * g4 + 1] - mean) * rstd, gv.y, bv.y);
-    y[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean) * rstd, gv.z, bv.z);
-    y[4 * g4 + 3] = fmaf((x[4 * g4 + 3] - mean) * rstd, gv.w, bv.w);
+    y[4 * g4 + 0] = fmaf(fmaf(x[4 * g4 + 0], rstd, nmr), gv.x, bv.x);
+    y[4 * g4 + 1] = fmaf(fmaf(x[4 * g4 + 1], rstd, nmr), gv.y, bv.y);
+    y[4 * g4 + 2] = fmaf(fmaf(x[4 * g4 + 2], rstd, nmr), gv.z, bv.z);
+    y[4 * g4 + 3] = fmaf(fmaf(x[4 * g4 + 3], rstd, nmr), gv.w, bv.w);
   }
 }
 
@@ -151,8 +151,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint64_t* h_full = a3_ready + 1;   // [2] MMA -> epilogue: H[i] holds an FF1 / QKV chunk
   uint64_t* ah_ready = h_full + 2;   // [2] epilogue -> MMA: H[i] drained (and AH[i] written in the FF phase)
   uint64_t* ah_free = ah_ready + 2;  // [2] MMA -> epilogue: FF2 MMAs that read AH[i] have retired
-  uint64_t* u_full = ah_free + 2;    // [2] TMA -> epilogue: staging pair i holds a chunk of the u tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 2);
+  uint64_t* u_full = ah_free + 2;    // TMA -> epilogue: the u tile sits in the staging boxes (AH region + A3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,13 +189,13 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       mbar_init(&empty[i], kCS);  // released by the MMA warp of every CTA of the cluster
     }
     mbar_init(d_full, 1);
-    mbar_init(a3_ready, kEpiThreads);
+    mbar_init(a3_ready, kEpiWarps);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&h_full[i], 1);
-      mbar_init(&ah_ready[i], kEpiThreads);
+      mbar_init(&ah_ready[i], kEpiWarps);
       mbar_init(&ah_free[i], 1);
-      mbar_init(&u_full[i], 1);
     }
+    mbar_init(u_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -371,23 +371,24 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   } else {
     // ======================================================================== epilogue warps
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int hf = (warp - kFirstEpiWarp) >> 2;  // column half
+    const int cg = (warp - kFirstEpiWarp) >> 2;  // column group: 64 of D's 256 columns, 32 of an H chunk's 128
     const int row = q * 32 + lane;
     const int sw = row & 7;
     const bool leader = threadIdx.x == kFirstEpiWarp * 32;  // issues the TMA loads / stores of the staging boxes
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    // Outside the FF phase the AH region is free: 4 staging boxes of 16 KB (128 rows x 128 B, 128B swizzle) through
-    // which u is loaded and u'' / qkv / tail are stored with TMA, so every global access is a full-line burst.
+    // Staging boxes (16 KB = 128 rows x 128 B, 128B swizzle) for TMA loads of u and TMA stores of u'' / qkv / tail:
+    // outside the FF phase the AH region holds 4 of them; while the out-proj MMAs run, A3 is free as well and
+    // takes the other half of the u tile.  Thread (row, cg) only ever touches row `row` of box `cg`, in both regions.
     uint8_t* stage = sAH;
-    uint32_t d_cnt = 0;
+    uint32_t d_cnt = 0, u_cnt = 0;
     uint32_t h_cnt0 = 0, h_cnt1 = 0;    // H[i] fills consumed
     uint32_t ah_cnt0 = 0, ah_cnt1 = 0;  // AH[i] writes done
-    uint32_t uf_cnt0 = 0, uf_cnt1 = 0;  // u_full[i] phases consumed
-    auto load_u = [&](int ch, int row0) {  // leader: both column halves of 32-column chunk ch -> staging pair ch&1
-      const int b = ch & 1;
-      mbar_arrive_expect_tx(&u_full[b], 2 * kSlotBytes);
-      tma_load_2d(stage + (b * 2 + 0) * kSlotBytes, &mapU, &u_full[b], ch * 32, row0);
-      tma_load_2d(stage + (b * 2 + 1) * kSlotBytes, &mapU, &u_full[b], 128 + ch * 32, row0);
+    // one arrival per warp: every lane's smem / TMEM accesses are ordered before lane 0's arrive by __syncwarp
+    auto warp_arrive = [&](uint64_t* bar) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
     };
     for (int g = group0; g < n_groups; g += group_step) {
       const int row0 = (g * kCS + rank) * kTileM;
@@ -404,62 +405,57 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     if (tle) tle[(i)] = clock64();    \
   } while (0)
       if (leader) {
-        bulk_wait_read<0>();  // the previous tile's stores have left the staging boxes
-        load_u(0, row0);
-        load_u(1, row0);
+        // the previous tile's stores have left the staging boxes; its QKV MMAs (A3 readers) retired before the
+        // last h_full this thread waited on
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(u_full, 8 * kSlotBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tma_load_2d(stage + k * kSlotBytes, &mapU, u_full, k * 64, row0);
+          tma_load_2d(sA3 + k * kSlotBytes, &mapU, u_full, k * 64 + 32, row0);
+        }
       }
 
       // ------------------------------------------------ out-proj epilogue: u' = D + bo + u ; n3 = LN(u')
       {
+        float x[2][32];
+        mbar_wait(u_full, u_cnt & 1);
+        u_cnt += 1;
         mbar_wait(d_full, d_cnt & 1);
         d_cnt += 1;
         tc_fence_after();
         TLE(32);
         RowStats st;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = hf * 128 + ch * 32;
-          const int b = ch & 1;
-          mbar_wait(&u_full[b], (b ? uf_cnt1 : uf_cnt0) & 1);
-          if (b) uf_cnt1 += 1;
-          else uf_cnt0 += 1;
-          const uint8_t* urow = stage + (b * 2 + hf) * kSlotBytes + row * 128;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemD + col, d);
+        for (int ch = 0; ch < 2; ++ch) {
+          const int col = cg * 64 + ch * 32;
+          const uint8_t* urow = (ch ? sA3 : stage) + cg * kSlotBytes + row * 128;
+          tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x[ch]));
           tmem_ld_wait();
-          float x[32];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 uv = *reinterpret_cast<const float4*>(urow + ((g ^ sw) << 4));
-            const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[g];
-            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + bo.x + uv.x;
-            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + bo.y + uv.y;
-            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + bo.z + uv.z;
-            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + bo.w + uv.w;
+          for (int k = 0; k < 8; ++k) {
+            const float4 uv = *reinterpret_cast<const float4*>(urow + ((k ^ sw) << 4));
+            const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[k];
+            x[ch][4 * k + 0] += bo.x + uv.x;
+            x[ch][4 * k + 1] += bo.y + uv.y;
+            x[ch][4 * k + 2] += bo.z + uv.z;
+            x[ch][4 * k + 3] += bo.w + uv.w;
           }
-          st.add32(x);
-          tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x));
-          if (ch < 2) {  // staging pair b has been read by everyone: refill it with chunk ch+2
-            epi_barrier();
-            if (leader) load_u(ch + 2, row0);
-          }
+          st.add32(x[ch]);
+          tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x[ch]));
+        }
+        float mean, rstd;
+        combine_groups(st, sRed, cg, row, mean, rstd);
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int col = cg * 64 + ch * 32;
+          float y[32];
+          normalize32(x[ch], rstd, nmr, sVec + V_G3 + col, sVec + V_BE3 + col, y);
+          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, y);
         }
         tmem_st_wait();
-        float mean, rstd;
-        combine_halves(st, sRed, hf, row, mean, rstd);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = hf * 128 + ch * 32;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemD + col, d);
-          tmem_ld_wait();
-          float y[32];
-          normalize32(reinterpret_cast<const float(&)[32]>(d), mean, rstd, sVec + V_G3 + col, sVec + V_BE3 + col, y);
-          store_row_chunks(sA3 + (col >> 6) * kSlotBytes + row * 128, sw, (ch & 1) * 4, y);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(a3_ready);
+        warp_arrive(a3_ready);
         TLE(33);
       }
 
@@ -470,36 +466,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         if (i) h_cnt1 += 1;
         else h_cnt0 += 1;
         tc_fence_after();
-        if (c == 4) TLE(56);
-        float y[2][32];
+        float y[32];
+        tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
+        tmem_ld_wait();
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int col = hf * 64 + sub * 32;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemH + i * 128 + col, d);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b1 = reinterpret_cast<const float4*>(sVec + V_B1 + c * 128 + col)[g];
-            y[sub][4 * g + 0] = gelu_erf(__uint_as_float(d[4 * g + 0]) + b1.x);
-            y[sub][4 * g + 1] = gelu_erf(__uint_as_float(d[4 * g + 1]) + b1.y);
-            y[sub][4 * g + 2] = gelu_erf(__uint_as_float(d[4 * g + 2]) + b1.z);
-            y[sub][4 * g + 3] = gelu_erf(__uint_as_float(d[4 * g + 3]) + b1.w);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const float4 b1 = reinterpret_cast<const float4*>(sVec + V_B1 + c * 128 + cg * 32)[k];
+          y[4 * k + 0] = gelu_fast(y[4 * k + 0] + b1.x);
+          y[4 * k + 1] = gelu_fast(y[4 * k + 1] + b1.y);
+          y[4 * k + 2] = gelu_fast(y[4 * k + 2] + b1.z);
+          y[4 * k + 3] = gelu_fast(y[4 * k + 3] + b1.w);
         }
-        if (c == 4) TLE(57);
         const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
         if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
         if (i) ah_cnt1 += 1;
         else ah_cnt0 += 1;
-        if (c == 4) TLE(58);
-        uint8_t* dst = sAH + i * 2 * kSlotBytes + hf * kSlotBytes + row * 128;
-        store_row_chunks(dst, sw, 0, y[0]);
-        store_row_chunks(dst, sw, 4, y[1]);
-        if (c == 4) TLE(59);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&ah_ready[i]);
+        store_row_chunks(sAH + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
+        warp_arrive(&ah_ready[i]);
         TLE(34 + c);
       }
 
@@ -508,28 +491,32 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       d_cnt += 1;
       tc_fence_after();
       TLE(42);
-      if (!do_qkv) {
-        // masked bf16 copy of u'' -> 4 staging boxes (column quarter = hf*2 + ch/2) -> TMA store
+      float x[2][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = hf * 128 + ch * 32;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemD + col, d);
-          tmem_ld_wait();
-          float x[32];
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col = cg * 64 + ch * 32;
+        tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x[ch]));
+        tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
-            x[4 * g + 0] = valid ? __uint_as_float(d[4 * g + 0]) + b2.x : 0.f;
-            x[4 * g + 1] = valid ? __uint_as_float(d[4 * g + 1]) + b2.y : 0.f;
-            x[4 * g + 2] = valid ? __uint_as_float(d[4 * g + 2]) + b2.z : 0.f;
-            x[4 * g + 3] = valid ? __uint_as_float(d[4 * g + 3]) + b2.w : 0.f;
-          }
-          store_row_chunks(stage + (hf * 2 + (ch >> 1)) * kSlotBytes + row * 128, sw, (ch & 1) * 4, x);
+        for (int k = 0; k < 8; ++k) {
+          const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[k];
+          x[ch][4 * k + 0] += b2.x;
+          x[ch][4 * k + 1] += b2.y;
+          x[ch][4 * k + 2] += b2.z;
+          x[ch][4 * k + 3] += b2.w;
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(a3_ready);
+      }
+      if (!do_qkv) {
+        // masked bf16 copy of u'': this thread's 64 columns are one full row of staging box cg -> TMA store
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (!valid) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[ch][k] = 0.f;
+          }
+          store_row_chunks(stage + cg * kSlotBytes + row * 128, sw, ch * 4, x[ch]);
+        }
+        warp_arrive(a3_ready);  // D is drained
         epi_barrier();
         if (leader) {
 #pragma unroll
@@ -538,88 +525,61 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         }
       } else {
         RowStats st;
+        st.add32(x[0]);
+        st.add32(x[1]);
+        // u'' (fp32) leaves through the 4 staging boxes in two rounds of 32 columns per column group
+        auto stage_u = [&](const float (&v)[32]) {
+          uint8_t* dst = stage + cg * kSlotBytes + row * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = hf * 128 + ch * 32;
-          const int b = ch & 1;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemD + col, d);
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
-            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + b2.x;
-            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + b2.y;
-            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + b2.z;
-            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + b2.w;
-          }
-          st.add32(x);
-          if (ch >= 2) {  // the store of chunk ch-2 must have left staging pair b
-            if (leader) bulk_wait_read<1>();
-            epi_barrier();
-          }
-          uint8_t* dst = stage + (b * 2 + hf) * kSlotBytes + row * 128;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(dst + ((g ^ sw) << 4)) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(dst + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           fence_proxy_async_smem();
-          epi_barrier();
-          if (leader) {
-            tma_store_2d(&mapU, stage + (b * 2 + 0) * kSlotBytes, ch * 32, row0);
-            tma_store_2d(&mapU, stage + (b * 2 + 1) * kSlotBytes, 128 + ch * 32, row0);
-            bulk_commit();
-          }
-        }
+        };
+        auto store_u = [&](int ch) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tma_store_2d(&mapU, stage + k * kSlotBytes, k * 64 + ch * 32, row0);
+          bulk_commit();
+        };
+        stage_u(x[0]);
         float mean, rstd;
-        combine_halves(st, sRed + 2 * kTileM, hf, row, mean, rstd);
+        combine_groups(st, sRed, cg, row, mean, rstd);  // contains the barrier that also publishes round 0
+        if (leader) store_u(0);
+        const float nmr = -mean * rstd;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = hf * 128 + ch * 32;
-          uint32_t d[32];
-          tmem_ld32(trow + kTmemD + col, d);
-          tmem_ld_wait();
-          float x[32], y[32];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[g];
-            x[4 * g + 0] = __uint_as_float(d[4 * g + 0]) + b2.x;
-            x[4 * g + 1] = __uint_as_float(d[4 * g + 1]) + b2.y;
-            x[4 * g + 2] = __uint_as_float(d[4 * g + 2]) + b2.z;
-            x[4 * g + 3] = __uint_as_float(d[4 * g + 3]) + b2.w;
-          }
-          normalize32(x, mean, rstd, sVec + V_G1N + col, sVec + V_BE1N + col, y);
-          store_row_chunks(sA3 + (col >> 6) * kSlotBytes + row * 128, sw, (ch & 1) * 4, y);
+        for (int ch = 0; ch < 2; ++ch) {
+          const int col = cg * 64 + ch * 32;
+          float y[32];
+          normalize32(x[ch], rstd, nmr, sVec + V_G1N + col, sVec + V_BE1N + col, y);
+          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, y);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(a3_ready);
+        warp_arrive(a3_ready);  // n1 in A3, D drained: the QKV MMAs may start
         TLE(43);
+        if (leader) bulk_wait_read<0>();
+        epi_barrier();
+        stage_u(x[1]);
+        epi_barrier();
+        if (leader) {
+          store_u(1);
+          bulk_wait_read<0>();
+        }
+        epi_barrier();
 
-        // -------------------------------------------- QKV chunks of the next block -> staging -> TMA store
+        // -------------------------------------------- QKV chunks of the next block -> staging pair -> TMA store
         for (int c = 0; c < kQKV / 128; ++c) {
           const int i = c & 1;
           mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
           if (i) h_cnt1 += 1;
           else h_cnt0 += 1;
           tc_fence_after();
-          if (c == 6) TLE(60);
-          uint32_t d0[32], d1[32];
-          tmem_ld32(trow + kTmemH + i * 128 + hf * 64, d0);
-          tmem_ld32(trow + kTmemH + i * 128 + hf * 64 + 32, d1);
+          float y[32];
+          tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
           tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&ah_ready[i]);  // H[i] is drained: the MMA warp may refill it
-          if (c == 6) TLE(61);
-          if (leader) bulk_wait_read<1>();  // the store issued two chunks ago has left staging pair i
-          epi_barrier();
-          if (c == 6) TLE(62);
-          uint8_t* dst = stage + (i * 2 + hf) * kSlotBytes + row * 128;
-          store_row_chunks(dst, sw, 0, reinterpret_cast<const float(&)[32]>(d0));
-          store_row_chunks(dst, sw, 4, reinterpret_cast<const float(&)[32]>(d1));
+          warp_arrive(&ah_ready[i]);  // H[i] is drained: the MMA warp may refill it
+          // staging pair i is free: the leader waited for the store of chunk c-2 before the barrier of chunk c-1
+          store_row_chunks(stage + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
           fence_proxy_async_smem();
+          if (leader) bulk_wait_read<0>();
           epi_barrier();
-          if (c == 6) TLE(63);
           if (leader) {
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 0) * kSlotBytes, c * 128, row0);
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 1) * kSlotBytes, c * 128 + 64, row0);
