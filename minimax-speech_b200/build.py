@@ -7,7 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libls_b200.so")
+# LS_LIB (development aid): load / build an alternative library, e.g. one compiled with LS_BUILD_DEFINES="-DTBLOCK_CLUSTER=1"
+LIB = os.environ.get("LS_LIB") or os.path.join(HERE, "libls_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]
 
@@ -30,7 +31,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("LS_BUILD_DEFINES", "").split() + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

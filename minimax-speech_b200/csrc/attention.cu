@@ -5,10 +5,13 @@
 // reference materialises per block group (flow/decoder.py:441-445, utils/mask.py:161-236, utils/common.py:160-168):
 // the key-padding mask is a per-utterance key bound, the streaming block-causal mask (chunk 50) a per-row bound.
 //
-// One CTA = 128 query rows of one (batch row, head).  S = Q K^T and O_j = P V run on tcgen05 with fp32
-// accumulators in TMEM; 8 softmax warps (two threads per query row, 64 keys each, row max / sum exchanged through
-// smem) run the online softmax, write P as bf16 into a 128B-swizzled K-major smem tile and keep the running
-// output in registers.  Two CTAs share an SM so one CTA's MMAs overlap the other's softmax.
+// One CTA = 128 query rows of one (batch row, head); two CTAs share an SM.  S = Q K^T and O += P V run on tcgen05 with
+// fp32 accumulators in TMEM (S: columns [0,128), O: [128,192)).  Four softmax warps own one query row per thread
+// (no cross-thread exchange): the 128 scores of a key tile are pulled into registers once, the row maximum only
+// moves when it grows by more than 2^8 (so O, which stays in TMEM and is accumulated by the tensor core across
+// key tiles, is rescaled rarely and only by rows that need it), P goes to a 128B-swizzled K-major smem tile.
+// The control warp's single thread issues TMA loads and MMAs; S(j+1) is issued before P(j) V(j), so the next
+// tile's scores are ready while the softmax warps are still writing P(j).
 #include <cmath>
 
 #include "kernels.h"
@@ -22,21 +25,54 @@ constexpr int kQ = 128;
 constexpr int kKV = 128;
 constexpr int kD = 64;
 constexpr int kTile = kQ * kD * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kSoftmaxWarps = 8;                   // warp w: TMEM lane quarter w%4, key half w/4
+constexpr int kSoftmaxWarps = 4;    // warp w owns TMEM lanes [32w, 32w+32) = query rows
 constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
 constexpr int kAttnThreads = kSoftmaxThreads + 32;  // + control warp
-constexpr int kAttnSmem = 6 * kTile + 1024 + 128 + 3 * 1024;  // Q, K x2, V, P x2, align slack, barriers, exchange
-constexpr int kAttnTmemCols = 256;                 // S: cols [0,128)   O_j: cols [128,192)
+constexpr int kAttnSmem = 6 * kTile + 1024 + 256;   // Q, K x2, V, P x2 (two 64-key K blocks), align slack, barriers
+constexpr int kAttnTmemCols = 256;                  // S: cols [0,128)   O: cols [128,192)
+constexpr float kRescaleThreshold = 8.0f;
+#ifndef ATTN_POLY_MASK
+#define ATTN_POLY_MASK 0x00
+#endif
+constexpr int kPolyExpMask = ATTN_POLY_MASK;  // of every 8 score pairs, the ones whose exp2 runs on the FMA pipe           // log2 units: P stays below 2^8 between rescales
 
-__device__ __forceinline__ void softmax_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory");
+// p[i] = 2^(s[i]*c - m) for 32 scores, masked beyond `nvalid`; returns the packed bf16 pairs and adds to the row sum
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float m, int nvalid, uint32_t (&packed)[16],
+                                          float& sum0, float& sum1) {
+  const float nm = -m;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a, b;
+    ffma2(a, b, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, c, nm, nm);
+    if (kPolyExpMask & (1 << ((i >> 1) & 7))) {  // this pair on the FMA pipe
+      ex2_poly2(a, b);
+    } else {
+      a = ex2_approx(a);
+      b = ex2_approx(b);
+    }
+    if (nvalid < 32) {
+      a = i < nvalid ? a : 0.f;
+      b = i + 1 < nvalid ? b : 0.f;
+    }
+    fadd2(sum0, sum1, sum0, sum1, a, b);
+    packed[i >> 1] = pack_bf16x2(a, b);
+  }
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // lengths and QKV come from earlier kernels
   const int q0 = blockIdx.x * kQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  long long* tl = (p.timeline && cta_lin < 148) ? p.timeline + (size_t)cta_lin * 64 : nullptr;
+#define TL(i)                    \
+  do {                           \
+    if (tl) tl[(i)] = clock64(); \
+  } while (0)
+  if (threadIdx.x == 0) TL(0);
   int len = p.lengths ? p.lengths[b] : p.T;
   if (len > p.T) len = p.T;
   if (q0 >= len) return;  // query tile is padding only: its rows are masked downstream
@@ -54,12 +90,11 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   uint64_t* bar_q = bars;
   uint64_t* bar_k = bars + 1;  // [2]
   uint64_t* bar_v = bars + 3;
-  uint64_t* bar_s = bars + 4;
-  uint64_t* bar_p = bars + 5;
-  uint64_t* bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  float* s_max = reinterpret_cast<float*>(bars + 16);  // [2 parity][2 half][128]
-  float* s_sum = s_max + 2 * 2 * kQ;                   // [2 half][128]
+  uint64_t* bar_s = bars + 4;  // MMA -> softmax: S(j) in TMEM
+  uint64_t* bar_p = bars + 5;  // softmax -> MMA: P(j) in smem, S(j) consumed, O rescaled
+  uint64_t* bar_o = bars + 6;  // MMA -> softmax / loader: P(j) V(j) retired
+  uint64_t* bar_f = bars + 7;  // softmax -> MMA: S(j) is in registers, the S columns may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,8 +106,9 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       mbar_init(&bar_k[1], 1);
       mbar_init(bar_v, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, kSoftmaxThreads);
+      mbar_init(bar_p, kSoftmaxWarps);
       mbar_init(bar_o, 1);
+      mbar_init(bar_f, kSoftmaxWarps);
       fence_barrier_init();
     }
     __syncwarp();
@@ -83,6 +119,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(15);
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
 
@@ -110,150 +147,178 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
         for (int k = 0; k < kD / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(bar_s);
       };
+      TL(1);
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
+      TL(2);
       issue_s(0);
+      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP));
+      const uint64_t dp1 = make_smem_desc_sw128(smem_u32(sP + kTile));
+      const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV));
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(bar_p, j & 1);
-        mbar_wait(bar_v, j & 1);
+        // the softmax warps hold S(j) in registers: the next scores can be computed while they work on this tile
+        mbar_wait(bar_f, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < kKV / 16; ++kk) {
-          const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + (kk >> 2) * kTile)) + 2 * (kk & 3);
-          const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + kk * 2048));
-          umma_bf16(tmem_o, dp, dv, idesc_o, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_o);
         if (j + 1 < nkv) {
           mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
-          mbar_wait(bar_o, j & 1);  // P V_j retired: V, P and K_j buffers are free
+        }
+        if (j + 2 < nkv) {  // S(j) has retired (the softmax warps read it): K buffer j&1 is free
+          mbar_arrive_expect_tx(&bar_k[j & 1], kTile);
+          tma_load_3d(sK + (j & 1) * kTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
+        }
+        mbar_wait(bar_p, j & 1);  // P(j) written, O rescaled where needed
+        tc_fence_after();
+        if (j < 4) TL(3 + 2 * j);
+        mbar_wait(bar_v, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kKV / 16; ++kk)  // V rows of 16 keys are 2048 B apart (>> 4 = 128 in the descriptor)
+          umma_bf16(tmem_o, (kk < 4 ? dp0 : dp1) + 2 * (kk & 3), dv0 + 128 * kk, idesc_o, (j | kk) != 0 ? 1u : 0u);
+        umma_commit(bar_o);
+        if (j < 4) TL(4 + 2 * j);
+        if (j + 1 < nkv) {
+          mbar_wait(bar_o, j & 1);  // P(j) V(j) retired: the V buffer is free
           mbar_arrive_expect_tx(bar_v, kTile);
           tma_load_3d(sV, &mapQKV, bar_v, colv, (j + 1) * kKV, b);
-          if (j + 2 < nkv) {
-            mbar_arrive_expect_tx(&bar_k[j & 1], kTile);
-            tma_load_3d(sK + (j & 1) * kTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
-          }
         }
       }
     }
   } else {
-    // ------------------------------------------------ softmax warps: 2 threads per query row (64 keys each)
-    const int quarter = warp & 3;
-    const int half = warp >> 2;
-    const int r = quarter * 32 + lane;
+    // ------------------------------------------------ softmax warps: one thread per query row
+    const int r = warp * 32 + lane;
     const int qi = q0 + r;
     int limit = len;
     if (p.chunk > 0) limit = min(len, (qi / p.chunk + 1) * p.chunk);
     const float c = p.scale_log2e;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_s + lane_addr + (uint32_t)(half * 64);
-    const uint32_t o_addr = tmem_o + lane_addr + (uint32_t)(half * 32);
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t s_addr = tmem_s + lane_addr;
+    const uint32_t o_addr = tmem_o + lane_addr;
     float m = -INFINITY, l = 0.f;
-    float o[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    uint8_t* prow = sP + half * kTile + r * 128;  // this thread's 64 keys = one 128-byte swizzled row
+    uint8_t* prow = sP + r * 128;  // 64 keys = one 128-byte swizzled row per K block
     const int sw = r & 7;
 
+    long long* tls = threadIdx.x == 0 ? tl : nullptr;
+#define TLS(i)                     \
+  do {                             \
+    if (tls) tls[(i)] = clock64(); \
+  } while (0)
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      const int nvalid = limit - j * kKV - half * 64;  // valid keys among this thread's 64
+      if (j < 4) TLS(16 + 6 * j);
+      uint32_t s[4][32];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld32(s_addr + cc * 32, s[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_f);
+      if (j < 4) TLS(17 + 6 * j);
+      const int nvalid = limit - j * kKV;  // valid keys of this row in this tile (may be <= 0 for streaming rows)
       float mx = -INFINITY;
+      if (nvalid >= kKV) {
+        float pm[8];  // independent chains: the reduction is latency-, not issue-bound
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t s[32];
-        tmem_ld32(s_addr + cc * 32, s);
-        tmem_ld_wait();
-        if (nvalid >= 64) {
+        for (int a = 0; a < 8; ++a) pm[a] = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            pm[(i >> 1) & 7] = fmaxf(pm[(i >> 1) & 7], fmaxf(__uint_as_float(s[cc][i]), __uint_as_float(s[cc][i + 1])));
+        mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[cc][i]));
+      }
+      // lazy running maximum: move it only when it grows by more than the threshold (first tile: always)
+      if (j < 4) TLS(18 + 6 * j);
+      const float mt = mx * c;
+      const bool grow = mt > m + kRescaleThreshold;  // false for mt = -inf; true for m = -inf and finite mt
+      const float m_new = grow ? mt : m;
+      const float alpha = (grow && j > 0) ? ex2_approx(m - m_new) : 1.0f;
+      const float m_use = m_new == -INFINITY ? 0.f : m_new;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) exp_chunk(s[cc], c, m_use, nvalid - cc * 32, pk[cc], sum0, sum1);
+      l = fmaf(l, alpha, sum0 + sum1);
+      m = m_new;
+      if (j < 4) TLS(19 + 6 * j);
+
+      if (j > 0) {
+        mbar_wait(bar_o, (j - 1) & 1);  // P(j-1) V(j-1) retired: O is stable and the P tile may be overwritten
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + hh * 32, o);
+          }
+          tmem_st_wait();
         }
       }
-      float* xm = s_max + (j & 1) * 2 * kQ;
-      xm[half * kQ + r] = mx;
-      softmax_barrier();
-      mx = fmaxf(mx, xm[(half ^ 1) * kQ + r]);
-      const float m_new = fmaxf(m, mx * c);
-      const float m_use = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = ex2_approx(m - m_use);
-      float rowsum = 0.f;
+      if (j < 4) TLS(20 + 6 * j);
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t s[32];
-        tmem_ld32(s_addr + cc * 32, s);
-        tmem_ld_wait();
-        float pv[32];
-        if (nvalid >= 64) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m_use));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(s[i]), c, -m_use));
-            pv[i] = cc * 32 + i < nvalid ? e : 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+      for (int cc = 0; cc < 4; ++cc) {
+        uint8_t* blk = prow + (cc >> 1) * kTile;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 v;
-          v.x = pack_bf16x2(pv[8 * q4 + 0], pv[8 * q4 + 1]);
-          v.y = pack_bf16x2(pv[8 * q4 + 2], pv[8 * q4 + 3]);
-          v.z = pack_bf16x2(pv[8 * q4 + 4], pv[8 * q4 + 5]);
-          v.w = pack_bf16x2(pv[8 * q4 + 6], pv[8 * q4 + 7]);
-          const int ch = cc * 4 + q4;
-          *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = v;
+          const uint4 v = make_uint4(pk[cc][4 * q4], pk[cc][4 * q4 + 1], pk[cc][4 * q4 + 2], pk[cc][4 * q4 + 3]);
+          const int ch = (cc & 1) * 4 + q4;
+          *reinterpret_cast<uint4*>(blk + ((ch ^ sw) << 4)) = v;
         }
       }
-      l = fmaf(l, alpha, rowsum);
-      m = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
-
-      mbar_wait(bar_o, j & 1);
-      tc_fence_after();
-      {
-        uint32_t s[32];
-        tmem_ld32(o_addr, s);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(s[i]));
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (j < 4) TLS(21 + 6 * j);
     }
-    s_sum[half * kQ + r] = l;
-    softmax_barrier();
-    l += s_sum[(half ^ 1) * kQ + r];
-    if (qi < p.T) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = p.out + ((long long)b * p.T + qi) * (p.H * kD) + h * kD + half * 32;
+
+    mbar_wait(bar_o, (nkv - 1) & 1);
+    tc_fence_after();
+    TLS(40);
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __nv_bfloat16* dst = p.out + ((long long)b * p.T + qi) * (p.H * kD) + h * kD;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
-        v.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        v.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        v.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + 8 * g) = v;
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tmem_ld32(o_addr + hh * 32, o);
+      tmem_ld_wait();
+      if (qi < p.T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * g) = v;
+        }
       }
     }
   }
 
+  if (threadIdx.x == 0) TL(41);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TL(42);
   if (warp == kSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kAttnTmemCols);
   }
+#undef TL
+#undef TLS
 }
 
 }  // namespace
@@ -269,9 +334,10 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
   dim3 grid((p.T + kQ - 1) / kQ, p.H, p.B);
   const double bh = (double)p.B * p.H;
   ProfScope prof(stream, PK_ATTENTION, 4.0 * bh * p.T * (double)p.T * kD, bh * p.T * kD * 2.0 * 4.0);
-  attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(mapQKV, p);
   count_launch();
-  return cudaGetLastError();
+  AttnParams pp = p;
+  pp.timeline = (g_debug_buffer && g_debug_bytes >= 148 * 64 * 8) ? g_debug_buffer : nullptr;
+  return launch_pdl(attn_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, pp);
 }
 
 }  // namespace ls

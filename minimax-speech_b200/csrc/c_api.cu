@@ -12,7 +12,22 @@ namespace ls {
 
 std::atomic<long long> g_launch_count{0};
 long long* g_debug_buffer = nullptr;
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LS_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 long long g_debug_bytes = 0;
+int conv_halo_mode() {  // 0: per-tap boxes; 1: halo box, descriptor base offset set; 2: halo box, base offset 0
+  static const int mode = [] {
+    const char* e = getenv("LS_CONV_HALO");
+    return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2;
+  }();
+  return mode;
+}
+bool conv_halo_enabled() { return conv_halo_mode() != 0; }
 
 static thread_local std::string t_error;
 void set_error(const char* fmt, ...) {
@@ -197,10 +212,12 @@ int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream) {
     LS_CUDA(cudaGetDevice(&dev));
     LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CUtensorMap a0, a1, w;
-    ls::require(ls::make_act_map(&a0, d->a0, d->a0_C, d->T_in, d->B, d->a0_C, (long long)d->T_in * d->a0_C, 128),
+    const bool halo = ls::conv_halo_enabled();
+    const int box = halo ? ls::conv_halo_box_rows(d->taps, d->dil) : 128;
+    ls::require(ls::make_act_map(&a0, d->a0, d->a0_C, d->T_in, d->B, d->a0_C, (long long)d->T_in * d->a0_C, box),
                 "tensor map a0", LS_ERR_CUDA);
     if (d->a1)
-      ls::require(ls::make_act_map(&a1, d->a1, d->a1_C, d->T_in, d->B, d->a1_C, (long long)d->T_in * d->a1_C, 128),
+      ls::require(ls::make_act_map(&a1, d->a1, d->a1_C, d->T_in, d->B, d->a1_C, (long long)d->T_in * d->a1_C, box),
                   "tensor map a1", LS_ERR_CUDA);
     else
       a1 = a0;
@@ -216,7 +233,7 @@ int32_t ls_test_conv_gemm(const ls_conv_gemm_desc* d, void* stream) {
     p.p1_a = d->p1_a, p.p1_b = d->p1_b, p.n_store = d->n_store;
     p.out_ld = d->out_ld, p.out_shift = d->out_shift, p.out_bstride = d->out_bstride, p.out_alloc = d->out_alloc;
     p.out_valid_mul = d->out_valid_mul;
-    p.k_true = d->K, p.tag = 0;
+    p.k_true = d->K, p.tag = 0, p.halo_mode = ls::conv_halo_mode();
     LS_CUDA(ls::launch_conv_gemm(a0, a1, w, p, sms, (cudaStream_t)stream));
   });
 }

@@ -28,12 +28,20 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kFirstEpiWarp = 2;
+#ifndef CONV_PRODUCER_WARPS
+#define CONV_PRODUCER_WARPS 3
+#endif
+constexpr int kProducerWarps = CONV_PRODUCER_WARPS;  // warp 0: activation boxes; warps 1..: weight boxes (one thread each)
+constexpr int kWeightProducers = kProducerWarps - 1;
+static_assert(kProducerWarps >= 2, "need one activation and at least one weight producer");
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kFirstEpiWarp = kProducerWarps + 1;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
+
 constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
-constexpr int kSmemBudget = 206 * 1024;             // for the operand ring
+constexpr int kSmemBudget = 174 * 1024;             // for the operand rings
 
 struct TileCoord {
   int b, mt, nt;
@@ -140,38 +148,178 @@ __device__ __forceinline__ void row_stats(const float (&v)[4][16], float2* red, 
   rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
 }
 
+
+// ---- coalesced global access for the epilogue --------------------------------------------------------------------
+// TMEM hands every thread one output ROW (32x32b loads), so a direct store makes each warp instruction touch 32
+// different rows with 16 B each: partial sectors and 32 lines per instruction (measured: 7 B/clk per SM).  Each warp
+// therefore transposes one 16-column chunk at a time through a private 2 KB staging buffer: rows are written/read by
+// their owner threads, global memory is accessed with consecutive lanes on consecutive 16 B pieces of a row
+// (fp32: 8 rows x 64 B per instruction, bf16: 16 rows x 32 B), i.e. whole 32 B sectors only.
+// 16 B units are XOR-swizzled so that both access patterns are bank-conflict free.
+constexpr int kStageBytesPerWarp = 2048;
+__device__ __forceinline__ int stg_f32(int row, int unit) { return row * 64 + ((unit ^ ((row >> 1) & 3)) << 4); }
+__device__ __forceinline__ int stg_b16(int row, int unit) { return row * 32 + ((unit ^ ((row >> 2) & 1)) << 4); }
+
+// geometry of one warp's 32 rows for the coalesced side
+struct WarpRows {
+  long long t_base;        // time index of the warp's first row inside the batch item
+  long long out_ld, out_shift, valid, alloc;
+  int M;
+  __device__ __forceinline__ int state(int rr, int n, long long* flat) const {  // same rule as ChunkStore::state
+    const long long t = t_base + rr;
+    const long long f = t * out_ld + out_shift + n;
+    *flat = f;
+    if (t >= M || f < 0) return 0;
+    if (f + 16 <= valid) return 2;
+    if (f + 16 <= alloc) return 1;
+    return 0;
+  }
+};
+
+// v (this thread's row, 16 fp32) += addend chunk, fetched coalesced
+template <bool kF32>
+__device__ __forceinline__ void add_chunk(uint8_t* stg, int lane, const WarpRows& wr, int n, const void* base,
+                                          float (&v)[16]) {
+  if (kF32) {
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int rr = ps * 8 + (lane >> 2), seg = lane & 3;
+      long long flat;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wr.state(rr, n, &flat) == 2) a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + flat + seg * 4);
+      *reinterpret_cast<float4*>(stg + stg_f32(rr, seg)) = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 a = *reinterpret_cast<const float4*>(stg + stg_f32(lane, u));
+      v[4 * u] += a.x, v[4 * u + 1] += a.y, v[4 * u + 2] += a.z, v[4 * u + 3] += a.w;
+    }
+  } else {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int rr = ps * 16 + (lane >> 1), seg = lane & 1;
+      long long flat;
+      uint4 a = make_uint4(0u, 0u, 0u, 0u);
+      if (wr.state(rr, n, &flat) == 2) a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + flat + seg * 8);
+      *reinterpret_cast<uint4*>(stg + stg_b16(rr, seg)) = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint4 a = *reinterpret_cast<const uint4*>(stg + stg_b16(lane, u));
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[8 * u + 2 * k] += __low2float(h2);
+        v[8 * u + 2 * k + 1] += __high2float(h2);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// store this thread's row chunk (16 fp32 values) coalesced, as fp32 or bf16; rows in the zero-fill range get zeros
+template <bool kF32>
+__device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRows& wr, int n, void* base,
+                                            const float (&v)[16]) {
+  if (kF32) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<float4*>(stg + stg_f32(lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int rr = ps * 8 + (lane >> 2), seg = lane & 3;
+      long long flat;
+      const int st = wr.state(rr, n, &flat);
+      if (st != 0) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (st == 2) a = *reinterpret_cast<const float4*>(stg + stg_f32(rr, seg));
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + flat + seg * 4) = a;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      *reinterpret_cast<uint4*>(stg + stg_b16(lane, u)) =
+          make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+    __syncwarp();
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int rr = ps * 16 + (lane >> 1), seg = lane & 1;
+      long long flat;
+      const int st = wr.state(rr, n, &flat);
+      if (st != 0) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        if (st == 2) a = *reinterpret_cast<const uint4*>(stg + stg_b16(rr, seg));
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + flat + seg * 8) = a;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// The epilogue mode (activation, outputs, residual, time embedding) is a template parameter for the combinations the
+// engines launch (-1 = decided at run time: the generic instance, used by everything else).  A specialised instance
+// carries a fraction of the generic epilogue's code: the unrolled epilogue is executed once per tile, so its
+// footprint in the instruction cache -- not its instruction count -- is what the generic instance pays for.
+template <int kAct, int kOut0, int kOut1, int kAdd, int kTemb>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvGemmParams p,
-                 const int stages, const int tmem_cols, const int acc_stride) {
+                 const int tmem_cols, const int acc_stride) {
+  const int act = kAct >= 0 ? kAct : p.act;
+  const int out0_dtype = kOut0 >= 0 ? kOut0 : p.out0_dtype;
+  const int out1_mode = kOut1 >= 0 ? kOut1 : p.out1_mode;
+  const int add_dtype = kAdd >= 0 ? kAdd : (p.addend ? p.addend_dtype : OUT_NONE);  // OUT_NONE: no residual
+  const bool has_temb = kTemb >= 0 ? kTemb != 0 : p.temb != nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Two operand rings.  A stage: one (128 + halo)-row x 64-channel activation box (halo = (taps-1)*dil rows when
+  // p.halo_mode, so the box is fetched ONCE per K block and every tap reads it through a row-shifted descriptor;
+  // without halo_mode the box is 128 rows and is fetched per tap).  B stage: one block_n x 64 weight box per (K block, tap).
+  const int a_bytes = ls_conv_a_stage_bytes(p.a_box_rows);
   const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxStages;
-  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.a_stages * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxStages;
+  uint64_t* b_full = bars + 2 * kMaxStages;
+  uint64_t* b_empty = bars + 3 * kMaxStages;
+  uint64_t* tfull = bars + 4 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float2* red_base = reinterpret_cast<float2*>(bars + 32);  // 256 B after the barriers
+  float2* red_base = reinterpret_cast<float2*>(bars + 64);  // 512 B after the barriers
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(red_base) + kRedBytes;  // per-epilogue-warp transpose buffers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int n_tiles = p.N / p.block_n;
   const int total_tiles = p.B * m_tiles * n_tiles;
-  const int k_iters = p.taps * p.kb_per_tap;
+  const bool halo = p.halo_mode != 0;
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 64 : nullptr;
+#define TL(i)                    \
+  do {                           \
+    if (tl) tl[(i)] = clock64(); \
+  } while (0)
+  if (threadIdx.x == 0) TL(0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapA1);
     prefetch_tmap(&mapW);
   }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+  if (warp == kMmaWarp && lane == 0) {
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -184,64 +332,104 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(1);
+  pdl_wait();
+  if (threadIdx.x == 0) TL(2);  // everything above overlapped the previous kernel's tail; activations are read only from here on
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp < kProducerWarps) {
+    // ------------------------------------------------------------ TMA producers
+    // A thread can start a TMA load only every ~500 clk (issue latency; profiles/micro/tma_bw3.cu) but different warps
+    // overlap.  Warp 0 issues every activation box; warps 1.. share the weight boxes, warp w taking those whose sequence
+    // number is (w-1) mod kWeightProducers.  Interleaving P producers over a ring of D stages keeps the parity waits
+    // unambiguous only while P <= D (a producer is then never two uses ahead of the consumer): launch_conv_gemm
+    // guarantees b_stages >= kWeightProducers, and the activation ring (1-3 stages) has a single producer.
+    // (Separate warps, not lanes: a lane blocked in mbarrier.try_wait suspends its whole warp.)
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int b_seq = 0;
+      const uint32_t a_tx = (uint32_t)p.a_box_rows * 128u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
         if (tile_skipped(p, tc)) continue;
         const int t0 = tc.mt * kBlockM;
         const int n0 = tc.nt * p.block_n;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int trow = t0 + tap * p.dil - p.pad;
-          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            if (kb < p.kb_split)
-              tma_load_3d(sa, &mapA0, &full[stage], kb * kBlockK, trow, tc.b);
-            else
-              tma_load_3d(sa, &mapA1, &full[stage], (kb - p.kb_split) * kBlockK, trow, tc.b);
-            tma_load_2d(sa + kABytes, &mapW, &full[stage], kb * kBlockK, tap * p.N + n0);
-            if (++stage == stages) stage = 0, phase ^= 1;
+        for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (warp == 0) {
+              if (!halo || tap == 0) {
+                const int trow = t0 - p.pad + (halo ? 0 : tap * p.dil);
+                mbar_wait(&a_empty[as], aph ^ 1);
+                uint8_t* sa = smem_a + (size_t)as * a_bytes;
+                mbar_arrive_expect_tx(&a_full[as], a_tx);
+                if (kb < p.kb_split)
+                  tma_load_3d(sa, &mapA0, &a_full[as], kb * kBlockK, trow, tc.b);
+                else
+                  tma_load_3d(sa, &mapA1, &a_full[as], (kb - p.kb_split) * kBlockK, trow, tc.b);
+                if (++as == p.a_stages) as = 0, aph ^= 1;
+              }
+            } else {
+              if (b_seq == warp - 1) {
+                mbar_wait(&b_empty[bs], bph ^ 1);
+                mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
+                tma_load_2d(smem_b + (size_t)bs * b_bytes, &mapW, &b_full[bs], kb * kBlockK, tap * p.N + n0);
+              }
+              if (++b_seq == kWeightProducers) b_seq = 0;
+              if (++bs == p.b_stages) bs = 0, bph ^= 1;
+            }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int n_it = 0;  // timeline aid
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
         if (tile_skipped(p, tc)) continue;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes);
+        for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (!halo || tap == 0) {
+              mbar_wait(&a_full[as], aph);
+              tc_fence_after();
+            }
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            if (tl && n_it < 24) tl[8 + n_it] = clock64();
+            ++n_it;
+            // tap t of the halo box = the same rows shifted down by t*dil: start address + t*dil*128 B, with the
+            // swizzle phase of the first row in the descriptor's base-offset field
+            const int shift = halo ? tap * p.dil : 0;
+            const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + (size_t)as * a_bytes) + (uint32_t)shift * 128u,
+                                                        p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
+            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + (size_t)bs * b_bytes));
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
-          if (++stage == stages) stage = 0, phase ^= 1;
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            umma_commit(&b_empty[bs]);
+            if (++bs == p.b_stages) bs = 0, bph ^= 1;
+            if (!halo || tap == p.taps - 1) {
+              umma_commit(&a_empty[as]);
+              if (++as == p.a_stages) as = 0, aph ^= 1;
+            }
+          }
         }
         umma_commit(&tfull[acc]);
+        if (tl && n_it <= p.taps * p.kb_per_tap) tl[32] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -252,6 +440,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int g = (warp - kFirstEpiWarp) >> 2;  // column group: owns 16-column chunks g, g+4, g+8, g+12
     const int row = q * 32 + lane;
     const int n_chunks = p.block_n >> 4;
+    uint8_t* stg = stg_base + (warp - kFirstEpiWarp) * kStageBytesPerWarp;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
@@ -277,9 +466,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           for (int i = 0; i < 16; ++i) zero[i] = 0.f;
           for (int c = g; c < n_chunks; c += 4) {
             const int n = n0 + c * 16;
-            if (p.out0_dtype == OUT_F32) st.f32(out0f, row_flat + n, n, zero);
-            else if (p.out0_dtype == OUT_BF16) st.bf16(out0h, row_flat + n, n, zero);
-            if (p.out1_mode != OUT1_NONE) st.bf16(out1, row_flat + n, n, zero);
+            if (out0_dtype == OUT_F32) st.f32(out0f, row_flat + n, n, zero);
+            else if (out0_dtype == OUT_BF16) st.bf16(out0h, row_flat + n, n, zero);
+            if (out1_mode != OUT1_NONE) st.bf16(out1, row_flat + n, n, zero);
           }
         }
         continue;
@@ -287,209 +476,213 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       st.valid = p.lengths ? min((long long)p.lengths[tc.b] * p.out_valid_mul, p.out_alloc) : p.out_alloc;
       const float* addf = reinterpret_cast<const float*>(p.addend) + boff;
       const __nv_bfloat16* addh = reinterpret_cast<const __nv_bfloat16*>(p.addend) + boff;
-      const float* temb = p.temb ? p.temb + (long long)tc.b * p.temb_bstride : nullptr;
+      const float* temb = has_temb ? p.temb + (long long)tc.b * p.temb_bstride : nullptr;
       float2* red = red_base + parity * (2 * 4 * kBlockM);
       parity ^= 1;
 
-      // ---- accumulators -> registers in one burst, then hand the TMEM stage back to the MMA warp
+      // ---- streaming epilogue: one 16-column chunk at a time, re-read from TMEM in every pass (TMEM reads are cheap,
+      // registers are not: with ~220 KB of shared memory there is hardly any L1 left to absorb a spill).  LayerNorm
+      // needs whole-row statistics first, so those modes make an extra pass; the second LayerNorm (OUT1_LN) parks the
+      // finished values back in the accumulator columns (tcgen05.st) and re-reads them once its statistics are known.
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      long long* tle = (threadIdx.x == kFirstEpiWarp * 32 && tile == (int)blockIdx.x) ? tl : nullptr;
+      if (tle) tle[40] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-      float v[4][16];
+      // accumulator chunk c + bias, then the pointwise activations
+      auto load_x = [&](int c, float (&x)[16]) {
+        tmem_ld16(taddr + (uint32_t)(c * 16), reinterpret_cast<uint32_t(&)[16]>(x));
+        tmem_ld_wait();
+        if (p.bias) {
+          const int ch0 = (n0 + c * 16) % p.chan_mod;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (g + 4 * j < n_chunks) tmem_ld16(taddr + (uint32_t)((g + 4 * j) * 16), reinterpret_cast<uint32_t(&)[16]>(v[j]));
-      tmem_ld_wait();
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + g4);
+            x[4 * g4] += bv.x, x[4 * g4 + 1] += bv.y, x[4 * g4 + 2] += bv.z, x[4 * g4 + 3] += bv.w;
+          }
+        }
+        if (act == ACT_LRELU || act == ACT_LRELU_TANH) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = x[i] > 0.f ? x[i] : 0.1f * x[i];
+          if (act == ACT_LRELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = tanhf(x[i]);
+          }
+        } else if (act == ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = gelu_erf(x[i]);
+        }
+      };
+      // statistics of this thread's 64 columns (4 chunks), merged chunk by chunk (Chan), then across the 4 column
+      // groups through shared memory
+      struct Stats {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        __device__ __forceinline__ void add16(const float (&x)[16]) {
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sm += x[i];
+          const float cm = sm * (1.0f / 16.0f);
+          float cm2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float d = x[i] - cm;
+            cm2 = fmaf(d, d, cm2);
+          }
+          const float nn = n + 16.0f;
+          const float delta = cm - mean;
+          mean += delta * (16.0f / nn);
+          m2 += cm2 + delta * delta * (n * 16.0f / nn);
+          n = nn;
+        }
+      };
+      auto combine = [&](const Stats& stt, float2* r, float& mean, float& rstd) {
+        r[g * kBlockM + row] = make_float2(stt.mean, stt.m2);
+        epi_barrier();
+        const float2 a = r[row], b = r[kBlockM + row], c = r[2 * kBlockM + row], d = r[3 * kBlockM + row];
+        mean = 0.25f * (a.x + b.x + c.x + d.x);
+        const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
+        const float M2 = a.y + b.y + c.y + d.y + 64.0f * (da * da + db * db + dc * dc + dd * dd);
+        rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
+      };
+
+      float mean1 = 0.f, rstd1 = 1.f;
+      if (act == ACT_LN_MISH) {  // pass A: LayerNorm statistics of the 256-wide row (block_n == N == 256)
+        Stats s1;
+#pragma unroll 1
+        for (int c = g; c < n_chunks; c += 4) {
+          float x[16];
+          load_x(c, x);
+          s1.add16(x);
+        }
+        combine(s1, red, mean1, rstd1);
+      }
+      if (tle) tle[45] = clock64();
+
+      WarpRows wr;
+      wr.t_base = (long long)tc.mt * kBlockM + q * 32;
+      wr.out_ld = p.out_ld, wr.out_shift = p.out_shift, wr.valid = st.valid, wr.alloc = st.alloc, wr.M = p.M;
+      Stats s2;
+      // pass B: finish the values, store the primary / copy / snake outputs
+#pragma unroll 1
+      for (int c = g; c < n_chunks; c += 4) {
+        float x[16];
+        load_x(c, x);
+        const int n = n0 + c * 16;
+        if (act == ACT_LN_MISH) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + c * 16) + g4);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + c * 16) + g4);
+            x[4 * g4 + 0] = mish_f(fmaf((x[4 * g4 + 0] - mean1) * rstd1, gm.x, bt.x));
+            x[4 * g4 + 1] = mish_f(fmaf((x[4 * g4 + 1] - mean1) * rstd1, gm.y, bt.y));
+            x[4 * g4 + 2] = mish_f(fmaf((x[4 * g4 + 2] - mean1) * rstd1, gm.z, bt.z));
+            x[4 * g4 + 3] = mish_f(fmaf((x[4 * g4 + 3] - mean1) * rstd1, gm.w, bt.w));
+          }
+        }
+        if (has_temb) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 tv = __ldg(reinterpret_cast<const float4*>(temb + n) + g4);
+            x[4 * g4] += tv.x, x[4 * g4 + 1] += tv.y, x[4 * g4 + 2] += tv.z, x[4 * g4 + 3] += tv.w;
+          }
+        }
+        const long long flat = row_flat + n;
+        const bool partial = n + 16 > p.n_store;  // only the padded final conv (n_store = 1)
+        if (add_dtype != OUT_NONE && !partial) {
+          if (add_dtype == OUT_F32) add_chunk<true>(stg, lane, wr, n, addf, x);
+          else add_chunk<false>(stg, lane, wr, n, addh, x);
+        }
+        if (partial) {  // scalar tail: column 0 of consecutive rows is contiguous when out_ld == n_store == 1
+          const int stt = st.state(flat, max(p.n_store - n, 1));
+          if (stt != 0 && n < p.n_store) {
+            for (int i = 0; i < 16 && n + i < p.n_store; ++i) {
+              const float xv = stt == 2 ? x[i] : 0.f;
+              if (out0_dtype == OUT_F32) out0f[flat + i] = xv;
+              else if (out0_dtype == OUT_BF16) out0h[flat + i] = __float2bfloat16(xv);
+              if (out1_mode == OUT1_COPY) out1[flat + i] = __float2bfloat16(xv);
+            }
+          }
+        } else {
+          if (out0_dtype == OUT_F32) store_chunk<true>(stg, lane, wr, n, out0f, x);
+          else if (out0_dtype == OUT_BF16) store_chunk<false>(stg, lane, wr, n, out0h, x);
+          if (out1_mode == OUT1_COPY) {
+            store_chunk<false>(stg, lane, wr, n, out1, x);
+          } else if (out1_mode == OUT1_SNAKE) {
+            const int ch0 = n % p.chan_mod;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 al = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + g4);
+              const float4 ia = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + g4);
+              x[4 * g4 + 0] = snake_f(x[4 * g4 + 0], al.x, ia.x);
+              x[4 * g4 + 1] = snake_f(x[4 * g4 + 1], al.y, ia.y);
+              x[4 * g4 + 2] = snake_f(x[4 * g4 + 2], al.z, ia.z);
+              x[4 * g4 + 3] = snake_f(x[4 * g4 + 3], al.w, ia.w);
+            }
+            store_chunk<false>(stg, lane, wr, n, out1, x);
+          } else if (out1_mode == OUT1_LN) {
+            s2.add16(x);
+            tmem_st16(taddr + (uint32_t)(c * 16), reinterpret_cast<const uint32_t(&)[16]>(x));
+          }
+        }
+      }
+      if (tle) tle[42] = clock64();
+      if (out1_mode == OUT1_LN) {  // pass C: second output = LayerNorm(u), the bf16 operand of the next GEMM
+        tmem_st_wait();
+        float mean2, rstd2;
+        combine(s2, red + 4 * kBlockM, mean2, rstd2);
+#pragma unroll 1
+        for (int c = g; c < n_chunks; c += 4) {
+          float x[16];
+          tmem_ld16(taddr + (uint32_t)(c * 16), reinterpret_cast<uint32_t(&)[16]>(x));
+          tmem_ld_wait();
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.p1_a + c * 16) + g4);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.p1_b + c * 16) + g4);
+            x[4 * g4 + 0] = fmaf((x[4 * g4 + 0] - mean2) * rstd2, ga.x, be.x);
+            x[4 * g4 + 1] = fmaf((x[4 * g4 + 1] - mean2) * rstd2, ga.y, be.y);
+            x[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean2) * rstd2, ga.z, be.z);
+            x[4 * g4 + 3] = fmaf((x[4 * g4 + 3] - mean2) * rstd2, ga.w, be.w);
+          }
+          store_chunk<false>(stg, lane, wr, n0 + c * 16, out1, x);
+        }
+      }
+      // every TMEM access of this tile is done: hand the accumulator stage back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-
-      // ---- bias + pointwise activation, in place
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (g + 4 * j < n_chunks) {
-          const int ch0 = (n0 + (g + 4 * j) * 16) % p.chan_mod;
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + g4);
-            float* x = &v[j][4 * g4];
-            x[0] += bv.x, x[1] += bv.y, x[2] += bv.z, x[3] += bv.w;
-            if (p.act == ACT_LRELU || p.act == ACT_LRELU_TANH) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) x[i] = x[i] > 0.f ? x[i] : 0.1f * x[i];
-              if (p.act == ACT_LRELU_TANH) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = tanhf(x[i]);
-              }
-            } else if (p.act == ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) x[i] = gelu_erf(x[i]);
-            }
-          }
-        }
-      }
-
-      if (p.act == ACT_LN_MISH) {  // LayerNorm over the 256-wide row, then Mish
-        float mean, rstd;
-        row_stats(v, red, g, row, mean, rstd);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + (g + 4 * j) * 16) + g4);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + (g + 4 * j) * 16) + g4);
-            float* x = &v[j][4 * g4];
-            x[0] = mish_f(fmaf((x[0] - mean) * rstd, gm.x, bt.x));
-            x[1] = mish_f(fmaf((x[1] - mean) * rstd, gm.y, bt.y));
-            x[2] = mish_f(fmaf((x[2] - mean) * rstd, gm.z, bt.z));
-            x[3] = mish_f(fmaf((x[3] - mean) * rstd, gm.w, bt.w));
-          }
-        }
-      }
-
-      // ---- time-embedding add, residual add, primary store, copy / snake secondary store
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (g + 4 * j < n_chunks) {
-          const int n = n0 + (g + 4 * j) * 16;
-          const long long flat = row_flat + n;
-          const bool partial = n + 16 > p.n_store;  // only the padded final conv (n_store = 1)
-          const int stt = st.state(flat, partial ? max(p.n_store - n, 1) : 16);
-          if (temb) {
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 tv = __ldg(reinterpret_cast<const float4*>(temb + n) + g4);
-              float* x = &v[j][4 * g4];
-              x[0] += tv.x, x[1] += tv.y, x[2] += tv.z, x[3] += tv.w;
-            }
-          }
-          if (p.addend && stt == 2) {
-            if (p.addend_dtype == OUT_F32) {
-#pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {
-                const float4 a = *reinterpret_cast<const float4*>(addf + flat + 4 * g4);
-                float* x = &v[j][4 * g4];
-                x[0] += a.x, x[1] += a.y, x[2] += a.z, x[3] += a.w;
-              }
-            } else {
-#pragma unroll
-              for (int g8 = 0; g8 < 2; ++g8) {
-                const uint4 a = *reinterpret_cast<const uint4*>(addh + flat + 8 * g8);
-                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                  v[j][8 * g8 + 2 * k] += __low2float(h2);
-                  v[j][8 * g8 + 2 * k + 1] += __high2float(h2);
-                }
-              }
-            }
-          }
-          if (stt != 0 && n < p.n_store) {
-            if (partial) {  // scalar tail
-              for (int i = 0; i < 16 && n + i < p.n_store; ++i) {
-                const float x = stt == 2 ? v[j][i] : 0.f;
-                if (p.out0_dtype == OUT_F32) out0f[flat + i] = x;
-                else if (p.out0_dtype == OUT_BF16) out0h[flat + i] = __float2bfloat16(x);
-                if (p.out1_mode == OUT1_COPY) out1[flat + i] = __float2bfloat16(x);
-              }
-            } else {
-              if (p.out0_dtype == OUT_F32) {
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                  const float* x = &v[j][4 * g4];
-                  reinterpret_cast<float4*>(out0f + flat)[g4] =
-                      stt == 2 ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-              } else if (p.out0_dtype == OUT_BF16) {
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) {
-                  const float* x = &v[j][8 * g8];
-                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                  if (stt == 2)
-                    o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                   pack_bf16x2(x[6], x[7]));
-                  reinterpret_cast<uint4*>(out0h + flat)[g8] = o;
-                }
-              }
-              if (p.out1_mode == OUT1_COPY) {
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) {
-                  const float* x = &v[j][8 * g8];
-                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                  if (stt == 2)
-                    o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                   pack_bf16x2(x[6], x[7]));
-                  reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
-                }
-              } else if (p.out1_mode == OUT1_SNAKE) {
-                const int ch0 = n % p.chan_mod;
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) {
-                  const float* x = &v[j][8 * g8];
-                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                  if (stt == 2) {
-                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + 2 * g8);
-                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + 2 * g8 + 1);
-                    const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + 2 * g8);
-                    const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + 2 * g8 + 1);
-                    o.x = pack_bf16x2(snake_f(x[0], a0.x, i0.x), snake_f(x[1], a0.y, i0.y));
-                    o.y = pack_bf16x2(snake_f(x[2], a0.z, i0.z), snake_f(x[3], a0.w, i0.w));
-                    o.z = pack_bf16x2(snake_f(x[4], a1.x, i1.x), snake_f(x[5], a1.y, i1.y));
-                    o.w = pack_bf16x2(snake_f(x[6], a1.z, i1.z), snake_f(x[7], a1.w, i1.w));
-                  }
-                  reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
-                }
-              }
-            }
-          }
-        }
-      }
-
-      if (p.out1_mode == OUT1_LN) {  // second output = LayerNorm(u), bf16 operand of the next GEMM
-        float mean, rstd;
-        row_stats(v, red + 4 * kBlockM, g, row, mean, rstd);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + (g + 4 * j) * 16;
-          const long long flat = row_flat + n;
-          const int stt = st.state(flat);
-          if (stt == 0) continue;
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            const float* x = &v[j][8 * g8];
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (stt == 2) {
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.p1_a + (g + 4 * j) * 16) + 2 * g8);
-              const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.p1_a + (g + 4 * j) * 16) + 2 * g8 + 1);
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.p1_b + (g + 4 * j) * 16) + 2 * g8);
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.p1_b + (g + 4 * j) * 16) + 2 * g8 + 1);
-              o.x = pack_bf16x2(fmaf((x[0] - mean) * rstd, a0.x, b0.x), fmaf((x[1] - mean) * rstd, a0.y, b0.y));
-              o.y = pack_bf16x2(fmaf((x[2] - mean) * rstd, a0.z, b0.z), fmaf((x[3] - mean) * rstd, a0.w, b0.w));
-              o.z = pack_bf16x2(fmaf((x[4] - mean) * rstd, a1.x, b1.x), fmaf((x[5] - mean) * rstd, a1.y, b1.y));
-              o.w = pack_bf16x2(fmaf((x[6] - mean) * rstd, a1.z, b1.z), fmaf((x[7] - mean) * rstd, a1.w, b1.w));
-            }
-            reinterpret_cast<uint4*>(out1 + flat)[g8] = o;
-          }
-        }
-      }
     }
   }
 
+  if (threadIdx.x == kFirstEpiWarp * 32) TL(43);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TL(44);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
   }
+#undef TL
 }
 
 int pow2_at_least(int x, int lo) {
   int v = lo;
   while (v < x) v <<= 1;
   return v;
+}
+
+template <int kAct, int kOut0, int kOut1, int kAdd, int kTemb>
+cudaError_t launch_instance(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
+                            const CUtensorMap& mapW, const ConvGemmParams& pp, int tmem_cols, int acc_stride) {
+  auto* kernel = conv_gemm_kernel<kAct, kOut0, kOut1, kAdd, kTemb>;
+  static bool attr_done = false;  // one flag per instance
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, 1, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
 }
 
 }  // namespace
@@ -500,21 +693,29 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   if ((p.act == ACT_LN_MISH || p.out1_mode == OUT1_LN) && p.block_n != p.N) return cudaErrorInvalidValue;
   if (p.out1_mode == OUT1_LN && p.out0_dtype != OUT_F32) return cudaErrorInvalidValue;
   if (p.out1_mode != OUT1_NONE && p.out1 == nullptr) return cudaErrorInvalidValue;
-  const int stage_bytes = kABytes + p.block_n * kBlockK * 2;
-  int stages = kSmemBudget / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return cudaErrorInvalidValue;
+  ConvGemmParams pp = p;
+  pp.timeline = (g_debug_buffer && g_debug_bytes >= 148 * 64 * 8) ? g_debug_buffer : nullptr;
+  pp.a_box_rows = p.halo_mode ? conv_halo_box_rows(p.taps, p.dil) : kBlockM;
+  if (pp.a_box_rows > 256) return cudaErrorInvalidValue;  // TMA box limit
+  const int a_bytes = ls_conv_a_stage_bytes(pp.a_box_rows);
+  const int b_bytes = p.block_n * kBlockK * 2;
+  if (p.halo_mode && p.taps > 1) {
+    // one A box feeds `taps` B boxes: two A stages are enough, the rest of the budget goes to the weight ring
+    pp.a_stages = p.kb_per_tap > 1 ? 2 : 1;
+    if (p.kb_per_tap > 1 && 3 * a_bytes + 4 * b_bytes <= kSmemBudget) pp.a_stages = 3;
+    pp.b_stages = (kSmemBudget - pp.a_stages * a_bytes) / b_bytes;
+  } else {
+    pp.a_stages = pp.b_stages = kSmemBudget / (a_bytes + b_bytes);
+  }
+  if (pp.a_stages > kMaxStages) pp.a_stages = kMaxStages;
+  if (pp.b_stages > kMaxStages) pp.b_stages = kMaxStages;
+  if (pp.a_stages < 1 || pp.b_stages < 2 || pp.b_stages < kWeightProducers) return cudaErrorInvalidValue;
   const int acc_stride = pow2_at_least(p.block_n, 32);
   const int tmem_cols = 2 * acc_stride;
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + kRedBytes;
+  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + 512 + kRedBytes +
+                kEpiWarps * kStageBytesPerWarp;
   // tmem_cols == 512 must never share an SM with a second CTA of this kernel (alloc would spin):
   if (tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const long long total = (long long)p.B * m_tiles * (p.N / p.block_n);
   if (total <= 0) return cudaSuccess;
@@ -526,9 +727,27 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                        (p.addend ? (p.addend_dtype == OUT_F32 ? 4.0 : 2.0) : 0.0);
   ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
                  rows * kt * 2.0 + (double)p.taps * p.N * kt * 2.0 + rows * (p.n_store < p.N ? p.n_store : p.N) * out_b);
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(mapA0, mapA1, mapW, p, stages, tmem_cols, acc_stride);
   count_launch();
-  return cudaGetLastError();
+  const int add = p.addend ? p.addend_dtype : OUT_NONE;
+  const int temb = p.temb ? 1 : 0;
+#define LS_CONV_CASE(A, O0, O1, AD, TE)                                                                          \
+  if (p.act == (A) && p.out0_dtype == (O0) && p.out1_mode == (O1) && add == (AD) && temb == (TE))               \
+    return launch_instance<A, O0, O1, AD, TE>(grid, smem, stream, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
+  // flow estimator: resnet conv1 | res_conv, final_proj | resnet conv2 | QKV, down / up conv | final block
+  LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 1)
+  LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_NONE, OUT_NONE, 0)
+  LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_LN, OUT_F32, 0)
+  LS_CONV_CASE(ACT_NONE, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
+  LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
+  // DAC decoder: de_conv_pre | input conv, conv7 | transposed conv | conv1 + residual (x kept / last unit) | final conv
+  LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
+  LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_NONE, 0)
+  LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_SNAKE, OUT_NONE, 0)
+  LS_CONV_CASE(ACT_LRELU, OUT_F32, OUT1_SNAKE, OUT_F32, 0)
+  LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_F32, 0)
+  LS_CONV_CASE(ACT_LRELU_TANH, OUT_F32, OUT1_NONE, OUT_NONE, 0)
+#undef LS_CONV_CASE
+  return launch_instance<-1, -1, -1, -1, -1>(grid, smem, stream, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
 }
 
 }  // namespace ls

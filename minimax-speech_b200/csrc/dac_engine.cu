@@ -93,8 +93,14 @@ struct DacEngine::StageW {
   PackedLinear up;
   UnitW unit[3];
 };
+// sA[i]/sB[i]: stage-i views (i = 0: output of the input conv).  Every consumer of a buffer gets a view whose box
+// carries the halo of its convolution: up = 2-tap transposed conv, d[j] = conv7 with dilation 1 / 3 / 9.
 struct DacEngine::Plan {
-  CUtensorMap zt, a0, sA[6], sB[6];  // sA[i]/sB[i]: stage-i views (i = 0: output of the input conv)
+  CUtensorMap zt, a0;
+  struct {
+    CUtensorMap up, d[3];
+  } sA[6];
+  CUtensorMap sB[6];
 };
 
 DacEngine::~DacEngine() {
@@ -204,18 +210,21 @@ const DacEngine::Plan& DacEngine::plan_for(int B, int L) {
   auto it = plans_.find(key);
   if (it != plans_.end()) return *it->second;
   auto pl = std::make_unique<Plan>();
-  auto mk = [&](CUtensorMap* m, size_t off, int C, long long rows) {
-    require(make_act_map(m, ws_base_ + off, C, (int)rows, B, C, rows * C, 128),
+  const bool halo = conv_halo_enabled();
+  auto mk = [&](CUtensorMap* m, size_t off, int C, long long rows, int taps, int dil) {
+    require(make_act_map(m, ws_base_ + off, C, (int)rows, B, C, rows * C, halo ? conv_halo_box_rows(taps, dil) : 128),
             "cuTensorMapEncodeTiled failed for an activation buffer", LS_ERR_CUDA);
   };
-  mk(&pl->zt, o_zt_, latent_, L);
-  mk(&pl->a0, o_a0_, latent_, L);
-  mk(&pl->sA[0], o_sA_[0], dim_, L);
+  static const int dils[3] = {1, 3, 9};
+  mk(&pl->zt, o_zt_, latent_, L, 1, 1);
+  mk(&pl->a0, o_a0_, latent_, L, 7, 1);
+  mk(&pl->sA[0].up, o_sA_[0], dim_, L, 2, 1);
   long long rows = L;
   for (size_t i = 0; i < stages_.size(); ++i) {
     rows *= stages_[i].stride;
-    mk(&pl->sA[i + 1], o_sA_[(i + 1) & 1], stages_[i].cout, rows);
-    mk(&pl->sB[i + 1], o_sB_, stages_[i].cout, rows);
+    mk(&pl->sA[i + 1].up, o_sA_[(i + 1) & 1], stages_[i].cout, rows, 2, 1);
+    for (int j = 0; j < 3; ++j) mk(&pl->sA[i + 1].d[j], o_sA_[(i + 1) & 1], stages_[i].cout, rows, 7, dils[j]);
+    mk(&pl->sB[i + 1], o_sB_, stages_[i].cout, rows, 1, 1);
   }
   const Plan& ref = *pl;
   plans_[key] = std::move(pl);
@@ -229,6 +238,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
   ensure_workspace(B, L);
   const Plan& pl = plan_for(B, L);
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
+  const bool halo = conv_halo_enabled();
 
   // generic launcher: rows = output rows per item of this layer, C_out = channel count of the output layout
   auto conv = [&](const CUtensorMap& a, const PackedLinear& w, long long rows, int rate, int dil, ConvGemmParams p) {
@@ -243,7 +253,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       p.out_ld = w.N, p.out_shift = 0, p.out_bstride = rows * w.N, p.out_alloc = rows * w.N;
       p.out_valid_mul = (long long)rate * w.N;
     }
-    p.k_true = w.K, p.tag = 1;
+    p.k_true = w.K, p.tag = 1, p.halo_mode = halo ? conv_halo_mode() : 0;
     LS_CUDA(launch_conv_gemm(a, a, w.map, p, num_sms_, s));
   };
 
@@ -282,8 +292,8 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       p.n_store = st.up.N;
       p.out_ld = st.up.N, p.out_shift = -(long long)padT * st.cout;
       p.out_bstride = rows * st.cout, p.out_alloc = rows * st.cout, p.out_valid_mul = (long long)rate * st.cout;
-      p.k_true = st.cin, p.tag = 1;
-      LS_CUDA(launch_conv_gemm(pl.sA[i], pl.sA[i], st.up.map, p, num_sms_, s));
+      p.k_true = st.cin, p.tag = 1, p.halo_mode = halo ? conv_halo_mode() : 0;
+      LS_CUDA(launch_conv_gemm(pl.sA[i].up, pl.sA[i].up, st.up.map, p, num_sms_, s));
     }
     static const int dils[3] = {1, 3, 9};
     for (int j = 0; j < 3; ++j) {
@@ -291,7 +301,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       {  // Snake (already applied) -> conv7 dilated -> LeakyReLU -> Snake
         ConvGemmParams p{};
         p.act = ACT_LRELU, p.out1 = sB, p.out1_mode = OUT1_SNAKE, p.p1_a = f32(u.a2), p.p1_b = f32(u.ia2);
-        conv(pl.sA[i + 1], u.conv7, rows, rate, dils[j], p);
+        conv(pl.sA[i + 1].d[j], u.conv7, rows, rate, dils[j], p);
       }
       {  // conv1 -> LeakyReLU -> + x ; secondary output = Snake of whatever consumes x next
         ConvGemmParams p{};
@@ -312,7 +322,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
     p.act = ACT_LRELU_TANH, p.out0 = wav, p.out0_dtype = OUT_F32;
     p.chan_mod = 16, p.n_store = 1, p.zero_skipped = 1;
     p.out_ld = 1, p.out_shift = 0, p.out_bstride = rows, p.out_alloc = rows, p.out_valid_mul = rate;
-    conv(pl.sA[stages_.size()], final_, rows, rate, 1, p);
+    conv(pl.sA[stages_.size()].d[0], final_, rows, rate, 1, p);
   }
 }
 

@@ -72,8 +72,12 @@ struct FlowEngine::GroupW {
   std::vector<TBlockW> tb;
 };
 
+// activation views: k1 = 128-row boxes (linear / 1x1 layers), k3 = boxes with the 2-row halo of a causal k=3 conv
+struct ActMaps {
+  CUtensorMap k1, k3;
+};
 struct FlowEngine::Plan {
-  CUtensorMap xin, hA, hB, skip, nrm, qkv, att, ff;
+  ActMaps xin, hA, hB, skip, nrm, qkv, att, ff;
   // flattened [B2*T][C] views for the fused block kernel (TMA loads and stores)
   CUtensorMap att_flat, u_flat, qkv_flat, tail_skip, tail_hB;
 };
@@ -269,8 +273,10 @@ const FlowEngine::Plan& FlowEngine::plan_for(int B2, int T) {
   if (it != plans_.end()) return *it->second;
   auto pl = std::make_unique<Plan>();
   const int inner = heads_ * 64;
-  auto mk = [&](CUtensorMap* m, size_t off, int C) {
-    require(make_act_map(m, ws_base_ + off, C, T, B2, C, (long long)T * C, 128),
+  const int box3 = conv_halo_enabled() ? conv_halo_box_rows(3, 1) : 128;
+  auto mk = [&](ActMaps* m, size_t off, int C) {
+    require(make_act_map(&m->k1, ws_base_ + off, C, T, B2, C, (long long)T * C, 128) &&
+                make_act_map(&m->k3, ws_base_ + off, C, T, B2, C, (long long)T * C, box3),
             "cuTensorMapEncodeTiled failed for an activation buffer", LS_ERR_CUDA);
   };
   mk(&pl->xin, o_xin_, in_ch_);
@@ -318,7 +324,10 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   const int* lengths = ws<int>(o_len_);
   const int inner = heads_ * 64;
 
-  auto gemm = [&](const CUtensorMap& a0, const CUtensorMap* a1, int a0_channels, const PackedLinear& w, const Epi& e) {
+  const bool halo = conv_halo_enabled();
+  auto gemm = [&](const ActMaps& am0, const ActMaps* am1, int a0_channels, const PackedLinear& w, const Epi& e) {
+    const CUtensorMap& a0 = w.taps > 1 ? am0.k3 : am0.k1;
+    const CUtensorMap* a1 = am1 ? (w.taps > 1 ? &am1->k3 : &am1->k1) : nullptr;
     ConvGemmParams p{};
     p.B = B2, p.M = T, p.N = w.N, p.block_n = w.block_n;
     p.taps = w.taps, p.dil = 1, p.pad = w.taps - 1;  // causal: left context only (decoder.py:59-62)
@@ -332,6 +341,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
     p.out_ld = w.N, p.out_shift = 0, p.out_bstride = (long long)T * w.N, p.out_alloc = (long long)T * w.N;
     p.out_valid_mul = w.N;
     p.k_true = w.K, p.tag = 0, p.zero_skipped = e.zero_skipped;
+    p.halo_mode = halo ? conv_halo_mode() : 0;
     LS_CUDA(launch_conv_gemm(a0, a1 ? *a1 : a0, w.map, p, num_sms_, s));
   };
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
@@ -341,7 +351,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
 
   // One resnet + n_blocks transformer blocks (decoder.py:437-452 / 459-473 / 475-491).
   // `a0`(+`a1`) = masked bf16 input; `tail` = bf16 buffer that receives the masked group output.
-  auto group = [&](int gi, const CUtensorMap& a0, const CUtensorMap* a1, int a0_ch, void* tail) {
+  auto group = [&](int gi, const ActMaps& a0, const ActMaps* a1, int a0_ch, void* tail) {
     const GroupW& g = groups_[gi];
     {  // block1: conv3 -> LN -> Mish -> mask, then + Linear(Mish(temb))   (matcha decoder.py:57-58)
       Epi e;
@@ -368,7 +378,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
       ap.scale_log2e = 0.125f * 1.4426950408889634f;
       ap.out = ws<__nv_bfloat16>(o_att_);
-      LS_CUDA(launch_attention(pl.qkv, ap, s));
+      LS_CUDA(launch_attention(pl.qkv.k1, ap, s));
     };
     if (fused_blocks_) {
       // QKV of the first block from the resnet's LayerNorm output; every later QKV comes out of the fused kernel
@@ -404,7 +414,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
         ap.scale_log2e = 0.125f * 1.4426950408889634f;
         ap.out = ws<__nv_bfloat16>(o_att_);
-        LS_CUDA(launch_attention(pl.qkv, ap, s));
+        LS_CUDA(launch_attention(pl.qkv.k1, ap, s));
       }
       {  // to_out + residual, then LayerNorm(norm3)
         Epi e;

@@ -13,6 +13,34 @@ extern long long* g_debug_buffer;              // device buffer for kernel timel
 extern long long g_debug_bytes;
 inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 
+// Launch with programmatic dependent launch enabled: the kernel may start (up to its griddepcontrol.wait) while the
+// previous kernel of the stream drains.  Only for kernels that execute pdl_wait() before touching global memory an
+// earlier kernel wrote.  `cluster` > 1 adds a cluster dimension.  LS_NO_PDL=1 in the environment turns it off.
+bool pdl_enabled();
+bool conv_halo_enabled();
+int conv_halo_mode();  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr, cfg.numAttrs = n;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4 };
 enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 };
 enum Out1Mode : int { OUT1_NONE = 0, OUT1_LN = 1, OUT1_COPY = 2, OUT1_SNAKE = 3 };
@@ -55,7 +83,16 @@ struct ConvGemmParams {
   long long out_ld, out_shift, out_bstride, out_alloc, out_valid_mul;
   // accounting only (profiler): true K per tap and which engine launched it (0 flow, 1 DAC)
   int k_true, tag;
+  // A-operand staging.  halo_mode 1: the caller's activation maps have boxes of 128 + (taps-1)*dil rows and the
+  // kernel fetches each K block of the input ONCE, reading tap t through a descriptor shifted by t*dil rows;
+  // halo_mode 0: 128-row boxes fetched per tap.  The remaining fields are filled in by launch_conv_gemm.
+  int halo_mode;
+  int a_box_rows, a_stages, b_stages;
+  long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps of the first tile, or nullptr
 };
+// rows of the activation box a conv with this geometry needs in halo mode (make_act_map's box_rows)
+inline int conv_halo_box_rows(int taps, int dil) { return 128 + (taps - 1) * dil; }
+__host__ __device__ constexpr int ls_conv_a_stage_bytes(int box_rows) { return ((box_rows + 7) / 8) * 1024; }
 
 // Tensor maps are created on the host (tma_host.cpp helpers) and passed by value.
 cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
@@ -68,6 +105,7 @@ struct AttnParams {
   int chunk;            // >0: block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
   float scale_log2e;    // softmax scale * log2(e)
   __nv_bfloat16* out;   // [B][T][H*64]
+  long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps, or nullptr
 };
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);
 
@@ -75,7 +113,9 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
 // residual, then either the next block's LayerNorm + QKV projection (tail_mode 0) or a masked bf16 copy of the
 // residual stream (tail_mode 1).  Fixed estimator geometry: C = 256, 8 heads x 64, FF = 1024.
 #define TBLOCK_VEC_FLOATS 2560
-#define TBLOCK_CLUSTER 2                           /* CTAs per cluster sharing every weight box by TMA multicast */
+#ifndef TBLOCK_CLUSTER
+#define TBLOCK_CLUSTER 1                           /* CTAs per cluster sharing every weight box by TMA multicast */
+#endif
 #define TBLOCK_WBOX_ROWS (128 / TBLOCK_CLUSTER)    /* box rows of the weight tensor maps */
 struct TBlockParams {
   int R;               // rows = batch rows x T (time-major, flattened)

@@ -47,6 +47,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel of the stream (launched with the programmatic-serialization attribute) may
+// start its prologue once every CTA of this grid has executed this (or exited).  wait: blocks until every
+// prerequisite grid has completed and its memory is visible -- nothing written by an earlier kernel may be read,
+// and nothing an earlier kernel reads may be written, before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------ register re-balancing between warp roles
+// Executed by every warp of a warpgroup (4 consecutive warps).  The load/MMA warpgroup hands registers back, the
+// epilogue warpgroups take them: with ~220 KB of shared memory per CTA the L1 that would absorb spills is almost
+// gone, so a spilled epilogue register costs an L2 round trip.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -182,14 +199,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// lane i of the warp writes 16 consecutive fp32 columns of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, 128-byte swizzle, tile rows of 128 B (64 bf16) packed densely.
 //   K-major : 8-row groups 1024 B apart (SBO); K advances inside the 128 B row (+32 B per UMMA_K=16).
 //   MN-major: rows are K indices, the 128 B row holds 64 MN elements; 8-row K groups 1024 B apart (SBO).
 // bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SW128).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+//       [49,52) base offset = (start address >> 7) & 7 when the start is not aligned to the 1024 B swizzle atom
+//       (a K-major tile entered at a row that is not a multiple of 8: row-shifted views of one tile).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;            // LBO = 16 B (unused: one swizzle atom wide)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO = 1024 B
@@ -211,6 +239,39 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): two results per issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for a pair of arguments <= 127 on the FMA pipe only (no MUFU): round-to-nearest split x = n + f, f in
+// [-0.5, 0.5], cubic minimax fit of 2^f (relative error 7.5e-5, far below the bf16 rounding of the result), and n added
+// into the exponent field.  Used for part of the attention probabilities: the MUFU pipe (16 ex2 / clk / SM) is what
+// bounds the softmax, the FMA pipe has room.
+__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float r0, r1, n0, n1, f0, f1, p0, p1;
+  fadd2(r0, r1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, r0, r1, -kMagic, -kMagic);
+  ffma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);
+  ffma2(p0, p1, f0, f1, 0.0551716685f, 0.0551716685f, 0.2426111251f, 0.2426111251f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.6932609677f, 0.6932609677f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.9999280572f, 0.9999280572f);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;

@@ -32,13 +32,19 @@ constexpr int kC = 256, kInner = 512, kFF = 1024, kQKV = 1536;
 constexpr int kTileM = 128;
 constexpr int kSlotBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
 constexpr int kSlots = 5;
+#ifndef TBLOCK_PRODUCER_WARPS
+#define TBLOCK_PRODUCER_WARPS 3
+#endif
+constexpr int kProducerWarps = TBLOCK_PRODUCER_WARPS;  // warps 0..: one TMA-issuing thread each (issue latencies overlap)
+constexpr int kMmaWarp = kProducerWarps;
+static_assert(kProducerWarps <= 5, "interleaved producers must not outnumber the ring slots (parity waits)");
 constexpr int kCS = TBLOCK_CLUSTER;          // CTAs per cluster: each loads 1/kCS of every weight box and multicasts it
 constexpr int kPartRows = 128 / kCS;         // weight rows per CTA per box
 constexpr int kPartBytes = kPartRows * 128;
 constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kFirstEpiWarp = 2;
+constexpr int kFirstEpiWarp = kProducerWarps + 1;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 
 constexpr int kOffA3 = 0;
@@ -169,7 +175,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       if (!tile_all_padding(p, (g * kCS + r) * kTileM)) return false;
     return true;
   };
-  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 64 : nullptr;
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 128 : nullptr;
 #define TL(i)                         \
   do {                                \
     if (tl) tl[(i)] = clock64();      \
@@ -198,7 +204,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     mbar_init(u_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -206,59 +212,63 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   if (warp >= kFirstEpiWarp) {
     for (int i = threadIdx.x - kFirstEpiWarp * 32; i < TBLOCK_VEC_FLOATS; i += kEpiThreads) sVec[i] = __ldg(p.vec + i);
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (kCS > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the prologue above (and the weight-vector preload) overlapped the attention kernel's tail
 
-  if (warp == 0) {
-    // ======================================================================== TMA producer
+  if (warp < kProducerWarps) {
+    // ======================================================================== TMA producers
+    // One thread can only start a TMA load every ~500 clk (issue latency, measured: profiles/micro/tma_bw3.cu), far
+    // less than the MMA warp consumes, but different warps overlap.  kProducerWarps threads walk the same fixed load
+    // sequence of a tile; warp w issues the loads whose sequence number is w mod kProducerWarps.  (Separate warps, not
+    // lanes of one warp: a lane blocked in mbarrier.try_wait suspends its whole warp.)
     if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      // weight box (128 rows x 64 K): this CTA fetches rows [rank*kPartRows, +kPartRows) for the whole cluster
-      auto load = [&](const CUtensorMap* m, int c0, int c1) {
-        mbar_wait(&empty[slot], phase ^ 1);
-        uint8_t* dst = sRing + slot * kSlotBytes;
-        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-        if (kCS > 1) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
-        else tma_load_2d(dst, m, &full[slot], c0, c1);
-        if (++slot == kSlots) slot = 0, phase ^= 1;
-      };
-      auto load_rows = [&](const CUtensorMap* m, int c0, int c1) {  // this CTA's own activation rows
-        mbar_wait(&empty[slot], phase ^ 1);
-        uint8_t* dst = sRing + slot * kSlotBytes;
-        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-        tma_load_2d(dst, m, &full[slot], c0, c1);
-        if (++slot == kSlots) slot = 0, phase ^= 1;
-      };
-      auto ff1 = [&](int c) {
-        for (int kb = 0; kb < kC / 64; ++kb) load(&mapW1, kb * 64, c * 128);
-      };
+      const int per_tile = do_qkv ? 136 : 88;
+      long long seq0 = 0;  // sequence number of the tile's first load (slot = seq % kSlots, use = seq / kSlots)
       for (int g = group0; g < n_groups; g += group_step) {
         const int row0 = (g * kCS + rank) * kTileM;
         if (group_skipped(g)) continue;
-        for (int kb = 0; kb < kInner / 64; ++kb) {
-          load_rows(&mapAtt, kb * 64, row0);
-          load(&mapWo, kb * 64, 0);
-          load(&mapWo, kb * 64, 128);
-        }
-        ff1(0);
-        ff1(1);
-        for (int c = 0; c < kFF / 128; ++c) {
-          for (int kb2 = 0; kb2 < 2; ++kb2) {
-            load(&mapW2, c * 128 + kb2 * 64, 0);
-            load(&mapW2, c * 128 + kb2 * 64, 128);
+        for (int i = warp; i < per_tile; i += kProducerWarps) {
+          // decode load i of the tile: (tensor map, column, row), in exactly the order the MMA warp consumes them
+          const CUtensorMap* m;
+          int c0, c1;
+          bool own_rows = false;
+          if (i < 24) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
+            const int kb = i / 3, r = i - kb * 3;
+            if (r == 0) m = &mapAtt, c0 = kb * 64, c1 = row0, own_rows = true;
+            else m = &mapWo, c0 = kb * 64, c1 = (r - 1) * 128;
+          } else if (i < 32) {  // FF1 chunks 0 and 1
+            const int j = i - 24;
+            m = &mapW1, c0 = (j & 3) * 64, c1 = (j >> 2) * 128;
+          } else if (i < 88) {  // per FF chunk c: W2 (2 K blocks x 2 row halves), then FF1 chunk c+2
+            const int j = i - 32;
+            int c, r;
+            if (j < 48) c = j >> 3, r = j & 7;
+            else c = 6 + ((j - 48) >> 2), r = (j - 48) & 3;
+            if (r < 4) m = &mapW2, c0 = c * 128 + (r >> 1) * 64, c1 = (r & 1) * 128;
+            else m = &mapW1, c0 = (r - 4) * 64, c1 = (c + 2) * 128;
+          } else {  // next block's QKV weight, 12 chunks of 128 rows
+            const int j = i - 88;
+            m = &mapWqkv, c0 = (j & 3) * 64, c1 = (j >> 2) * 128;
           }
-          if (c + 2 < kFF / 128) ff1(c + 2);
+          const long long seq = seq0 + i;
+          const int slot = (int)(seq % kSlots);
+          const uint32_t use = (uint32_t)(seq / kSlots);
+          mbar_wait(&empty[slot], (use & 1) ^ 1);
+          if (tl && seq < 48) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
+          uint8_t* dst = sRing + slot * kSlotBytes;
+          mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+          if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
+          else tma_load_2d(dst, m, &full[slot], c0, c1);
         }
-        if (do_qkv)
-          for (int c = 0; c < kQKV / 128; ++c)
-            for (int kb = 0; kb < kC / 64; ++kb) load(&mapWqkv, kb * 64, c * 128);
+        seq0 += per_tile;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ======================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kTileM, 128, false, false);
@@ -268,12 +278,15 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       uint32_t fills0 = 0, fills1 = 0;      // fills issued into H[i]
       uint32_t drained0 = 0, drained1 = 0;  // fills of H[i] known to be consumed by the epilogue
       // wait for the ring slot `ahead` positions after the current one; returns its descriptor
+      int n_full = 0;  // timeline aid: arrival of the first slots as seen by this thread
       auto slot_desc = [&](int ahead) -> uint64_t {
         int s = slot + ahead;
         uint32_t ph = phase;
         if (s >= kSlots) s -= kSlots, ph ^= 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (tl && n_full < 16) tl[112 + n_full] = clock64();
+        n_full += (ahead == 0);
         return make_smem_desc_sw128(smem_u32(sRing + s * kSlotBytes));
       };
       auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
@@ -404,15 +417,18 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   do {                                \
     if (tle) tle[(i)] = clock64();    \
   } while (0)
-      if (leader) {
-        // the previous tile's stores have left the staging boxes; its QKV MMAs (A3 readers) retired before the
-        // last h_full this thread waited on
-        bulk_wait_read<0>();
-        mbar_arrive_expect_tx(u_full, 8 * kSlotBytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          tma_load_2d(stage + k * kSlotBytes, &mapU, u_full, k * 64, row0);
-          tma_load_2d(sA3 + k * kSlotBytes, &mapU, u_full, k * 64 + 32, row0);
+      if (warp == kFirstEpiWarp) {
+        if (leader) {
+          // the previous tile's stores have left the staging boxes; its QKV MMAs (A3 readers) retired before the
+          // last h_full this thread waited on
+          bulk_wait_read<0>();
+          mbar_arrive_expect_tx(u_full, 8 * kSlotBytes);
+        }
+        __syncwarp();
+        if (lane < 8) {  // one box per lane: the issue latencies overlap
+          const int k = lane >> 1;
+          if (lane & 1) tma_load_2d(sA3 + k * kSlotBytes, &mapU, u_full, k * 64 + 32, row0);
+          else tma_load_2d(stage + k * kSlotBytes, &mapU, u_full, k * 64, row0);
         }
       }
 
@@ -595,7 +611,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (kCS > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -633,17 +649,11 @@ cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sm
   const double macs = (double)kInner * kC + 2.0 * kC * kFF + (p.tail_mode == 0 ? (double)kC * kQKV : 0.0);
   const double bytes = rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0)) + macs * 2.0;
   TBlockParams pp = p;
-  pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 64 * 8) ? g_debug_buffer : nullptr;
+  pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 128 * 8) ? g_debug_buffer : nullptr;
   ProfScope prof(stream, PK_TBLOCK, 2.0 * rows * macs, bytes);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmemBytes, cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tblock_kernel, m.att, m.wo, m.w1, m.w2, m.wqkv, m.u, m.qkv_out, m.tail_out, pp);
   count_launch();
-  return e != cudaSuccess ? e : cudaGetLastError();
+  return launch_pdl(tblock_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, stream, kCS, m.att, m.wo, m.w1,
+                    m.w2, m.wqkv, m.u, m.qkv_out, m.tail_out, pp);
 }
 
 }  // namespace ls

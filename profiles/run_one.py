@@ -19,7 +19,10 @@ dac = DACVAEDecoder()
 mu, mask, spks, cond = [t.to(dev) for t in synth.batch_inputs([T] * B)]
 for it in range(2):  # pass 0 = warm-up (allocations, tensor maps); pass 1 = the one to look at
     torch.cuda.synchronize()
+    if it == 1:
+        torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off: only pass 1 is captured
     lat, _ = cfm(mu=mu, mask=mask, n_timesteps=1, spks=spks, cond=cond)
     wav = dac.decode(lat)
     torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print("ok", float(wav.abs().max()))

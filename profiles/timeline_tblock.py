@@ -10,13 +10,13 @@ import profiles.time_kernels as tk
 
 DEV = torch.device("cuda:0")
 lib = native.load()
-buf = torch.zeros(148 * 64, dtype=torch.int64, device=DEV)
+buf = torch.zeros(148 * 128, dtype=torch.int64, device=DEV)
 R = int(os.environ.get("LS_R", "16000"))
 tk.tblock(R, 0)
 lib.ls_debug_set_buffer(native.ptr(buf), buf.numel() * 8)
 tk.tblock(R, 0)
 lib.ls_debug_set_buffer(None, 0)
-t = buf.view(148, 64).cpu()
+t = buf.view(148, 128).cpu()
 for cta in (0, 60, 124):
     r = t[cta]
     base = int(r[0])
@@ -24,5 +24,5 @@ for cta in (0, 60, 124):
     print(f"--- CTA {cta}  (cycles since MMA-thread start)")
     print("MMA :", " ".join(f"{names.get(i, str(i))}={int(r[i]) - base}" for i in range(0, 27) if int(r[i])))
     print("EPI :", " ".join(f"{i}={int(r[i]) - base}" for i in range(32, 56) if int(r[i])))
-    print("FF chunk 4 (h_full, math done, ah_free ok, stored):", [int(r[i]) - base for i in range(56, 60)], "end", int(r[38]) - base)
-    print("QKV chunk 6 (h_full, drained, staging free, staged):", [int(r[i]) - base for i in range(60, 64)], "end", int(r[50]) - base)
+    print("LOAD slot-free time of loads 0..47:", [int(r[64 + i]) - base if int(r[64 + i]) else None for i in range(48)])
+    print("MMA saw slots 0..15 full at:", [int(r[112 + i]) - base for i in range(16)])
