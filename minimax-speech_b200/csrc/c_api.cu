@@ -261,7 +261,7 @@ int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1
     int dev = 0, sms = 0;
     LS_CUDA(cudaGetDevice(&dev));
     LS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    ls::require(tail_mode == 0 ? qkv_out != nullptr : tail_out != nullptr, "ls_test_tblock: missing output");
+    ls::require(tail_mode != 1 ? qkv_out != nullptr : tail_out != nullptr, "ls_test_tblock: missing output");
     ls::TBlockMaps m;
     ls::require(ls::make_tile_map(&m.att, att, 2, 512, R, 128) && ls::make_tile_map(&m.u, u, 4, 256, R, 128),
                 "tensor map att / u", LS_ERR_CUDA);
@@ -271,7 +271,7 @@ int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1
                     ls::make_weight_map(&m.wqkv, wqkv, 256, 1536, TBLOCK_WBOX_ROWS),
                 "tensor map weights", LS_ERR_CUDA);
     m.qkv_out = m.att, m.tail_out = m.att;
-    if (tail_mode == 0)
+    if (tail_mode != 1)
       ls::require(ls::make_tile_map(&m.qkv_out, qkv_out, 2, 1536, R, 128), "tensor map qkv", LS_ERR_CUDA);
     else
       ls::require(ls::make_tile_map(&m.tail_out, tail_out, 2, 256, R, 128), "tensor map tail", LS_ERR_CUDA);

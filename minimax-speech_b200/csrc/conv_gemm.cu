@@ -352,13 +352,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      int b_seq = 0;
+      int b_seq = 0, p_tile = 0;
       const uint32_t a_tx = (uint32_t)p.a_box_rows * 128u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
         if (tile_skipped(p, tc)) continue;
         const int t0 = tc.mt * kBlockM;
         const int n0 = tc.nt * p.block_n;
+        if (tl && warp == 0 && p_tile < 8) tl[56 + p_tile] = clock64();
+        ++p_tile;
         for (int kb = 0; kb < p.kb_per_tap; ++kb) {
           for (int tap = 0; tap < p.taps; ++tap) {
             if (warp == 0) {
@@ -394,7 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      int n_it = 0;  // timeline aid
+      int n_it = 0, n_tile = 0;  // timeline aid
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
         if (tile_skipped(p, tc)) continue;
@@ -430,6 +432,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         umma_commit(&tfull[acc]);
         if (tl && n_it <= p.taps * p.kb_per_tap) tl[32] = clock64();
+        if (tl && n_tile < 8) tl[24 + n_tile] = clock64();  // (overlaps the late k-iteration stamps: fine for multi-tile runs)
+        ++n_tile;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -444,6 +448,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t parity = 0;
+    int e_tile = 0;  // timeline aid
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
       const int t = tc.mt * kBlockM + row;
@@ -648,6 +653,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
       }
       // every TMEM access of this tile is done: hand the accumulator stage back to the MMA warp
+      if (tl && threadIdx.x == kFirstEpiWarp * 32 && e_tile < 8) tl[48 + e_tile] = clock64();
+      ++e_tile;
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
@@ -737,6 +744,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 1)
   LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_NONE, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_LN, OUT_F32, 0)
+  LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_NONE, OUT_F32, 0)
   LS_CONV_CASE(ACT_NONE, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
   // DAC decoder: de_conv_pre | input conv, conv7 | transposed conv | conv1 + residual (x kept / last unit) | final conv

@@ -70,6 +70,7 @@ struct FlowEngine::TBlockW {
 struct FlowEngine::GroupW {
   ResnetW res;
   std::vector<TBlockW> tb;
+  size_t head_vec = 0;  // fused-kernel vector pack holding norm1 of the first block (head mode: LayerNorm + QKV)
 };
 
 // activation views: k1 = 128-row boxes (linear / 1x1 layers), k3 = boxes with the 2-row halo of a causal k=3 conv
@@ -182,6 +183,11 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
   // fused transformer-block kernel: bo | norm3 | ff bias 1 | ff bias 2 | norm1 of the NEXT block of the group
   fused_blocks_ = C_ == 256 && inner == 512;
   if (fused_blocks_) {
+    for (auto& g : groups_) {
+      g.head_vec = arena_.reserve(TBLOCK_VEC_FLOATS * 4);
+      std::memcpy(arena_.host(g.head_vec) + (size_t)2048 * 4, arena_.host(g.tb[0].n1g), 256 * 4);
+      std::memcpy(arena_.host(g.head_vec) + (size_t)2304 * 4, arena_.host(g.tb[0].n1b), 256 * 4);
+    }
     for (auto& g : groups_)
       for (size_t j = 0; j < g.tb.size(); ++j) {
         TBlockW& t = g.tb[j];
@@ -370,7 +376,8 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       e.act = ACT_LN_MISH, e.ln_g = f32(g.res.ln2g), e.ln_b = f32(g.res.ln2b);
       e.addend = r, e.addend_dtype = OUT_F32;
       e.out0 = u, e.out0_dtype = OUT_F32;
-      e.out1 = ws<void>(o_nrm_), e.out1_mode = OUT1_LN, e.p1_a = f32(g.tb[0].n1g), e.p1_b = f32(g.tb[0].n1b);
+      if (!fused_blocks_)  // the fused path computes LayerNorm(norm1) + QKV of the first block from u (head launch)
+        e.out1 = ws<void>(o_nrm_), e.out1_mode = OUT1_LN, e.p1_a = f32(g.tb[0].n1g), e.p1_b = f32(g.tb[0].n1b);
       gemm(pl.hA, nullptr, 0, g.res.conv2, e);
     }
     auto attention = [&]() {
@@ -381,11 +388,15 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       LS_CUDA(launch_attention(pl.qkv.k1, ap, s));
     };
     if (fused_blocks_) {
-      // QKV of the first block from the resnet's LayerNorm output; every later QKV comes out of the fused kernel
+      // QKV of the first block: LayerNorm(norm1) + projection straight from u (head mode of the fused kernel);
+      // every later QKV comes out of the previous block's launch
       {
-        Epi e;
-        e.out1 = ws<void>(o_qkv_), e.out1_mode = OUT1_COPY;
-        gemm(pl.nrm, nullptr, 0, g.tb[0].qkv, e);
+        TBlockParams tp{};
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2;
+        TBlockMaps tm;
+        tm.att = pl.att_flat, tm.wo = g.tb[0].m_out, tm.w1 = g.tb[0].m_ff1, tm.w2 = g.tb[0].m_ff2;  // unused in head mode
+        tm.wqkv = g.tb[0].m_qkv, tm.u = pl.u_flat, tm.qkv_out = pl.qkv_flat, tm.tail_out = pl.tail_hB;
+        LS_CUDA(launch_tblock(tm, tp, num_sms_, s));
       }
       for (int j = 0; j < n_blocks_; ++j) {
         const TBlockW& t = g.tb[j];

@@ -122,7 +122,8 @@ struct TBlockParams {
   int T;               // rows per batch row (only used with lengths)
   const int* lengths;  // [R / T] valid frames per batch row, or nullptr
   const float* vec;    // device, TBLOCK_VEC_FLOATS: bo[256] g3[256] be3[256] b1[1024] b2[256] g1n[256] be1n[256]
-  int tail_mode;       // 0: u updated in place + next block's QKV written; 1: masked bf16 copy of u'' written
+  int tail_mode;       // 0: u updated in place + next block's QKV written; 1: masked bf16 copy of u'' written;
+                       // 2: "head" of a block group: only LayerNorm(u; g1n, be1n) + QKV (att, Wo, W1, W2 unused)
   long long* timeline; // development aid (ls_debug_set_buffer): [grid][64] clock64 stamps of the first tile, or nullptr
 };
 // Every global tensor is reached through TMA (loads and stores), 128-row boxes, 128-byte swizzle:

@@ -43,6 +43,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef LS_WAIT_SLEEP_NS
+    __nanosleep(LS_WAIT_SLEEP_NS);  // back off: hundreds of polling threads otherwise crowd out the TMA / MMA issuers
+#endif
     if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }

@@ -163,7 +163,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.R + kTileM - 1) / kTileM;
-  const bool do_qkv = p.tail_mode == 0;
+  const bool head = p.tail_mode == 2;    // LayerNorm(u) + QKV only: the first block of a group
+  const bool do_qkv = p.tail_mode != 1;
   // Clusters of kCS CTAs walk the tiles together (tile = group*kCS + rank): all of them stream the same weight
   // sequence, so each CTA fetches 1/kCS of every weight box from L2 and multicasts it to the whole cluster.  A group
   // past the end of the tensor (rows >= R) is a phantom tile: TMA reads zeros and drops the stores.
@@ -227,7 +228,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     // sequence of a tile; warp w issues the loads whose sequence number is w mod kProducerWarps.  (Separate warps, not
     // lanes of one warp: a lane blocked in mbarrier.try_wait suspends its whole warp.)
     if (lane == 0) {
-      const int per_tile = do_qkv ? 136 : 88;
+      const int per_tile = head ? 48 : (do_qkv ? 136 : 88);
       long long seq0 = 0;  // sequence number of the tile's first load (slot = seq % kSlots, use = seq / kSlots)
       for (int g = group0; g < n_groups; g += group_step) {
         const int row0 = (g * kCS + rank) * kTileM;
@@ -237,7 +238,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           const CUtensorMap* m;
           int c0, c1;
           bool own_rows = false;
-          if (i < 24) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
+          if (head) {  // QKV weight only
+            m = &mapWqkv, c0 = (i & 3) * 64, c1 = (i >> 2) * 128;
+          } else if (i < 24) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
             const int kb = i / 3, r = i - kb * 3;
             if (r == 0) m = &mapAtt, c0 = kb * 64, c1 = row0, own_rows = true;
             else m = &mapWo, c0 = kb * 64, c1 = (r - 1) * 128;
@@ -325,6 +328,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       for (int g = group0; g < n_groups; g += group_step) {
         if (group_skipped(g)) continue;
         if (g != group0) tl = nullptr;
+        if (!head) {
         // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
         for (int kb = 0; kb < kInner / 64; ++kb) {
           const uint64_t adesc = slot_desc(0);
@@ -368,7 +372,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         }
         umma_commit(d_full);
         TL(12);
-        // ---- tail: D drained by the epilogue (and, tail 0, next block's LayerNorm written to A3)
+        }  // !head
+        // ---- tail: D drained by the epilogue (and, tail 0 / 2, the LayerNorm output written to A3)
         mbar_wait(a3_ready, a3_cnt & 1);
         a3_cnt += 1;
         tc_fence_after();
@@ -434,41 +439,56 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
 
       // ------------------------------------------------ out-proj epilogue: u' = D + bo + u ; n3 = LN(u')
       {
-        float x[2][32];
         mbar_wait(u_full, u_cnt & 1);
         u_cnt += 1;
-        mbar_wait(d_full, d_cnt & 1);
-        d_cnt += 1;
+        if (!head) {
+          mbar_wait(d_full, d_cnt & 1);
+          d_cnt += 1;
+        }
         tc_fence_after();
         TLE(32);
+        // Only 32 values are live at a time: u' goes back to TMEM (FF2 accumulates onto it anyway) and is re-read
+        // for the LayerNorm pass.  Registers are scarce here -- a spill costs an L2 round trip, the L1 is all smem.
         RowStats st;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int col = cg * 64 + ch * 32;
           const uint8_t* urow = (ch ? sA3 : stage) + cg * kSlotBytes + row * 128;
-          tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x[ch]));
-          tmem_ld_wait();
+          float x[32];
+          if (head) {  // x = u
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 uv = *reinterpret_cast<const float4*>(urow + ((k ^ sw) << 4));
-            const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[k];
-            x[ch][4 * k + 0] += bo.x + uv.x;
-            x[ch][4 * k + 1] += bo.y + uv.y;
-            x[ch][4 * k + 2] += bo.z + uv.z;
-            x[ch][4 * k + 3] += bo.w + uv.w;
+            for (int k = 0; k < 8; ++k) {
+              const float4 uv = *reinterpret_cast<const float4*>(urow + ((k ^ sw) << 4));
+              x[4 * k + 0] = uv.x, x[4 * k + 1] = uv.y, x[4 * k + 2] = uv.z, x[4 * k + 3] = uv.w;
+            }
+          } else {
+            tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x));
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 uv = *reinterpret_cast<const float4*>(urow + ((k ^ sw) << 4));
+              const float4 bo = reinterpret_cast<const float4*>(sVec + V_BO + col)[k];
+              x[4 * k + 0] += bo.x + uv.x;
+              x[4 * k + 1] += bo.y + uv.y;
+              x[4 * k + 2] += bo.z + uv.z;
+              x[4 * k + 3] += bo.w + uv.w;
+            }
           }
-          st.add32(x[ch]);
-          tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x[ch]));
+          st.add32(x);
+          tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x));
         }
+        tmem_st_wait();
         float mean, rstd;
-        combine_groups(st, sRed, cg, row, mean, rstd);
-        const float nmr = -mean * rstd;
-#pragma unroll
+        combine_groups(st, sRed, cg, row, mean, rstd);  // the barrier inside also orders every thread's u reads
+        const float nmr = -mean * rstd;                 // before the A3 writes below (A3 held half of the u tile)
+#pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int col = cg * 64 + ch * 32;
-          float y[32];
-          normalize32(x[ch], rstd, nmr, sVec + V_G3 + col, sVec + V_BE3 + col, y);
-          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, y);
+          float x[32];
+          tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x));
+          tmem_ld_wait();
+          normalize32(x, rstd, nmr, sVec + (head ? V_G1N : V_G3) + col, sVec + (head ? V_BE1N : V_BE3) + col, x);
+          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, x);
         }
         tmem_st_wait();
         warp_arrive(a3_ready);
@@ -476,7 +496,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       }
 
       // ------------------------------------------------ FF1 chunks: AH[i] = gelu(H[i] + b1)
-      for (int c = 0; c < kFF / 128; ++c) {
+      for (int c = 0; c < (head ? 0 : kFF / 128); ++c) {
         const int i = c & 1;
         mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
         if (i) h_cnt1 += 1;
@@ -503,34 +523,39 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       }
 
       // ------------------------------------------------ FF2 epilogue: u'' = D + b2
-      mbar_wait(d_full, d_cnt & 1);
-      d_cnt += 1;
-      tc_fence_after();
+      if (!head) {
+        mbar_wait(d_full, d_cnt & 1);
+        d_cnt += 1;
+        tc_fence_after();
+      }
       TLE(42);
-      float x[2][32];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      // u'' = D + b2, 32 columns at a time (see the register note above)
+      auto load_u2 = [&](int ch, float (&x)[32]) {
         const int col = cg * 64 + ch * 32;
-        tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x[ch]));
+        tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x));
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 b2 = reinterpret_cast<const float4*>(sVec + V_B2 + col)[k];
-          x[ch][4 * k + 0] += b2.x;
-          x[ch][4 * k + 1] += b2.y;
-          x[ch][4 * k + 2] += b2.z;
-          x[ch][4 * k + 3] += b2.w;
+          x[4 * k + 0] += b2.x;
+          x[4 * k + 1] += b2.y;
+          x[4 * k + 2] += b2.z;
+          x[4 * k + 3] += b2.w;
         }
-      }
-      if (!do_qkv) {
+      };
+      if (head) {
+        epi_barrier();  // every warp is done with the u staging boxes: the QKV chunks below reuse them
+      } else if (!do_qkv) {
         // masked bf16 copy of u'': this thread's 64 columns are one full row of staging box cg -> TMA store
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
+          float x[32];
+          load_u2(ch, x);
           if (!valid) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) x[ch][k] = 0.f;
+            for (int k = 0; k < 32; ++k) x[k] = 0.f;
           }
-          store_row_chunks(stage + cg * kSlotBytes + row * 128, sw, ch * 4, x[ch]);
+          store_row_chunks(stage + cg * kSlotBytes + row * 128, sw, ch * 4, x);
         }
         warp_arrive(a3_ready);  // D is drained
         epi_barrier();
@@ -540,9 +565,6 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           bulk_commit();
         }
       } else {
-        RowStats st;
-        st.add32(x[0]);
-        st.add32(x[1]);
         // u'' (fp32) leaves through the 4 staging boxes in two rounds of 32 columns per column group
         auto stage_u = [&](const float (&v)[32]) {
           uint8_t* dst = stage + cg * kSlotBytes + row * 128;
@@ -556,30 +578,52 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           for (int k = 0; k < 4; ++k) tma_store_2d(&mapU, stage + k * kSlotBytes, k * 64 + ch * 32, row0);
           bulk_commit();
         };
-        stage_u(x[0]);
+        // pass 1: finish u'' (bias), statistics, park it in D again; round 0 of the fp32 store is staged on the way
+        RowStats st;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[32];
+          load_u2(ch, x);
+          st.add32(x);
+          tmem_st32(trow + kTmemD + cg * 64 + ch * 32, reinterpret_cast<const uint32_t(&)[32]>(x));
+          if (ch == 0) stage_u(x);
+        }
+        tmem_st_wait();
         float mean, rstd;
         combine_groups(st, sRed, cg, row, mean, rstd);  // contains the barrier that also publishes round 0
         if (leader) store_u(0);
         const float nmr = -mean * rstd;
-#pragma unroll
+        // pass 2: next block's LayerNorm -> A3
+#pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int col = cg * 64 + ch * 32;
-          float y[32];
-          normalize32(x[ch], rstd, nmr, sVec + V_G1N + col, sVec + V_BE1N + col, y);
-          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, y);
+          float x[32];
+          tmem_ld32(trow + kTmemD + col, reinterpret_cast<uint32_t(&)[32]>(x));
+          tmem_ld_wait();
+          normalize32(x, rstd, nmr, sVec + V_G1N + col, sVec + V_BE1N + col, x);
+          store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, x);
         }
-        warp_arrive(a3_ready);  // n1 in A3, D drained: the QKV MMAs may start
-        TLE(43);
-        if (leader) bulk_wait_read<0>();
-        epi_barrier();
-        stage_u(x[1]);
+        // round 1 of the fp32 store re-reads its 32 columns from D.  D is rewritten only by the next tile's
+        // out-proj MMAs, which are issued after all 12 QKV chunks -- and those need every epilogue warp to have
+        // drained chunks 0..9, i.e. to be past this point.
+        {
+          float x[32];
+          tmem_ld32(trow + kTmemD + cg * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(x));
+          tmem_ld_wait();
+          warp_arrive(a3_ready);  // n1 in A3: the QKV MMAs may start
+          TLE(43);
+          if (leader) bulk_wait_read<0>();
+          epi_barrier();
+          stage_u(x);
+        }
         epi_barrier();
         if (leader) {
           store_u(1);
-          bulk_wait_read<0>();
+          bulk_wait_read<0>();  // the QKV chunks below reuse the staging boxes
         }
         epi_barrier();
-
+      }
+      if (do_qkv) {
         // -------------------------------------------- QKV chunks of the next block -> staging pair -> TMA store
         for (int c = 0; c < kQKV / 128; ++c) {
           const int i = c & 1;
@@ -594,7 +638,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           // staging pair i is free: the leader waited for the store of chunk c-2 before the barrier of chunk c-1
           store_row_chunks(stage + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
           fence_proxy_async_smem();
-          if (leader) bulk_wait_read<0>();
+          if (leader) bulk_wait_read<0>();  // store of chunk c-1 (issued a whole chunk ago) has left pair i^1
           epi_barrier();
           if (leader) {
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 0) * kSlotBytes, c * 128, row0);
@@ -646,8 +690,10 @@ cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sm
   }
   const int grid = (n_groups < max_clusters ? n_groups : max_clusters) * kCS;
   const double rows = (double)p.R;
-  const double macs = (double)kInner * kC + 2.0 * kC * kFF + (p.tail_mode == 0 ? (double)kC * kQKV : 0.0);
-  const double bytes = rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0)) + macs * 2.0;
+  const double macs = (p.tail_mode == 2 ? 0.0 : (double)kInner * kC + 2.0 * kC * kFF) + (p.tail_mode != 1 ? (double)kC * kQKV : 0.0);
+  const double bytes = (p.tail_mode == 2 ? rows * (kC * 4.0 + kQKV * 2.0)
+                                          : rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0))) +
+                       macs * 2.0;
   TBlockParams pp = p;
   pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 128 * 8) ? g_debug_buffer : nullptr;
   ProfScope prof(stream, PK_TBLOCK, 2.0 * rows * macs, bytes);

@@ -42,7 +42,7 @@ def tblock(R, tail_mode=0):
                                         native.ptr(wq), native.ptr(vec), native.ptr(qkv), native.ptr(tail), None, R, R,
                                         tail_mode, s), "tblock")
     us = timeit(fn)
-    macs = 512 * 256 + 2 * 256 * 1024 + (256 * 1536 if tail_mode == 0 else 0)
+    macs = (0 if tail_mode == 2 else 512 * 256 + 2 * 256 * 1024) + (256 * 1536 if tail_mode != 1 else 0)
     print(f"tblock R={R} tail={tail_mode}: {us:8.1f} us  {2.0 * R * macs / us / 1e6:7.1f} TFLOP/s")
 
 
@@ -60,7 +60,7 @@ def attention(B, T, H=8):
 
 if __name__ == "__main__":
     for R in (16000, 96000):
-        for tm in (0, 1):
+        for tm in (0, 1, 2):
             tblock(R, tm)
     attention(32, 500)
     attention(64, 1500)

@@ -287,7 +287,7 @@ def _tblock_ref(att, u, wo, w1, w2, wqkv, vec):
 
 def _tblock(att, u, wo, w1, w2, wqkv, vec, tail_mode, lengths=None, T=None):
     R = att.shape[0]
-    qkv = torch.full((R, 1536), float("nan"), device=DEV, dtype=torch.bfloat16) if tail_mode == 0 else None
+    qkv = torch.full((R, 1536), float("nan"), device=DEV, dtype=torch.bfloat16) if tail_mode != 1 else None
     tail = torch.full((R, 256), float("nan"), device=DEV, dtype=torch.bfloat16) if tail_mode == 1 else None
     native.check(native.load().ls_test_tblock(native.ptr(att), native.ptr(u), native.ptr(wo), native.ptr(w1),
                                               native.ptr(w2), native.ptr(wqkv), native.ptr(vec), native.ptr(qkv),
@@ -305,6 +305,20 @@ def test_tblock_qkv_tail(R):
     qkv, _ = _tblock(ops[0], u, *ops[2:], tail_mode=0)
     assert rel(u, u_ref) < 2e-3, rel(u, u_ref)       # bf16 rounding of the FF intermediate on both sides
     assert rel(qkv.float(), qkv_ref) < 6e-3, rel(qkv.float(), qkv_ref)
+
+
+@pytest.mark.parametrize("R", [128, 300, 128 * 151 + 17])
+def test_tblock_head_mode_layernorm_qkv_only(R):
+    """tail_mode 2: qkv = LayerNorm(u; norm1) . Wqkv^T, u untouched (first block of a group)."""
+    ops = _tblock_operands(R, 11 + R)
+    att, u0, wo, w1, w2, wqkv, vec = ops
+    g1n, be1n = vec[2048:2304], vec[2304:2560]
+    n1 = bf16(F.layer_norm(u0, (256,), g1n, be1n, 1e-5)).float()
+    qkv_ref = n1 @ wqkv.float().T
+    u = u0.clone()
+    qkv, _ = _tblock(att, u, wo, w1, w2, wqkv, vec, tail_mode=2)
+    assert torch.equal(u, u0)
+    assert rel(qkv.float(), qkv_ref) < 4e-3, rel(qkv.float(), qkv_ref)
 
 
 def test_tblock_masked_copy_tail_and_tile_skip():
