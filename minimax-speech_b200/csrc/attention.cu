@@ -34,10 +34,15 @@ constexpr float kRescaleThreshold = 8.0f;
 #ifndef ATTN_POLY_MASK
 #define ATTN_POLY_MASK 0x00
 #endif
+#ifndef ATTN_STAGGER_CLK
+#define ATTN_STAGGER_CLK 0  // measured on B200: 0 -> 39.8 us, 700 -> 41.4, 1300 -> 42.6, 2000 -> 41.5 (B=32, T=500)
+#endif
+constexpr long long kStaggerClk = ATTN_STAGGER_CLK;
+__device__ unsigned int g_sm_arrivals[256];  // CTAs that ever started on each SM (only the parity is used)
 constexpr int kPolyExpMask = ATTN_POLY_MASK;  // of every 8 score pairs, the ones whose exp2 runs on the FMA pipe           // log2 units: P stays below 2^8 between rescales
 
-// p[i] = 2^(s[i]*c - m) for 32 scores, masked beyond `nvalid`; returns the packed bf16 pairs and adds to the row sum
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float m, int nvalid, uint32_t (&packed)[16],
+// p[i] = 2^(s[i]*c - m) for 32 scores (masked scores are -inf -> 0); returns the packed bf16 pairs and adds to the row sum
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, float m, uint32_t (&packed)[16],
                                           float& sum0, float& sum1) {
   const float nm = -m;
 #pragma unroll
@@ -50,19 +55,15 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, floa
       a = ex2_approx(a);
       b = ex2_approx(b);
     }
-    if (nvalid < 32) {
-      a = i < nvalid ? a : 0.f;
-      b = i + 1 < nvalid ? b : 0.f;
-    }
     fadd2(sum0, sum1, sum0, sum1, a, b);
     packed[i >> 1] = pack_bf16x2(a, b);
   }
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ AttnParams p) {
+attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapOut,
+            const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
-  pdl_wait();  // lengths and QKV come from earlier kernels
   const int q0 = blockIdx.x * kQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -73,12 +74,6 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
     if (tl) tl[(i)] = clock64(); \
   } while (0)
   if (threadIdx.x == 0) TL(0);
-  int len = p.lengths ? p.lengths[b] : p.T;
-  if (len > p.T) len = p.T;
-  if (q0 >= len) return;  // query tile is padding only: its rows are masked downstream
-  int tile_limit = len;
-  if (p.chunk > 0) tile_limit = min(len, ((q0 + kQ - 1) / p.chunk + 1) * p.chunk);
-  const int nkv = (tile_limit + kKV - 1) / kKV;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,6 +96,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   if (warp == kSoftmaxWarps) {
     if (lane == 0) {
       prefetch_tmap(&mapQKV);
+      prefetch_tmap(&mapOut);
       mbar_init(bar_q, 1);
       mbar_init(&bar_k[0], 1);
       mbar_init(&bar_k[1], 1);
@@ -122,8 +118,18 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   if (threadIdx.x == 0) TL(15);
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
+  // Everything above (barriers, TMEM) overlapped the previous kernel's tail; lengths and QKV are read from here on.
+  pdl_wait();
+  int len = p.lengths ? p.lengths[b] : p.T;
+  if (len > p.T) len = p.T;
+  int tile_limit = len;
+  if (p.chunk > 0) tile_limit = min(len, ((q0 + kQ - 1) / p.chunk + 1) * p.chunk);
+  // a query tile that is padding only does no work: its rows are masked downstream
+  const int nkv = q0 >= len ? 0 : (tile_limit + kKV - 1) / kKV;
 
-  if (warp == kSoftmaxWarps) {
+  if (nkv == 0) {
+    // fall through to the common exit (TMEM is released there)
+  } else if (warp == kSoftmaxWarps) {
     if (lane == 0) {
       // ------------------------------------------------ control thread: TMA loads + MMA issue
       const int inner = p.H * kD;
@@ -152,6 +158,20 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
       TL(2);
+      if (kStaggerClk > 0) {
+        // Two CTAs share an SM and would run in lockstep (they start together and slow each other down equally in
+        // the MUFU-bound exp phase), leaving the MUFU pipe idle while both are in their load / max / store phases.
+        // Every second CTA to arrive on an SM during the first wave therefore starts half a tile period late.
+        uint32_t smid, nsm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const uint32_t arrival = atomicAdd(&g_sm_arrivals[smid & 255u], 1u);
+        if ((arrival & 1u) && (uint32_t)cta_lin < 2u * nsm) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < kStaggerClk) {
+          }
+        }
+      }
       issue_s(0);
       const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t dp1 = make_smem_desc_sw128(smem_u32(sP + kTile));
@@ -218,24 +238,22 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       if (lane == 0) mbar_arrive(bar_f);
       if (j < 4) TLS(17 + 6 * j);
       const int nvalid = limit - j * kKV;  // valid keys of this row in this tile (may be <= 0 for streaming rows)
-      float mx = -INFINITY;
-      if (nvalid >= kKV) {
-        float pm[8];  // independent chains: the reduction is latency-, not issue-bound
-#pragma unroll
-        for (int a = 0; a < 8; ++a) pm[a] = -INFINITY;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            pm[(i >> 1) & 7] = fmaxf(pm[(i >> 1) & 7], fmaxf(__uint_as_float(s[cc][i]), __uint_as_float(s[cc][i + 1])));
-        mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
-      } else {
+      if (nvalid < kKV) {  // masked keys: -inf scores (exp2 -> 0); only the last key tile of a row pays for this
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(s[cc][i]));
+            if (cc * 32 + i >= nvalid) s[cc][i] = 0xff800000u;
       }
+      float pm[8];  // independent chains: the reduction is latency-, not issue-bound
+#pragma unroll
+      for (int a = 0; a < 8; ++a) pm[a] = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          pm[(i >> 1) & 7] = fmaxf(pm[(i >> 1) & 7], fmaxf(__uint_as_float(s[cc][i]), __uint_as_float(s[cc][i + 1])));
+      const float mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
       // lazy running maximum: move it only when it grows by more than the threshold (first tile: always)
       if (j < 4) TLS(18 + 6 * j);
       const float mt = mx * c;
@@ -246,7 +264,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[4][16];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) exp_chunk(s[cc], c, m_use, nvalid - cc * 32, pk[cc], sum0, sum1);
+      for (int cc = 0; cc < 4; ++cc) exp_chunk(s[cc], c, m_use, pk[cc], sum0, sum1);
       l = fmaf(l, alpha, sum0 + sum1);
       m = m_new;
       if (j < 4) TLS(19 + 6 * j);
@@ -289,23 +307,31 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
     tc_fence_after();
     TLS(40);
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-    __nv_bfloat16* dst = p.out + ((long long)b * p.T + qi) * (p.H * kD) + h * kD;
+    // O / l -> bf16 -> this row's 128-byte line of the (now idle) Q tile, 128B-swizzled; each warp then hands its 32
+    // rows to one TMA store (rows past T are clipped by the tensor map).  A direct store would make every warp
+    // instruction touch 32 different rows with 16 B each.
+    uint8_t* orow = sQ + r * 128;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       uint32_t o[32];
       tmem_ld32(o_addr + hh * 32, o);
       tmem_ld_wait();
-      if (qi < p.T) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * g) = v;
-        }
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+        v.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+        v.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+        v.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + (((hh * 4 + g) ^ sw) << 4)) = v;
       }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && q0 + warp * 32 < p.T) {
+      tma_store_3d(&mapOut, sQ + warp * 32 * 128, h * kD, q0 + warp * 32, b);
+      bulk_commit();
+      bulk_wait_read<0>();  // the CTA may exit (and its shared memory be reused) once the source has been read
     }
   }
 
@@ -337,7 +363,26 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
   count_launch();
   AttnParams pp = p;
   pp.timeline = (g_debug_buffer && g_debug_bytes >= 148 * 64 * 8) ? g_debug_buffer : nullptr;
-  return launch_pdl(attn_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, pp);
+  // output tensor map ([B][T][H*64] bf16, 32-row boxes: one TMA store per softmax warp), cached per (buffer, shape)
+  struct OutMap {
+    const void* out = nullptr;
+    int B = 0, T = 0, H = 0;
+    CUtensorMap map;
+  };
+  static thread_local OutMap cache[8];
+  static thread_local int next = 0;
+  const OutMap* hit = nullptr;
+  for (const OutMap& e : cache)
+    if (e.out == p.out && e.B == p.B && e.T == p.T && e.H == p.H) hit = &e;
+  if (!hit) {
+    OutMap& e = cache[next];
+    next = (next + 1) % 8;
+    e.out = nullptr;
+    if (!make_act_map(&e.map, p.out, p.H * kD, p.T, p.B, p.H * kD, (long long)p.T * p.H * kD, 32)) return cudaErrorInvalidValue;
+    e.out = p.out, e.B = p.B, e.T = p.T, e.H = p.H;
+    hit = &e;
+  }
+  return launch_pdl(attn_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, hit->map, pp);
 }
 
 }  // namespace ls
