@@ -38,7 +38,7 @@ constexpr int kMmaWarp = kProducerWarps;
 constexpr int kFirstEpiWarp = kProducerWarps + 1;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
 constexpr int kSmemBudget = 174 * 1024;             // for the operand rings
@@ -176,39 +176,58 @@ struct WarpRows {
   }
 };
 
-// v (this thread's row, 16 fp32) += addend chunk, fetched coalesced
+// Residual (addend) chunk, fetched coalesced into registers: fp32 = 4 x 16 B per lane (8 rows x 64 B per instruction),
+// bf16 = 2 x 16 B per lane (16 rows x 32 B).  Issued before the accumulator is waited for, so the global latency
+// overlaps the MMA wait and the other chunks instead of sitting in the middle of the chunk's dependent chain.
+struct AddRegs {
+  uint4 v[4];
+};
 template <bool kF32>
-__device__ __forceinline__ void add_chunk(uint8_t* stg, int lane, const WarpRows& wr, int n, const void* base,
-                                          float (&v)[16]) {
+__device__ __forceinline__ void fetch_chunk(int lane, const WarpRows& wr, int n, const void* base, AddRegs& a) {
   if (kF32) {
 #pragma unroll
     for (int ps = 0; ps < 4; ++ps) {
       const int rr = ps * 8 + (lane >> 2), seg = lane & 3;
       long long flat;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (wr.state(rr, n, &flat) == 2) a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + flat + seg * 4);
-      *reinterpret_cast<float4*>(stg + stg_f32(rr, seg)) = a;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 a = *reinterpret_cast<const float4*>(stg + stg_f32(lane, u));
-      v[4 * u] += a.x, v[4 * u + 1] += a.y, v[4 * u + 2] += a.z, v[4 * u + 3] += a.w;
+      a.v[ps] = make_uint4(0u, 0u, 0u, 0u);
+      if (wr.state(rr, n, &flat) == 2) a.v[ps] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + flat + seg * 4);
     }
   } else {
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
       const int rr = ps * 16 + (lane >> 1), seg = lane & 1;
       long long flat;
-      uint4 a = make_uint4(0u, 0u, 0u, 0u);
-      if (wr.state(rr, n, &flat) == 2) a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + flat + seg * 8);
-      *reinterpret_cast<uint4*>(stg + stg_b16(rr, seg)) = a;
+      a.v[ps] = make_uint4(0u, 0u, 0u, 0u);
+      if (wr.state(rr, n, &flat) == 2) a.v[ps] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + flat + seg * 8);
+    }
+  }
+}
+// v (this thread's row, 16 fp32) += the fetched chunk, transposed through the warp's staging buffer
+template <bool kF32>
+__device__ __forceinline__ void apply_chunk(uint8_t* stg, int lane, const AddRegs& a, float (&v)[16]) {
+  if (kF32) {
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int rr = ps * 8 + (lane >> 2), seg = lane & 3;
+      *reinterpret_cast<uint4*>(stg + stg_f32(rr, seg)) = a.v[ps];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 t = *reinterpret_cast<const float4*>(stg + stg_f32(lane, u));
+      v[4 * u] += t.x, v[4 * u + 1] += t.y, v[4 * u + 2] += t.z, v[4 * u + 3] += t.w;
+    }
+  } else {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int rr = ps * 16 + (lane >> 1), seg = lane & 1;
+      *reinterpret_cast<uint4*>(stg + stg_b16(rr, seg)) = a.v[ps];
     }
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const uint4 a = *reinterpret_cast<const uint4*>(stg + stg_b16(lane, u));
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+      const uint4 t = *reinterpret_cast<const uint4*>(stg + stg_b16(lane, u));
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
@@ -293,8 +312,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tfull = bars + 4 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float2* red_base = reinterpret_cast<float2*>(bars + 64);  // 512 B after the barriers
+  float2* red_base = reinterpret_cast<float2*>(bars + 4 * kMaxStages + 8);  // after the barriers + TMEM slot
   uint8_t* stg_base = reinterpret_cast<uint8_t*>(red_base) + kRedBytes;  // per-epilogue-warp transpose buffers
+  float* svec = reinterpret_cast<float*>(stg_base + kEpiWarps * kStageBytesPerWarp);  // per-channel epilogue vectors
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -332,6 +352,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     tmem_relinquish();
   }
+  // Per-channel vectors (bias, LayerNorm affine, Snake alpha) are weights: they are copied into shared memory here,
+  // before the PDL wait.  Read from global in the epilogue, each of them is a dependent L2 round trip per chunk.
+  {
+    auto stage_vec = [&](int off, const float* src, int n) {
+      if (off >= 0)
+        for (int i = threadIdx.x; i < n; i += kThreads) svec[off + i] = __ldg(src + i);
+    };
+    stage_vec(p.sv_bias, p.bias, p.chan_mod);
+    stage_vec(p.sv_p1a, p.p1_a, p.chan_mod);
+    stage_vec(p.sv_p1b, p.p1_b, p.chan_mod);
+    stage_vec(p.sv_lng, p.ln_g, p.N);
+    stage_vec(p.sv_lnb, p.ln_b, p.N);
+  }
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
@@ -349,6 +382,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // unambiguous only while P <= D (a producer is then never two uses ahead of the consumer): launch_conv_gemm
     // guarantees b_stages >= kWeightProducers, and the activation ring (1-3 stages) has a single producer.
     // (Separate warps, not lanes: a lane blocked in mbarrier.try_wait suspends its whole warp.)
+    // (Issuing the weight boxes from 4 or 8 lanes of one warp instead was measured: no change.)
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -375,9 +409,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                   tma_load_3d(sa, &mapA1, &a_full[as], (kb - p.kb_split) * kBlockK, trow, tc.b);
                 if (++as == p.a_stages) as = 0, aph ^= 1;
               }
-            } else {
+            } else if (!p.b_resident || p_tile == 1) {  // resident weights: fetched with the CTA's first tile only
               if (b_seq == warp - 1) {
-                mbar_wait(&b_empty[bs], bph ^ 1);
+                if (!p.b_resident) mbar_wait(&b_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
                 tma_load_2d(smem_b + (size_t)bs * b_bytes, &mapW, &b_full[bs], kb * kBlockK, tap * p.N + n0);
               }
@@ -409,8 +443,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               mbar_wait(&a_full[as], aph);
               tc_fence_after();
             }
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
+            if (!p.b_resident || n_tile == 0) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+            }
             if (tl && n_it < 24) tl[8 + n_it] = clock64();
             ++n_it;
             // tap t of the halo box = the same rows shifted down by t*dil: start address + t*dil*128 B, with the
@@ -422,7 +458,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
-            umma_commit(&b_empty[bs]);
+            if (!p.b_resident) umma_commit(&b_empty[bs]);
             if (++bs == p.b_stages) bs = 0, bph ^= 1;
             if (!halo || tap == p.taps - 1) {
               umma_commit(&a_empty[as]);
@@ -489,6 +525,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       // registers are not: with ~220 KB of shared memory there is hardly any L1 left to absorb a spill).  LayerNorm
       // needs whole-row statistics first, so those modes make an extra pass; the second LayerNorm (OUT1_LN) parks the
       // finished values back in the accumulator columns (tcgen05.st) and re-reads them once its statistics are known.
+      WarpRows wr;
+      wr.t_base = (long long)tc.mt * kBlockM + q * 32;
+      wr.out_ld = p.out_ld, wr.out_shift = p.out_shift, wr.valid = st.valid, wr.alloc = st.alloc, wr.M = p.M;
+      // residual chunks of this tile: the first of this warp's chunks is fetched now (see fetch_chunk); the
+      // next tile's residual rows are pulled into L2 so that its fetches do not wait for HBM
+      constexpr int kPre = 1;  // (2 spills in the 96-register epilogue; later chunks hit L2 thanks to the prefetch below)
+#ifndef CONV_PRE
+#define CONV_PRE 0  // measured: the 16 extra live registers spill, and the spills cost more than the L2 hit they hide
+#endif
+      const bool pre_ok = CONV_PRE && add_dtype != OUT_NONE && act != ACT_LN_MISH;  // (LayerNorm epilogues: registers are scarce)
+      AddRegs pre0;
+      if (pre_ok) {
+        auto fetch = [&](int k, AddRegs& a) {
+          const int c = g + 4 * k;
+          const int n = n0 + c * 16;
+          if (c < n_chunks && n + 16 <= p.n_store) {
+            if (add_dtype == OUT_F32) fetch_chunk<true>(lane, wr, n, addf, a);
+            else fetch_chunk<false>(lane, wr, n, addh, a);
+          }
+        };
+        fetch(0, pre0);
+      }
+      if (add_dtype != OUT_NONE) {
+        const int nxt = tile + (int)gridDim.x;
+        if (nxt < total_tiles) {
+          const TileCoord nc = decode_tile(nxt, m_tiles, n_tiles);
+          const int esz = add_dtype == OUT_F32 ? 4 : 2;
+          const int lines = (p.block_n * esz + 127) >> 7;  // 128-byte lines per row (the first may start mid-line)
+          const uint8_t* nb = reinterpret_cast<const uint8_t*>(p.addend) + (long long)nc.b * p.out_bstride * esz;
+          for (int i = threadIdx.x - kFirstEpiWarp * 32; i < kBlockM * lines; i += kEpiThreads) {
+            const int rr = i / lines, ln = i - rr * lines;
+            const long long tt = (long long)nc.mt * kBlockM + rr;
+            const long long f = tt * p.out_ld + p.out_shift + nc.nt * p.block_n;
+            if (tt < p.M && f >= 0 && f + p.block_n <= p.out_alloc)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + f * esz + ln * 128));
+          }
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       long long* tle = (threadIdx.x == kFirstEpiWarp * 32 && tile == (int)blockIdx.x) ? tl : nullptr;
@@ -500,9 +574,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         tmem_ld_wait();
         if (p.bias) {
           const int ch0 = (n0 + c * 16) % p.chan_mod;
+          const float4* bp = reinterpret_cast<const float4*>(p.sv_bias >= 0 ? svec + p.sv_bias + ch0 : p.bias + ch0);
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + g4);
+            const float4 bv = bp[g4];
             x[4 * g4] += bv.x, x[4 * g4 + 1] += bv.y, x[4 * g4 + 2] += bv.z, x[4 * g4 + 3] += bv.w;
           }
         }
@@ -563,9 +638,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       if (tle) tle[45] = clock64();
 
-      WarpRows wr;
-      wr.t_base = (long long)tc.mt * kBlockM + q * 32;
-      wr.out_ld = p.out_ld, wr.out_shift = p.out_shift, wr.valid = st.valid, wr.alloc = st.alloc, wr.M = p.M;
       Stats s2;
       // pass B: finish the values, store the primary / copy / snake outputs
 #pragma unroll 1
@@ -576,8 +648,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (act == ACT_LN_MISH) {
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + c * 16) + g4);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + c * 16) + g4);
+            const float4 gm = reinterpret_cast<const float4*>(p.sv_lng >= 0 ? svec + p.sv_lng + c * 16 : p.ln_g + c * 16)[g4];
+            const float4 bt = reinterpret_cast<const float4*>(p.sv_lnb >= 0 ? svec + p.sv_lnb + c * 16 : p.ln_b + c * 16)[g4];
             x[4 * g4 + 0] = mish_f(fmaf((x[4 * g4 + 0] - mean1) * rstd1, gm.x, bt.x));
             x[4 * g4 + 1] = mish_f(fmaf((x[4 * g4 + 1] - mean1) * rstd1, gm.y, bt.y));
             x[4 * g4 + 2] = mish_f(fmaf((x[4 * g4 + 2] - mean1) * rstd1, gm.z, bt.z));
@@ -592,10 +664,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
         }
         const long long flat = row_flat + n;
-        const bool partial = n + 16 > p.n_store;  // only the padded final conv (n_store = 1)
+        // only the padded final conv (n_store = 1): the scalar tail indexes x dynamically, which would put x in local
+        // memory for every instance that contains it
+        const bool partial = (kAct == ACT_LRELU_TANH || kAct < 0) && n + 16 > p.n_store;
         if (add_dtype != OUT_NONE && !partial) {
-          if (add_dtype == OUT_F32) add_chunk<true>(stg, lane, wr, n, addf, x);
-          else add_chunk<false>(stg, lane, wr, n, addh, x);
+          const int k = (c - g) >> 2;
+          if (pre_ok && k < kPre) {
+            if (add_dtype == OUT_F32) apply_chunk<true>(stg, lane, pre0, x);
+            else apply_chunk<false>(stg, lane, pre0, x);
+          } else {
+            AddRegs a;
+            if (add_dtype == OUT_F32) fetch_chunk<true>(lane, wr, n, addf, a), apply_chunk<true>(stg, lane, a, x);
+            else fetch_chunk<false>(lane, wr, n, addh, a), apply_chunk<false>(stg, lane, a, x);
+          }
         }
         if (partial) {  // scalar tail: column 0 of consecutive rows is contiguous when out_ld == n_store == 1
           const int stt = st.state(flat, max(p.n_store - n, 1));
@@ -616,8 +697,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const int ch0 = n % p.chan_mod;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 al = __ldg(reinterpret_cast<const float4*>(p.p1_a + ch0) + g4);
-              const float4 ia = __ldg(reinterpret_cast<const float4*>(p.p1_b + ch0) + g4);
+              const float4 al = reinterpret_cast<const float4*>(p.sv_p1a >= 0 ? svec + p.sv_p1a + ch0 : p.p1_a + ch0)[g4];
+              const float4 ia = reinterpret_cast<const float4*>(p.sv_p1b >= 0 ? svec + p.sv_p1b + ch0 : p.p1_b + ch0)[g4];
               x[4 * g4 + 0] = snake_f(x[4 * g4 + 0], al.x, ia.x);
               x[4 * g4 + 1] = snake_f(x[4 * g4 + 1], al.y, ia.y);
               x[4 * g4 + 2] = snake_f(x[4 * g4 + 2], al.z, ia.z);
@@ -642,8 +723,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.p1_a + c * 16) + g4);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(p.p1_b + c * 16) + g4);
+            const float4 ga = reinterpret_cast<const float4*>(p.sv_p1a >= 0 ? svec + p.sv_p1a + c * 16 : p.p1_a + c * 16)[g4];
+            const float4 be = reinterpret_cast<const float4*>(p.sv_p1b >= 0 ? svec + p.sv_p1b + c * 16 : p.p1_b + c * 16)[g4];
             x[4 * g4 + 0] = fmaf((x[4 * g4 + 0] - mean2) * rstd2, ga.x, be.x);
             x[4 * g4 + 1] = fmaf((x[4 * g4 + 1] - mean2) * rstd2, ga.y, be.y);
             x[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean2) * rstd2, ga.z, be.z);
@@ -706,21 +787,44 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   if (pp.a_box_rows > 256) return cudaErrorInvalidValue;  // TMA box limit
   const int a_bytes = ls_conv_a_stage_bytes(pp.a_box_rows);
   const int b_bytes = p.block_n * kBlockK * 2;
-  if (p.halo_mode && p.taps > 1) {
+  // per-channel epilogue vectors staged in shared memory (up to 16 KB; larger ones stay in global memory)
+  pp.sv_bias = pp.sv_p1a = pp.sv_p1b = pp.sv_lng = pp.sv_lnb = -1;
+  pp.sv_floats = 0;
+  {
+    auto place = [&](int& off, const void* ptr, int n) {
+      if (ptr && (pp.sv_floats + n) * 4 <= 16 * 1024) off = pp.sv_floats, pp.sv_floats += (n + 3) & ~3;
+    };
+    place(pp.sv_bias, p.bias, p.chan_mod);
+    if (p.out1_mode == OUT1_SNAKE || p.out1_mode == OUT1_LN) place(pp.sv_p1a, p.p1_a, p.chan_mod), place(pp.sv_p1b, p.p1_b, p.chan_mod);
+    if (p.act == ACT_LN_MISH) place(pp.sv_lng, p.ln_g, p.N), place(pp.sv_lnb, p.ln_b, p.N);
+  }
+  const int budget = kSmemBudget - pp.sv_floats * 4;
+  const int m_tiles_ = (p.M + kBlockM - 1) / kBlockM;
+  const long long tiles_per_cta = ((long long)p.B * m_tiles_ * (p.N / p.block_n) + num_sms - 1) / num_sms;
+  const int w_boxes = p.taps * p.kb_per_tap;
+  pp.b_resident = 0;
+  if (p.N == p.block_n && tiles_per_cta >= 3 && w_boxes <= kMaxStages && w_boxes >= kWeightProducers &&
+      w_boxes * b_bytes + 3 * a_bytes <= budget && conv_resident_enabled()) {
+    // small weight tensors (DAC stages with C <= 96, 1x1 layers): resident weights, the whole budget left to activations
+    pp.b_resident = 1;
+    pp.b_stages = w_boxes;
+    pp.a_stages = (budget - w_boxes * b_bytes) / a_bytes;
+    if (pp.a_stages > 6) pp.a_stages = 6;
+  } else if (p.halo_mode && p.taps > 1) {
     // one A box feeds `taps` B boxes: two A stages are enough, the rest of the budget goes to the weight ring
     pp.a_stages = p.kb_per_tap > 1 ? 2 : 1;
-    if (p.kb_per_tap > 1 && 3 * a_bytes + 4 * b_bytes <= kSmemBudget) pp.a_stages = 3;
-    pp.b_stages = (kSmemBudget - pp.a_stages * a_bytes) / b_bytes;
+    if (p.kb_per_tap > 1 && 3 * a_bytes + 4 * b_bytes <= budget) pp.a_stages = 3;
+    pp.b_stages = (budget - pp.a_stages * a_bytes) / b_bytes;
   } else {
-    pp.a_stages = pp.b_stages = kSmemBudget / (a_bytes + b_bytes);
+    pp.a_stages = pp.b_stages = budget / (a_bytes + b_bytes);
   }
   if (pp.a_stages > kMaxStages) pp.a_stages = kMaxStages;
   if (pp.b_stages > kMaxStages) pp.b_stages = kMaxStages;
   if (pp.a_stages < 1 || pp.b_stages < 2 || pp.b_stages < kWeightProducers) return cudaErrorInvalidValue;
   const int acc_stride = pow2_at_least(p.block_n, 32);
   const int tmem_cols = 2 * acc_stride;
-  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + 512 + kRedBytes +
-                kEpiWarps * kStageBytesPerWarp;
+  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + (4 * kMaxStages + 8) * 8 + kRedBytes +
+                kEpiWarps * kStageBytesPerWarp + (size_t)pp.sv_floats * 4;
   // tmem_cols == 512 must never share an SM with a second CTA of this kernel (alloc would spin):
   if (tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;

@@ -18,7 +18,8 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 // earlier kernel wrote.  `cluster` > 1 adds a cluster dimension.  LS_NO_PDL=1 in the environment turns it off.
 bool pdl_enabled();
 bool conv_halo_enabled();
-int conv_halo_mode();  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
+int conv_halo_mode();
+bool conv_resident_enabled();  // LS_CONV_RESIDENT=0: always stream the weights through the ring (development aid)  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               int cluster, Args&&... args) {
@@ -88,6 +89,11 @@ struct ConvGemmParams {
   // halo_mode 0: 128-row boxes fetched per tap.  The remaining fields are filled in by launch_conv_gemm.
   int halo_mode;
   int a_box_rows, a_stages, b_stages;
+  // b_resident: the whole weight tensor of the launch fits in the B ring (b_stages == taps*kb_per_tap, one N tile):
+  // it is fetched once per CTA and stays in shared memory for every tile.
+  int b_resident;
+  // per-channel epilogue vectors staged in shared memory (float offsets into the vector area, -1 = read from global)
+  int sv_bias, sv_p1a, sv_p1b, sv_lng, sv_lnb, sv_floats;
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps of the first tile, or nullptr
 };
 // rows of the activation box a conv with this geometry needs in halo mode (make_act_map's box_rows)
