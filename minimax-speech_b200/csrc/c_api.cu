@@ -272,10 +272,12 @@ int32_t ls_test_tblock(const void* att, float* u, const void* wo, const void* w1
     ls::TBlockMaps m;
     ls::require(ls::make_tile_map(&m.att, att, 2, 512, R, 128) && ls::make_tile_map(&m.u, u, 4, 256, R, 128),
                 "tensor map att / u", LS_ERR_CUDA);
-    ls::require(ls::make_weight_map(&m.wo, wo, 512, 256, TBLOCK_WBOX_ROWS) &&
-                    ls::make_weight_map(&m.w1, w1, 256, 1024, TBLOCK_WBOX_ROWS) &&
-                    ls::make_weight_map(&m.w2, w2, 1024, 256, TBLOCK_WBOX_ROWS) &&
-                    ls::make_weight_map(&m.wqkv, wqkv, 256, 1536, TBLOCK_WBOX_ROWS),
+    ls::require(ls::make_weight_map(&m.wo, wo, 512, 256, TBLOCK_WIDE_BOX_ROWS) &&
+                    ls::make_weight_map(&m.w2, w2, 1024, 256, TBLOCK_WIDE_BOX_ROWS) &&
+                    (TBLOCK_PAIR ? ls::make_weight_map_kb(&m.w1, w1, 256, 1024, 64, 2) &&
+                                       ls::make_weight_map_kb(&m.wqkv, wqkv, 256, 1536, 64, 2)
+                                 : ls::make_weight_map(&m.w1, w1, 256, 1024, TBLOCK_WBOX_ROWS) &&
+                                       ls::make_weight_map(&m.wqkv, wqkv, 256, 1536, TBLOCK_WBOX_ROWS)),
                 "tensor map weights", LS_ERR_CUDA);
     m.qkv_out = m.att, m.tail_out = m.att;
     if (tail_mode != 1)

@@ -210,10 +210,12 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
   if (fused_blocks_) {
     for (auto& g : groups_)
       for (auto& t : g.tb) {
-        require(make_weight_map(&t.m_out, arena_.ptr<uint8_t>(t.out.w_off), 512, 256, TBLOCK_WBOX_ROWS) &&
-                    make_weight_map(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, TBLOCK_WBOX_ROWS) &&
-                    make_weight_map(&t.m_ff2, arena_.ptr<uint8_t>(t.ff2.w_off), 1024, 256, TBLOCK_WBOX_ROWS) &&
-                    make_weight_map(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, TBLOCK_WBOX_ROWS),
+        require(make_weight_map(&t.m_out, arena_.ptr<uint8_t>(t.out.w_off), 512, 256, TBLOCK_WIDE_BOX_ROWS) &&
+                    make_weight_map(&t.m_ff2, arena_.ptr<uint8_t>(t.ff2.w_off), 1024, 256, TBLOCK_WIDE_BOX_ROWS) &&
+                    (TBLOCK_PAIR ? make_weight_map_kb(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, 64, 2) &&
+                                       make_weight_map_kb(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, 64, 2)
+                                 : make_weight_map(&t.m_ff1, arena_.ptr<uint8_t>(t.ff1.w_off), 256, 1024, TBLOCK_WBOX_ROWS) &&
+                                       make_weight_map(&t.m_qkv, arena_.ptr<uint8_t>(t.qkv.w_off), 256, 1536, TBLOCK_WBOX_ROWS)),
                 "cuTensorMapEncodeTiled failed for a fused-block weight matrix", LS_ERR_CUDA);
       }
   }

@@ -119,10 +119,20 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
 // residual, then either the next block's LayerNorm + QKV projection (tail_mode 0) or a masked bf16 copy of the
 // residual stream (tail_mode 1).  Fixed estimator geometry: C = 256, 8 heads x 64, FF = 1024.
 #define TBLOCK_VEC_FLOATS 2560
+#ifndef TBLOCK_PAIR
+#define TBLOCK_PAIR 0                              /* 1: CTA pairs (tcgen05 cta_group::2): each CTA streams HALF of every weight box */
+#endif
+#if TBLOCK_PAIR
+#undef TBLOCK_CLUSTER
+#define TBLOCK_CLUSTER 2
+#endif
 #ifndef TBLOCK_CLUSTER
 #define TBLOCK_CLUSTER 1                           /* CTAs per cluster sharing every weight box by TMA multicast */
 #endif
 #define TBLOCK_WBOX_ROWS (128 / TBLOCK_CLUSTER)    /* box rows of the weight tensor maps */
+/* Pair mode weight maps: Wo / W2 (the pair's N = 256 operands) = 2-D, 128-row boxes; W1 / Wqkv (N = 128 chunks) = 3-D
+   [64][rows][K/64] with boxes of 64 rows x 2 K blocks (make_weight_map_kb). */
+#define TBLOCK_WIDE_BOX_ROWS (TBLOCK_PAIR ? 128 : TBLOCK_WBOX_ROWS)
 struct TBlockParams {
   int R;               // rows = batch rows x T (time-major, flattened)
   int T;               // rows per batch row (only used with lengths)
@@ -176,6 +186,9 @@ cudaError_t launch_time_embed(const TimeEmbedParams& p, cudaStream_t s);
 
 // ---- host helpers (tma_host.cu) ----
 // bf16 activation [B][T][C] viewed through 64 x rows x 1 boxes with 128B swizzle (OOB -> zero)
+// bf16 weights [rows][K] viewed as [64][rows][K/64]: one box = box_rows rows x box_kb 64-wide K blocks, landing in
+// shared memory as box_kb consecutive 128B-swizzled tiles of box_rows rows
+bool make_weight_map_kb(CUtensorMap* map, const void* base, int K, int rows, int box_rows, int box_kb);
 bool make_act_map(CUtensorMap* map, const void* base, int C, int T, int B, long long row_stride_elems,
                   long long batch_stride_elems, int box_rows);
 // bf16 weight matrix [rows][K] with 64 x box_rows boxes

@@ -31,13 +31,27 @@ namespace {
 constexpr int kC = 256, kInner = 512, kFF = 1024, kQKV = 1536;
 constexpr int kTileM = 128;
 constexpr int kSlotBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
+// Pair mode (TBLOCK_PAIR): the two CTAs of a cluster form one 256-row tcgen05 cta_group::2 MMA.  Each CTA keeps its
+// own 128 rows of A and D and provides HALF of every weight box (64 rows, 8 KB), so the ring holds twice as many
+// boxes and each SM pulls half the weight bytes per tile -- the weight stream is what bounds this kernel.
+constexpr bool kPair = TBLOCK_PAIR != 0;
+// One TMA instruction per issuing warp is in flight at a time (measured), so pair mode spends its halved weight bytes on
+// HALF AS MANY instructions of the same 16 KB: 128 own rows of Wo / W2 (the pair's N = 256 operand), or two K blocks of a
+// 64-row half of a W1 / Wqkv chunk (3-D box), per instruction.
+constexpr int kRingSlotBytes = kSlotBytes;
 constexpr int kSlots = 5;
 #ifndef TBLOCK_PRODUCER_WARPS
 #define TBLOCK_PRODUCER_WARPS 3
 #endif
 constexpr int kProducerWarps = TBLOCK_PRODUCER_WARPS;  // warps 0..: one TMA-issuing thread each (issue latencies overlap)
 constexpr int kMmaWarp = kProducerWarps;
-static_assert(kProducerWarps <= 5, "interleaved producers must not outnumber the ring slots (parity waits)");
+#ifndef TBLOCK_PRODUCER_LANES
+#define TBLOCK_PRODUCER_LANES 1
+#endif
+constexpr int kProducerLanes = TBLOCK_PRODUCER_LANES;  // issuing lanes per producer warp
+constexpr int kIssuers = kProducerWarps * kProducerLanes;
+static_assert(kIssuers <= kSlots, "interleaved producers must not outnumber the ring slots (parity waits)");
+static_assert(!kPair || TBLOCK_CLUSTER == 2, "pair mode is a cluster of two");
 constexpr int kCS = TBLOCK_CLUSTER;          // CTAs per cluster: each loads 1/kCS of every weight box and multicasts it
 constexpr int kPartRows = 128 / kCS;         // weight rows per CTA per box
 constexpr int kPartBytes = kPartRows * 128;
@@ -50,7 +64,7 @@ constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 constexpr int kOffA3 = 0;
 constexpr int kOffAH = 4 * kSlotBytes;
 constexpr int kOffRing = kOffAH + 4 * kSlotBytes;
-constexpr int kOffVec = kOffRing + kSlots * kSlotBytes;
+constexpr int kOffVec = kOffRing + kSlots * kRingSlotBytes;
 constexpr int kOffRed = kOffVec + TBLOCK_VEC_FLOATS * 4;
 constexpr int kOffBars = kOffRed + 4 * kTileM * 8;  // [column group][row] float2
 constexpr int kSmemBytes = kOffBars + 256 + 1024;
@@ -192,14 +206,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     prefetch_tmap(&mapQkvOut);
     prefetch_tmap(&mapTail);
     for (int i = 0; i < kSlots; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kCS);  // released by the MMA warp of every CTA of the cluster
+      mbar_init(&full[i], kPair ? 2 : 1);        // pair: one arrive.expect_tx per CTA, on the leader's barrier
+      mbar_init(&empty[i], kPair ? 1 : kCS);     // multicast: released by the MMA warp of every CTA of the cluster
     }
     mbar_init(d_full, 1);
-    mbar_init(a3_ready, kEpiWarps);
+    mbar_init(a3_ready, kPair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogue warps arrive at the leader
     for (int i = 0; i < 2; ++i) {
       mbar_init(&h_full[i], 1);
-      mbar_init(&ah_ready[i], kEpiWarps);
+      mbar_init(&ah_ready[i], kPair ? 2 * kEpiWarps : kEpiWarps);
       mbar_init(&ah_free[i], 1);
     }
     mbar_init(u_full, 1);
@@ -207,8 +221,13 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   }
   if (warp == kMmaWarp) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   if (warp >= kFirstEpiWarp) {
     for (int i = threadIdx.x - kFirstEpiWarp * 32; i < TBLOCK_VEC_FLOATS; i += kEpiThreads) sVec[i] = __ldg(p.vec + i);
@@ -227,18 +246,42 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     // less than the MMA warp consumes, but different warps overlap.  kProducerWarps threads walk the same fixed load
     // sequence of a tile; warp w issues the loads whose sequence number is w mod kProducerWarps.  (Separate warps, not
     // lanes of one warp: a lane blocked in mbarrier.try_wait suspends its whole warp.)
-    if (lane == 0) {
-      const int per_tile = head ? 48 : (do_qkv ? 136 : 88);
+    if (lane < kProducerLanes) {
+      const int issuer = warp * kProducerLanes + lane;
+      const int per_tile = kPair ? (head ? 24 : (do_qkv ? 72 : 48)) : (head ? 48 : (do_qkv ? 136 : 88));
       long long seq0 = 0;  // sequence number of the tile's first load (slot = seq % kSlots, use = seq / kSlots)
       for (int g = group0; g < n_groups; g += group_step) {
         const int row0 = (g * kCS + rank) * kTileM;
         if (group_skipped(g)) continue;
-        for (int i = warp; i < per_tile; i += kProducerWarps) {
+        for (int i = issuer; i < per_tile; i += kIssuers) {
           // decode load i of the tile: (tensor map, column, row), in exactly the order the MMA warp consumes them
           const CUtensorMap* m;
           int c0, c1;
           bool own_rows = false;
-          if (head) {  // QKV weight only
+          int c2 = -1;  // >= 0: 3-D weight box (pair mode: 64 rows x 2 K blocks), third coordinate
+          if (kPair) {
+            auto chunk_half = [&](const CUtensorMap* wm, int chunk, int half) {  // W1 / Wqkv chunk: this CTA's 64 rows
+              m = wm, c0 = 0, c1 = chunk * 128 + rank * kPartRows, c2 = half * 2;
+            };
+            if (head) {
+              chunk_half(&mapWqkv, i >> 1, i & 1);
+            } else if (i < 16) {  // out-proj: per K block the att box (own rows), then this CTA's 128 rows of Wo
+              const int kb = i >> 1;
+              if ((i & 1) == 0) m = &mapAtt, c0 = kb * 64, c1 = row0, own_rows = true;
+              else m = &mapWo, c0 = kb * 64, c1 = rank * 128, own_rows = true;
+            } else if (i < 20) {  // FF1 chunks 0 and 1
+              chunk_half(&mapW1, (i - 16) >> 1, i & 1);
+            } else if (i < 48) {  // per FF chunk c: W2 (2 K blocks, this CTA's 128 rows), then FF1 chunk c+2
+              const int j = i - 20;
+              int c, r;
+              if (j < 24) c = j >> 2, r = j & 3;
+              else c = 6 + ((j - 24) >> 1), r = (j - 24) & 1;
+              if (r < 2) m = &mapW2, c0 = c * 128 + r * 64, c1 = rank * 128, own_rows = true;
+              else chunk_half(&mapW1, c + 2, r - 2);
+            } else {  // next block's QKV weight, 12 chunks
+              chunk_half(&mapWqkv, (i - 48) >> 1, i & 1);
+            }
+          } else if (head) {  // QKV weight only
             m = &mapWqkv, c0 = (i & 3) * 64, c1 = (i >> 2) * 128;
           } else if (i < 24) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
             const int kb = i / 3, r = i - kb * 3;
@@ -263,18 +306,39 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           const uint32_t use = (uint32_t)(seq / kSlots);
           mbar_wait(&empty[slot], (use & 1) ^ 1);
           if (tl && seq < 48) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
-          uint8_t* dst = sRing + slot * kSlotBytes;
-          mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-          if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
-          else tma_load_2d(dst, m, &full[slot], c0, c1);
+          uint8_t* dst = sRing + slot * kRingSlotBytes;
+          if (kPair) {
+            // this CTA's half of the box (own rows for att), completion signalled on the LEADER's barrier
+            const uint32_t fb = cluster_addr(&full[slot], 0);
+            mbar_arrive_expect_tx_cluster(fb, kRingSlotBytes);
+            if (c2 >= 0) tma_load_3d_pair(dst, m, fb, c0, c1, c2);
+            else tma_load_2d_pair(dst, m, fb, c0, c1);
+          } else {
+            mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+            if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
+            else tma_load_2d(dst, m, &full[slot], c0, c1);
+          }
         }
         seq0 += per_tile;
       }
     }
   } else if (warp == kMmaWarp) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, 128, false, false);
+    if (lane == 0 && (!kPair || rank == 0)) {  // pair: the leader CTA issues every MMA of both CTAs
+      const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kTileM : kTileM, 128, false, false);
+      const uint32_t idesc256 = make_idesc_bf16(2 * kTileM, 256, false, false);  // pair: one N = 256 MMA fills D
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (kPair) umma_bf16_pair(d, ad, bd, idesc, acc);
+        else umma_bf16(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {  // MMA -> epilogue barriers exist in both CTAs
+        if (kPair) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      auto wait_epi = [&](uint64_t* bar, uint32_t parity) {  // epilogue -> MMA (pair: arrivals come from both CTAs)
+        if (kPair) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+      };
       int slot = 0;
       uint32_t phase = 0;
       uint32_t a3_cnt = 0;
@@ -286,15 +350,17 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         int s = slot + ahead;
         uint32_t ph = phase;
         if (s >= kSlots) s -= kSlots, ph ^= 1;
-        mbar_wait(&full[s], ph);
+        if (kPair) mbar_wait_cluster(&full[s], ph);
+        else mbar_wait(&full[s], ph);
         tc_fence_after();
         if (tl && n_full < 16) tl[112 + n_full] = clock64();
         n_full += (ahead == 0);
-        return make_smem_desc_sw128(smem_u32(sRing + s * kSlotBytes));
+        return make_smem_desc_sw128(smem_u32(sRing + s * kRingSlotBytes));
       };
       auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
         for (int j = 0; j < n; ++j) {
-          if (kCS > 1) umma_commit_mc(&empty[slot], kCtaMask);
+          if (kPair) umma_commit_pair(&empty[slot]);
+          else if (kCS > 1) umma_commit_mc(&empty[slot], kCtaMask);
           else umma_commit(&empty[slot]);
           if (++slot == kSlots) slot = 0, phase ^= 1;
         }
@@ -302,7 +368,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       auto wait_drained = [&](int i) {  // the epilogue has finished with the latest fill of H[i]
         const uint32_t f = i ? fills1 : fills0;
         if ((i ? drained1 : drained0) < f) {
-          mbar_wait(&ah_ready[i], (f - 1) & 1);
+          wait_epi(&ah_ready[i], (f - 1) & 1);
           tc_fence_after();
           if (i) drained1 = f;
           else drained0 = f;
@@ -313,13 +379,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         wait_drained(i);
         const uint32_t d = tmem_base + kTmemH + (uint32_t)i * 128;
         for (int kb = 0; kb < kC / 64; ++kb) {
-          const uint64_t bdesc = slot_desc(0);
+          // pair: a slot holds two K blocks of this CTA's 64 weight rows (8 KB each)
+          const uint64_t bdesc = slot_desc(0) + (kPair ? (uint64_t)((kb & 1) * (8192 >> 4)) : 0);
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA3 + kb * kSlotBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          release(1);
+          for (int k = 0; k < 4; ++k) mma(d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          if (!kPair || (kb & 1)) release(1);
         }
-        umma_commit(&h_full[i]);
+        commit(&h_full[i]);
         if (i) fills1 += 1;
         else fills0 += 1;
       };
@@ -333,20 +400,27 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         for (int kb = 0; kb < kInner / 64; ++kb) {
           const uint64_t adesc = slot_desc(0);
           const uint64_t b0 = slot_desc(1);
+          if (kPair) {  // b0 = this CTA's 128 rows of Wo: the pair's operand is all 256
+            if (kb == 0) TL(1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, (kb | k) != 0 ? 1u : 0u);
+            release(2);
+            continue;
+          }
           const uint64_t b1 = slot_desc(2);
           if (kb == 0) TL(1);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            umma_bf16(dD, adesc + 2 * k, b0 + 2 * k, idesc, acc);
-            umma_bf16(dD + 128, adesc + 2 * k, b1 + 2 * k, idesc, acc);
+            mma(dD, adesc + 2 * k, b0 + 2 * k, acc);
+            mma(dD + 128, adesc + 2 * k, b1 + 2 * k, acc);
           }
           release(3);
         }
-        umma_commit(d_full);
+        commit(d_full);
         TL(2);
         // ---- FF: H[c&1] = n3 . W1[c]^T ; D += gelu(H[c&1]) . W2[:, c]^T
-        mbar_wait(a3_ready, a3_cnt & 1);  // n3 in A3, u' written back to D
+        wait_epi(a3_ready, a3_cnt & 1);  // n3 in A3, u' written back to D
         a3_cnt += 1;
         tc_fence_after();
         TL(3);
@@ -359,22 +433,28 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
             const uint64_t b0 = slot_desc(0);
+            if (kPair) {  // this CTA's 128 rows of W2[:, chunk]: one N = 256 MMA per K step
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, 1u);
+              release(1);
+              continue;
+            }
             const uint64_t b1 = slot_desc(1);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_bf16(dD, adesc + 2 * k, b0 + 2 * k, idesc, 1u);
-              umma_bf16(dD + 128, adesc + 2 * k, b1 + 2 * k, idesc, 1u);
+              mma(dD, adesc + 2 * k, b0 + 2 * k, 1u);
+              mma(dD + 128, adesc + 2 * k, b1 + 2 * k, 1u);
             }
             release(2);
           }
-          umma_commit(&ah_free[i]);
+          commit(&ah_free[i]);
           if (c + 2 < kFF / 128) gemm_from_a3(i);
         }
-        umma_commit(d_full);
+        commit(d_full);
         TL(12);
         }  // !head
         // ---- tail: D drained by the epilogue (and, tail 0 / 2, the LayerNorm output written to A3)
-        mbar_wait(a3_ready, a3_cnt & 1);
+        wait_epi(a3_ready, a3_cnt & 1);
         a3_cnt += 1;
         tc_fence_after();
         TL(13);
@@ -406,7 +486,10 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(cluster_addr(bar, 0));  // epilogue -> MMA barriers live in the leader CTA
+        else mbar_arrive(bar);
+      }
     };
     for (int g = group0; g < n_groups; g += group_step) {
       const int row0 = (g * kCS + rank) * kTileM;
@@ -657,7 +740,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   if (kCS > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 

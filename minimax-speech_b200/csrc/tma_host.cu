@@ -50,6 +50,18 @@ bool make_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bo
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_weight_map_kb(CUtensorMap* map, const void* base, int K, int rows, int box_rows, int box_kb) {
+  EncodeFn enc = get_encode();
+  if (!enc || K % 64) return false;
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(K / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_kb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_tile_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, int box_rows) {
   EncodeFn enc = get_encode();
   if (!enc || (elem_bytes != 2 && elem_bytes != 4)) return false;
