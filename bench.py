@@ -79,6 +79,36 @@ def cpu_baseline(a, esd, dsd):
                       f"{torch.get_num_threads()} threads, {total:.2f} s"}
 
 
+def gpu_eager_baseline(a, esd, dsd, dev):
+    """The denominator north_star names: the reference algorithm as eager PyTorch ON THE GPU (fp32 and bf16 autocast),
+    one utterance at a time like the reference's solve_euler.  The reference itself is Python + absent third-party
+    packages and cannot travel to this box, so this runs the oracle restatement (plain torch ops) on cuda."""
+    import minimax_speech_b200.synth as synth
+    from oracle import restatement as O
+    T = int(round(a.seconds * FRAME_RATE))
+    e_gpu = {k: v.to(dev) for k, v in esd.items()}
+    d_gpu = {k: v.to(dev) for k, v in dsd.items()}
+    noise = synth.fixed_noise().to(dev)
+    inputs = [[t.to(dev) for t in synth.batch_inputs([T], first_index=i)] for i in range(2)]
+    out = {"unit": UNIT, "kind": "port", "sample": f"2 of {a.batch} utterances, batch 1 each, oracle/restatement.py as eager "
+           f"PyTorch on cuda ({a.n_timesteps} steps CFG + DAC decode), best of 2 passes"}
+    for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        best = None
+        for _ in range(3):  # pass 0 = warm-up (cuDNN / cuBLAS heuristics)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.inference_mode(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                for mu, mask, spks, cond in inputs:
+                    lat = O.cfm_forward(e_gpu, noise, mu, mask, a.n_timesteps, 1.0, spks, cond)
+                    O.dac_decode(d_gpu, lat.float())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or _ == 1 else min(best, ms)
+        out[name] = len(inputs) * a.seconds / (best / 1000.0)
+    return out
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -291,8 +321,9 @@ def run_b200(a):
                     "avg_launch_us": 1000.0 * prof[dom]["ms"] / prof[dom]["launches"],
                     "hbm_peak_gbs": peak_bw}
 
-    cb = None
+    cb, eager = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        eager = gpu_eager_baseline(a, esd, dsd, dev)
         cb = cpu_baseline(a, esd, dsd)
 
     if rank == 0:
@@ -300,7 +331,8 @@ def run_b200(a):
                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_of(a),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_rec, "roofline": roofline,
-               "kernels": kernels, "cpu_baseline": cb, "audio_seconds_per_step": audio_per_step}
+               "kernels": kernels, "cpu_baseline": cb, "gpu_eager_baseline": eager,
+               "audio_seconds_per_step": audio_per_step}
         print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()

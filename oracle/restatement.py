@@ -31,7 +31,7 @@ import torch.nn.functional as F
 def sinusoidal_pos_emb(t, dim=320, scale=1000.0):
     """matcha/models/components/decoder.py:14-29."""
     half = dim // 2
-    f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    f = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device) * -(math.log(10000.0) / (half - 1)))
     e = scale * t.float().unsqueeze(1) * f.unsqueeze(0)
     return torch.cat([e.sin(), e.cos()], dim=-1)
 
@@ -71,7 +71,7 @@ def attention_bias(mask, streaming, chunk):
     m = mask.bool()
     B, _, T = m.shape
     if streaming and chunk > 0:
-        pos = torch.arange(T)
+        pos = torch.arange(T, device=mask.device)
         block_end = (torch.div(pos, chunk, rounding_mode="trunc") + 1) * chunk  # mask.py:154-157
         cm = pos.unsqueeze(0) < block_end.unsqueeze(1)
         m = m & cm.unsqueeze(0)
@@ -180,8 +180,8 @@ def solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate=0.7, streaming=Fal
 def cfm_forward(sd, noise, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False,
                 cfg_rate=0.7, heads=8, chunk=50):
     """CausalConditionalCFM.forward flow_matching.py:323-348.  ``noise`` = rand_noise [1,80,>=T]."""
-    z = noise[:, :, :mu.shape[2]].to(mu.dtype).expand(mu.shape[0], -1, -1) * temperature
-    t_span = cosine_t_span(n_timesteps, mu.dtype)
+    z = noise[:, :, :mu.shape[2]].to(device=mu.device, dtype=mu.dtype).expand(mu.shape[0], -1, -1) * temperature
+    t_span = cosine_t_span(n_timesteps, mu.dtype).to(mu.device)
     return solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate, streaming, heads, chunk)
 
 
@@ -249,7 +249,7 @@ def dac_decode_varlen(sd, z, lengths):
     while f"decoder.model.{k}.block.1.weight_v" in sd:
         hop *= sd[f"decoder.model.{k}.block.1.weight_v"].shape[-1] // 2
         k += 1
-    out = torch.zeros(z.shape[0], 1, z.shape[2] * hop)
+    out = torch.zeros(z.shape[0], 1, z.shape[2] * hop, device=z.device)
     for b, n in enumerate(lengths):
         out[b, :, :n * hop] = dac_decode(sd, z[b:b + 1, :, :n])[0]
     return out

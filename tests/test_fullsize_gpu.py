@@ -1,0 +1,129 @@
+"""Parity at BASELINE.json's full sizes (B200), through properties that do not need the CPU oracle to run the whole
+workload: batch == per-utterance (utterances are independent on this path: SURVEY.md section 8e), truncation
+invariance of the DAC decoder outside its receptive field, plus oracle checks on single utterances / crops.
+
+  configs[1]  16 x 10 s, 10-step Euler + CFG, + DAC decode
+  configs[2]  DAC-VAE decoder only, 64 x 30 s latents
+  configs[3]  n_timesteps = 32, 30 s utterances, batch 32 (one rank's share at 1 GPU)
+  configs[4]  mixed-length 2-30 s utterances, padded + masked (one rank's share of the 256: 32 utterances)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import minimax_speech_b200.synth as synth  # noqa: E402
+from minimax_speech_b200.dac import DACVAEDecoder  # noqa: E402
+from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder  # noqa: E402
+from minimax_speech_b200.pipeline import Synthesizer, shard_utterances  # noqa: E402
+from oracle import restatement as O  # noqa: E402
+
+DEV = torch.device("cuda:0")
+LATENT_TOL = 1e-2  # north_star: bf16 mode
+SNR_MIN_DB = 30.0
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+@pytest.fixture(scope="module")
+def models():
+    esd = synth.estimator_state_dict(1986, "reference")  # the bench's weights (reference initialisers)
+    dsd = synth.dac_decoder_state_dict(0, "reference")
+    est = CausalConditionalDecoder()
+    est.load_state_dict(esd)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    dac = DACVAEDecoder()
+    dac.load_state_dict(dsd)
+    return esd, dsd, cfm, dac
+
+
+def _single(cfm, mu, mask, spks, cond, b, n, steps):
+    y, _ = cfm(mu=mu[b:b + 1, :, :n].to(DEV), mask=mask[b:b + 1, :, :n].to(DEV), n_timesteps=steps,
+               spks=spks[b:b + 1].to(DEV), cond=cond[b:b + 1, :, :n].to(DEV))
+    return y[0].cpu()
+
+
+def test_config1_batch16_10s_10steps(models):
+    esd, dsd, cfm, dac = models
+    T = 500
+    mu, mask, spks, cond = synth.batch_inputs([T] * 16)
+    lat, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=10, spks=spks.to(DEV), cond=cond.to(DEV))
+    assert lat.shape == (16, 80, T) and lat.dtype == torch.float32 and bool(torch.isfinite(lat).all())
+    for b in (0, 9, 15):  # batch == per-utterance
+        e = O.rel_l2(lat[b].cpu(), _single(cfm, mu, mask, spks, cond, b, T, 10))
+        assert e < 1e-5, (b, e)
+    with torch.inference_mode():  # one utterance against the oracle, full length, all 10 steps
+        ref = O.cfm_forward(esd, synth.fixed_noise(), mu[3:4], mask[3:4], 10, 1.0, spks[3:4], cond[3:4])
+    e = O.rel_l2(lat[3:4].cpu(), ref)
+    print(f"config 1, utterance 3: latent rel-L2 {e:.3e}")
+    assert e < LATENT_TOL
+    wav = dac.decode(lat)
+    assert wav.shape == (16, 1, T * 480) and float(wav.abs().max()) <= 1.0
+    with torch.inference_mode():
+        wav_ref = O.dac_decode(dsd, ref)
+    s = O.snr_db(wav[3:4].cpu(), wav_ref)
+    print(f"config 1, utterance 3: end-to-end waveform SNR {s:.1f} dB")
+    assert s > SNR_MIN_DB
+
+
+def test_config2_dac_only_batch64_30s(models):
+    esd, dsd, cfm, dac = models
+    L = 1500
+    z = torch.cat([synth.dac_latents(100 + b, L) for b in range(64)], 0)
+    wav = dac.decode(z.to(DEV))
+    assert wav.shape == (64, 1, L * 480) and bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
+    for b in (0, 63):  # batch == per-utterance
+        one = dac.decode(z[b:b + 1].to(DEV))
+        assert O.snr_db(wav[b:b + 1].cpu(), one.cpu()) > 60.0
+    # truncation invariance + oracle on a crop: a latent frame reaches at most 15 frames ahead
+    crop, safe = 200, 180
+    with torch.inference_mode():
+        ref = O.dac_decode(dsd, z[7:8, :, :crop])
+    s = O.snr_db(wav[7:8, :, :safe * 480].cpu(), ref[:, :, :safe * 480])
+    print(f"config 2, utterance 7, first {safe} frames: SNR {s:.1f} dB")
+    assert s > SNR_MIN_DB
+
+
+def test_config3_32steps_30s_batch32(models):
+    esd, dsd, cfm, dac = models
+    T = 1500
+    mu, mask, spks, cond = synth.batch_inputs([T] * 32, first_index=300)
+    lat, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=32, spks=spks.to(DEV), cond=cond.to(DEV))
+    assert lat.shape == (32, 80, T) and bool(torch.isfinite(lat).all())
+    for b in (5, 31):
+        e = O.rel_l2(lat[b].cpu(), _single(cfm, mu, mask, spks, cond, b, T, 32))
+        assert e < 1e-5, (b, e)
+    # oracle at full length, 2 steps (the per-step arithmetic is the same for every step count)
+    y2 = _single(cfm, mu, mask, spks, cond, 2, T, 2)
+    with torch.inference_mode():
+        ref = O.cfm_forward(esd, synth.fixed_noise(), mu[2:3], mask[2:3], 2, 1.0, spks[2:3], cond[2:3])
+    e = O.rel_l2(y2[None], ref)
+    print(f"config 3 shape (T = 1500), 2 steps: latent rel-L2 {e:.3e}")
+    assert e < LATENT_TOL
+
+
+def test_config4_mixed_lengths_one_rank_share(models):
+    esd, dsd, cfm, dac = models
+    lengths_all = synth.mixed_lengths(256)
+    shard = shard_utterances(lengths_all, 8)[0]  # rank 0's utterances of the 8-GPU run
+    lengths = [lengths_all[i] for i in shard]
+    assert len(lengths) >= 16 and max(lengths) <= 1500 and min(lengths) >= 100
+    mu, mask, spks, cond = synth.batch_inputs(lengths, first_index=1000)
+    syn = Synthesizer(cfm, dac)
+    lat, _ = cfm(mu=mu.to(DEV), mask=mask.to(DEV), n_timesteps=10, spks=spks.to(DEV), cond=cond.to(DEV))
+    wav = syn(mu.to(DEV), mask.to(DEV), spks.to(DEV), cond.to(DEV), n_timesteps=10)
+    order = np.argsort(lengths)
+    for b in (int(order[0]), int(order[len(order) // 2]), int(order[-1])):
+        n = lengths[b]
+        one = _single(cfm, mu, mask, spks, cond, b, n, 10)
+        e = O.rel_l2(lat[b, :, :n].cpu(), one)
+        assert e < 1e-5, (b, n, e)
+        assert float(lat[b, :, n:].abs().max() if n < lat.shape[2] else 0.0) == 0.0  # padding stays zero
+        w1 = dac.decode(one[None].to(DEV))
+        assert O.snr_db(wav[b:b + 1, :, :n * 480].cpu(), w1.cpu()) > 60.0
+        assert float(wav[b, :, n * 480:].abs().max() if n * 480 < wav.shape[2] else 0.0) == 0.0
