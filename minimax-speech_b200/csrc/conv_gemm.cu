@@ -17,6 +17,10 @@
 //   warps 2-17 epilogue (512 threads): warp w owns TMEM lanes 32*(w%4).. (= 32 output rows) and every 4th
 //              16-column chunk; accumulators are pulled into registers in one burst and the TMEM stage is
 //              released immediately, LayerNorm statistics are combined across the 4 column groups through smem
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+
 #include "kernels.h"
 #include "profiler.h"
 #include "ptx.cuh"
@@ -41,7 +45,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 16;
 
 constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
-constexpr int kSmemBudget = 174 * 1024;             // for the operand rings
+constexpr int kSmemBudget = 157 * 1024;             // for the operand rings
 
 struct TileCoord {
   int b, mt, nt;
@@ -156,7 +160,8 @@ __device__ __forceinline__ void row_stats(const float (&v)[4][16], float2* red, 
 // their owner threads, global memory is accessed with consecutive lanes on consecutive 16 B pieces of a row
 // (fp32: 8 rows x 64 B per instruction, bf16: 16 rows x 32 B), i.e. whole 32 B sectors only.
 // 16 B units are XOR-swizzled so that both access patterns are bank-conflict free.
-constexpr int kStageBytesPerWarp = 2048;
+constexpr int kStageBytesPerWarp = 3072;  // [0,2048): fp32 chunk / residual transposes, [2048,3072): bf16 chunk
+constexpr int kStageB16Off = 2048;
 __device__ __forceinline__ int stg_f32(int row, int unit) { return row * 64 + ((unit ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ int stg_b16(int row, int unit) { return row * 32 + ((unit ^ ((row >> 2) & 1)) << 4); }
 
@@ -281,6 +286,45 @@ __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRo
   __syncwarp();
 }
 
+// Dense outputs ([B][M][N], whole rows stored) leave through TMA instead: the staging layouts above ARE TMA's 64 B
+// (fp32) / 32 B (bf16) swizzle patterns, so the warp writes its 32 rows x 16 columns once and one lane hands the
+// buffer to cp.async.bulk.tensor (box 16 x 32; rows past M are clipped by the tensor map).  Rows past the valid
+// length are written as zeros.  Before a staging region is rewritten, the bulk group that last read it must be done:
+// kPending = how many younger groups of this lane may still be in flight at that point.
+template <bool kF32, int kPending>
+__device__ __forceinline__ void store_chunk_tma(uint8_t* stg, int lane, const CUtensorMap* map, int n, int t_base, int b,
+                                                bool row_valid, const float (&v)[16]) {
+  if (lane == 0) bulk_wait_read<kPending>();
+  __syncwarp();
+  if (kF32) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<float4*>(stg + stg_f32(lane, u)) =
+          row_valid ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    uint8_t* sb = stg + kStageB16Off;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      *reinterpret_cast<uint4*>(sb + stg_b16(lane, u)) =
+          row_valid ? make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]))
+                    : make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(map, kF32 ? stg : stg + kStageB16Off, n, t_base, b);
+    bulk_commit();
+  }
+}
+
+template <bool kF32>
+__device__ __forceinline__ void store_chunk_tma_p(bool one_pending, uint8_t* stg, int lane, const CUtensorMap* map, int n,
+                                                  int t_base, int b, bool row_valid, const float (&v)[16]) {
+  if (one_pending) store_chunk_tma<kF32, 1>(stg, lane, map, n, t_base, b, row_valid, v);
+  else store_chunk_tma<kF32, 0>(stg, lane, map, n, t_base, b, row_valid, v);
+}
+
 // The epilogue mode (activation, outputs, residual, time embedding) is a template parameter for the combinations the
 // engines launch (-1 = decided at run time: the generic instance, used by everything else).  A specialised instance
 // carries a fraction of the generic epilogue's code: the unrolled epilogue is executed once per tile, so its
@@ -288,7 +332,8 @@ __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRo
 template <int kAct, int kOut0, int kOut1, int kAdd, int kTemb>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvGemmParams p,
+                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut0,
+                 const __grid_constant__ CUtensorMap mapOut1, const __grid_constant__ ConvGemmParams p,
                  const int tmem_cols, const int acc_stride) {
   const int act = kAct >= 0 ? kAct : p.act;
   const int out0_dtype = kOut0 >= 0 ? kOut0 : p.out0_dtype;
@@ -312,7 +357,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tfull = bars + 4 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float2* red_base = reinterpret_cast<float2*>(bars + 4 * kMaxStages + 8);  // after the barriers + TMEM slot
+  float2* red_base = reinterpret_cast<float2*>(bars + 128);  // 1 KB for the barriers + TMEM slot (keeps the staging
+                                                             // buffers below aligned for TMA)
   uint8_t* stg_base = reinterpret_cast<uint8_t*>(red_base) + kRedBytes;  // per-epilogue-warp transpose buffers
   float* svec = reinterpret_cast<float*>(stg_base + kEpiWarps * kStageBytesPerWarp);  // per-channel epilogue vectors
 
@@ -333,6 +379,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapA1);
     prefetch_tmap(&mapW);
+    if (p.tma_out) {
+      prefetch_tmap(&mapOut0);
+      prefetch_tmap(&mapOut1);
+    }
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
@@ -528,6 +578,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       WarpRows wr;
       wr.t_base = (long long)tc.mt * kBlockM + q * 32;
       wr.out_ld = p.out_ld, wr.out_shift = p.out_shift, wr.valid = st.valid, wr.alloc = st.alloc, wr.M = p.M;
+      // TMA-store mode: this thread's row is stored with values iff it lies inside the valid length (else zeros)
+      const bool tma_out = p.tma_out != 0;
+      const bool row_valid = st.row_in && row_flat + p.N <= st.valid;
+      const int tma_t = tc.mt * kBlockM + q * 32;  // first row of this warp
+      // fp32 out0 and a bf16 out1 alternate between two staging regions: one younger bulk group may be in flight
+      const bool one_pending = out0_dtype == OUT_F32 && (out1_mode == OUT1_COPY || out1_mode == OUT1_SNAKE);
       // residual chunks of this tile: the first of this warp's chunks is fetched now (see fetch_chunk); the
       // next tile's residual rows are pulled into L2 so that its fetches do not wait for HBM
       constexpr int kPre = 1;  // (2 spills in the 96-register epilogue; later chunks hit L2 thanks to the prefetch below)
@@ -668,6 +724,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // memory for every instance that contains it
         const bool partial = (kAct == ACT_LRELU_TANH || kAct < 0) && n + 16 > p.n_store;
         if (add_dtype != OUT_NONE && !partial) {
+          if (tma_out && out0_dtype == OUT_F32) {  // the transposes below reuse the fp32 staging region
+            if (lane == 0) {
+              if (one_pending) bulk_wait_read<1>();
+              else bulk_wait_read<0>();
+            }
+            __syncwarp();
+          }
           const int k = (c - g) >> 2;
           if (pre_ok && k < kPre) {
             if (add_dtype == OUT_F32) apply_chunk<true>(stg, lane, pre0, x);
@@ -689,10 +752,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
           }
         } else {
-          if (out0_dtype == OUT_F32) store_chunk<true>(stg, lane, wr, n, out0f, x);
-          else if (out0_dtype == OUT_BF16) store_chunk<false>(stg, lane, wr, n, out0h, x);
+          if (tma_out) {
+            if (out0_dtype == OUT_F32) store_chunk_tma_p<true>(one_pending, stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
+            else if (out0_dtype == OUT_BF16) store_chunk_tma<false, 0>(stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
+          } else {
+            if (out0_dtype == OUT_F32) store_chunk<true>(stg, lane, wr, n, out0f, x);
+            else if (out0_dtype == OUT_BF16) store_chunk<false>(stg, lane, wr, n, out0h, x);
+          }
           if (out1_mode == OUT1_COPY) {
-            store_chunk<false>(stg, lane, wr, n, out1, x);
+            if (tma_out) store_chunk_tma_p<false>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
+            else store_chunk<false>(stg, lane, wr, n, out1, x);
           } else if (out1_mode == OUT1_SNAKE) {
             const int ch0 = n % p.chan_mod;
 #pragma unroll
@@ -704,7 +773,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               x[4 * g4 + 2] = snake_f(x[4 * g4 + 2], al.z, ia.z);
               x[4 * g4 + 3] = snake_f(x[4 * g4 + 3], al.w, ia.w);
             }
-            store_chunk<false>(stg, lane, wr, n, out1, x);
+            if (tma_out) store_chunk_tma_p<false>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
+            else store_chunk<false>(stg, lane, wr, n, out1, x);
           } else if (out1_mode == OUT1_LN) {
             s2.add16(x);
             tmem_st16(taddr + (uint32_t)(c * 16), reinterpret_cast<const uint32_t(&)[16]>(x));
@@ -730,7 +800,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             x[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean2) * rstd2, ga.z, be.z);
             x[4 * g4 + 3] = fmaf((x[4 * g4 + 3] - mean2) * rstd2, ga.w, be.w);
           }
-          store_chunk<false>(stg, lane, wr, n0 + c * 16, out1, x);
+          if (tma_out) store_chunk_tma<false, 0>(stg, lane, &mapOut1, n0 + c * 16, tma_t, tc.b, row_valid, x);
+          else store_chunk<false>(stg, lane, wr, n0 + c * 16, out1, x);
         }
       }
       // every TMEM access of this tile is done: hand the accumulator stage back to the MMA warp
@@ -741,6 +812,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_out && lane == 0) bulk_wait<0>();  // every bulk store of this lane has been written
   }
 
   if (threadIdx.x == kFirstEpiWarp * 32) TL(43);
@@ -762,7 +834,8 @@ int pow2_at_least(int x, int lo) {
 
 template <int kAct, int kOut0, int kOut1, int kAdd, int kTemb>
 cudaError_t launch_instance(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
-                            const CUtensorMap& mapW, const ConvGemmParams& pp, int tmem_cols, int acc_stride) {
+                            const CUtensorMap& mapW, const CUtensorMap& mapO0, const CUtensorMap& mapO1,
+                            const ConvGemmParams& pp, int tmem_cols, int acc_stride) {
   auto* kernel = conv_gemm_kernel<kAct, kOut0, kOut1, kAdd, kTemb>;
   static bool attr_done = false;  // one flag per instance
   if (!attr_done) {
@@ -770,7 +843,8 @@ cudaError_t launch_instance(int grid, size_t smem, cudaStream_t stream, const CU
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  return launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, 1, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
+  return launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, 1, mapA0, mapA1, mapW, mapO0, mapO1, pp, tmem_cols,
+                    acc_stride);
 }
 
 }  // namespace
@@ -823,7 +897,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   if (pp.a_stages < 1 || pp.b_stages < 2 || pp.b_stages < kWeightProducers) return cudaErrorInvalidValue;
   const int acc_stride = pow2_at_least(p.block_n, 32);
   const int tmem_cols = 2 * acc_stride;
-  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + (4 * kMaxStages + 8) * 8 + kRedBytes +
+  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + 1024 + kRedBytes +
                 kEpiWarps * kStageBytesPerWarp + (size_t)pp.sv_floats * 4;
   // tmem_cols == 512 must never share an SM with a second CTA of this kernel (alloc would spin):
   if (tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;
@@ -839,11 +913,36 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
                  rows * kt * 2.0 + (double)p.taps * p.N * kt * 2.0 + rows * (p.n_store < p.N ? p.n_store : p.N) * out_b);
   count_launch();
+  // dense outputs go out through TMA stores (see store_chunk_tma); tensor maps cached per (buffer, shape)
+  static thread_local std::unordered_map<std::string, CUtensorMap> out_maps;
+  auto out_map = [&](const void* base, int elem_bytes) -> const CUtensorMap* {
+    char key[96];
+    snprintf(key, sizeof key, "%p/%d/%d/%d/%d", base, elem_bytes, p.N, p.M, p.B);
+    auto it = out_maps.find(key);
+    if (it == out_maps.end()) {
+      CUtensorMap m;
+      if (!make_out_map(&m, base, elem_bytes, p.N, p.M, p.B)) return nullptr;
+      if (out_maps.size() > 4096) out_maps.clear();
+      it = out_maps.emplace(key, m).first;
+    }
+    return &it->second;
+  };
+  const bool dense = p.out_ld == p.N && p.out_shift == 0 && p.n_store == p.N && p.out_bstride == (long long)p.M * p.N &&
+                     p.out_alloc == (long long)p.M * p.N && (p.out_valid_mul % p.N) == 0 && p.N % 16 == 0 &&
+                     (p.out0_dtype != OUT_NONE || p.out1_mode != OUT1_NONE) && conv_tma_out_enabled();
+  const CUtensorMap* mo0 = &mapW;  // placeholders when unused
+  const CUtensorMap* mo1 = &mapW;
+  pp.tma_out = 0;
+  if (dense) {
+    const CUtensorMap* a = p.out0_dtype != OUT_NONE ? out_map(p.out0, p.out0_dtype == OUT_F32 ? 4 : 2) : &mapW;
+    const CUtensorMap* b = p.out1_mode != OUT1_NONE ? out_map(p.out1, 2) : &mapW;
+    if (a && b) mo0 = a, mo1 = b, pp.tma_out = 1;
+  }
   const int add = p.addend ? p.addend_dtype : OUT_NONE;
   const int temb = p.temb ? 1 : 0;
 #define LS_CONV_CASE(A, O0, O1, AD, TE)                                                                          \
   if (p.act == (A) && p.out0_dtype == (O0) && p.out1_mode == (O1) && add == (AD) && temb == (TE))               \
-    return launch_instance<A, O0, O1, AD, TE>(grid, smem, stream, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
+    return launch_instance<A, O0, O1, AD, TE>(grid, smem, stream, mapA0, mapA1, mapW, *mo0, *mo1, pp, tmem_cols, acc_stride);
   // flow estimator: resnet conv1 | res_conv, final_proj | resnet conv2 | QKV, down / up conv | final block
   LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 1)
   LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_NONE, OUT_NONE, 0)
@@ -859,7 +958,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_F32, 0)
   LS_CONV_CASE(ACT_LRELU_TANH, OUT_F32, OUT1_NONE, OUT_NONE, 0)
 #undef LS_CONV_CASE
-  return launch_instance<-1, -1, -1, -1, -1>(grid, smem, stream, mapA0, mapA1, mapW, pp, tmem_cols, acc_stride);
+  return launch_instance<-1, -1, -1, -1, -1>(grid, smem, stream, mapA0, mapA1, mapW, *mo0, *mo1, pp, tmem_cols, acc_stride);
 }
 
 }  // namespace ls

@@ -19,7 +19,8 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 bool pdl_enabled();
 bool conv_halo_enabled();
 int conv_halo_mode();
-bool conv_resident_enabled();  // LS_CONV_RESIDENT=0: always stream the weights through the ring (development aid)  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
+bool conv_resident_enabled();
+bool conv_tma_out_enabled();   // LS_CONV_TMA_OUT=0: epilogue stores through the LSU (development aid)  // LS_CONV_RESIDENT=0: always stream the weights through the ring (development aid)  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               int cluster, Args&&... args) {
@@ -92,6 +93,7 @@ struct ConvGemmParams {
   // b_resident: the whole weight tensor of the launch fits in the B ring (b_stages == taps*kb_per_tap, one N tile):
   // it is fetched once per CTA and stays in shared memory for every tile.
   int b_resident;
+  int tma_out;  // dense [B][M][N] outputs are stored with cp.async.bulk.tensor (filled in by launch_conv_gemm)
   // per-channel epilogue vectors staged in shared memory (float offsets into the vector area, -1 = read from global)
   int sv_bias, sv_p1a, sv_p1b, sv_lng, sv_lnb, sv_floats;
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps of the first tile, or nullptr
@@ -189,6 +191,8 @@ cudaError_t launch_time_embed(const TimeEmbedParams& p, cudaStream_t s);
 // bf16 weights [rows][K] viewed as [64][rows][K/64]: one box = box_rows rows x box_kb 64-wide K blocks, landing in
 // shared memory as box_kb consecutive 128B-swizzled tiles of box_rows rows
 bool make_weight_map_kb(CUtensorMap* map, const void* base, int K, int rows, int box_rows, int box_kb);
+// output tensor [B][M][N] (fp32 or bf16) for the conv epilogue's TMA stores: box 16 columns x 32 rows, 64 B / 32 B swizzle
+bool make_out_map(CUtensorMap* map, const void* base, int elem_bytes, int N, int M, int B);
 bool make_act_map(CUtensorMap* map, const void* base, int C, int T, int B, long long row_stride_elems,
                   long long batch_stride_elems, int box_rows);
 // bf16 weight matrix [rows][K] with 64 x box_rows boxes

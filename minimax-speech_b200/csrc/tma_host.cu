@@ -62,6 +62,19 @@ bool make_weight_map_kb(CUtensorMap* map, const void* base, int K, int rows, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_out_map(CUtensorMap* map, const void* base, int elem_bytes, int N, int M, int B) {
+  EncodeFn enc = get_encode();
+  if (!enc || (elem_bytes != 2 && elem_bytes != 4) || N % 16) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)N * elem_bytes, (cuuint64_t)M * N * elem_bytes};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+             const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_tile_map(CUtensorMap* map, const void* base, int elem_bytes, long long cols, long long rows, int box_rows) {
   EncodeFn enc = get_encode();
   if (!enc || (elem_bytes != 2 && elem_bytes != 4)) return false;
