@@ -19,7 +19,8 @@ def run(name, fn):
     rel = lambda i: int(r[i]) - base if int(r[i]) else None
     print(f"=== {name}: {us:.0f} us\n  producer tile starts {[rel(56+i) for i in range(8)]}\n  MMA tile commits     {[rel(24+i) for i in range(8)]}\n  epilogue tile done   {[rel(48+i) for i in range(8)]}\n  MMA saw B box of k-iter 0..15 at {[rel(8+i) for i in range(16)]} setup {rel(1)} pdl {rel(2)}")
 g = torch.Generator(device="cpu").manual_seed(0)
-B, L, C = 16, 120000, 96   # 10 s at 12 kHz
+C = int(os.environ.get('LS_C', '96'))
+B, L = 16, 120000 * 96 // C   # 10 s at 12 kHz (C = 96) / 24 kHz (C = 48)
 a = tk.bf16(torch.randn(B, L, C, generator=g)).to(DEV)
 w7 = tk.bf16(torch.randn(7, C, C, generator=g) / math.sqrt(7 * C)).to(DEV)
 w1 = tk.bf16(torch.randn(1, C, C, generator=g) / math.sqrt(C)).to(DEV)
@@ -28,5 +29,5 @@ al = (0.5 + torch.rand(C, generator=g)).to(DEV); ia = (1.0 / (al + 1e-9))
 out1 = torch.zeros(B, L, C, device=DEV, dtype=torch.bfloat16)
 x = torch.randn(B, L, C, device=DEV)
 for dil in (1, 9):
-    run(f"conv7 dil {dil} (C=96): lrelu + snake bf16 out", lambda: tk.conv_gemm(a, w7, dil=dil, pad=3 * dil, bias=bias, act=native.ACT_LRELU, out1=out1, out1_mode=native.OUT1_SNAKE, p1=(al, ia)))
-run("conv1 (C=96): lrelu + x residual f32 in/out + snake bf16 out", lambda: tk.conv_gemm(a, w1, bias=bias, act=native.ACT_LRELU, addend=x, out0=x, out1=out1, out1_mode=native.OUT1_SNAKE, p1=(al, ia)))
+    run(f"conv7 dil {dil} : lrelu + snake bf16 out", lambda: tk.conv_gemm(a, w7, dil=dil, pad=3 * dil, bias=bias, act=native.ACT_LRELU, out1=out1, out1_mode=native.OUT1_SNAKE, p1=(al, ia)))
+run("conv1 : lrelu + x residual f32 in/out + snake bf16 out", lambda: tk.conv_gemm(a, w1, bias=bias, act=native.ACT_LRELU, addend=x, out0=x, out1=out1, out1_mode=native.OUT1_SNAKE, p1=(al, ia)))
