@@ -56,6 +56,9 @@ int32_t ls_device_check(int32_t device, int32_t* sm_count, int32_t* cc_major, in
 
 /* ---- flow: CausalConditionalDecoder estimator + Euler/CFG solve ---- */
 int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);
+/* fp32 mode (north_star: latents within 1e-4 of the fp32 reference): the same handle type and calls, computed end to
+ * end in fp32 on the CUDA cores with unfused kernels.  A validation mode, one to two orders of magnitude slower. */
+int32_t ls_flow_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);
 void ls_flow_destroy(ls_flow* h);
 
 /* One estimator evaluation.  rows = batch rows as the reference passes them (2 for CFG at B=1).
@@ -75,6 +78,7 @@ int32_t ls_flow_solve(ls_flow* h, const float* mu, const float* mask, const floa
 
 /* ---- DAC-VAE decoder ---- */
 int32_t ls_dac_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_dac** out);
+int32_t ls_dac_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_dac** out);
 void ls_dac_destroy(ls_dac* h);
 int32_t ls_dac_hop_length(const ls_dac* h);
 /* z [B,80,L] -> wav [B,1,L*hop].  lengths (DEVICE int32 [B], may be NULL): valid latent frames per item;

@@ -5,6 +5,7 @@
 
 #include "dac_engine.h"
 #include "engine_common.h"
+#include "f32_path.h"
 #include "flow_engine.h"
 #include "profiler.h"
 
@@ -74,13 +75,32 @@ static int32_t guarded(F&& f) {
 }  // namespace ls
 
 struct ls_flow {
-  std::unique_ptr<ls::FlowEngine> eng;
+  std::unique_ptr<ls::FlowEngine> eng;        // bf16 tensor-core path (default)
+  std::unique_ptr<ls::FlowEngineF32> eng32;   // fp32 mode (ls_flow_create_fp32)
+  int feat() const { return eng ? eng->feat() : eng32->feat(); }
+  int device() const { return eng ? eng->device() : eng32->device(); }
+  template <typename... A>
+  void solve(A&&... a) {
+    if (eng) eng->solve(std::forward<A>(a)...);
+    else eng32->solve(std::forward<A>(a)...);
+  }
+  template <typename... A>
+  void estimator_forward(A&&... a) {
+    if (eng) eng->estimator_forward(std::forward<A>(a)...);
+    else eng32->estimator_forward(std::forward<A>(a)...);
+  }
   // staging for ls_synthesize_host
   float* stage = nullptr;
   size_t stage_bytes = 0;
 };
 struct ls_dac {
   std::unique_ptr<ls::DacEngine> eng;
+  std::unique_ptr<ls::DacEngineF32> eng32;
+  int hop() const { return eng ? eng->hop() : eng32->hop(); }
+  void decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s) {
+    if (eng) eng->decode(z, lengths, wav, B, L, s);
+    else eng32->decode(z, lengths, wav, B, L, s);
+  }
 };
 
 extern "C" {
@@ -109,6 +129,15 @@ int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t devi
     *out = h.release();
   });
 }
+int32_t ls_flow_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_flow_create_fp32: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_flow>();
+    h->eng32 = std::make_unique<ls::FlowEngineF32>(w, device);
+    *out = h.release();
+  });
+}
 void ls_flow_destroy(ls_flow* h) {
   if (!h) return;
   if (h->stage) cudaFree(h->stage);
@@ -120,7 +149,7 @@ int32_t ls_flow_estimator_forward(ls_flow* h, const float* x, const float* mask,
                                   int32_t streaming, void* stream) {
   return ls::guarded([&] {
     ls::require(h && x && mask && mu && t && spks && cond && out, "ls_flow_estimator_forward: null argument");
-    h->eng->estimator_forward(x, mask, mu, t, spks, cond, out, rows, T, streaming != 0, (cudaStream_t)stream);
+    h->estimator_forward(x, mask, mu, t, spks, cond, out, rows, T, streaming != 0, (cudaStream_t)stream);
   });
 }
 
@@ -130,8 +159,8 @@ int32_t ls_flow_solve(ls_flow* h, const float* mu, const float* mask, const floa
                       void* stream) {
   return ls::guarded([&] {
     ls::require(h && mu && mask && spks && cond && noise && t_span_host && out, "ls_flow_solve: null argument");
-    h->eng->solve(mu, mask, spks, cond, noise, noise_stride, t_span_host, n_timesteps, temperature, cfg_rate,
-                  streaming != 0, out, B, T, (cudaStream_t)stream);
+    h->solve(mu, mask, spks, cond, noise, noise_stride, t_span_host, n_timesteps, temperature, cfg_rate, streaming != 0,
+             out, B, T, (cudaStream_t)stream);
   });
 }
 
@@ -144,14 +173,23 @@ int32_t ls_dac_create(const ls_tensor* weights, int32_t n_weights, int32_t devic
     *out = h.release();
   });
 }
+int32_t ls_dac_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_dac** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_dac_create_fp32: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_dac>();
+    h->eng32 = std::make_unique<ls::DacEngineF32>(w, device);
+    *out = h.release();
+  });
+}
 void ls_dac_destroy(ls_dac* h) { delete h; }
-int32_t ls_dac_hop_length(const ls_dac* h) { return h ? h->eng->hop() : 0; }
+int32_t ls_dac_hop_length(const ls_dac* h) { return h ? h->hop() : 0; }
 
 int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* wav, int32_t B, int32_t L,
                       void* stream) {
   return ls::guarded([&] {
     ls::require(h && z && wav, "ls_dac_decode: null argument");
-    h->eng->decode(z, lengths, wav, B, L, (cudaStream_t)stream);
+    h->decode(z, lengths, wav, B, L, (cudaStream_t)stream);
   });
 }
 
@@ -164,13 +202,13 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
                 "ls_synthesize_host: null argument");
     ls::require(B > 0 && T > 0, "B and T must be positive");
     cudaStream_t s = (cudaStream_t)stream;
-    const int F = flow->eng->feat();
-    const int hop = dac->eng->hop();
+    const int F = flow->feat();
+    const int hop = dac->hop();
     const size_t n_mu = (size_t)B * F * T, n_mask = (size_t)B * T, n_spk = (size_t)B * F;
     const size_t n_wav = (size_t)B * T * hop;
     // staging layout: mu | cond | latent | mask | spks | lengths(int) | wav
     const size_t need = (3 * n_mu + n_mask + n_spk + (size_t)B + n_wav) * sizeof(float) + 7 * 256;
-    LS_CUDA(cudaSetDevice(flow->eng->device()));
+    LS_CUDA(cudaSetDevice(flow->device()));
     if (need > flow->stage_bytes) {
       LS_CUDA(cudaStreamSynchronize(s));
       if (flow->stage) cudaFree(flow->stage);
@@ -190,10 +228,10 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
     LS_CUDA(cudaMemcpyAsync(d_cond, cond_host, n_mu * 4, cudaMemcpyHostToDevice, s));
     LS_CUDA(cudaMemcpyAsync(d_mask, mask_host, n_mask * 4, cudaMemcpyHostToDevice, s));
     LS_CUDA(cudaMemcpyAsync(d_spk, spks_host, n_spk * 4, cudaMemcpyHostToDevice, s));
-    flow->eng->solve(d_mu, d_mask, d_spk, d_cond, noise_dev, noise_stride, t_span_host, n_timesteps, temperature,
-                     cfg_rate, false, d_lat, B, T, s);
+    flow->solve(d_mu, d_mask, d_spk, d_cond, noise_dev, noise_stride, t_span_host, n_timesteps, temperature, cfg_rate, false,
+                d_lat, B, T, s);
     LS_CUDA(ls::launch_mask_to_lengths(d_mask, d_len, B, T, 1, s));
-    dac->eng->decode(d_lat, d_len, d_wav, B, T, s);
+    dac->decode(d_lat, d_len, d_wav, B, T, s);
     LS_CUDA(cudaMemcpyAsync(wav_host, d_wav, n_wav * 4, cudaMemcpyDeviceToHost, s));
     LS_CUDA(cudaStreamSynchronize(s));
   });

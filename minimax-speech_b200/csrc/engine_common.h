@@ -44,6 +44,7 @@ class Weights {
     if (it == map_.end()) throw EngineError(LS_ERR_WEIGHTS, "missing weight '" + name + "'");
     return *it->second;
   }
+  const std::map<std::string, const ls_tensor*>& all() const { return map_; }
   const ls_tensor& get(const std::string& name, std::initializer_list<long long> shape) const {
     const ls_tensor& t = get(name);
     bool ok = t.ndim == (int)shape.size();

@@ -1,0 +1,616 @@
+// fp32 mode of the hot path: see f32_path.h.  Plain CUDA-core kernels in the reference's NCT layout, one per
+// reference op, no fusion, accurate libm (no fast-math intrinsics).  Reference lines next to each kernel.
+#include <cmath>
+
+#include "f32_path.h"
+
+namespace ls {
+namespace {
+
+constexpr int kTB = 128;  // threads per block: one thread per time step
+constexpr int kNB = 4;    // output channels per thread
+
+inline dim3 grid_t(int T, int n, int B) { return dim3((unsigned)((T + kTB - 1) / kTB), (unsigned)n, (unsigned)B); }
+#define F32_LAUNCH(kernel, grid, block, stream, ...)   \
+  do {                                                 \
+    count_launch();                                    \
+    kernel<<<grid, block, 0, stream>>>(__VA_ARGS__);   \
+    LS_CUDA(cudaGetLastError());                       \
+  } while (0)
+
+// out[b,n,t] = act(bias[n] + sum_c sum_k in[b,c,t + k*dil - pad] * m_in[b,t'] * w[n,c,k]) * m_out[b,t]
+// Conv1d / CausalConv1d (pad = K-1, flow/decoder.py:36-62) / 1x1 / Linear over channels; x*mask fused on the input
+// (decoder.py:68, matcha decoder.py:60) and on the output (decoder.py:496).  lrelu < 0: no activation.
+__global__ void __launch_bounds__(kTB) conv1d_nct_kernel(const float* __restrict__ in, const float* __restrict__ m_in,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ out, const float* __restrict__ m_out, int Cin,
+                                                         int T, int N, int K, int dil, int pad, float lrelu) {
+  const int t = blockIdx.x * kTB + threadIdx.x;
+  const int n0 = blockIdx.y * kNB;
+  const int b = blockIdx.z;
+  if (t >= T) return;
+  float acc[kNB];
+#pragma unroll
+  for (int j = 0; j < kNB; ++j) acc[j] = (bias && n0 + j < N) ? bias[n0 + j] : 0.f;
+  const float* inb = in + (size_t)b * Cin * T;
+  const float* mb = m_in ? m_in + (size_t)b * T : nullptr;
+  for (int k = 0; k < K; ++k) {
+    const int tt = t + k * dil - pad;
+    if (tt < 0 || tt >= T) continue;
+    const float mv = mb ? mb[tt] : 1.f;
+    for (int c = 0; c < Cin; ++c) {
+      const float v = inb[(size_t)c * T + tt] * mv;
+#pragma unroll
+      for (int j = 0; j < kNB; ++j)
+        if (n0 + j < N) acc[j] = fmaf(v, w[((size_t)(n0 + j) * Cin + c) * K + k], acc[j]);
+    }
+  }
+  const float mo = m_out ? m_out[(size_t)b * T + t] : 1.f;
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+    if (n0 + j < N) {
+      float y = acc[j];
+      if (lrelu >= 0.f) y = y > 0.f ? y : lrelu * y;
+      out[((size_t)b * N + n0 + j) * T + t] = y * mo;
+    }
+}
+
+// ConvTranspose1d (dac-vae/model.py:255-262): out[b,n,t] = bias[n] + sum_c sum_{k: (t+pad-k) % s == 0} in[b,c,(t+pad-k)/s] w[c,n,k]
+__global__ void __launch_bounds__(kTB) convt1d_nct_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int Cin,
+                                                          int Lin, int N, int K, int stride, int pad, int Lout) {
+  const int t = blockIdx.x * kTB + threadIdx.x;
+  const int n0 = blockIdx.y * kNB;
+  const int b = blockIdx.z;
+  if (t >= Lout) return;
+  float acc[kNB];
+#pragma unroll
+  for (int j = 0; j < kNB; ++j) acc[j] = n0 + j < N ? bias[n0 + j] : 0.f;
+  const float* inb = in + (size_t)b * Cin * Lin;
+  for (int k = (t + pad) % stride; k < K; k += stride) {
+    const int i = (t + pad - k) / stride;
+    if (t + pad - k < 0 || i >= Lin) continue;
+    for (int c = 0; c < Cin; ++c) {
+      const float v = inb[(size_t)c * Lin + i];
+#pragma unroll
+      for (int j = 0; j < kNB; ++j)
+        if (n0 + j < N) acc[j] = fmaf(v, w[((size_t)c * N + n0 + j) * K + k], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+    if (n0 + j < N) out[((size_t)b * N + n0 + j) * Lout + t] = acc[j];
+}
+
+__device__ __forceinline__ float mish_exact(float x) {  // F.mish: x * tanh(softplus(x)), softplus threshold 20
+  const float sp = x > 20.f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+
+// LayerNorm over the channel dim of [B,C,T] per (b,t), eps 1e-5 (decoder.py:70-76 via two transposes;
+// transformer.py:243,303), then optionally Mish, * mask, + vec[b,c] (the time-embedding add, matcha decoder.py:58)
+__global__ void __launch_bounds__(kTB) layernorm_nct_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                            const float* __restrict__ be, float* __restrict__ y, int C,
+                                                            int T, int do_mish, const float* __restrict__ mask,
+                                                            const float* __restrict__ vec) {
+  const int t = blockIdx.x * kTB + threadIdx.x;
+  const int b = blockIdx.z;
+  if (t >= T) return;
+  const float* xb = x + (size_t)b * C * T + t;
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) mean += xb[(size_t)c * T];
+  mean /= (float)C;
+  float var = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = xb[(size_t)c * T] - mean;
+    var = fmaf(d, d, var);
+  }
+  const float rstd = 1.0f / sqrtf(var / (float)C + 1e-5f);
+  const float mv = mask ? mask[(size_t)b * T + t] : 1.f;
+  float* yb = y + (size_t)b * C * T + t;
+  for (int c = 0; c < C; ++c) {
+    float v = (xb[(size_t)c * T] - mean) * rstd * g[c] + be[c];
+    if (do_mish) v = mish_exact(v);
+    v *= mv;
+    if (vec) v += vec[(size_t)b * C + c];
+    yb[(size_t)c * T] = v;
+  }
+}
+
+// diffusers Attention / AttnProcessor2_0 on q,k,v [R,H*64,T] with the additive mask of mask.py:161-236 +
+// common.py:160-168: key j visible iff j < len[r] (and, streaming, j < (i/chunk+1)*chunk); a query row with no
+// visible key sees every key (mask.py:233-235).  One thread per (r, h, query).
+__global__ void __launch_bounds__(kTB) attention_nct_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ v, float* __restrict__ o,
+                                                            const int* __restrict__ lens, int H, int T, int chunk,
+                                                            float scale) {
+  const int i = blockIdx.x * kTB + threadIdx.x;
+  const int h = blockIdx.y, r = blockIdx.z;
+  if (i >= T) return;
+  const size_t base = ((size_t)r * H + h) * 64 * T;
+  int limit = lens[r];
+  if (chunk > 0) limit = min(limit, (i / chunk + 1) * chunk);
+  if (limit <= 0) limit = T;
+  float qr[64], acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) qr[d] = q[base + (size_t)d * T + i], acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < limit; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s = fmaf(qr[d], k[base + (size_t)d * T + j], s);
+    s *= scale;
+    const float m_new = fmaxf(m, s);
+    const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
+    const float p = expf(s - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = fmaf(p, v[base + (size_t)d * T + j], acc[d] * corr);
+    m = m_new;
+  }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[base + (size_t)d * T + i] = acc[d] * inv;
+}
+
+enum { EW_ADD = 0, EW_GELU = 1, EW_TANH = 2 };
+__global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n, int op) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = a[i];
+  float r;
+  if (op == EW_ADD) r = x + b[i];
+  else if (op == EW_GELU) r = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // F.gelu(approximate="none")
+  else r = tanhf(x);
+  y[i] = r;
+}
+// snake(x) = x + (alpha + 1e-9)^-1 sin^2(alpha x), alpha per channel (dac-vae/layers.py:18-24)
+__global__ void snake_nct_kernel(const float* __restrict__ x, const float* __restrict__ alpha, float* __restrict__ y, int C,
+                                 int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = alpha[(i / T) % C];
+  const float sn = sinf(a * x[i]);
+  y[i] = x[i] + (1.0f / (a + 1e-9f)) * sn * sn;
+}
+// y[r,n] = act_out(bias[n] + sum_k act_in(x[r,k]) w[n,k]); act_in: 0 none, 1 Mish; act_out: 0 none, 1 SiLU
+__global__ void linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ y, int R, int K, int N, int act_in, int act_out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= N) return;
+  float acc = bias ? bias[n] : 0.f;
+  for (int k = 0; k < K; ++k) {
+    float v = x[(size_t)r * K + k];
+    if (act_in == 1) v = mish_exact(v);
+    acc = fmaf(v, w[(size_t)n * K + k], acc);
+  }
+  if (act_out == 1) acc = acc / (1.0f + expf(-acc));
+  y[(size_t)r * N + n] = acc;
+}
+// SinusoidalPosEmb (matcha decoder.py:14-29): [sin(1000 t f_i) | cos(1000 t f_i)], f_i = exp(-i ln(1e4)/(half-1))
+__global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ y, int R, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  const int half = dim / 2;
+  if (i >= half) return;
+  const float f = expf((float)i * -(logf(10000.0f) / (float)(half - 1)));
+  const float e = 1000.0f * t[r] * f;
+  y[(size_t)r * dim + i] = sinf(e);
+  y[(size_t)r * dim + half + i] = cosf(e);
+}
+// h0 = cat[x | mu | spks (broadcast over T) | cond] (flow/decoder.py:427-433)
+__global__ void build_input_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ spks,
+                                   const float* __restrict__ cond, float* __restrict__ h, int F, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  const int c = (int)((i / T) % (4 * F));
+  const size_t r = i / ((size_t)T * 4 * F);
+  const int part = c / F, cc = c % F;
+  const size_t src = (r * F + cc) * T + t;
+  h[i] = part == 0 ? x[src] : part == 1 ? mu[src] : part == 2 ? spks[r * F + cc] : cond[src];
+}
+__global__ void cat_channels_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int Ca,
+                                    int Cb, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  const int c = (int)((i / T) % (Ca + Cb));
+  const size_t r = i / ((size_t)T * (Ca + Cb));
+  y[i] = c < Ca ? a[(r * Ca + c) * T + t] : b[(r * Cb + c - Ca) * T + t];
+}
+__global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restrict__ lens, int T) {
+  const int r = blockIdx.x;
+  int n = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) n += mask[(size_t)r * T + t] != 0.f;
+  __shared__ int sh[32];
+  for (int o = 16; o; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) tot += sh[i];
+    lens[r] = tot;
+  }
+}
+// CFG batch of flow_matching.py:105-110 for B >= 1: rows [0,B) conditional, [B,2B) with mu = spks = cond = 0
+__global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ cond,
+                                const float* __restrict__ mask, float* __restrict__ x2, float* __restrict__ mu2,
+                                float* __restrict__ cond2, float* __restrict__ mask2, int F, int T, int B) {
+  const size_t n = (size_t)B * F * T;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    x2[i] = x[i], x2[n + i] = x[i];
+    mu2[i] = mu[i], mu2[n + i] = 0.f;
+    cond2[i] = cond[i], cond2[n + i] = 0.f;
+  }
+  const size_t nm = (size_t)B * T;
+  if (i < nm) mask2[i] = mask[i], mask2[nm + i] = mask[i];
+}
+__global__ void cfg_small_kernel(const float* __restrict__ spks, float* __restrict__ spks2, float* __restrict__ t2, float t,
+                                 int F, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * F) spks2[i] = spks[i], spks2[B * F + i] = 0.f;
+  if (i < 2 * B) t2[i] = t;
+}
+// x += dt * ((1 + w) v_c - w v_u)   (flow_matching.py:118-121)
+__global__ void euler_kernel(float* __restrict__ x, const float* __restrict__ v, float dt, float w, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vv = (1.0f + w) * v[i] - w * v[n + i];
+  x[i] = x[i] + dt * vv;
+}
+__global__ void init_noise_kernel(const float* __restrict__ noise, long long stride, float temperature, float* __restrict__ x,
+                                  int F, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  const int c = (int)((i / T) % F);
+  x[i] = noise[(size_t)c * stride + t] * temperature;
+}
+__global__ void mul_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y, int C, int T,
+                                size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = x[i] * mask[(i / ((size_t)C * T)) * T + i % T];
+}
+
+inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
+
+void conv1d(const float* in, const float* m_in, const float* w, const float* bias, float* out, const float* m_out, int B,
+            int Cin, int T, int N, int K, int dil, int pad, float lrelu, cudaStream_t s) {
+  F32_LAUNCH(conv1d_nct_kernel, grid_t(T, (N + kNB - 1) / kNB, B), kTB, s, in, m_in, w, bias, out, m_out, Cin, T, N, K, dil,
+             pad, lrelu);
+}
+void ew(const float* a, const float* b, float* y, size_t n, int op, cudaStream_t s) {
+  F32_LAUNCH(ew_kernel, blocks(n), 256, s, a, b, y, n, op);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- infrastructure
+F32Weights::~F32Weights() {
+  for (auto& kv : items_)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+}
+void F32Weights::add(const std::string& name, const float* host, size_t n, std::vector<long long> shape) {
+  Item it;
+  LS_CUDA(cudaMalloc(&it.dev, (n ? n : 1) * sizeof(float)));
+  LS_CUDA(cudaMemcpy(it.dev, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  it.shape = std::move(shape);
+  items_[name] = it;
+}
+const float* F32Weights::ptr(const std::string& name) const {
+  auto it = items_.find(name);
+  if (it == items_.end()) throw EngineError(LS_ERR_WEIGHTS, "missing weight '" + name + "'");
+  return it->second.dev;
+}
+const std::vector<long long>& F32Weights::shape(const std::string& name) const {
+  auto it = items_.find(name);
+  if (it == items_.end()) throw EngineError(LS_ERR_WEIGHTS, "missing weight '" + name + "'");
+  return it->second.shape;
+}
+F32Scratch::~F32Scratch() {
+  if (base_) cudaFree(base_);
+  for (float* p : retired_) cudaFree(p);
+}
+float* F32Scratch::get(size_t n, cudaStream_t) {
+  n = (n + 63) & ~size_t(63);
+  if (used_ + n > cap_) {
+    // grow: the old block stays alive (kernels already queued may still use pointers into it)
+    const size_t want = (used_ + n) * 2 + (size_t(1) << 20);
+    if (base_) retired_.push_back(base_);
+    LS_CUDA(cudaMalloc(&base_, want * sizeof(float)));
+    cap_ = want, used_ = 0;
+  }
+  float* p = base_ + used_;
+  used_ += n;
+  return p;
+}
+
+static void upload_all(const Weights& w, F32Weights* dst) {
+  for (const auto& kv : w.all()) {
+    const ls_tensor& t = *kv.second;
+    size_t n = 1;
+    std::vector<long long> shape;
+    for (int i = 0; i < t.ndim; ++i) n *= (size_t)t.shape[i], shape.push_back(t.shape[i]);
+    dst->add(kv.first, t.data, n, shape);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- flow (estimator + solve)
+FlowEngineF32::FlowEngineF32(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  upload_all(w, &w_);
+  while (w_.has("down_blocks.0.1." + std::to_string(n_blocks_) + ".norm1.weight")) ++n_blocks_;
+  while (w_.has("mid_blocks." + std::to_string(n_mid_) + ".0.mlp.1.weight")) ++n_mid_;
+  C_ = (int)w_.shape("final_proj.weight")[1];
+  feat_ = (int)w_.shape("final_proj.weight")[0];
+  require(n_blocks_ > 0 && (int)w_.shape("down_blocks.0.1.0.attn1.to_q.weight")[0] == heads_ * 64,
+          "fp32 estimator: expected 8 heads x 64", LS_ERR_UNSUPPORTED);
+}
+
+// CausalBlock1D (decoder.py:65-78): conv3 causal on x*mask -> LayerNorm(C) -> Mish -> *mask (-> + addvec)
+float* FlowEngineF32::causal_block(const std::string& p, const float* x, int cin, const float* mask, const float* addvec,
+                                   int R, int T, cudaStream_t s) {
+  float* c = scratch_.get((size_t)R * C_ * T, s);
+  conv1d(x, mask, w_.ptr(p + ".block.0.weight"), w_.ptr(p + ".block.0.bias"), c, nullptr, R, cin, T, C_, 3, 1, 2, -1.f, s);
+  float* y = scratch_.get((size_t)R * C_ * T, s);
+  F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, R), kTB, s, c, w_.ptr(p + ".block.2.weight"), w_.ptr(p + ".block.2.bias"), y,
+             C_, T, 1, mask, addvec);
+  return y;
+}
+
+// ResnetBlock1D.forward (matcha decoder.py:56-61) with causal blocks (flow/decoder.py:81-85)
+float* FlowEngineF32::resnet(const std::string& p, const float* x, int cin, const float* mask, const float* temb, int R,
+                             int T, cudaStream_t s) {
+  float* tvec = scratch_.get((size_t)R * C_, s);
+  F32_LAUNCH(linear_rows_kernel, dim3((C_ + 127) / 128, R), 128, s, temb, w_.ptr(p + ".mlp.1.weight"),
+             w_.ptr(p + ".mlp.1.bias"), tvec, R, (int)w_.shape(p + ".mlp.1.weight")[1], C_, 1, 0);
+  float* h = causal_block(p + ".block1", x, cin, mask, tvec, R, T, s);
+  float* h2 = causal_block(p + ".block2", h, C_, mask, nullptr, R, T, s);
+  float* rc = scratch_.get((size_t)R * C_ * T, s);
+  conv1d(x, mask, w_.ptr(p + ".res_conv.weight"), w_.ptr(p + ".res_conv.bias"), rc, nullptr, R, cin, T, C_, 1, 1, 0, -1.f, s);
+  ew(h2, rc, h2, (size_t)R * C_ * T, EW_ADD, s);
+  return h2;
+}
+
+// one resnet + n_blocks BasicTransformerBlocks (transformer.py:243-316), all in NCT (a Linear is a 1x1 conv)
+float* FlowEngineF32::group(const std::string& prefix, const float* h, int cin, const float* mask, const float* temb,
+                            const int* lens, int R, int T, bool streaming, cudaStream_t s) {
+  float* u = resnet(prefix + ".0", h, cin, mask, temb, R, T, s);
+  const size_t n = (size_t)R * C_ * T;
+  const int inner = heads_ * 64;
+  for (int j = 0; j < n_blocks_; ++j) {
+    const std::string p = prefix + ".1." + std::to_string(j);
+    float* nrm = scratch_.get(n, s);
+    F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, R), kTB, s, u, w_.ptr(p + ".norm1.weight"), w_.ptr(p + ".norm1.bias"), nrm,
+               C_, T, 0, (const float*)nullptr, (const float*)nullptr);
+    float* q = scratch_.get((size_t)R * inner * T, s);
+    float* k = scratch_.get((size_t)R * inner * T, s);
+    float* v = scratch_.get((size_t)R * inner * T, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn1.to_q.weight"), nullptr, q, nullptr, R, C_, T, inner, 1, 1, 0, -1.f, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn1.to_k.weight"), nullptr, k, nullptr, R, C_, T, inner, 1, 1, 0, -1.f, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn1.to_v.weight"), nullptr, v, nullptr, R, C_, T, inner, 1, 1, 0, -1.f, s);
+    float* att = scratch_.get((size_t)R * inner * T, s);
+    F32_LAUNCH(attention_nct_kernel, grid_t(T, heads_, R), kTB, s, q, k, v, att, lens, heads_, T, streaming ? chunk_ : 0,
+               0.125f);
+    float* o = scratch_.get(n, s);
+    conv1d(att, nullptr, w_.ptr(p + ".attn1.to_out.0.weight"), w_.ptr(p + ".attn1.to_out.0.bias"), o, nullptr, R, inner, T,
+           C_, 1, 1, 0, -1.f, s);
+    float* u1 = scratch_.get(n, s);
+    ew(u, o, u1, n, EW_ADD, s);
+    F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, R), kTB, s, u1, w_.ptr(p + ".norm3.weight"), w_.ptr(p + ".norm3.bias"), nrm,
+               C_, T, 0, (const float*)nullptr, (const float*)nullptr);
+    const int ff = (int)w_.shape(p + ".ff.net.0.proj.weight")[0];
+    float* hh = scratch_.get((size_t)R * ff * T, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".ff.net.0.proj.weight"), w_.ptr(p + ".ff.net.0.proj.bias"), hh, nullptr, R, C_, T, ff, 1,
+           1, 0, -1.f, s);
+    ew(hh, nullptr, hh, (size_t)R * ff * T, EW_GELU, s);
+    conv1d(hh, nullptr, w_.ptr(p + ".ff.net.2.weight"), w_.ptr(p + ".ff.net.2.bias"), o, nullptr, R, ff, T, C_, 1, 1, 0, -1.f,
+           s);
+    float* u2 = scratch_.get(n, s);
+    ew(u1, o, u2, n, EW_ADD, s);
+    u = u2;
+  }
+  return u;
+}
+
+// CausalConditionalDecoder.forward (flow/decoder.py:405-496), channels = [C]
+void FlowEngineF32::run(const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                        const float* cond, float* out, int R, int T, bool streaming, cudaStream_t s) {
+  const int F = feat_;
+  int* lens = reinterpret_cast<int*>(scratch_.get((size_t)R, s));
+  F32_LAUNCH(mask_lengths_kernel, R, 256, s, mask, lens, T);
+  // time embedding: sinusoid -> Linear -> SiLU -> Linear (matcha decoder.py:14-29, 73-117)
+  const int tdim = (int)w_.shape("time_mlp.linear_1.weight")[1], thid = (int)w_.shape("time_mlp.linear_1.weight")[0];
+  float* e0 = scratch_.get((size_t)R * tdim, s);
+  F32_LAUNCH(sinusoid_kernel, dim3((tdim / 2 + 127) / 128, R), 128, s, t, e0, R, tdim);
+  float* e1 = scratch_.get((size_t)R * thid, s);
+  F32_LAUNCH(linear_rows_kernel, dim3((thid + 127) / 128, R), 128, s, e0, w_.ptr("time_mlp.linear_1.weight"),
+             w_.ptr("time_mlp.linear_1.bias"), e1, R, tdim, thid, 0, 1);
+  float* temb = scratch_.get((size_t)R * thid, s);
+  F32_LAUNCH(linear_rows_kernel, dim3((thid + 127) / 128, R), 128, s, e1, w_.ptr("time_mlp.linear_2.weight"),
+             w_.ptr("time_mlp.linear_2.bias"), temb, R, thid, thid, 0, 0);
+  const size_t n_in = (size_t)R * 4 * F * T;
+  float* h0 = scratch_.get(n_in, s);
+  F32_LAUNCH(build_input_kernel, blocks(n_in), 256, s, x, mu, spks, cond, h0, F, T, n_in);
+
+  float* h = group("down_blocks.0", h0, 4 * F, mask, temb, lens, R, T, streaming, s);
+  float* skip = h;
+  float* d = scratch_.get((size_t)R * C_ * T, s);
+  conv1d(h, mask, w_.ptr("down_blocks.0.2.weight"), w_.ptr("down_blocks.0.2.bias"), d, nullptr, R, C_, T, C_, 3, 1, 2, -1.f, s);
+  h = d;
+  for (int i = 0; i < n_mid_; ++i) h = group("mid_blocks." + std::to_string(i), h, C_, mask, temb, lens, R, T, streaming, s);
+  const size_t n_cat = (size_t)R * 2 * C_ * T;
+  float* cat = scratch_.get(n_cat, s);
+  F32_LAUNCH(cat_channels_kernel, blocks(n_cat), 256, s, h, skip, cat, C_, C_, T, n_cat);
+  h = group("up_blocks.0", cat, 2 * C_, mask, temb, lens, R, T, streaming, s);
+  float* uo = scratch_.get((size_t)R * C_ * T, s);
+  conv1d(h, mask, w_.ptr("up_blocks.0.2.weight"), w_.ptr("up_blocks.0.2.bias"), uo, nullptr, R, C_, T, C_, 3, 1, 2, -1.f, s);
+  float* fb = causal_block("final_block", uo, C_, mask, nullptr, R, T, s);
+  conv1d(fb, mask, w_.ptr("final_proj.weight"), w_.ptr("final_proj.bias"), out, mask, R, C_, T, F, 1, 1, 0, -1.f, s);
+}
+
+void FlowEngineF32::estimator_forward(const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                                      const float* cond, float* out, int rows, int T, bool streaming, cudaStream_t s) {
+  require(rows > 0 && T > 0, "rows and T must be positive");
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  // out may alias x: compute into scratch, then copy
+  float* tmp = scratch_.get((size_t)rows * feat_ * T, s);
+  run(x, mask, mu, t, spks, cond, tmp, rows, T, streaming, s);
+  LS_CUDA(cudaMemcpyAsync(out, tmp, (size_t)rows * feat_ * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+// CausalConditionalCFM.forward + ConditionalCFM.solve_euler (flow_matching.py:323-348, 74-126), B >= 1
+void FlowEngineF32::solve(const float* mu, const float* mask, const float* spks, const float* cond, const float* noise,
+                          long long noise_stride, const float* t_span, int n_steps, float temperature, float cfg_rate,
+                          bool streaming, float* out, int B, int T, cudaStream_t s) {
+  require(B > 0 && T > 0 && n_steps > 0, "B, T and n_timesteps must be positive");
+  require(noise_stride >= T, "noise buffer shorter than T");
+  LS_CUDA(cudaSetDevice(device_));
+  const int F = feat_;
+  const size_t n = (size_t)B * F * T;
+  float t = t_span[0], dt = t_span[1] - t_span[0];
+  // persistent state across steps lives at the bottom of the scratch block of the first step; to keep it simple the
+  // state is kept in `out` (fp32 [B,80,T]) itself
+  scratch_.reset();
+  F32_LAUNCH(init_noise_kernel, blocks(n), 256, s, noise, noise_stride, temperature, out, F, T, n);
+  for (int step = 1; step <= n_steps; ++step) {
+    scratch_.reset();
+    float* x2 = scratch_.get(2 * n, s);
+    float* mu2 = scratch_.get(2 * n, s);
+    float* cond2 = scratch_.get(2 * n, s);
+    float* mask2 = scratch_.get((size_t)2 * B * T, s);
+    float* spks2 = scratch_.get((size_t)2 * B * F, s);
+    float* t2 = scratch_.get((size_t)2 * B, s);
+    float* v = scratch_.get(2 * n, s);
+    F32_LAUNCH(cfg_pack_kernel, blocks(n > (size_t)B * T ? n : (size_t)B * T), 256, s, out, mu, cond, mask, x2, mu2, cond2, mask2,
+               F, T, B);
+    F32_LAUNCH(cfg_small_kernel, blocks((size_t)B * F + 2 * B), 256, s, spks, spks2, t2, t, F, B);
+    run(x2, mask2, mu2, t2, spks2, cond2, v, 2 * B, T, streaming, s);
+    F32_LAUNCH(euler_kernel, blocks(n), 256, s, out, v, dt, cfg_rate, n);
+    t = t + dt;
+    if (step < n_steps) dt = t_span[step + 1] - t;
+  }
+  F32_LAUNCH(mul_mask_kernel, blocks(n), 256, s, out, mask, out, F, T, n);  // API: zero where mask == 0
+}
+
+// ---------------------------------------------------------------------------------------------- DAC-VAE decoder
+DacEngineF32::DacEngineF32(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  // fold weight-norm (layers.py:9-14): w = g * v / ||v||, norm over all dims but 0 (dim 0 = Cin for ConvTranspose1d)
+  for (const auto& kv : w.all()) {
+    const std::string& name = kv.first;
+    const ls_tensor& t = *kv.second;
+    size_t n = 1;
+    std::vector<long long> shape;
+    for (int i = 0; i < t.ndim; ++i) n *= (size_t)t.shape[i], shape.push_back(t.shape[i]);
+    const std::string suf_v = ".weight_v";
+    if (name.size() > suf_v.size() && name.compare(name.size() - suf_v.size(), suf_v.size(), suf_v) == 0) {
+      const std::string base = name.substr(0, name.size() - suf_v.size());
+      const ls_tensor& g = w.get(base + ".weight_g");
+      const size_t d0 = (size_t)t.shape[0], inner = n / d0;
+      std::vector<float> folded(n);
+      for (size_t i = 0; i < d0; ++i) {
+        double ss = 0.0;
+        for (size_t j = 0; j < inner; ++j) ss += (double)t.data[i * inner + j] * t.data[i * inner + j];
+        const float scale = g.data[i] / (float)std::sqrt(ss);
+        for (size_t j = 0; j < inner; ++j) folded[i * inner + j] = t.data[i * inner + j] * scale;
+      }
+      w_.add(base + ".weight", folded.data(), n, shape);
+    } else if (name.find(".weight_g") == std::string::npos) {
+      w_.add(name, t.data, n, shape);
+    }
+  }
+  latent_ = (int)w_.shape("de_conv_pre.0.weight")[1];
+  while (w_.has("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight")) {
+    const auto& sh = w_.shape("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight");
+    rates_.push_back((int)sh[2] / 2);
+  }
+  require(!rates_.empty(), "fp32 DAC decoder: no decoder blocks found", LS_ERR_WEIGHTS);
+  hop_ = 1;
+  for (int r : rates_) hop_ *= r;
+}
+
+// Decoder (dac-vae/model.py:326-379) after de_conv_pre (model.py:485-488); every Conv1d is followed by LeakyReLU(0.1)
+// (the shadowing WNConv1d, model.py:509-514)
+void DacEngineF32::decode_dense(const float* z, long long z_bstride, float* wav, long long wav_bstride, int B, int L,
+                                int L_alloc, cudaStream_t s) {
+  (void)L_alloc;
+  auto W = [&](const std::string& p) { return w_.ptr(p + ".weight"); };
+  auto Bv = [&](const std::string& p) { return w_.ptr(p + ".bias"); };
+  // gather the batch into a dense [B,latent,L] buffer (rows of z may be longer than L)
+  float* zin = scratch_.get((size_t)B * latent_ * L, s);
+  for (int b = 0; b < B; ++b)
+    LS_CUDA(cudaMemcpy2DAsync(zin + (size_t)b * latent_ * L, (size_t)L * 4, z + (size_t)b * z_bstride, (size_t)(z_bstride / latent_) * 4,
+                              (size_t)L * 4, latent_, cudaMemcpyDeviceToDevice, s));
+  int C = latent_;
+  float* x = scratch_.get((size_t)B * C * L, s);
+  conv1d(zin, nullptr, W("de_conv_pre.0"), Bv("de_conv_pre.0"), x, nullptr, B, C, L, C, 1, 1, 0, 0.1f, s);
+  const int dim = (int)w_.shape("decoder.model.0.0.weight")[0];
+  float* y = scratch_.get((size_t)B * dim * L, s);
+  conv1d(x, nullptr, W("decoder.model.0.0"), Bv("decoder.model.0.0"), y, nullptr, B, C, L, dim, 7, 1, 3, 0.1f, s);
+  x = y, C = dim;
+  int len = L;
+  for (size_t i = 0; i < rates_.size(); ++i) {
+    const std::string p = "decoder.model." + std::to_string(i + 1) + ".block";
+    const int st = rates_[i], Cout = C / 2, Lout = len * st;
+    const size_t n_in = (size_t)B * C * len, n_out = (size_t)B * Cout * Lout;
+    float* sn = scratch_.get(n_in, s);
+    F32_LAUNCH(snake_nct_kernel, blocks(n_in), 256, s, x, w_.ptr(p + ".0.alpha"), sn, C, len, n_in);
+    float* up = scratch_.get(n_out, s);
+    F32_LAUNCH(convt1d_nct_kernel, grid_t(Lout, (Cout + kNB - 1) / kNB, B), kTB, s, sn, W(p + ".1"), Bv(p + ".1"), up, C, len, Cout,
+               2 * st, st, (st + 1) / 2, Lout);
+    x = up, C = Cout, len = Lout;
+    const int dils[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) {  // ResidualUnit (model.py:107-143)
+      const std::string u = p + "." + std::to_string(j + 2) + ".block";
+      float* a = scratch_.get(n_out, s);
+      F32_LAUNCH(snake_nct_kernel, blocks(n_out), 256, s, x, w_.ptr(u + ".0.alpha"), a, C, len, n_out);
+      float* c7 = scratch_.get(n_out, s);
+      conv1d(a, nullptr, W(u + ".1.0"), Bv(u + ".1.0"), c7, nullptr, B, C, len, C, 7, dils[j], 3 * dils[j], 0.1f, s);
+      F32_LAUNCH(snake_nct_kernel, blocks(n_out), 256, s, c7, w_.ptr(u + ".2.alpha"), a, C, len, n_out);
+      conv1d(a, nullptr, W(u + ".3.0"), Bv(u + ".3.0"), c7, nullptr, B, C, len, C, 1, 1, 0, 0.1f, s);
+      float* xn = scratch_.get(n_out, s);
+      ew(x, c7, xn, n_out, EW_ADD, s);
+      x = xn;
+    }
+  }
+  const int nst = (int)rates_.size();
+  const size_t n_last = (size_t)B * C * len;
+  float* sn = scratch_.get(n_last, s);
+  F32_LAUNCH(snake_nct_kernel, blocks(n_last), 256, s, x, w_.ptr("decoder.model." + std::to_string(nst + 1) + ".alpha"), sn, C, len,
+             n_last);
+  const std::string fin = "decoder.model." + std::to_string(nst + 2) + ".0";
+  float* fo = scratch_.get((size_t)B * len, s);
+  conv1d(sn, nullptr, W(fin), Bv(fin), fo, nullptr, B, C, len, 1, 7, 1, 3, 0.1f, s);
+  ew(fo, nullptr, fo, (size_t)B * len, EW_TANH, s);
+  for (int b = 0; b < B; ++b)
+    LS_CUDA(cudaMemcpyAsync(wav + (size_t)b * wav_bstride, fo + (size_t)b * len, (size_t)len * 4, cudaMemcpyDeviceToDevice, s));
+}
+
+void DacEngineF32::decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s) {
+  require(B > 0 && L > 0, "B and L must be positive");
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  if (!lengths) {
+    decode_dense(z, (long long)latent_ * L, wav, (long long)L * hop_, B, L, L, s);
+    return;
+  }
+  // per-utterance semantics: each item is decoded alone at its own length (what a loop over the reference gives)
+  std::vector<int> h(B);
+  LS_CUDA(cudaMemcpyAsync(h.data(), lengths, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  LS_CUDA(cudaStreamSynchronize(s));
+  LS_CUDA(cudaMemsetAsync(wav, 0, (size_t)B * L * hop_ * sizeof(float), s));
+  for (int b = 0; b < B; ++b) {
+    const int n = h[b] < L ? h[b] : L;
+    if (n <= 0) continue;
+    scratch_.reset();
+    decode_dense(z + (size_t)b * latent_ * L, (long long)latent_ * L, wav + (size_t)b * L * hop_, (long long)L * hop_, 1, n, L, s);
+  }
+}
+
+}  // namespace ls

@@ -1,0 +1,88 @@
+// fp32 mode of the hot path ("<= 1e-4 in fp32 mode", north_star): the same call surface as FlowEngine / DacEngine,
+// computed end to end in fp32 on the CUDA cores with plain (unfused) kernels in the reference's own NCT layout.
+// It exists to show that the data flow -- masks, padding, causal convolutions, weight-norm folding, CFG, the Euler
+// update -- is the reference's, free of bf16 rounding; it is a validation mode, not the fast path.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine_common.h"
+
+namespace ls {
+
+// every state_dict tensor as a device fp32 array, by name
+class F32Weights {
+ public:
+  F32Weights() = default;
+  ~F32Weights();
+  void add(const std::string& name, const float* host, size_t n, std::vector<long long> shape);
+  const float* ptr(const std::string& name) const;
+  const std::vector<long long>& shape(const std::string& name) const;
+  bool has(const std::string& name) const { return items_.count(name) != 0; }
+
+ private:
+  struct Item {
+    float* dev = nullptr;
+    std::vector<long long> shape;
+  };
+  std::map<std::string, Item> items_;
+};
+
+// grow-only scratch memory, bump-allocated per call (no allocation once every shape has been seen)
+class F32Scratch {
+ public:
+  ~F32Scratch();
+  void reset() { used_ = 0; }
+  float* get(size_t n_floats, cudaStream_t s);
+
+ private:
+  float* base_ = nullptr;
+  size_t cap_ = 0, used_ = 0;
+  std::vector<float*> retired_;  // outgrown blocks stay alive until destruction (in-flight kernels may use them)
+};
+
+class FlowEngineF32 {
+ public:
+  FlowEngineF32(const Weights& w, int device);
+  void estimator_forward(const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                         const float* cond, float* out, int rows, int T, bool streaming, cudaStream_t s);
+  void solve(const float* mu, const float* mask, const float* spks, const float* cond, const float* noise,
+             long long noise_stride, const float* t_span, int n_steps, float temperature, float cfg_rate,
+             bool streaming, float* out, int B, int T, cudaStream_t s);
+  int feat() const { return feat_; }
+  int device() const { return device_; }
+
+ private:
+  void run(const float* x, const float* mask, const float* mu, const float* t, const float* spks, const float* cond,
+           float* out, int R, int T, bool streaming, cudaStream_t s);
+  float* group(const std::string& prefix, const float* h, int cin, const float* mask, const float* temb,
+               const int* lens, int R, int T, bool streaming, cudaStream_t s);
+  float* resnet(const std::string& p, const float* x, int cin, const float* mask, const float* temb, int R, int T,
+                cudaStream_t s);
+  float* causal_block(const std::string& p, const float* x, int cin, const float* mask, const float* addvec, int R,
+                      int T, cudaStream_t s);
+  int device_ = 0, feat_ = 80, C_ = 256, heads_ = 8, n_blocks_ = 0, n_mid_ = 0, chunk_ = 50;
+  F32Weights w_;
+  F32Scratch scratch_;
+};
+
+class DacEngineF32 {
+ public:
+  DacEngineF32(const Weights& w, int device);
+  void decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s);
+  int hop() const { return hop_; }
+  int latent_dim() const { return latent_; }
+  int device() const { return device_; }
+
+ private:
+  void decode_dense(const float* z, long long z_bstride, float* wav, long long wav_bstride, int B, int L, int L_alloc,
+                    cudaStream_t s);
+  int device_ = 0, latent_ = 80, hop_ = 1;
+  std::vector<int> rates_;
+  F32Weights w_;  // weight-norm folded: "<prefix>.weight", "<prefix>.bias", "<prefix>.alpha"
+  F32Scratch scratch_;
+};
+
+}  // namespace ls

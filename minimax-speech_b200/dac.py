@@ -15,8 +15,9 @@ from .flow import _as_f32, _register_tree
 
 class DACVAEDecoder(nn.Module):
     def __init__(self, latent_dim=80, decoder_dim=1536, decoder_rates=(5, 4, 4, 3, 2), sample_rate=24000,
-                 d_out=1, weight_seed=0, **_ignored):
+                 d_out=1, weight_seed=0, precision="bf16", **_ignored):
         super().__init__()
+        self.precision = native.check_precision(precision)
         if d_out != 1:
             raise NotImplementedError("mono output only (configx2.yml: d_out=1)")
         self.latent_dim, self.decoder_dim, self.decoder_rates = latent_dim, decoder_dim, list(decoder_rates)
@@ -44,8 +45,8 @@ class DACVAEDecoder(nn.Module):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
-        if self._handle is None or self._handle.device != device:
-            self._handle = native.DacHandle(self.state_dict(), device)
+        if self._handle is None or self._handle.device != device or self._handle.precision != self.precision:
+            self._handle = native.DacHandle(self.state_dict(), device, self.precision)
         return self._handle
 
     @torch.inference_mode()

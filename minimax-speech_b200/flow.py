@@ -61,8 +61,9 @@ class CausalConditionalDecoder(nn.Module):
 
     def __init__(self, in_channels=320, out_channels=80, channels=(256,), dropout=0.0, attention_head_dim=64,
                  n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn="gelu", static_chunk_size=50,
-                 num_decoding_left_chunks=-1, weight_seed=1986):
+                 num_decoding_left_chunks=-1, weight_seed=1986, precision="bf16"):
         super().__init__()
+        self.precision = native.check_precision(precision)
         channels = tuple(channels)
         if channels != (256,) or attention_head_dim != 64 or act_fn != "gelu" or in_channels != 4 * out_channels:
             raise NotImplementedError("B200 estimator covers config.yaml's CausalConditionalDecoder: "
@@ -84,8 +85,8 @@ class CausalConditionalDecoder(nn.Module):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
-        if self._handle is None or self._handle.device != device:
-            self._handle = native.FlowHandle(self.state_dict(), device)
+        if self._handle is None or self._handle.device != device or self._handle.precision != self.precision:
+            self._handle = native.FlowHandle(self.state_dict(), device, self.precision)
         return self._handle
 
     @torch.inference_mode()

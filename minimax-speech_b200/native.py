@@ -14,7 +14,8 @@ ACT_NONE, ACT_LRELU, ACT_GELU, ACT_LN_MISH, ACT_LRELU_TANH = range(5)
 OUT_NONE, OUT_F32, OUT_BF16 = range(3)
 OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
-EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_destroy",
+EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32",
+           "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
            "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
 
@@ -80,6 +81,8 @@ def load():
         lib.ls_launch_count.restype = i64
         lib.ls_device_check.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         lib.ls_flow_create.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_flow_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_dac_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_flow_destroy.argtypes = [vp]
         lib.ls_flow_destroy.restype = None
         lib.ls_flow_estimator_forward.argtypes = [vp] * 8 + [i32, i32, i32, vp]
@@ -149,16 +152,26 @@ def tensor_table(state_dict):
     return arr, keep
 
 
+def check_precision(precision):
+    """"bf16": tensor-core path (bf16 operands, fp32 accumulation; latents within 1e-2 of the fp32 reference);
+    "fp32": validation mode, fp32 end to end on the CUDA cores (within 1e-4)."""
+    if precision not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', not {precision!r}")
+    return precision
+
+
 class FlowHandle:
     """Owns an ls_flow*: the packed estimator weights + workspace on one device."""
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, precision="bf16"):
         lib = load()
         self.device = torch.device(device)
+        self.precision = check_precision(precision)
         arr, keep = tensor_table(state_dict)
         h = C.c_void_p()
+        create = lib.ls_flow_create if precision == "bf16" else lib.ls_flow_create_fp32
         with torch.cuda.device(self.device):
-            check(lib.ls_flow_create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_flow_create")
+            check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_flow_create")
         self._h = h
 
     def __del__(self):
@@ -186,13 +199,15 @@ class FlowHandle:
 
 
 class DacHandle:
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, precision="bf16"):
         lib = load()
         self.device = torch.device(device)
+        self.precision = check_precision(precision)
         arr, keep = tensor_table(state_dict)
         h = C.c_void_p()
+        create = lib.ls_dac_create if precision == "bf16" else lib.ls_dac_create_fp32
         with torch.cuda.device(self.device):
-            check(lib.ls_dac_create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_dac_create")
+            check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_dac_create")
         self._h = h
         self.hop_length = int(lib.ls_dac_hop_length(h))
 
