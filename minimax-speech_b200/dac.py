@@ -54,7 +54,11 @@ class DACVAEDecoder(nn.Module):
         """``lengths`` (optional int tensor [B]): valid latent frames per item of a right-padded batch; each item
         is then decoded exactly as if alone (the reference decodes one utterance per call)."""
         dev = z.device
+        if z.dim() != 3 or z.shape[1] != self.latent_dim or z.shape[2] < 1:
+            raise ValueError(f"z must be [B, {self.latent_dim}, L >= 1], got {tuple(z.shape)}")
         if lengths is not None:
+            if lengths.numel() != z.shape[0]:
+                raise ValueError(f"lengths must have {z.shape[0]} entries")
             lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
         return self.handle(dev).decode(_as_f32(z, dev), lengths)
 

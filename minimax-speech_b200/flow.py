@@ -92,11 +92,18 @@ class CausalConditionalDecoder(nn.Module):
     @torch.inference_mode()
     def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
         dev = x.device
-        rows, _, T = x.shape
+        if x.dim() != 3 or x.shape[1] != self.out_channels or x.shape[2] < 1:
+            raise ValueError(f"x must be [rows, {self.out_channels}, T >= 1], got {tuple(x.shape)}")
+        rows, F, T = x.shape
         spks = torch.zeros(rows, self.out_channels, device=dev) if spks is None else spks
         cond = torch.zeros_like(x) if cond is None else cond
+        if tuple(mu.shape) != (rows, F, T) or tuple(cond.shape) != (rows, F, T) or tuple(mask.shape) != (rows, 1, T) \
+                or tuple(spks.shape) != (rows, F):
+            raise ValueError("estimator inputs: x, mu, cond [rows,80,T], mask [rows,1,T], spks [rows,80]")
         _check_prefix_mask(mask)
         t = t.reshape(-1).expand(rows) if t.numel() == 1 else t
+        if t.numel() != rows:
+            raise ValueError(f"t must have {rows} entries")
         out = self.handle(dev).estimator_forward(_as_f32(x, dev), _as_f32(mask, dev), _as_f32(mu, dev),
                                                  _as_f32(t, dev), _as_f32(spks, dev), _as_f32(cond, dev), streaming)
         return out.to(x.dtype)
@@ -120,10 +127,27 @@ class ConditionalCFM(nn.Module):
             t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
         return t_span
 
+    def _check_inputs(self, mu, mask, spks, cond, n_timesteps):
+        """Shapes are validated here: past this point only raw pointers and sizes cross the C ABI."""
+        feat = self.estimator.out_channels
+        if mu.dim() != 3 or mu.shape[1] != feat or mu.shape[2] < 1 or n_timesteps < 1:
+            raise ValueError(f"mu must be [B, {feat}, T >= 1] and n_timesteps >= 1 (got {tuple(mu.shape)}, "
+                             f"{n_timesteps} steps)")
+        B, F, T = mu.shape
+        if tuple(mask.shape) != (B, 1, T):
+            raise ValueError(f"mask must be [{B}, 1, {T}], got {tuple(mask.shape)}")
+        if spks is not None and tuple(spks.shape) != (B, F):
+            raise ValueError(f"spks must be [{B}, {F}], got {tuple(spks.shape)}")
+        if cond is not None and tuple(cond.shape) != (B, F, T):
+            raise ValueError(f"cond must be [{B}, {F}, {T}], got {tuple(cond.shape)}")
+
     def _solve(self, z, t_span, mu, mask, spks, cond, streaming=False):
         """z: [1 or B, 80, >=T] noise rows (row stride may exceed T)."""
         dev = mu.device
+        self._check_inputs(mu, mask, spks, cond, len(t_span) - 1)
         B, F, T = mu.shape
+        if z.dim() != 3 or z.shape[1] != F or z.shape[2] < T:
+            raise ValueError(f"noise must be [1, {F}, >= {T}], got {tuple(z.shape)}")
         _check_prefix_mask(mask)
         if z.shape[0] != 1:
             raise NotImplementedError("per-utterance noise: pass z with a single leading row shared by the batch")
@@ -185,6 +209,7 @@ class CausalConditionalCFM(ConditionalCFM):
     def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False):
         """flow_matching.py:323-348 -> ``(latent [B,80,T] fp32, None)``; B >= 1 (per-utterance semantics)."""
         dev = mu.device
+        self._check_inputs(mu, mask, spks, cond, n_timesteps)
         B, F, T = mu.shape
         if T > self.rand_noise.shape[2]:
             raise ValueError(f"T={T} exceeds the fixed-noise buffer ({self.rand_noise.shape[2]} frames)")
