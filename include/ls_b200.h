@@ -86,6 +86,13 @@ int32_t ls_dac_hop_length(const ls_dac* h);
 int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* wav, int32_t B, int32_t L,
                       void* stream);
 
+/* DACVAE.encode (dac-vae/model.py:469-483; bulk latent extraction, dac-vae/extract_dac_latents.py:20-54): audio
+ * [B,1,S] with S a multiple of the hop -> z, m, logs, each [B,latent,S/hop]; z = m + noise * exp(logs) with the
+ * caller's noise [B,latent,S/hop] (NULL: z = m).  fp32-mode handles only (the handle's weights must contain the
+ * encoder.* / en_conv_post.* entries); LS_ERR_UNSUPPORTED on a tensor-core handle. */
+int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* z, float* m, float* logs, int32_t B,
+                      int32_t S, void* stream);
+
 /* ---- end to end with HOST buffers (pinned or pageable): H2D copies, solve, decode, D2H copy, and a
  * stream synchronise all happen inside the call.  wav_host: [B,1,T*hop]. */
 int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,

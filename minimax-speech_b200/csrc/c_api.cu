@@ -193,6 +193,16 @@ int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* 
   });
 }
 
+int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* z, float* m, float* logs, int32_t B,
+                      int32_t S, void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && audio && z && m && logs, "ls_dac_encode: null argument");
+    ls::require(h->eng32 != nullptr, "ls_dac_encode: the encoder exists in fp32 mode only (create the handle with "
+                                     "ls_dac_create_fp32)", LS_ERR_UNSUPPORTED);
+    h->eng32->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
+  });
+}
+
 int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,
                            const float* spks_host, const float* cond_host, const float* noise_dev,
                            int64_t noise_stride, const float* t_span_host, int32_t n_timesteps, float temperature,

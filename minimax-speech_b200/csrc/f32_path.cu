@@ -24,7 +24,9 @@ inline dim3 grid_t(int T, int n, int B) { return dim3((unsigned)((T + kTB - 1) /
 __global__ void __launch_bounds__(kTB) conv1d_nct_kernel(const float* __restrict__ in, const float* __restrict__ m_in,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ out, const float* __restrict__ m_out, int Cin,
-                                                         int T, int N, int K, int dil, int pad, float lrelu) {
+                                                         int Tin, int T, int N, int K, int dil, int pad, int stride,
+                                                         float lrelu) {
+  // Tin: input length, T: output length; stride > 1 = the encoder's downsampling convs (dac-vae/model.py:183-189)
   const int t = blockIdx.x * kTB + threadIdx.x;
   const int n0 = blockIdx.y * kNB;
   const int b = blockIdx.z;
@@ -32,14 +34,14 @@ __global__ void __launch_bounds__(kTB) conv1d_nct_kernel(const float* __restrict
   float acc[kNB];
 #pragma unroll
   for (int j = 0; j < kNB; ++j) acc[j] = (bias && n0 + j < N) ? bias[n0 + j] : 0.f;
-  const float* inb = in + (size_t)b * Cin * T;
-  const float* mb = m_in ? m_in + (size_t)b * T : nullptr;
+  const float* inb = in + (size_t)b * Cin * Tin;
+  const float* mb = m_in ? m_in + (size_t)b * Tin : nullptr;
   for (int k = 0; k < K; ++k) {
-    const int tt = t + k * dil - pad;
-    if (tt < 0 || tt >= T) continue;
+    const int tt = t * stride + k * dil - pad;
+    if (tt < 0 || tt >= Tin) continue;
     const float mv = mb ? mb[tt] : 1.f;
     for (int c = 0; c < Cin; ++c) {
-      const float v = inb[(size_t)c * T + tt] * mv;
+      const float v = inb[(size_t)c * Tin + tt] * mv;
 #pragma unroll
       for (int j = 0; j < kNB; ++j)
         if (n0 + j < N) acc[j] = fmaf(v, w[((size_t)(n0 + j) * Cin + c) * K + k], acc[j]);
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kTB) attention_nct_kernel(const float* __restr
   for (int d = 0; d < 64; ++d) o[base + (size_t)d * T + i] = acc[d] * inv;
 }
 
-enum { EW_ADD = 0, EW_GELU = 1, EW_TANH = 2 };
+enum { EW_ADD = 0, EW_GELU = 1, EW_TANH = 2, EW_LRELU001 = 3 };
 __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n, int op) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -161,7 +163,8 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
   float r;
   if (op == EW_ADD) r = x + b[i];
   else if (op == EW_GELU) r = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // F.gelu(approximate="none")
-  else r = tanhf(x);
+  else if (op == EW_TANH) r = tanhf(x);
+  else r = x > 0.f ? x : 0.01f * x;  // F.leaky_relu default slope (dac-vae/model.py:475)
   y[i] = r;
 }
 // snake(x) = x + (alpha + 1e-9)^-1 sin^2(alpha x), alpha per channel (dac-vae/layers.py:18-24)
@@ -276,12 +279,27 @@ __global__ void mul_mask_kernel(const float* __restrict__ x, const float* __rest
   y[i] = x[i] * mask[(i / ((size_t)C * T)) * T + i % T];
 }
 
+// m, logs = split(x); logs = clamp(logs, -14, 14); z = m + noise * exp(logs)   (dac-vae/model.py:477-481)
+__global__ void reparam_kernel(const float* __restrict__ x, const float* __restrict__ noise, float* __restrict__ z,
+                               float* __restrict__ m, float* __restrict__ logs, int latent, int L, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % L);
+  const int c = (int)((i / L) % latent);
+  const size_t b = i / ((size_t)L * latent);
+  const float mv = x[(b * 2 * latent + c) * L + t];
+  const float lv = fminf(fmaxf(x[(b * 2 * latent + latent + c) * L + t], -14.0f), 14.0f);
+  m[i] = mv, logs[i] = lv;
+  z[i] = noise ? mv + noise[i] * expf(lv) : mv;
+}
+
 inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
 
 void conv1d(const float* in, const float* m_in, const float* w, const float* bias, float* out, const float* m_out, int B,
-            int Cin, int T, int N, int K, int dil, int pad, float lrelu, cudaStream_t s) {
-  F32_LAUNCH(conv1d_nct_kernel, grid_t(T, (N + kNB - 1) / kNB, B), kTB, s, in, m_in, w, bias, out, m_out, Cin, T, N, K, dil,
-             pad, lrelu);
+            int Cin, int T, int N, int K, int dil, int pad, float lrelu, cudaStream_t s, int stride = 1) {
+  const int Tout = stride == 1 ? T : (T + 2 * pad - K) / stride + 1;
+  F32_LAUNCH(conv1d_nct_kernel, grid_t(Tout, (N + kNB - 1) / kNB, B), kTB, s, in, m_in, w, bias, out, m_out, Cin, T, Tout, N,
+             K, dil, pad, stride, lrelu);
 }
 void ew(const float* a, const float* b, float* y, size_t n, int op, cudaStream_t s) {
   F32_LAUNCH(ew_kernel, blocks(n), 256, s, a, b, y, n, op);
@@ -525,14 +543,78 @@ DacEngineF32::DacEngineF32(const Weights& w, int device) : device_(device) {
       w_.add(name, t.data, n, shape);
     }
   }
-  latent_ = (int)w_.shape("de_conv_pre.0.weight")[1];
-  while (w_.has("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight")) {
-    const auto& sh = w_.shape("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight");
-    rates_.push_back((int)sh[2] / 2);
+  if (w_.has("de_conv_pre.0.weight")) {
+    latent_ = (int)w_.shape("de_conv_pre.0.weight")[1];
+    while (w_.has("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight")) {
+      const auto& sh = w_.shape("decoder.model." + std::to_string(rates_.size() + 1) + ".block.1.weight");
+      rates_.push_back((int)sh[2] / 2);
+    }
   }
-  require(!rates_.empty(), "fp32 DAC decoder: no decoder blocks found", LS_ERR_WEIGHTS);
+  if (w_.has("en_conv_post.0.weight")) {
+    latent_ = (int)w_.shape("en_conv_post.0.weight")[1];
+    while (w_.has("encoder.block." + std::to_string(enc_rates_.size() + 1) + ".block.4.0.weight")) {
+      const auto& sh = w_.shape("encoder.block." + std::to_string(enc_rates_.size() + 1) + ".block.4.0.weight");
+      enc_rates_.push_back((int)sh[2] / 2);
+    }
+  }
+  require(!rates_.empty() || !enc_rates_.empty(), "fp32 DAC-VAE: neither decoder nor encoder weights found", LS_ERR_WEIGHTS);
   hop_ = 1;
-  for (int r : rates_) hop_ *= r;
+  for (int r : (rates_.empty() ? enc_rates_ : rates_)) hop_ *= r;
+}
+
+// ResidualUnit (dac-vae/model.py:107-143): x + LReLU(conv1(snake(LReLU(conv7_dil(snake(x))))))
+float* DacEngineF32::residual_unit(const std::string& u, const float* x, int B, int C, int len, int dil, cudaStream_t s) {
+  const size_t n = (size_t)B * C * len;
+  float* a = scratch_.get(n, s);
+  F32_LAUNCH(snake_nct_kernel, blocks(n), 256, s, x, w_.ptr(u + ".0.alpha"), a, C, len, n);
+  float* c7 = scratch_.get(n, s);
+  conv1d(a, nullptr, w_.ptr(u + ".1.0.weight"), w_.ptr(u + ".1.0.bias"), c7, nullptr, B, C, len, C, 7, dil, 3 * dil, 0.1f, s);
+  F32_LAUNCH(snake_nct_kernel, blocks(n), 256, s, c7, w_.ptr(u + ".2.alpha"), a, C, len, n);
+  conv1d(a, nullptr, w_.ptr(u + ".3.0.weight"), w_.ptr(u + ".3.0.bias"), c7, nullptr, B, C, len, C, 1, 1, 0, 0.1f, s);
+  float* xn = scratch_.get(n, s);
+  ew(x, c7, xn, n, EW_ADD, s);
+  return xn;
+}
+
+// DACVAE.encode (dac-vae/model.py:469-483) after Encoder (model.py:146-234); audio [B,1,S], S a multiple of the hop
+void DacEngineF32::encode(const float* audio, const float* noise, float* z, float* m, float* logs, int B, int S,
+                          cudaStream_t s) {
+  require(!enc_rates_.empty(), "this handle holds no encoder weights", LS_ERR_WEIGHTS);
+  int hop = 1;
+  for (int r : enc_rates_) hop *= r;
+  require(B > 0 && S > 0 && S % hop == 0, "audio length must be a positive multiple of the hop (pad first, model.py:455-462)");
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  int C = (int)w_.shape("encoder.block.0.0.weight")[0], len = S;
+  float* x = scratch_.get((size_t)B * C * len, s);
+  conv1d(audio, nullptr, w_.ptr("encoder.block.0.0.weight"), w_.ptr("encoder.block.0.0.bias"), x, nullptr, B, 1, len, C, 7, 1, 3,
+         0.1f, s);
+  const int dils[3] = {1, 3, 9};
+  for (size_t i = 0; i < enc_rates_.size(); ++i) {
+    const std::string p = "encoder.block." + std::to_string(i + 1) + ".block";
+    for (int j = 0; j < 3; ++j) x = residual_unit(p + "." + std::to_string(j) + ".block", x, B, C, len, dils[j], s);
+    const size_t n = (size_t)B * C * len;
+    float* sn = scratch_.get(n, s);
+    F32_LAUNCH(snake_nct_kernel, blocks(n), 256, s, x, w_.ptr(p + ".3.alpha"), sn, C, len, n);
+    const int st = enc_rates_[i];
+    float* d = scratch_.get((size_t)B * 2 * C * (len / st), s);
+    conv1d(sn, nullptr, w_.ptr(p + ".4.0.weight"), w_.ptr(p + ".4.0.bias"), d, nullptr, B, C, len, 2 * C, 2 * st, 1, (st + 1) / 2,
+           0.1f, s, st);
+    x = d, C *= 2, len /= st;
+  }
+  const int nst = (int)enc_rates_.size();
+  const size_t n = (size_t)B * C * len;
+  float* sn = scratch_.get(n, s);
+  F32_LAUNCH(snake_nct_kernel, blocks(n), 256, s, x, w_.ptr("encoder.block." + std::to_string(nst + 1) + ".alpha"), sn, C, len, n);
+  const std::string fin = "encoder.block." + std::to_string(nst + 2) + ".0";
+  float* y = scratch_.get((size_t)B * latent_ * len, s);
+  conv1d(sn, nullptr, w_.ptr(fin + ".weight"), w_.ptr(fin + ".bias"), y, nullptr, B, C, len, latent_, 3, 1, 1, 0.1f, s);
+  ew(y, nullptr, y, (size_t)B * latent_ * len, EW_LRELU001, s);
+  float* post = scratch_.get((size_t)B * 2 * latent_ * len, s);
+  conv1d(y, nullptr, w_.ptr("en_conv_post.0.weight"), w_.ptr("en_conv_post.0.bias"), post, nullptr, B, latent_, len, 2 * latent_,
+         1, 1, 0, 0.1f, s);
+  const size_t nz = (size_t)B * latent_ * len;
+  F32_LAUNCH(reparam_kernel, blocks(nz), 256, s, post, noise, z, m, logs, latent_, len, nz);
 }
 
 // Decoder (dac-vae/model.py:326-379) after de_conv_pre (model.py:485-488); every Conv1d is followed by LeakyReLU(0.1)
@@ -566,18 +648,7 @@ void DacEngineF32::decode_dense(const float* z, long long z_bstride, float* wav,
                2 * st, st, (st + 1) / 2, Lout);
     x = up, C = Cout, len = Lout;
     const int dils[3] = {1, 3, 9};
-    for (int j = 0; j < 3; ++j) {  // ResidualUnit (model.py:107-143)
-      const std::string u = p + "." + std::to_string(j + 2) + ".block";
-      float* a = scratch_.get(n_out, s);
-      F32_LAUNCH(snake_nct_kernel, blocks(n_out), 256, s, x, w_.ptr(u + ".0.alpha"), a, C, len, n_out);
-      float* c7 = scratch_.get(n_out, s);
-      conv1d(a, nullptr, W(u + ".1.0"), Bv(u + ".1.0"), c7, nullptr, B, C, len, C, 7, dils[j], 3 * dils[j], 0.1f, s);
-      F32_LAUNCH(snake_nct_kernel, blocks(n_out), 256, s, c7, w_.ptr(u + ".2.alpha"), a, C, len, n_out);
-      conv1d(a, nullptr, W(u + ".3.0"), Bv(u + ".3.0"), c7, nullptr, B, C, len, C, 1, 1, 0, 0.1f, s);
-      float* xn = scratch_.get(n_out, s);
-      ew(x, c7, xn, n_out, EW_ADD, s);
-      x = xn;
-    }
+    for (int j = 0; j < 3; ++j) x = residual_unit(p + "." + std::to_string(j + 2) + ".block", x, B, C, len, dils[j], s);
   }
   const int nst = (int)rates_.size();
   const size_t n_last = (size_t)B * C * len;
@@ -594,6 +665,7 @@ void DacEngineF32::decode_dense(const float* z, long long z_bstride, float* wav,
 
 void DacEngineF32::decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s) {
   require(B > 0 && L > 0, "B and L must be positive");
+  require(!rates_.empty(), "this handle holds no decoder weights", LS_ERR_WEIGHTS);
   LS_CUDA(cudaSetDevice(device_));
   scratch_.reset();
   if (!lengths) {

@@ -72,15 +72,20 @@ class DacEngineF32 {
  public:
   DacEngineF32(const Weights& w, int device);
   void decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s);
+  // DACVAE.encode: audio [B,1,S] -> z, m, logs [B,latent,S/hop]; noise (nullable) [B,latent,S/hop]
+  void encode(const float* audio, const float* noise, float* z, float* m, float* logs, int B, int S, cudaStream_t s);
+  bool has_encoder() const { return !enc_rates_.empty(); }
+  bool has_decoder() const { return !rates_.empty(); }
   int hop() const { return hop_; }
   int latent_dim() const { return latent_; }
   int device() const { return device_; }
 
  private:
+  float* residual_unit(const std::string& u, const float* x, int B, int C, int len, int dil, cudaStream_t s);
   void decode_dense(const float* z, long long z_bstride, float* wav, long long wav_bstride, int B, int L, int L_alloc,
                     cudaStream_t s);
   int device_ = 0, latent_ = 80, hop_ = 1;
-  std::vector<int> rates_;
+  std::vector<int> rates_, enc_rates_;
   F32Weights w_;  // weight-norm folded: "<prefix>.weight", "<prefix>.bias", "<prefix>.alpha"
   F32Scratch scratch_;
 };

@@ -65,6 +65,60 @@ class DACVAEDecoder(nn.Module):
     forward = decode
 
 
+class DACVAEEncoder(nn.Module):
+    """``DACVAE.encode`` (dac-vae/model.py:469-483) -- SURVEY section 8 row f-3, the path the reference's multi-GPU
+    latent extraction tool runs (extract_dac_latents.py:20-54).  fp32 mode only in this round: the same CUDA-core
+    kernels as the decoder's fp32 mode; the tensor-core encoder is not built yet."""
+
+    def __init__(self, encoder_dim=64, encoder_rates=(2, 3, 4, 4, 5), latent_dim=80, sample_rate=24000, d_in=1,
+                 weight_seed=0, precision="fp32", **_ignored):
+        super().__init__()
+        if precision != "fp32":
+            raise NotImplementedError("the DAC-VAE encoder runs in fp32 mode only (the tensor-core path is not built yet)")
+        if d_in != 1:
+            raise NotImplementedError("mono input only (configx2.yml: d_in=1)")
+        self.precision, self.latent_dim, self.sample_rate = precision, latent_dim, sample_rate
+        self.hop_length = 1
+        for r in encoder_rates:
+            self.hop_length *= r
+        _register_tree(self, synth.dac_encoder_state_dict(weight_seed, "reference", encoder_dim=encoder_dim,
+                                                          encoder_rates=encoder_rates, latent_dim=latent_dim))
+        self._handle = None
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._handle = None
+        keep = {k: v for k, v in state_dict.items() if k.startswith(("encoder.", "en_conv_post."))}
+        return super().load_state_dict(keep, strict=strict, **kw)
+
+    def handle(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
+        if self._handle is None or self._handle.device != device:
+            self._handle = native.DacHandle(self.state_dict(), device, "fp32")
+        return self._handle
+
+    def preprocess(self, audio_data):
+        """Right-pad to a multiple of the hop (model.py:455-462)."""
+        pad = (-audio_data.shape[-1]) % self.hop_length
+        return torch.nn.functional.pad(audio_data, (0, pad))
+
+    @torch.inference_mode()
+    def encode(self, audio_data, noise=None):
+        """audio [B,1,S] (S a multiple of the hop) -> (z, m, logs).  ``noise`` ([B,latent,S/hop]) injects the sample
+        the reference draws with torch.randn_like; by default it is drawn here the same way."""
+        dev = audio_data.device
+        if audio_data.dim() != 3 or audio_data.shape[1] != 1 or audio_data.shape[2] % self.hop_length or \
+                audio_data.shape[2] < self.hop_length:
+            raise ValueError(f"audio must be [B, 1, S] with S a positive multiple of {self.hop_length}")
+        B, _, S = audio_data.shape
+        if noise is None:
+            noise = torch.randn(B, self.latent_dim, S // self.hop_length, device=dev)
+        elif tuple(noise.shape) != (B, self.latent_dim, S // self.hop_length):
+            raise ValueError("noise must be [B, latent, S / hop]")
+        return self.handle(dev).encode(_as_f32(audio_data, dev), _as_f32(noise, dev))
+
+
 def patch_reference_model(model):
     """Replace ``decode`` of a reference ``DACVAE`` instance by the B200 path (weights taken from it)."""
     sd = {k: v for k, v in model.state_dict().items() if k.startswith(("decoder.", "de_conv_pre."))}

@@ -14,7 +14,7 @@ ACT_NONE, ACT_LRELU, ACT_GELU, ACT_LN_MISH, ACT_LRELU_TANH = range(5)
 OUT_NONE, OUT_F32, OUT_BF16 = range(3)
 OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
-EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32",
+EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32", "ls_dac_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
            "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
@@ -92,6 +92,7 @@ def load():
         lib.ls_dac_destroy.restype = None
         lib.ls_dac_hop_length.argtypes = [vp]
         lib.ls_dac_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+        lib.ls_dac_encode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
         lib.ls_debug_set_buffer.argtypes = [vp, i64]
         lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
@@ -210,11 +211,23 @@ class DacHandle:
             check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_dac_create")
         self._h = h
         self.hop_length = int(lib.ls_dac_hop_length(h))
+        self.latent_dim = 80
+        for k, v in state_dict.items():
+            if k in ("en_conv_post.0.weight_v", "de_conv_pre.0.weight_v"):
+                self.latent_dim = int(v.shape[1])
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h and _lib is not None:
             _lib.ls_dac_destroy(h)
+
+    def encode(self, audio, noise=None):
+        B, _, S = audio.shape
+        latent, L = self.latent_dim, S // self.hop_length
+        z, m, logs = (torch.empty(B, latent, L, device=audio.device, dtype=torch.float32) for _ in range(3))
+        check(load().ls_dac_encode(self._h, ptr(audio), ptr(noise), ptr(z), ptr(m), ptr(logs), B, S,
+                                   current_stream_ptr(self.device)), "ls_dac_encode")
+        return z, m, logs
 
     def decode(self, z, lengths=None):
         B, _, L = z.shape

@@ -140,6 +140,57 @@ def dac_decoder_state_dict(seed=0, init="reference", latent_dim=80, decoder_dim=
     return sd
 
 
+def dac_encoder_state_dict(seed=0, init="reference", encoder_dim=64, encoder_rates=(2, 3, 4, 4, 5), latent_dim=80,
+                           d_in=1, **_):
+    """Keys/shapes of the ``encoder.*`` + ``en_conv_post.*`` part of ``DACVAE.state_dict()`` (dac-vae/model.py:146-234,
+    440-442; every WNConv1d is the shadowing Sequential(conv, LeakyReLU), hence the ".0")."""
+    test = init == "test"
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        w_shape, fan_in = (cout, cin, k), cin * k
+        v = _uniform(seed, name + ".0.weight_v", w_shape, 1.0 / math.sqrt(fan_in))
+        g = v.reshape(cout, -1).norm(dim=1).reshape(cout, 1, 1)
+        if test:
+            g = g * _uniform(seed, name + ".0.weight_g", (cout, 1, 1), 0.3).add(1.0)
+        sd[name + ".0.bias"] = (_uniform(seed, name + ".0.bias", (cout,), 1.0 / math.sqrt(fan_in)) if test
+                                else torch.zeros(cout))
+        sd[name + ".0.weight_g"] = g
+        sd[name + ".0.weight_v"] = v
+
+    def snake(name, c):
+        sd[name + ".alpha"] = _normal(seed, name + ".alpha", (1, c, 1), math.sqrt(2.0 / (c + 1)))
+
+    conv("encoder.block.0", encoder_dim, d_in, 7)
+    c = encoder_dim
+    for i, st in enumerate(encoder_rates):
+        p = f"encoder.block.{i + 1}.block"
+        for j in range(3):
+            q = f"{p}.{j}.block"
+            snake(q + ".0", c)
+            conv(q + ".1", c, c, 7)
+            snake(q + ".2", c)
+            conv(q + ".3", c, c, 1)
+        snake(p + ".3", c)
+        conv(p + ".4", 2 * c, c, 2 * st)
+        c *= 2
+    n = len(encoder_rates)
+    snake(f"encoder.block.{n + 1}", c)
+    conv(f"encoder.block.{n + 2}", latent_dim, c, 3)
+    conv("en_conv_post", 2 * latent_dim, latent_dim, 1)
+    return sd
+
+
+def audio_clip(index, samples):
+    """Synthetic mono audio in (-1, 1): a few sinusoids plus noise, deterministic per index."""
+    t = torch.arange(samples, dtype=torch.float32) / 24000.0
+    f = 380.0 + 300.0 * _uniform(9000 + index, "audio.f", (4,), 1.0)
+    a = 0.2 + 0.1 * _uniform(9000 + index, "audio.a", (4,), 1.0)
+    x = sum(a[i] * torch.sin(2 * math.pi * f[i] * t + i) for i in range(4))
+    x = x + 0.05 * _normal(9000 + index, "audio.n", (samples,), 1.0)
+    return x.clamp(-0.99, 0.99).reshape(1, 1, samples)
+
+
 def fixed_noise(frames=NOISE_FRAMES, channels=80):
     """``CausalConditionalCFM.rand_noise`` (flow_matching.py:320-321): seed-0 torch randn.
     Does not disturb the caller's global RNG state (the reference does)."""

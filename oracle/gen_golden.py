@@ -90,11 +90,30 @@ def main():
             print("dac", name, y.shape, float(y.abs().max()))
         np.savez_compressed(os.path.join(OUT, "dac_golden.npz"), **out)
 
+        # ---- DAC-VAE encode (model.py:469-483): m and logs are deterministic; z = m + randn * exp(logs) is not stored
+        esd = synth.dac_encoder_state_dict(DAC_SEED + 1, init="test")
+        missing, unexpected = dac.load_state_dict(esd, strict=False)
+        assert not unexpected and all(k.startswith(("decoder.", "de_conv_pre.")) for k in missing), (missing[:5], unexpected)
+        out = {"weights_seed": DAC_SEED + 1, "weights_checksum": synth.checksum(esd)}
+        import contextlib, io
+        for name, frames, idx in [("a", 12, 0), ("b", 3, 1)]:
+            audio = synth.audio_clip(idx, frames * 480)
+            with contextlib.redirect_stdout(io.StringIO()):  # the reference prints a shape
+                z, m, logs = dac.encode(audio)
+            out[f"enc_{name}_frames"] = frames
+            out[f"enc_{name}_index"] = idx
+            out[f"enc_{name}_m"] = m.numpy()
+            out[f"enc_{name}_logs"] = logs.numpy()
+            print("enc", name, m.shape, float(m.abs().mean()), float(logs.abs().mean()))
+        np.savez_compressed(os.path.join(OUT, "dac_enc_golden.npz"), **out)
+
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
         import json
         keys = {"estimator": {k: list(v.shape) for k, v in est.state_dict().items()},
                 "dac_decoder": {k: list(v.shape) for k, v in dac.state_dict().items()
-                                if k.startswith(("decoder.", "de_conv_pre."))}}
+                                if k.startswith(("decoder.", "de_conv_pre."))},
+                "dac_encoder": {k: list(v.shape) for k, v in dac.state_dict().items()
+                                if k.startswith(("encoder.", "en_conv_post."))}}
         with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
             json.dump(keys, f, indent=0, sort_keys=True)
 

@@ -241,6 +241,33 @@ def dac_decode(sd, z, taps=None):
     return torch.tanh(x)
 
 
+def dac_encode(sd, audio, noise=None):
+    """DACVAE.encode model.py:469-483 after Encoder (model.py:146-234): audio [B,1,S] (S a multiple of the hop) ->
+    (z, m, logs), each [B,latent,S/hop].  ``noise`` ([B,latent,L], optional) replaces torch.randn_like for parity
+    (z = m + noise * exp(logs)); without it z = m."""
+    rates = []
+    while f"encoder.block.{len(rates) + 1}.block.4.0.weight_v" in sd:
+        rates.append(sd[f"encoder.block.{len(rates) + 1}.block.4.0.weight_v"].shape[-1] // 2)
+    x = wn_conv_lrelu(sd, "encoder.block.0", audio, 1, 3)
+    for i, s in enumerate(rates):
+        p = f"encoder.block.{i + 1}.block"
+        for j, d in enumerate((1, 3, 9)):
+            x = residual_unit(sd, f"{p}.{j}", x, d)
+        x = snake(x, sd[p + ".3.alpha"])
+        x = F.leaky_relu(F.conv1d(x, wn_weight(sd, p + ".4.0"), sd[p + ".4.0.bias"], stride=s,
+                                  padding=math.ceil(s / 2)), 0.1)  # model.py:183-189 (+ the shadow's LeakyReLU)
+    n = len(rates)
+    x = snake(x, sd[f"encoder.block.{n + 1}.alpha"])
+    x = wn_conv_lrelu(sd, f"encoder.block.{n + 2}", x, 1, 1)
+    x = F.leaky_relu(x)  # model.py:475 (slope 0.01)
+    x = wn_conv_lrelu(sd, "en_conv_post", x)
+    latent = x.shape[1] // 2
+    m, logs = torch.split(x, latent, dim=1)
+    logs = torch.clamp(logs, min=-14.0, max=14.0)
+    z = m if noise is None else m + noise * torch.exp(logs)
+    return z, m, logs
+
+
 def dac_decode_varlen(sd, z, lengths):
     """Per-utterance semantics for a right-padded batch: utterance b is decoded alone at its own
     length (this is what a loop over the reference's ``decode`` gives); padding is zero."""

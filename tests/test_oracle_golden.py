@@ -82,3 +82,21 @@ def test_dac_varlen_is_per_utterance(dac):
         y1 = O.dac_decode(sd, z[1:2, :, :3])
     assert torch.equal(y[1, :, :1440], y1[0])
     assert float(y[1, :, 1440:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_dac_encode_matches_reference(golden_dir, case):
+    """oracle.dac_encode against DACVAE.encode of the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "dac_enc_golden.npz"))
+    sd = synth.dac_encoder_state_dict(int(g["weights_seed"]), init="test")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    audio = synth.audio_clip(int(g[f"enc_{case}_index"]), int(g[f"enc_{case}_frames"]) * 480)
+    with torch.inference_mode():
+        z, m, logs = O.dac_encode(sd, audio)
+    assert O.rel_l2(m, torch.from_numpy(g[f"enc_{case}_m"])) < 1e-5
+    assert O.rel_l2(logs, torch.from_numpy(g[f"enc_{case}_logs"])) < 1e-5
+    assert torch.equal(z, m)
+    noise = torch.ones_like(m)
+    with torch.inference_mode():
+        z2, _, _ = O.dac_encode(sd, audio, noise)
+    assert torch.allclose(z2, m + torch.exp(logs))
