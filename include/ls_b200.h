@@ -88,8 +88,8 @@ int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* 
 
 /* DACVAE.encode (dac-vae/model.py:469-483; bulk latent extraction, dac-vae/extract_dac_latents.py:20-54): audio
  * [B,1,S] with S a multiple of the hop -> z, m, logs, each [B,latent,S/hop]; z = m + noise * exp(logs) with the
- * caller's noise [B,latent,S/hop] (NULL: z = m).  fp32-mode handles only (the handle's weights must contain the
- * encoder.* / en_conv_post.* entries); LS_ERR_UNSUPPORTED on a tensor-core handle. */
+ * caller's noise [B,latent,S/hop] (NULL: z = m).  The handle's weights must contain the encoder.* / en_conv_post.*
+ * entries (ls_dac_create builds the decoder, the encoder, or both, from whatever the state dict holds). */
 int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* z, float* m, float* logs, int32_t B,
                       int32_t S, void* stream);
 

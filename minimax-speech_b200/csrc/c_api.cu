@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <mutex>
 
+#include "dac_enc_engine.h"
 #include "dac_engine.h"
 #include "engine_common.h"
 #include "f32_path.h"
@@ -94,12 +95,14 @@ struct ls_flow {
   size_t stage_bytes = 0;
 };
 struct ls_dac {
-  std::unique_ptr<ls::DacEngine> eng;
-  std::unique_ptr<ls::DacEngineF32> eng32;
-  int hop() const { return eng ? eng->hop() : eng32->hop(); }
+  std::unique_ptr<ls::DacEngine> eng;       // tensor-core decoder (state dict holds decoder.* / de_conv_pre.*)
+  std::unique_ptr<ls::DacEncEngine> enc;    // tensor-core encoder (state dict holds encoder.* / en_conv_post.*)
+  std::unique_ptr<ls::DacEngineF32> eng32;  // fp32 mode: both directions
+  int hop() const { return eng ? eng->hop() : enc ? enc->hop() : eng32->hop(); }
   void decode(const float* z, const int* lengths, float* wav, int B, int L, cudaStream_t s) {
     if (eng) eng->decode(z, lengths, wav, B, L, s);
-    else eng32->decode(z, lengths, wav, B, L, s);
+    else if (eng32) eng32->decode(z, lengths, wav, B, L, s);
+    else throw ls::EngineError(LS_ERR_WEIGHTS, "this handle holds no decoder weights");
   }
 };
 
@@ -169,7 +172,10 @@ int32_t ls_dac_create(const ls_tensor* weights, int32_t n_weights, int32_t devic
     ls::require(weights && out && n_weights > 0, "ls_dac_create: null argument");
     ls::Weights w(weights, n_weights);
     auto h = std::make_unique<ls_dac>();
-    h->eng = std::make_unique<ls::DacEngine>(w, device);
+    const bool has_dec = w.has("decoder.model.0.0.weight_v"), has_enc = w.has("encoder.block.0.0.weight_v");
+    ls::require(has_dec || has_enc, "ls_dac_create: neither decoder.* nor encoder.* weights found", LS_ERR_WEIGHTS);
+    if (has_dec) h->eng = std::make_unique<ls::DacEngine>(w, device);
+    if (has_enc) h->enc = std::make_unique<ls::DacEncEngine>(w, device);
     *out = h.release();
   });
 }
@@ -197,9 +203,10 @@ int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* 
                       int32_t S, void* stream) {
   return ls::guarded([&] {
     ls::require(h && audio && z && m && logs, "ls_dac_encode: null argument");
-    ls::require(h->eng32 != nullptr, "ls_dac_encode: the encoder exists in fp32 mode only (create the handle with "
-                                     "ls_dac_create_fp32)", LS_ERR_UNSUPPORTED);
-    h->eng32->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
+    ls::require(h->enc != nullptr || h->eng32 != nullptr, "ls_dac_encode: this handle holds no encoder weights",
+                LS_ERR_WEIGHTS);
+    if (h->enc) h->enc->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
+    else h->eng32->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
   });
 }
 

@@ -10,10 +10,9 @@
 #include "dac_engine.h"
 
 namespace ls {
-namespace {
 
 // Conv1d weight_v [N][K][taps] with weight_g [N] -> folded bf16 [taps][Npad][K]
-PackedLinear pack_wn_conv(Arena& a, const Weights& w, const std::string& p, int n_pad_to = 0) {
+PackedLinear pack_wn_conv(Arena& a, const Weights& w, const std::string& p, int n_pad_to) {
   const ls_tensor& v = w.get(p + ".weight_v");
   const ls_tensor& g = w.get(p + ".weight_g");
   const ls_tensor& b = w.get(p + ".bias");
@@ -42,6 +41,14 @@ PackedLinear pack_wn_conv(Arena& a, const Weights& w, const std::string& p, int 
   pl.has_bias = true;
   return pl;
 }
+
+void finalize_linear(const Arena& a, PackedLinear& pl) {
+  require(make_weight_map(&pl.map, a.ptr<uint8_t>(pl.w_off), pl.K, pl.taps * pl.N, pl.block_n),
+          "cuTensorMapEncodeTiled failed for a weight matrix", LS_ERR_CUDA);
+  pl.bias = a.ptr<float>(pl.bias_off);
+}
+
+namespace {
 
 // ConvTranspose1d weight_v [Cin][Cout][2s], weight_g [Cin] -> two-tap polyphase GEMM, bf16 [2][s*Cout][Cin]:
 //   out[q*s + phi - pad] = in[q] . W[:, :, phi] + in[q-1] . W[:, :, phi + s]        (model.py:255-262)
@@ -73,12 +80,6 @@ PackedLinear pack_wn_convT(Arena& a, const Weights& w, const std::string& p, int
   pl.bias_off = a.put_f32(b.data, cout);
   pl.has_bias = true;
   return pl;
-}
-
-void finalize_linear(const Arena& a, PackedLinear& pl) {
-  require(make_weight_map(&pl.map, a.ptr<uint8_t>(pl.w_off), pl.K, pl.taps * pl.N, pl.block_n),
-          "cuTensorMapEncodeTiled failed for a weight matrix", LS_ERR_CUDA);
-  pl.bias = a.ptr<float>(pl.bias_off);
 }
 
 }  // namespace

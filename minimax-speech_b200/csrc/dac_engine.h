@@ -7,6 +7,10 @@
 
 namespace ls {
 
+// shared with the encoder engine (dac_enc_engine.cu): weight-norm folding + bf16 [taps][N][K] packing
+PackedLinear pack_wn_conv(Arena& a, const Weights& w, const std::string& p, int n_pad_to = 0);
+void finalize_linear(const Arena& a, PackedLinear& pl);
+
 // DAC-VAE decoder (dac-vae/model.py:326-379, 485-488) on time-major activations.
 class DacEngine {
  public:

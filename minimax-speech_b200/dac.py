@@ -67,14 +67,13 @@ class DACVAEDecoder(nn.Module):
 
 class DACVAEEncoder(nn.Module):
     """``DACVAE.encode`` (dac-vae/model.py:469-483) -- SURVEY section 8 row f-3, the path the reference's multi-GPU
-    latent extraction tool runs (extract_dac_latents.py:20-54).  fp32 mode only in this round: the same CUDA-core
-    kernels as the decoder's fp32 mode; the tensor-core encoder is not built yet."""
+    latent extraction tool runs (extract_dac_latents.py:20-54).  precision="bf16": tensor-core path (every
+    ResidualUnit and downsampling convolution is an implicit-GEMM launch); "fp32": validation mode."""
 
     def __init__(self, encoder_dim=64, encoder_rates=(2, 3, 4, 4, 5), latent_dim=80, sample_rate=24000, d_in=1,
-                 weight_seed=0, precision="fp32", **_ignored):
+                 weight_seed=0, precision="bf16", **_ignored):
         super().__init__()
-        if precision != "fp32":
-            raise NotImplementedError("the DAC-VAE encoder runs in fp32 mode only (the tensor-core path is not built yet)")
+        native.check_precision(precision)
         if d_in != 1:
             raise NotImplementedError("mono input only (configx2.yml: d_in=1)")
         self.precision, self.latent_dim, self.sample_rate = precision, latent_dim, sample_rate
@@ -95,7 +94,7 @@ class DACVAEEncoder(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
         if self._handle is None or self._handle.device != device:
-            self._handle = native.DacHandle(self.state_dict(), device, "fp32")
+            self._handle = native.DacHandle(self.state_dict(), device, self.precision)
         return self._handle
 
     def preprocess(self, audio_data):
