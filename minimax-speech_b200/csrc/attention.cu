@@ -22,14 +22,18 @@ namespace ls {
 namespace {
 
 constexpr int kQ = 128;
-constexpr int kKV = 128;
+constexpr int kKV = ATTN_KV;       // keys per tile: 128 (2 CTAs per SM) or 64 (3 CTAs per SM, 128 TMEM columns each)
+constexpr int kChunks = kKV / 32;  // 32-score register chunks per row and tile
+constexpr int kPBlocks = kKV / 64; // 64-key K blocks of the P tile
+constexpr int kCtasPerSm = kKV == 128 ? 2 : 3;
 constexpr int kD = 64;
 constexpr int kTile = kQ * kD * 2;  // 16 KB: 128 rows x 128 B
 constexpr int kSoftmaxWarps = 4;    // warp w owns TMEM lanes [32w, 32w+32) = query rows
 constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
 constexpr int kAttnThreads = kSoftmaxThreads + 32;  // + control warp
-constexpr int kAttnSmem = 6 * kTile + 1024 + 256;   // Q, K x2, V, P x2 (two 64-key K blocks), align slack, barriers
-constexpr int kAttnTmemCols = 256;                  // S: cols [0,128)   O: cols [128,192)
+constexpr int kKVTile = kKV * kD * 2;  // one K or V tile: kKV rows x 128 B
+constexpr int kAttnSmem = kTile + 3 * kKVTile + kPBlocks * kTile + 1024 + 256;  // Q, K x2, V, P, align slack, barriers
+constexpr int kAttnTmemCols = kKV == 128 ? 256 : 128;  // S: cols [0,kKV)   O: cols [kKV,kKV+64)
 constexpr float kRescaleThreshold = 8.0f;
 #ifndef ATTN_POLY_MASK
 #define ATTN_POLY_MASK 0x00
@@ -60,7 +64,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, floa
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, kCtasPerSm)
 attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapOut,
             const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
@@ -79,9 +83,9 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;      // 2 stages
-  uint8_t* sV = smem + 3 * kTile;
-  uint8_t* sP = smem + 4 * kTile;  // 2 K-blocks of 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTile);
+  uint8_t* sV = sK + 2 * kKVTile;
+  uint8_t* sP = sV + kKVTile;      // kPBlocks K-blocks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBlocks * kTile);
   uint64_t* bar_q = bars;
   uint64_t* bar_k = bars + 1;  // [2]
   uint64_t* bar_v = bars + 3;
@@ -117,7 +121,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TL(15);
   const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + kKV;
   // Everything above (barriers, TMEM) overlapped the previous kernel's tail; lengths and QKV are read from here on.
   pdl_wait();
   int len = p.lengths ? p.lengths[b] : p.T;
@@ -134,21 +138,22 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       // ------------------------------------------------ control thread: TMA loads + MMA issue
       const int inner = p.H * kD;
       const int colq = h * kD, colk = inner + h * kD, colv = 2 * inner + h * kD;
-      mbar_arrive_expect_tx(bar_q, kTile);
-      tma_load_3d(sQ, &mapQKV, bar_q, colq, q0, b);
-      mbar_arrive_expect_tx(&bar_k[0], kTile);
+      mbar_arrive_expect_tx(bar_q, kTile);  // (the tensor map's boxes have kKV rows: the Q tile takes 128 / kKV loads)
+#pragma unroll
+      for (int i = 0; i < kQ / kKV; ++i) tma_load_3d(sQ + i * kKVTile, &mapQKV, bar_q, colq, q0 + i * kKV, b);
+      mbar_arrive_expect_tx(&bar_k[0], kKVTile);
       tma_load_3d(sK, &mapQKV, &bar_k[0], colk, 0, b);
-      mbar_arrive_expect_tx(bar_v, kTile);
+      mbar_arrive_expect_tx(bar_v, kKVTile);
       tma_load_3d(sV, &mapQKV, bar_v, colv, 0, b);
       if (nkv > 1) {
-        mbar_arrive_expect_tx(&bar_k[1], kTile);
-        tma_load_3d(sK + kTile, &mapQKV, &bar_k[1], colk, kKV, b);
+        mbar_arrive_expect_tx(&bar_k[1], kKVTile);
+        tma_load_3d(sK + kKVTile, &mapQKV, &bar_k[1], colk, kKV, b);
       }
       const uint32_t idesc_s = make_idesc_bf16(kQ, kKV, false, false);
       const uint32_t idesc_o = make_idesc_bf16(kQ, kD, false, true);  // B = V tile, MN-major
       const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ));
       auto issue_s = [&](int j) {
-        const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + (j & 1) * kTile));
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + (j & 1) * kKVTile));
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(bar_s);
@@ -186,8 +191,8 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
           issue_s(j + 1);
         }
         if (j + 2 < nkv) {  // S(j) has retired (the softmax warps read it): K buffer j&1 is free
-          mbar_arrive_expect_tx(&bar_k[j & 1], kTile);
-          tma_load_3d(sK + (j & 1) * kTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
+          mbar_arrive_expect_tx(&bar_k[j & 1], kKVTile);
+          tma_load_3d(sK + (j & 1) * kKVTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
         }
         mbar_wait(bar_p, j & 1);  // P(j) written, O rescaled where needed
         tc_fence_after();
@@ -201,7 +206,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
         if (j < 4) TL(4 + 2 * j);
         if (j + 1 < nkv) {
           mbar_wait(bar_o, j & 1);  // P(j) V(j) retired: the V buffer is free
-          mbar_arrive_expect_tx(bar_v, kTile);
+          mbar_arrive_expect_tx(bar_v, kKVTile);
           tma_load_3d(sV, &mapQKV, bar_v, colv, (j + 1) * kKV, b);
         }
       }
@@ -229,9 +234,9 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
       if (j < 4) TLS(16 + 6 * j);
-      uint32_t s[4][32];
+      uint32_t s[kChunks][32];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tmem_ld32(s_addr + cc * 32, s[cc]);
+      for (int cc = 0; cc < kChunks; ++cc) tmem_ld32(s_addr + cc * 32, s[cc]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -240,7 +245,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       const int nvalid = limit - j * kKV;  // valid keys of this row in this tile (may be <= 0 for streaming rows)
       if (nvalid < kKV) {  // masked keys: -inf scores (exp2 -> 0); only the last key tile of a row pays for this
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
+        for (int cc = 0; cc < kChunks; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (cc * 32 + i >= nvalid) s[cc][i] = 0xff800000u;
@@ -249,7 +254,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
 #pragma unroll
       for (int a = 0; a < 8; ++a) pm[a] = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
+      for (int cc = 0; cc < kChunks; ++cc)
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
           pm[(i >> 1) & 7] = fmaxf(pm[(i >> 1) & 7], fmaxf(__uint_as_float(s[cc][i]), __uint_as_float(s[cc][i + 1])));
@@ -262,9 +267,9 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       const float alpha = (grow && j > 0) ? ex2_approx(m - m_new) : 1.0f;
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[4][16];
+      uint32_t pk[kChunks][16];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) exp_chunk(s[cc], c, m_use, pk[cc], sum0, sum1);
+      for (int cc = 0; cc < kChunks; ++cc) exp_chunk(s[cc], c, m_use, pk[cc], sum0, sum1);
       l = fmaf(l, alpha, sum0 + sum1);
       m = m_new;
       if (j < 4) TLS(19 + 6 * j);
@@ -287,7 +292,7 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       }
       if (j < 4) TLS(20 + 6 * j);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < kChunks; ++cc) {
         uint8_t* blk = prow + (cc >> 1) * kTile;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {

@@ -312,7 +312,7 @@ int32_t ls_test_attention(const void* qkv, void* out, const int32_t* lengths, in
   return ls::guarded([&] {
     ls::require(qkv && out, "ls_test_attention: null argument");
     CUtensorMap m;
-    ls::require(ls::make_act_map(&m, qkv, 3 * H * 64, T, B, 3 * H * 64, (long long)T * 3 * H * 64, 128),
+    ls::require(ls::make_act_map(&m, qkv, 3 * H * 64, T, B, 3 * H * 64, (long long)T * 3 * H * 64, ATTN_KV),
                 "tensor map qkv", LS_ERR_CUDA);
     ls::AttnParams ap{};
     ap.B = B, ap.T = T, ap.H = H, ap.lengths = lengths, ap.chunk = chunk;

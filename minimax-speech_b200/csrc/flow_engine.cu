@@ -80,7 +80,7 @@ struct ActMaps {
 struct FlowEngine::Plan {
   ActMaps xin, hA, hB, skip, nrm, qkv, att, ff;
   // flattened [B2*T][C] views for the fused block kernel (TMA loads and stores)
-  CUtensorMap att_flat, u_flat, qkv_flat, tail_skip, tail_hB;
+  CUtensorMap att_flat, u_flat, qkv_flat, tail_skip, tail_hB, qkv_attn;
 };
 
 FlowEngine::~FlowEngine() {
@@ -293,6 +293,8 @@ const FlowEngine::Plan& FlowEngine::plan_for(int B2, int T) {
   mk(&pl->skip, o_skip_, C_);
   mk(&pl->nrm, o_nrm_, C_);
   mk(&pl->qkv, o_qkv_, 3 * inner);
+  require(make_act_map(&pl->qkv_attn, ws_base_ + o_qkv_, 3 * inner, T, B2, 3 * inner, (long long)T * 3 * inner, ATTN_KV),
+          "cuTensorMapEncodeTiled failed for the attention view of QKV", LS_ERR_CUDA);
   mk(&pl->att, o_att_, inner);
   mk(&pl->ff, o_ff_, 4 * C_);
   const long long R = (long long)B2 * T;
@@ -387,7 +389,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
       ap.scale_log2e = 0.125f * 1.4426950408889634f;
       ap.out = ws<__nv_bfloat16>(o_att_);
-      LS_CUDA(launch_attention(pl.qkv.k1, ap, s));
+      LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
     };
     if (fused_blocks_) {
       // QKV of the first block: LayerNorm(norm1) + projection straight from u (head mode of the fused kernel);
@@ -427,7 +429,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
         ap.scale_log2e = 0.125f * 1.4426950408889634f;
         ap.out = ws<__nv_bfloat16>(o_att_);
-        LS_CUDA(launch_attention(pl.qkv.k1, ap, s));
+        LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
       }
       {  // to_out + residual, then LayerNorm(norm3)
         Epi e;
