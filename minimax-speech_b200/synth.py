@@ -181,6 +181,63 @@ def dac_encoder_state_dict(seed=0, init="reference", encoder_dim=64, encoder_rat
     return sd
 
 
+def conformer_encoder_state_dict(seed=7, d=512, heads=8, ff=2048, num_blocks=6, num_up_blocks=4, out_dim=80, vocab=6561,
+                                 spk_dim=192, **_):
+    """Keys/shapes of the token -> mu front half of CausalMaskedDiffWithXvec (flow/flow.py:437-511): input_embedding,
+    encoder.* (UpsampleConformerEncoder, transformer/upsample_encoder.py), encoder_proj, spk_embed_affine_layer.
+    Test initialisation only (every tensor non-trivial)."""
+    sd = {}
+
+    def lin(name, n, k, bias=True):
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (n, k), 1.0 / math.sqrt(k))
+        if bias:
+            sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 1.0 / math.sqrt(k))
+
+    def ln(name, n):
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (n,), 0.2).add(1.0)
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 0.1)
+
+    def conv(name, n, c, k):
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (n, c, k), 1.0 / math.sqrt(c * k))
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 1.0 / math.sqrt(c * k))
+
+    def layer(p):
+        sd[p + ".self_attn.pos_bias_u"] = _uniform(seed, p + ".u", (heads, d // heads), 0.1)
+        sd[p + ".self_attn.pos_bias_v"] = _uniform(seed, p + ".v", (heads, d // heads), 0.1)
+        for nm in ("q", "k", "v", "out"):
+            lin(f"{p}.self_attn.linear_{nm}", d, d)
+        lin(p + ".self_attn.linear_pos", d, d, bias=False)
+        lin(p + ".feed_forward.w_1", ff, d)
+        lin(p + ".feed_forward.w_2", d, ff)
+        ln(p + ".norm_ff", d)
+        ln(p + ".norm_mha", d)
+
+    sd["input_embedding.weight"] = _normal(seed, "input_embedding.weight", (vocab, d), 1.0)
+    lin("encoder.embed.out.0", d, d)
+    ln("encoder.embed.out.1", d)
+    conv("encoder.pre_lookahead_layer.conv1", d, d, 4)
+    conv("encoder.pre_lookahead_layer.conv2", d, d, 3)
+    for i in range(num_blocks):
+        layer(f"encoder.encoders.{i}")
+    conv("encoder.up_layer.conv", d, d, 5)
+    lin("encoder.up_embed.out.0", d, d)
+    ln("encoder.up_embed.out.1", d)
+    for i in range(num_up_blocks):
+        layer(f"encoder.up_encoders.{i}")
+    ln("encoder.after_norm", d)
+    lin("encoder_proj", out_dim, d)
+    lin("spk_embed_affine_layer", out_dim, spk_dim)
+    return sd
+
+
+def token_inputs(index, n_tokens, vocab=6561, spk_dim=192):
+    """Synthetic FSQ tokens (25 Hz) and a speaker embedding."""
+    r = _rng(7000 + index, "tokens")
+    tok = torch.from_numpy(r.integers(0, vocab, size=(1, n_tokens)).astype(np.int64))
+    emb = _normal(7000 + index, "xvec", (1, spk_dim), 1.0)
+    return tok, emb
+
+
 def audio_clip(index, samples):
     """Synthetic mono audio in (-1, 1): a few sinusoids plus noise, deterministic per index."""
     t = torch.arange(samples, dtype=torch.float32) / 24000.0

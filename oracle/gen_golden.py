@@ -20,6 +20,7 @@ import minimax_speech_b200.synth as synth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 EST_SEED, DAC_SEED = 7, 11
+ENC_SEED = 7
 
 
 def est_inputs(lengths, seed):
@@ -106,6 +107,29 @@ def main():
             out[f"enc_{name}_logs"] = logs.numpy()
             print("enc", name, m.shape, float(m.abs().mean()), float(logs.abs().mean()))
         np.savez_compressed(os.path.join(OUT, "dac_enc_golden.npz"), **out)
+
+        # ---- token -> mu front half: the reference UpsampleConformerEncoder on embedded tokens
+        import importlib
+        R.install_stubs()
+        um = importlib.import_module("cosyvoice.transformer.upsample_encoder")
+        enc = um.UpsampleConformerEncoder(
+            input_size=512, output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+            positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True, input_layer="linear",
+            pos_enc_layer_type="rel_pos_espnet", selfattention_layer_type="rel_selfattn", use_cnn_module=False,
+            macaron_style=False, static_chunk_size=25).eval()  # config.yaml:73-88
+        csd = synth.conformer_encoder_state_dict(ENC_SEED)
+        enc.load_state_dict({k[len("encoder."):]: v for k, v in csd.items() if k.startswith("encoder.")}, strict=True)
+        out = {"weights_seed": ENC_SEED, "weights_checksum": synth.checksum(csd)}
+        for name, lens in [("a", [40]), ("b", [23, 15])]:
+            toks = [synth.token_inputs(i, n)[0] for i, n in enumerate(lens)]
+            x = torch.zeros(len(lens), max(lens), 512)
+            for b, t in enumerate(toks):
+                x[b, :t.shape[1]] = torch.nn.functional.embedding(t[0], csd["input_embedding.weight"])
+            h, _ = enc(x, torch.tensor(lens))
+            out[f"enc_{name}_lens"] = np.array(lens)
+            out[f"enc_{name}_h"] = h.numpy()
+            print("conformer", name, h.shape, float(h.abs().mean()))
+        np.savez_compressed(os.path.join(OUT, "conformer_golden.npz"), **out)
 
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
         import json

@@ -283,6 +283,98 @@ def dac_decode_varlen(sd, z, lengths):
 
 
 # --------------------------------------------------------------------------------------
+# token -> mu front half: flow/flow.py:437-511, transformer/upsample_encoder.py
+# --------------------------------------------------------------------------------------
+def rel_pos_emb(T, d):
+    """EspnetRelPositionalEncoding (transformer/embedding.py:224-300): [1, 2T-1, d], row n = relative position T-1-n."""
+    pos = torch.arange(T - 1, -T, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(2 * T - 1, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.unsqueeze(0)
+
+
+def rel_attention(sd, p, x, pos_emb, key_mask, heads):
+    """RelPositionMultiHeadedAttention.forward (transformer/attention.py:249-330) + forward_attention (:84-127).
+    x [B,T,d]; key_mask [B,T] bool; bd[i,j] = (q_i + v) . p[T-1-i+j] (the rel_shift of :225-247 in closed form)."""
+    B, T, d = x.shape
+    dk = d // heads
+    q = F.linear(x, sd[p + ".linear_q.weight"], sd[p + ".linear_q.bias"]).view(B, T, heads, dk)
+    k = F.linear(x, sd[p + ".linear_k.weight"], sd[p + ".linear_k.bias"]).view(B, T, heads, dk).transpose(1, 2)
+    v = F.linear(x, sd[p + ".linear_v.weight"], sd[p + ".linear_v.bias"]).view(B, T, heads, dk).transpose(1, 2)
+    pp = F.linear(pos_emb, sd[p + ".linear_pos.weight"]).view(1, -1, heads, dk).transpose(1, 2)  # [1,h,2T-1,dk]
+    qu = (q + sd[p + ".pos_bias_u"]).transpose(1, 2)
+    qv = (q + sd[p + ".pos_bias_v"]).transpose(1, 2)
+    ac = torch.matmul(qu, k.transpose(-2, -1))
+    bd_full = torch.matmul(qv, pp.transpose(-2, -1))  # [B,h,T,2T-1]
+    idx = (T - 1 - torch.arange(T).unsqueeze(1) + torch.arange(T).unsqueeze(0)).to(x.device)  # [T,T]
+    bd = torch.gather(bd_full, 3, idx.expand(B, heads, T, T))
+    scores = (ac + bd) / math.sqrt(dk)
+    dead = ~key_mask.view(B, 1, 1, T)
+    attn = torch.softmax(scores.masked_fill(dead, float("-inf")), dim=-1).masked_fill(dead, 0.0)
+    o = torch.matmul(attn, v).transpose(1, 2).reshape(B, T, d)
+    return F.linear(o, sd[p + ".linear_out.weight"], sd[p + ".linear_out.bias"])
+
+
+def conformer_layer(sd, p, x, pos_emb, key_mask, heads):
+    """ConformerEncoderLayer.forward (transformer/encoder_layer.py:109-) for normalize_before, no macaron, no conv
+    module (config.yaml:73-88): x += attn(LN(x)); x += FF(LN(x)), FF = w_2(swish(w_1(.)))."""
+    n = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm_mha.weight"], sd[p + ".norm_mha.bias"], 1e-5)
+    x = x + rel_attention(sd, p + ".self_attn", n, pos_emb, key_mask, heads)
+    n = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm_ff.weight"], sd[p + ".norm_ff.bias"], 1e-5)
+    h = F.silu(F.linear(n, sd[p + ".feed_forward.w_1.weight"], sd[p + ".feed_forward.w_1.bias"]))
+    return x + F.linear(h, sd[p + ".feed_forward.w_2.weight"], sd[p + ".feed_forward.w_2.bias"])
+
+
+def upsample_conformer_encode(sd, xs, lens, heads=8, prefix="encoder."):
+    """UpsampleConformerEncoder.forward (upsample_encoder.py:266-318), non-streaming, no look-ahead context
+    (the finalize=True call of flow.py:480-481).  xs [B,T,512] (embedded tokens), lens [B] -> ([B,2T,512], 2*lens)."""
+    P = prefix
+    B, T, d = xs.shape
+    key_mask = torch.arange(T, device=xs.device).unsqueeze(0) < lens.unsqueeze(1)
+
+    def embed(pp, x):  # LinearNoSubsampling (subsampling.py:69-113) + rel-pos encoding scale (embedding.py:268)
+        x = F.linear(x, sd[pp + ".out.0.weight"], sd[pp + ".out.0.bias"])
+        x = F.layer_norm(x, (d,), sd[pp + ".out.1.weight"], sd[pp + ".out.1.bias"], 1e-5)
+        return x * math.sqrt(d), rel_pos_emb(x.shape[1], d).to(x.device)
+
+    x, pos = embed(P + "embed", xs)
+    # PreLookaheadLayer (upsample_encoder.py:66-107) without context: right-pad 3, conv k=4, leaky_relu, causal conv k=3
+    y = F.pad(x.transpose(1, 2), (0, 3))
+    y = F.leaky_relu(F.conv1d(y, sd[P + "pre_lookahead_layer.conv1.weight"], sd[P + "pre_lookahead_layer.conv1.bias"]))
+    y = F.conv1d(F.pad(y, (2, 0)), sd[P + "pre_lookahead_layer.conv2.weight"], sd[P + "pre_lookahead_layer.conv2.bias"])
+    x = y.transpose(1, 2) + x
+    i = 0
+    while f"{P}encoders.{i}.norm_mha.weight" in sd:
+        x = conformer_layer(sd, f"{P}encoders.{i}", x, pos, key_mask, heads)
+        i += 1
+    # Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5
+    y = F.interpolate(x.transpose(1, 2), scale_factor=2.0, mode="nearest")
+    y = F.conv1d(F.pad(y, (4, 0)), sd[P + "up_layer.conv.weight"], sd[P + "up_layer.conv.bias"])
+    lens2 = lens * 2
+    key_mask = torch.arange(2 * T, device=xs.device).unsqueeze(0) < lens2.unsqueeze(1)
+    x, pos = embed(P + "up_embed", y.transpose(1, 2))
+    i = 0
+    while f"{P}up_encoders.{i}.norm_mha.weight" in sd:
+        x = conformer_layer(sd, f"{P}up_encoders.{i}", x, pos, key_mask, heads)
+        i += 1
+    x = F.layer_norm(x, (d,), sd[P + "after_norm.weight"], sd[P + "after_norm.bias"], 1e-5)
+    return x, lens2
+
+
+def tokens_to_mu(sd, token, embedding):
+    """CausalMaskedDiffWithXvec.inference front half (flow.py:461-489) for one utterance, finalize=True, no prompt:
+    (mu [1,80,2T], spks [1,80])."""
+    spks = F.linear(F.normalize(embedding, dim=1), sd["spk_embed_affine_layer.weight"], sd["spk_embed_affine_layer.bias"])
+    x = F.embedding(torch.clamp(token, min=0), sd["input_embedding.weight"])
+    lens = torch.tensor([token.shape[1]])
+    h, _ = upsample_conformer_encode(sd, x, lens)
+    mu = F.linear(h, sd["encoder_proj.weight"], sd["encoder_proj.bias"])
+    return mu.transpose(1, 2).contiguous(), spks
+
+
+# --------------------------------------------------------------------------------------
 # Parity metrics (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------
 

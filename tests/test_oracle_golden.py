@@ -100,3 +100,21 @@ def test_dac_encode_matches_reference(golden_dir, case):
     with torch.inference_mode():
         z2, _, _ = O.dac_encode(sd, audio, noise)
     assert torch.allclose(z2, m + torch.exp(logs))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_conformer_encoder_matches_reference(golden_dir, case):
+    """oracle.upsample_conformer_encode against the unmodified UpsampleConformerEncoder."""
+    g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
+    sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    lens = [int(v) for v in g[f"enc_{case}_lens"]]
+    x = torch.zeros(len(lens), max(lens), 512)
+    for b, n in enumerate(lens):
+        x[b, :n] = torch.nn.functional.embedding(synth.token_inputs(b, n)[0][0], sd["input_embedding.weight"])
+    with torch.inference_mode():
+        h, l2 = O.upsample_conformer_encode(sd, x, torch.tensor(lens))
+    ref = torch.from_numpy(g[f"enc_{case}_h"])
+    for b, n in enumerate(lens):
+        assert int(l2[b]) == 2 * n
+        assert O.rel_l2(h[b, :2 * n], ref[b, :2 * n]) < 1e-5
