@@ -93,6 +93,17 @@ int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* 
 int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* z, float* m, float* logs, int32_t B,
                       int32_t S, void* stream);
 
+/* ---- token -> mu front half: CausalMaskedDiffWithXvec.inference up to the decoder call
+ * (speech/cosyvoice/flow/flow.py:461-489): speaker-embedding normalise + affine, input embedding,
+ * UpsampleConformerEncoder (speech/cosyvoice/transformer/upsample_encoder.py:266-318), encoder_proj.
+ * fp32 mode only in this round; finalize = True, no prompt tokens, equal-length batches.
+ * tokens [B,T] int64 (25 Hz FSQ ids), embedding [B,192] -> mu [B,80,2T], spks [B,80] (the inputs of ls_flow_solve). */
+typedef struct ls_front ls_front;
+int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out);
+void ls_front_destroy(ls_front* h);
+int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
+                        int32_t T, void* stream);
+
 /* ---- end to end with HOST buffers (pinned or pageable): H2D copies, solve, decode, D2H copy, and a
  * stream synchronise all happen inside the call.  wav_host: [B,1,T*hop]. */
 int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,

@@ -106,7 +106,29 @@ struct ls_dac {
   }
 };
 
+struct ls_front {
+  std::unique_ptr<ls::FrontEngineF32> eng32;
+};
+
 extern "C" {
+
+int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_front_create_fp32: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_front>();
+    h->eng32 = std::make_unique<ls::FrontEngineF32>(w, device);
+    *out = h.release();
+  });
+}
+void ls_front_destroy(ls_front* h) { delete h; }
+int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
+                        int32_t T, void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
+    h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, (cudaStream_t)stream);
+  });
+}
 
 int32_t ls_abi_version(void) { return LS_ABI_VERSION; }
 const char* ls_last_error(void) { return ls::get_error(); }

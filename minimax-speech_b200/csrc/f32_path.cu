@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTB) attention_nct_kernel(const float* __restr
   for (int d = 0; d < 64; ++d) o[base + (size_t)d * T + i] = acc[d] * inv;
 }
 
-enum { EW_ADD = 0, EW_GELU = 1, EW_TANH = 2, EW_LRELU001 = 3 };
+enum { EW_ADD = 0, EW_GELU = 1, EW_TANH = 2, EW_LRELU001 = 3, EW_SILU = 4 };
 __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n, int op) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -164,6 +164,7 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
   if (op == EW_ADD) r = x + b[i];
   else if (op == EW_GELU) r = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // F.gelu(approximate="none")
   else if (op == EW_TANH) r = tanhf(x);
+  else if (op == EW_SILU) r = x / (1.0f + expf(-x));  // swish (transformer/positionwise_feed_forward.py:55)
   else r = x > 0.f ? x : 0.01f * x;  // F.leaky_relu default slope (dac-vae/model.py:475)
   y[i] = r;
 }
@@ -291,6 +292,91 @@ __global__ void reparam_kernel(const float* __restrict__ x, const float* __restr
   const float lv = fminf(fmaxf(x[(b * 2 * latent + latent + c) * L + t], -14.0f), 14.0f);
   m[i] = mv, logs[i] = lv;
   z[i] = noise ? mv + noise[i] * expf(lv) : mv;
+}
+
+// ---- token -> mu front half -------------------------------------------------------------
+// x[b,c,t] = E[clamp(tok[b,t], 0)][c]   (flow/flow.py:476: input_embedding(torch.clamp(token, min=0)))
+__global__ void embed_tokens_kernel(const long long* __restrict__ tok, const float* __restrict__ E, float* __restrict__ x, int d,
+                                    int T, int vocab, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  const int c = (int)((i / T) % d);
+  const size_t b = i / ((size_t)T * d);
+  long long id = tok[b * T + t];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  x[i] = E[(size_t)id * d + c];
+}
+__global__ void scale_kernel(float* __restrict__ x, float sc, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= sc;
+}
+// EspnetRelPositionalEncoding (transformer/embedding.py:224-300): pe[n][:] for relative position T-1-n, n in [0, 2T-1)
+__global__ void rel_pos_emb_kernel(float* __restrict__ pe, int T, int d) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  const int n = blockIdx.y;
+  if (c2 >= d / 2) return;
+  const float pos = (float)(T - 1 - n);
+  const float div = expf((float)(2 * c2) * -(logf(10000.0f) / (float)d));
+  pe[(size_t)n * d + 2 * c2] = sinf(pos * div);
+  pe[(size_t)n * d + 2 * c2 + 1] = cosf(pos * div);
+}
+// RelPositionMultiHeadedAttention (transformer/attention.py:249-330) on q,k,v [B,H*64,T] (NCT) and the projected
+// positions pp [2T-1][H*64]: score(i,j) = ((q_i + u) . k_j + (q_i + v) . pp[T-1-i+j]) / sqrt(64) for j < len[b]
+// (rel_shift of :225-247 in closed form); softmax; . v.  One thread per (b, h, query).
+__global__ void __launch_bounds__(kTB) rel_attention_nct_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                const float* __restrict__ v, const float* __restrict__ pp,
+                                                                const float* __restrict__ bu, const float* __restrict__ bv,
+                                                                float* __restrict__ o, int H, int T, int len) {
+  const int i = blockIdx.x * kTB + threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  if (i >= T) return;
+  const size_t base = ((size_t)b * H + h) * 64 * T;
+  const int inner = H * 64;
+  float qu[64], qv[64], acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) {
+    const float qq = q[base + (size_t)d * T + i];
+    qu[d] = qq + bu[h * 64 + d], qv[d] = qq + bv[h * 64 + d], acc[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < len; ++j) {
+    const float* pr = pp + (size_t)(T - 1 - i + j) * inner + h * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s = fmaf(qu[d], k[base + (size_t)d * T + j], fmaf(qv[d], pr[d], s));
+    s *= 0.125f;
+    const float m_new = fmaxf(m, s);
+    const float corr = expf(m - m_new);
+    const float p = expf(s - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = fmaf(p, v[base + (size_t)d * T + j], acc[d] * corr);
+    m = m_new;
+  }
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[base + (size_t)d * T + i] = acc[d] * inv;
+}
+// nearest-neighbour x2 along time (transformer/upsample_encoder.py:60)
+__global__ void upsample2_nct_kernel(const float* __restrict__ x, float* __restrict__ y, int T, size_t n_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const size_t row = i / (2 * (size_t)T);
+  const int t = (int)(i % (2 * (size_t)T));
+  y[i] = x[row * T + t / 2];
+}
+// F.normalize(x, dim=1) over rows [R][K] (flow.py:463)
+__global__ void normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int K) {
+  const int r = blockIdx.x;
+  __shared__ float sh;
+  if (threadIdx.x == 0) {
+    float ss = 0.f;
+    for (int k = 0; k < K; ++k) ss = fmaf(x[(size_t)r * K + k], x[(size_t)r * K + k], ss);
+    sh = fmaxf(sqrtf(ss), 1e-12f);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) y[(size_t)r * K + k] = x[(size_t)r * K + k] / sh;
 }
 
 inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
@@ -683,6 +769,116 @@ void DacEngineF32::decode(const float* z, const int* lengths, float* wav, int B,
     scratch_.reset();
     decode_dense(z + (size_t)b * latent_ * L, (long long)latent_ * L, wav + (size_t)b * L * hop_, (long long)L * hop_, 1, n, L, s);
   }
+}
+
+// ---------------------------------------------------------------------------------------------- token -> mu (f-1)
+FrontEngineF32::FrontEngineF32(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  upload_all(w, &w_);
+  d_ = (int)w_.shape("input_embedding.weight")[1];
+  vocab_ = (int)w_.shape("input_embedding.weight")[0];
+  out_ = (int)w_.shape("encoder_proj.weight")[0];
+  spk_ = (int)w_.shape("spk_embed_affine_layer.weight")[1];
+  heads_ = (int)w_.shape("encoder.encoders.0.self_attn.pos_bias_u")[0];
+  require(d_ == heads_ * 64, "fp32 token encoder: expected head dim 64", LS_ERR_UNSUPPORTED);
+  while (w_.has("encoder.encoders." + std::to_string(n_blocks_) + ".norm_mha.weight")) ++n_blocks_;
+  while (w_.has("encoder.up_encoders." + std::to_string(n_up_) + ".norm_mha.weight")) ++n_up_;
+}
+
+// ConformerEncoderLayer (normalize_before, no macaron, no conv module): x += attn(LN(x)); x += w_2(swish(w_1(LN(x))))
+float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, int B, int T, cudaStream_t s) {
+  const size_t n = (size_t)B * d_ * T;
+  const int P = 2 * T - 1;
+  float* nrm = scratch_.get(n, s);
+  F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, B), kTB, s, x, w_.ptr(p + ".norm_mha.weight"), w_.ptr(p + ".norm_mha.bias"), nrm, d_,
+             T, 0, (const float*)nullptr, (const float*)nullptr);
+  float* q = scratch_.get(n, s);
+  float* k = scratch_.get(n, s);
+  float* v = scratch_.get(n, s);
+  const std::string a = p + ".self_attn";
+  conv1d(nrm, nullptr, w_.ptr(a + ".linear_q.weight"), w_.ptr(a + ".linear_q.bias"), q, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
+  conv1d(nrm, nullptr, w_.ptr(a + ".linear_k.weight"), w_.ptr(a + ".linear_k.bias"), k, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
+  conv1d(nrm, nullptr, w_.ptr(a + ".linear_v.weight"), w_.ptr(a + ".linear_v.bias"), v, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
+  float* pp = scratch_.get((size_t)P * d_, s);
+  F32_LAUNCH(linear_rows_kernel, dim3((d_ + 127) / 128, P), 128, s, pe, w_.ptr(a + ".linear_pos.weight"), (const float*)nullptr, pp, P,
+             d_, d_, 0, 0);
+  float* att = scratch_.get(n, s);
+  F32_LAUNCH(rel_attention_nct_kernel, grid_t(T, heads_, B), kTB, s, q, k, v, pp, w_.ptr(a + ".pos_bias_u"), w_.ptr(a + ".pos_bias_v"),
+             att, heads_, T, T);
+  float* o = scratch_.get(n, s);
+  conv1d(att, nullptr, w_.ptr(a + ".linear_out.weight"), w_.ptr(a + ".linear_out.bias"), o, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
+  float* x1 = scratch_.get(n, s);
+  ew(x, o, x1, n, EW_ADD, s);
+  F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, B), kTB, s, x1, w_.ptr(p + ".norm_ff.weight"), w_.ptr(p + ".norm_ff.bias"), nrm, d_, T,
+             0, (const float*)nullptr, (const float*)nullptr);
+  const int ff = (int)w_.shape(p + ".feed_forward.w_1.weight")[0];
+  float* h = scratch_.get((size_t)B * ff * T, s);
+  conv1d(nrm, nullptr, w_.ptr(p + ".feed_forward.w_1.weight"), w_.ptr(p + ".feed_forward.w_1.bias"), h, nullptr, B, d_, T, ff, 1, 1, 0,
+         -1.f, s);
+  ew(h, nullptr, h, (size_t)B * ff * T, EW_SILU, s);
+  conv1d(h, nullptr, w_.ptr(p + ".feed_forward.w_2.weight"), w_.ptr(p + ".feed_forward.w_2.bias"), o, nullptr, B, ff, T, d_, 1, 1, 0,
+         -1.f, s);
+  float* x2 = scratch_.get(n, s);
+  ew(x1, o, x2, n, EW_ADD, s);
+  return x2;
+}
+
+// LinearNoSubsampling (subsampling.py:69-113) + the rel-pos encoding's input scale (embedding.py:268); pe = [2T-1][d]
+float* FrontEngineF32::embed(const std::string& p, const float* x, int B, int T, float** pe, cudaStream_t s) {
+  const size_t n = (size_t)B * d_ * T;
+  float* y = scratch_.get(n, s);
+  conv1d(x, nullptr, w_.ptr(p + ".out.0.weight"), w_.ptr(p + ".out.0.bias"), y, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
+  float* z = scratch_.get(n, s);
+  F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, B), kTB, s, y, w_.ptr(p + ".out.1.weight"), w_.ptr(p + ".out.1.bias"), z, d_, T, 0,
+             (const float*)nullptr, (const float*)nullptr);
+  F32_LAUNCH(scale_kernel, blocks(n), 256, s, z, sqrtf((float)d_), n);
+  *pe = scratch_.get((size_t)(2 * T - 1) * d_, s);
+  F32_LAUNCH(rel_pos_emb_kernel, dim3((d_ / 2 + 127) / 128, 2 * T - 1), 128, s, *pe, T, d_);
+  return z;
+}
+
+// CausalMaskedDiffWithXvec.inference front half (flow/flow.py:461-489), finalize = True, equal-length batch
+void FrontEngineF32::encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T,
+                            cudaStream_t s) {
+  require(B > 0 && T > 0, "B and T must be positive");
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  // speaker embedding: normalise, project (flow.py:463, 469)
+  float* en = scratch_.get((size_t)B * spk_, s);
+  F32_LAUNCH(normalize_rows_kernel, B, 128, s, embedding, en, spk_);
+  F32_LAUNCH(linear_rows_kernel, dim3((out_ + 127) / 128, B), 128, s, en, w_.ptr("spk_embed_affine_layer.weight"),
+             w_.ptr("spk_embed_affine_layer.bias"), spks, B, spk_, out_, 0, 0);
+  const size_t n = (size_t)B * d_ * T;
+  float* x0 = scratch_.get(n, s);
+  F32_LAUNCH(embed_tokens_kernel, blocks(n), 256, s, tokens, w_.ptr("input_embedding.weight"), x0, d_, T, vocab_, n);
+  float* pe = nullptr;
+  float* x = embed("encoder.embed", x0, B, T, &pe, s);
+  {  // PreLookaheadLayer (upsample_encoder.py:66-107), no context: right-pad 3, conv k=4, leaky_relu, causal conv k=3, + x
+    float* a = scratch_.get(n, s);
+    conv1d(x, nullptr, w_.ptr("encoder.pre_lookahead_layer.conv1.weight"), w_.ptr("encoder.pre_lookahead_layer.conv1.bias"), a,
+           nullptr, B, d_, T, d_, 4, 1, 0, 0.01f, s);
+    float* c = scratch_.get(n, s);
+    conv1d(a, nullptr, w_.ptr("encoder.pre_lookahead_layer.conv2.weight"), w_.ptr("encoder.pre_lookahead_layer.conv2.bias"), c,
+           nullptr, B, d_, T, d_, 3, 1, 2, -1.f, s);
+    float* r = scratch_.get(n, s);
+    ew(c, x, r, n, EW_ADD, s);
+    x = r;
+  }
+  for (int i = 0; i < n_blocks_; ++i) x = layer("encoder.encoders." + std::to_string(i), x, pe, B, T, s);
+  // Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5
+  const int T2 = 2 * T;
+  const size_t n2 = (size_t)B * d_ * T2;
+  float* up = scratch_.get(n2, s);
+  F32_LAUNCH(upsample2_nct_kernel, blocks(n2), 256, s, x, up, T, n2);
+  float* uc = scratch_.get(n2, s);
+  conv1d(up, nullptr, w_.ptr("encoder.up_layer.conv.weight"), w_.ptr("encoder.up_layer.conv.bias"), uc, nullptr, B, d_, T2, d_, 5, 1, 4,
+         -1.f, s);
+  x = embed("encoder.up_embed", uc, B, T2, &pe, s);
+  for (int i = 0; i < n_up_; ++i) x = layer("encoder.up_encoders." + std::to_string(i), x, pe, B, T2, s);
+  float* an = scratch_.get(n2, s);
+  F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x, w_.ptr("encoder.after_norm.weight"), w_.ptr("encoder.after_norm.bias"),
+             an, d_, T2, 0, (const float*)nullptr, (const float*)nullptr);
+  conv1d(an, nullptr, w_.ptr("encoder_proj.weight"), w_.ptr("encoder_proj.bias"), mu, nullptr, B, d_, T2, out_, 1, 1, 0, -1.f, s);
 }
 
 }  // namespace ls

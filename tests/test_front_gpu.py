@@ -1,0 +1,77 @@
+"""Token -> mu front half (SURVEY.md section 8 row f-1, fp32 mode) on the GPU against the reference's golden encoder
+outputs and the CPU oracle, then FSQ tokens -> waveform through the whole path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import minimax_speech_b200.synth as synth  # noqa: E402
+from minimax_speech_b200.dac import DACVAEDecoder  # noqa: E402
+from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder  # noqa: E402
+from minimax_speech_b200.front import TokenToMu  # noqa: E402
+from oracle import restatement as O  # noqa: E402
+
+DEV = torch.device("cuda:0")
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+@pytest.fixture(scope="module")
+def front(golden_dir):
+    g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
+    sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
+    f = TokenToMu()
+    f.load_state_dict(sd)
+    return g, sd, f
+
+
+def test_mu_vs_reference_golden(front):
+    """mu = encoder_proj(h) with h the unmodified reference encoder's output (golden case a, one utterance)."""
+    g, sd, f = front
+    tok, emb = synth.token_inputs(0, int(g["enc_a_lens"][0]))
+    mu, spks = f(tok.to(DEV), emb.to(DEV))
+    h = torch.from_numpy(g["enc_a_h"])
+    mu_ref = torch.nn.functional.linear(h, sd["encoder_proj.weight"], sd["encoder_proj.bias"]).transpose(1, 2)
+    e = O.rel_l2(mu.cpu(), mu_ref)
+    print(f"front mu vs reference golden: rel-L2 {e:.3e}")
+    assert mu.shape == (1, 80, 80) and e < 1e-4
+
+
+def test_batch_vs_oracle(front):
+    g, sd, f = front
+    toks, embs = zip(*[synth.token_inputs(20 + b, 37) for b in range(3)])
+    tok, emb = torch.cat(toks, 0), torch.cat(embs, 0)
+    mu, spks = f(tok.to(DEV), emb.to(DEV))
+    for b in range(3):
+        with torch.inference_mode():
+            mr, sr = O.tokens_to_mu(sd, tok[b:b + 1], emb[b:b + 1])
+        assert O.rel_l2(mu[b:b + 1].cpu(), mr) < 1e-4 and O.rel_l2(spks[b:b + 1].cpu(), sr) < 1e-5
+
+
+def test_tokens_to_waveform(front):
+    """Synthetic FSQ tokens -> mu -> 3-step CFM solve -> DAC decode (fp32 mode throughout) against the oracle."""
+    g, sd, f = front
+    esd = synth.estimator_state_dict(3, init="test", n_blocks=1, num_mid_blocks=1)
+    est = CausalConditionalDecoder(n_blocks=1, num_mid_blocks=1, precision="fp32")
+    est.load_state_dict(esd)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    dsd = synth.dac_decoder_state_dict(5, init="test")
+    dac = DACVAEDecoder(precision="fp32")
+    dac.load_state_dict(dsd)
+    tok, emb = synth.token_inputs(9, 25)  # one second of 25 Hz tokens
+    lat, _ = f.inference(tok.to(DEV), emb.to(DEV), cfm, n_timesteps=3)
+    wav = dac.decode(lat)
+    assert lat.shape == (1, 80, 50) and wav.shape == (1, 1, 24000)
+    with torch.inference_mode():
+        mu, spks = O.tokens_to_mu(sd, tok, emb)
+        mask = torch.ones(1, 1, 50)
+        lat_ref = O.cfm_forward(esd, synth.fixed_noise(), mu, mask, 3, 1.0, spks, torch.zeros_like(mu))
+        wav_ref = O.dac_decode(dsd, lat_ref)
+    e, s = O.rel_l2(lat.cpu(), lat_ref), O.snr_db(wav.cpu(), wav_ref)
+    print(f"tokens -> waveform (fp32): latent rel-L2 {e:.3e}, waveform SNR {s:.1f} dB")
+    assert e < 1e-4 and s > 80.0
