@@ -38,11 +38,6 @@ constexpr float kRescaleThreshold = 8.0f;
 #ifndef ATTN_POLY_MASK
 #define ATTN_POLY_MASK 0x00
 #endif
-#ifndef ATTN_STAGGER_CLK
-#define ATTN_STAGGER_CLK 0  // measured on B200: 0 -> 39.8 us, 700 -> 41.4, 1300 -> 42.6, 2000 -> 41.5 (B=32, T=500)
-#endif
-constexpr long long kStaggerClk = ATTN_STAGGER_CLK;
-__device__ unsigned int g_sm_arrivals[256];  // CTAs that ever started on each SM (only the parity is used)
 constexpr int kPolyExpMask = ATTN_POLY_MASK;  // of every 8 score pairs, the ones whose exp2 runs on the FMA pipe           // log2 units: P stays below 2^8 between rescales
 
 // p[i] = 2^(s[i]*c - m) for 32 scores (masked scores are -inf -> 0); returns the packed bf16 pairs and adds to the row sum
@@ -163,20 +158,6 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
       TL(2);
-      if (kStaggerClk > 0) {
-        // Two CTAs share an SM and would run in lockstep (they start together and slow each other down equally in
-        // the MUFU-bound exp phase), leaving the MUFU pipe idle while both are in their load / max / store phases.
-        // Every second CTA to arrive on an SM during the first wave therefore starts half a tile period late.
-        uint32_t smid, nsm;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-        const uint32_t arrival = atomicAdd(&g_sm_arrivals[smid & 255u], 1u);
-        if ((arrival & 1u) && (uint32_t)cta_lin < 2u * nsm) {
-          const long long t0 = clock64();
-          while (clock64() - t0 < kStaggerClk) {
-          }
-        }
-      }
       issue_s(0);
       const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t dp1 = make_smem_desc_sw128(smem_u32(sP + kTile));

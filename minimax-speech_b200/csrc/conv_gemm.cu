@@ -41,7 +41,6 @@ static_assert(kProducerWarps >= 2, "need one activation and at least one weight 
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kFirstEpiWarp = kProducerWarps + 1;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
-constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 16;
 
 constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
@@ -115,42 +114,7 @@ struct ChunkStore {
   }
 };
 
-__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + g);
-    v[4 * g] = t.x, v[4 * g + 1] = t.y, v[4 * g + 2] = t.z, v[4 * g + 3] = t.w;
-  }
-}
-
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-
-// LayerNorm statistics of a 256-wide row whose 4 x 64 column quarters live in 4 threads (one per column
-// group): per-thread (mean, M2), combined with the parallel-variance formula through shared memory.
-__device__ __forceinline__ void row_stats(const float (&v)[4][16], float2* red, int g, int row, float& mean,
-                                          float& rstd) {
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += v[j][i];
-  const float lm = s * (1.0f / 64.0f);
-  float m2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float d = v[j][i] - lm;
-      m2 = fmaf(d, d, m2);
-    }
-  red[g * kBlockM + row] = make_float2(lm, m2);
-  epi_barrier();
-  const float2 a = red[row], b = red[kBlockM + row], c = red[2 * kBlockM + row], d = red[3 * kBlockM + row];
-  mean = 0.25f * (a.x + b.x + c.x + d.x);
-  const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
-  const float M2 = a.y + b.y + c.y + d.y + 64.0f * (da * da + db * db + dc * dc + dd * dd);
-  rstd = rsqrtf(M2 * (1.0f / 256.0f) + 1e-5f);
-}
 
 
 // ---- coalesced global access for the epilogue --------------------------------------------------------------------

@@ -85,3 +85,48 @@ def gather_waveforms(wav, n_samples, index, dst=0, group=None):
             n = int(out[r, i, smax])
             res[int(out[r, i, smax + 1])] = out[r, i, :n]
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Bulk latent extraction: the reference's multi-GPU tool around DACVAE.encode (dac-vae/extract_dac_latents.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_files(n_files, rank, world_size):
+    """Contiguous per-rank slice, the last rank taking the remainder (extract_dac_latents.py:146-150)."""
+    per = n_files // world_size
+    start = rank * per
+    end = start + per if rank < world_size - 1 else n_files
+    return start, end
+
+
+def latent_record(z, mu, logs, sample_rate, n_samples, n_padded, path):
+    """The ``*_latent2x.pt`` dict of extract_dac_latents.py:184-196 (batch dim removed, CPU tensors)."""
+    z, mu, logs = z.squeeze(0).cpu(), mu.squeeze(0).cpu(), logs.squeeze(0).cpu()
+    return {"z": z, "mu": mu, "logs": logs, "sample_rate": sample_rate, "compression_ratio": n_padded // z.shape[-1],
+            "original_duration": n_samples / sample_rate, "original_samples": n_samples, "latent_shape": list(z.shape),
+            "original_path": path}
+
+
+def extract_latents(paths, load_audio, encoder, device, rank=0, world_size=1, save=True, generator=None):
+    """Encode this rank's share of ``paths`` one file at a time (like the reference) and write ``<stem>_latent2x.pt`` next
+    to each input.  ``load_audio(path) -> 1-D float tensor`` at ``encoder.sample_rate`` (the reference uses librosa, which
+    is not a dependency here).  Audio is clamped to [-1, 1] (:31) and right-padded to a multiple of the hop
+    (DACVAE.preprocess, model.py:455-462; the reference tool feeds the unpadded signal, so its last latent frame can
+    differ).  Returns the list of records (and output paths when saved)."""
+    import os
+    start, end = shard_files(len(paths), rank, world_size)
+    out = []
+    for path in paths[start:end]:
+        audio = torch.clamp(torch.as_tensor(load_audio(path), dtype=torch.float32).reshape(1, 1, -1), -1.0, 1.0)
+        n = audio.shape[-1]
+        padded = encoder.preprocess(audio)
+        L = padded.shape[-1] // encoder.hop_length
+        noise = torch.randn(1, encoder.latent_dim, L, generator=generator)
+        z, mu, logs = encoder.encode(padded.to(device), noise.to(device))
+        rec = latent_record(z, mu, logs, encoder.sample_rate, n, padded.shape[-1], path)
+        if save:
+            rec_path = os.path.splitext(path)[0] + "_latent2x.pt"
+            torch.save(rec, rec_path)
+            out.append((rec_path, rec))
+        else:
+            out.append((None, rec))
+    return out

@@ -84,3 +84,46 @@ def test_non_prefix_mask_rejected():
     m[0, 0, 3] = 0
     with pytest.raises(ValueError):
         _check_prefix_mask(m)
+
+
+def test_latent_extraction_sharding_and_record_format(tmp_path):
+    """pipeline.extract_latents: the reference tool's contiguous per-rank slices (extract_dac_latents.py:146-150) and its
+    ``*_latent2x.pt`` record (:184-196), with a stand-in encoder (the real one needs a GPU)."""
+    import torch
+    from minimax_speech_b200 import pipeline
+
+    for n, world in [(10, 4), (7, 8), (16, 2), (3, 1)]:
+        covered = []
+        for r in range(world):
+            s, e = pipeline.shard_files(n, r, world)
+            per = n // world
+            assert (s, e) == (r * per, r * per + per if r < world - 1 else n)
+            covered += list(range(s, e))
+        assert covered == list(range(n))
+
+    class FakeEncoder:
+        hop_length, latent_dim, sample_rate = 480, 80, 24000
+
+        def preprocess(self, a):
+            return torch.nn.functional.pad(a, (0, (-a.shape[-1]) % self.hop_length))
+
+        def encode(self, audio, noise):
+            L = audio.shape[-1] // self.hop_length
+            m = audio.reshape(1, 1, L, self.hop_length).mean(-1).expand(1, self.latent_dim, L).contiguous()
+            logs = torch.zeros_like(m)
+            return m + noise * torch.exp(logs), m, logs
+
+    paths = []
+    for i in range(5):
+        p = tmp_path / f"clip{i}.pt"
+        torch.save(torch.linspace(-2, 2, 1000 + 300 * i), p)
+        paths.append(str(p))
+    g = torch.Generator().manual_seed(0)
+    recs = pipeline.extract_latents(paths, torch.load, FakeEncoder(), "cpu", rank=1, world_size=2, generator=g)
+    assert [os.path.basename(p) for p, _ in recs] == ["clip2_latent2x.pt", "clip3_latent2x.pt", "clip4_latent2x.pt"]
+    path, rec = recs[0]
+    saved = torch.load(path)
+    assert set(saved) == {"z", "mu", "logs", "sample_rate", "compression_ratio", "original_duration", "original_samples",
+                          "latent_shape", "original_path"}
+    assert saved["compression_ratio"] == 480 and saved["original_samples"] == 1600 and saved["latent_shape"] == [80, 4]
+    assert saved["mu"].shape == (80, 4) and float(saved["mu"].abs().max()) <= 1.0  # clamped to [-1, 1] before encoding
