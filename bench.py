@@ -106,6 +106,24 @@ def gpu_eager_baseline(a, esd, dsd, dev):
             ms = e0.elapsed_time(e1)
             best = ms if best is None or _ == 1 else min(best, ms)
         out[name] = len(inputs) * a.seconds / (best / 1000.0)
+    # fairness figure (SURVEY section 8d ii): the same eager algorithm with the whole batch in one call (the estimator
+    # itself is batch-agnostic; the reference's solve_euler is not)
+    mu, mask, spks, cond = [t.to(dev) for t in synth.batch_inputs([T] * a.batch)]
+    for name, ctx in (("batched_fp32", None), ("batched_bf16_autocast", torch.bfloat16)):
+        best = None
+        for it in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.inference_mode(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                lat = O.cfm_forward(e_gpu, noise, mu, mask, a.n_timesteps, 1.0, spks, cond)
+                for b0 in range(0, a.batch, 4):  # decode in groups of 4: the eager decoder's activations are large
+                    O.dac_decode(d_gpu, lat[b0:b0 + 4].float())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if it == 0 else min(best, ms)
+        out[name] = a.batch * a.seconds / (best / 1000.0)
+    out["sample"] += f"; batched_*: all {a.batch} utterances in one call (DAC decode in groups of 4)"
     return out
 
 
@@ -233,8 +251,14 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
+    # warm-up: at least W (>= 3) steps AND at least ~1.5 s of work -- on a box that has just been handed out the first
+    # few hundred milliseconds run below the sustained clocks (measured: 96 vs 80 ms per step with 3 warm-up steps only)
+    n_warm, t_warm = 0, time.perf_counter()
+    while n_warm < max(a.warmup, 3) or (time.perf_counter() - t_warm < 1.5 and n_warm < 64):
         step()
+        n_warm += 1
+        if n_warm >= max(a.warmup, 3):
+            torch.cuda.synchronize()
     sync_all()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = native.launch_count()
@@ -328,7 +352,7 @@ def run_b200(a):
 
     if rank == 0:
         rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-               "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+               "warmup": n_warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_of(a),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_rec, "roofline": roofline,
                "kernels": kernels, "cpu_baseline": cb, "gpu_eager_baseline": eager,
