@@ -123,10 +123,11 @@ int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_
 }
 void ls_front_destroy(ls_front* h) { delete h; }
 int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
-                        int32_t T, void* stream) {
+                        int32_t T, int32_t n_context, int32_t streaming, void* stream) {
   return ls::guarded([&] {
     ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
-    h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, (cudaStream_t)stream);
+    h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
+                     (cudaStream_t)stream);
   });
 }
 

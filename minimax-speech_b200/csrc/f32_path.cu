@@ -327,10 +327,11 @@ __global__ void rel_pos_emb_kernel(float* __restrict__ pe, int T, int d) {
 __global__ void __launch_bounds__(kTB) rel_attention_nct_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                 const float* __restrict__ v, const float* __restrict__ pp,
                                                                 const float* __restrict__ bu, const float* __restrict__ bv,
-                                                                float* __restrict__ o, int H, int T, int len) {
+                                                                float* __restrict__ o, int H, int T, int len, int chunk) {
   const int i = blockIdx.x * kTB + threadIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   if (i >= T) return;
+  if (chunk > 0) len = min(len, (i / chunk + 1) * chunk);  // block-causal (utils/mask.py:127-158)
   const size_t base = ((size_t)b * H + h) * 64 * T;
   const int inner = H * 64;
   float qu[64], qv[64], acc[64];
@@ -358,6 +359,12 @@ __global__ void __launch_bounds__(kTB) rel_attention_nct_kernel(const float* __r
 #pragma unroll
   for (int d = 0; d < 64; ++d) o[base + (size_t)d * T + i] = acc[d] * inv;
 }
+// y[b,c,t] = x[b,c,t] for t < T of rows that are Tin long
+__global__ void slice_time_kernel(const float* __restrict__ x, float* __restrict__ y, int Tin, int T, size_t n_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  y[i] = x[(i / T) * Tin + i % T];
+}
 // nearest-neighbour x2 along time (transformer/upsample_encoder.py:60)
 __global__ void upsample2_nct_kernel(const float* __restrict__ x, float* __restrict__ y, int T, size_t n_out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,8 +389,8 @@ __global__ void normalize_rows_kernel(const float* __restrict__ x, float* __rest
 inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
 
 void conv1d(const float* in, const float* m_in, const float* w, const float* bias, float* out, const float* m_out, int B,
-            int Cin, int T, int N, int K, int dil, int pad, float lrelu, cudaStream_t s, int stride = 1) {
-  const int Tout = stride == 1 ? T : (T + 2 * pad - K) / stride + 1;
+            int Cin, int T, int N, int K, int dil, int pad, float lrelu, cudaStream_t s, int stride = 1, int t_out = 0) {
+  const int Tout = t_out > 0 ? t_out : (stride == 1 ? T : (T + 2 * pad - K) / stride + 1);
   F32_LAUNCH(conv1d_nct_kernel, grid_t(Tout, (N + kNB - 1) / kNB, B), kTB, s, in, m_in, w, bias, out, m_out, Cin, T, Tout, N,
              K, dil, pad, stride, lrelu);
 }
@@ -786,7 +793,7 @@ FrontEngineF32::FrontEngineF32(const Weights& w, int device) : device_(device) {
 }
 
 // ConformerEncoderLayer (normalize_before, no macaron, no conv module): x += attn(LN(x)); x += w_2(swish(w_1(LN(x))))
-float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, int B, int T, cudaStream_t s) {
+float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, int B, int T, int chunk, cudaStream_t s) {
   const size_t n = (size_t)B * d_ * T;
   const int P = 2 * T - 1;
   float* nrm = scratch_.get(n, s);
@@ -804,7 +811,7 @@ float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, in
              d_, d_, 0, 0);
   float* att = scratch_.get(n, s);
   F32_LAUNCH(rel_attention_nct_kernel, grid_t(T, heads_, B), kTB, s, q, k, v, pp, w_.ptr(a + ".pos_bias_u"), w_.ptr(a + ".pos_bias_v"),
-             att, heads_, T, T);
+             att, heads_, T, T, chunk);
   float* o = scratch_.get(n, s);
   conv1d(att, nullptr, w_.ptr(a + ".linear_out.weight"), w_.ptr(a + ".linear_out.bias"), o, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
   float* x1 = scratch_.get(n, s);
@@ -837,10 +844,13 @@ float* FrontEngineF32::embed(const std::string& p, const float* x, int B, int T,
   return z;
 }
 
-// CausalMaskedDiffWithXvec.inference front half (flow/flow.py:461-489), finalize = True, equal-length batch
-void FrontEngineF32::encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T,
-                            cudaStream_t s) {
-  require(B > 0 && T > 0, "B and T must be positive");
+// CausalMaskedDiffWithXvec.inference front half (flow/flow.py:461-489), equal-length batch.  n_context > 0: the last
+// n_context tokens are look-ahead context only (the finalize = False call, flow.py:482-489); streaming: block-causal
+// attention with chunk_ tokens at 25 Hz and 2*chunk_ frames at 50 Hz.
+void FrontEngineF32::encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T_all,
+                            int n_context, bool streaming, cudaStream_t s) {
+  const int T = T_all - n_context;
+  require(B > 0 && T > 0 && (n_context == 0 || n_context == 3), "B, T must be positive; context is 0 or 3 tokens");
   LS_CUDA(cudaSetDevice(device_));
   scratch_.reset();
   // speaker embedding: normalise, project (flow.py:463, 469)
@@ -848,15 +858,24 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
   F32_LAUNCH(normalize_rows_kernel, B, 128, s, embedding, en, spk_);
   F32_LAUNCH(linear_rows_kernel, dim3((out_ + 127) / 128, B), 128, s, en, w_.ptr("spk_embed_affine_layer.weight"),
              w_.ptr("spk_embed_affine_layer.bias"), spks, B, spk_, out_, 0, 0);
-  const size_t n = (size_t)B * d_ * T;
-  float* x0 = scratch_.get(n, s);
-  F32_LAUNCH(embed_tokens_kernel, blocks(n), 256, s, tokens, w_.ptr("input_embedding.weight"), x0, d_, T, vocab_, n);
-  float* pe = nullptr;
-  float* x = embed("encoder.embed", x0, B, T, &pe, s);
-  {  // PreLookaheadLayer (upsample_encoder.py:66-107), no context: right-pad 3, conv k=4, leaky_relu, causal conv k=3, + x
+  const size_t n_all = (size_t)B * d_ * T_all, n = (size_t)B * d_ * T;
+  float* x0 = scratch_.get(n_all, s);
+  F32_LAUNCH(embed_tokens_kernel, blocks(n_all), 256, s, tokens, w_.ptr("input_embedding.weight"), x0, d_, T_all, vocab_, n_all);
+  // embed (Linear, LayerNorm, scale) is position-independent: tokens and context go through it together
+  float* pe_all = nullptr;
+  float* xe = embed("encoder.embed", x0, B, T_all, &pe_all, s);
+  float* x = xe;
+  float* pe = pe_all;
+  if (n_context > 0) {
+    x = scratch_.get(n, s);
+    F32_LAUNCH(slice_time_kernel, blocks(n), 256, s, xe, x, T_all, T, n);
+    pe = scratch_.get((size_t)(2 * T - 1) * d_, s);
+    F32_LAUNCH(rel_pos_emb_kernel, dim3((d_ / 2 + 127) / 128, 2 * T - 1), 128, s, pe, T, d_);
+  }
+  {  // PreLookaheadLayer (upsample_encoder.py:66-107): [x | context or 3 zeros] -> conv k=4 -> leaky_relu -> causal conv k=3, + x
     float* a = scratch_.get(n, s);
-    conv1d(x, nullptr, w_.ptr("encoder.pre_lookahead_layer.conv1.weight"), w_.ptr("encoder.pre_lookahead_layer.conv1.bias"), a,
-           nullptr, B, d_, T, d_, 4, 1, 0, 0.01f, s);
+    conv1d(xe, nullptr, w_.ptr("encoder.pre_lookahead_layer.conv1.weight"), w_.ptr("encoder.pre_lookahead_layer.conv1.bias"), a,
+           nullptr, B, d_, T_all, d_, 4, 1, 0, 0.01f, s, 1, T);
     float* c = scratch_.get(n, s);
     conv1d(a, nullptr, w_.ptr("encoder.pre_lookahead_layer.conv2.weight"), w_.ptr("encoder.pre_lookahead_layer.conv2.bias"), c,
            nullptr, B, d_, T, d_, 3, 1, 2, -1.f, s);
@@ -864,7 +883,8 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
     ew(c, x, r, n, EW_ADD, s);
     x = r;
   }
-  for (int i = 0; i < n_blocks_; ++i) x = layer("encoder.encoders." + std::to_string(i), x, pe, B, T, s);
+  const int chunk = streaming ? chunk_ : 0;
+  for (int i = 0; i < n_blocks_; ++i) x = layer("encoder.encoders." + std::to_string(i), x, pe, B, T, chunk, s);
   // Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5
   const int T2 = 2 * T;
   const size_t n2 = (size_t)B * d_ * T2;
@@ -874,7 +894,7 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
   conv1d(up, nullptr, w_.ptr("encoder.up_layer.conv.weight"), w_.ptr("encoder.up_layer.conv.bias"), uc, nullptr, B, d_, T2, d_, 5, 1, 4,
          -1.f, s);
   x = embed("encoder.up_embed", uc, B, T2, &pe, s);
-  for (int i = 0; i < n_up_; ++i) x = layer("encoder.up_encoders." + std::to_string(i), x, pe, B, T2, s);
+  for (int i = 0; i < n_up_; ++i) x = layer("encoder.up_encoders." + std::to_string(i), x, pe, B, T2, 2 * chunk, s);
   float* an = scratch_.get(n2, s);
   F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x, w_.ptr("encoder.after_norm.weight"), w_.ptr("encoder.after_norm.bias"),
              an, d_, T2, 0, (const float*)nullptr, (const float*)nullptr);

@@ -2,7 +2,8 @@
 section 8 row f-1): speaker-embedding normalise + ``spk_embed_affine_layer``, ``input_embedding``, the
 ``UpsampleConformerEncoder`` (transformer/upsample_encoder.py) and ``encoder_proj``.  Parameters are registered under the
 reference's state_dict keys, so the flow checkpoint loads unchanged.  fp32 mode only in this round (CUDA-core kernels of
-csrc/f32_path.cu): finalize=True, no prompt, equal-length batches."""
+csrc/f32_path.cu): equal-length batches, no prompt; final chunks (finalize=True) and non-final chunks (3 look-ahead
+context tokens), optional block-causal streaming attention."""
 import torch
 import torch.nn as nn
 
@@ -38,21 +39,24 @@ class TokenToMu(nn.Module):
             self._handle = native.FrontHandle(self.state_dict(), device)
         return self._handle
 
+    pre_lookahead_len = 3
+
     @torch.inference_mode()
-    def forward(self, token, embedding):
-        """token [B,T] int64, embedding [B,192] -> (mu [B,80,2T], spks [B,80]): the ``mu`` / ``spks`` the reference hands to
-        ``self.decoder`` (flow.py:501-508)."""
-        if token.dim() != 2 or token.shape[1] < 1 or token.dtype != torch.int64:
-            raise ValueError("token must be an int64 tensor [B, T >= 1]")
+    def forward(self, token, embedding, finalize=True, streaming=False):
+        """token [B,T] int64, embedding [B,192] -> (mu [B,80,2T'], spks [B,80]): the ``mu`` / ``spks`` the reference hands to
+        ``self.decoder`` (flow.py:501-508).  finalize=False: the last 3 tokens are look-ahead context (T' = T - 3)."""
+        n_ctx = 0 if finalize else self.pre_lookahead_len
+        if token.dim() != 2 or token.shape[1] < 1 + n_ctx or token.dtype != torch.int64:
+            raise ValueError(f"token must be an int64 tensor [B, T >= {1 + n_ctx}]")
         if tuple(embedding.shape) != (token.shape[0], self.spk_embed_dim):
             raise ValueError(f"embedding must be [{token.shape[0]}, {self.spk_embed_dim}]")
         dev = token.device
-        return self.handle(dev).encode(token.contiguous(), _as_f32(embedding, dev))
+        return self.handle(dev).encode(token.contiguous(), _as_f32(embedding, dev), n_ctx, streaming)
 
     @torch.inference_mode()
-    def inference(self, token, embedding, decoder, n_timesteps=10, streaming=False):
-        """``CausalMaskedDiffWithXvec.inference`` without prompt (flow.py:437-511): tokens -> latents [B,80,2T]."""
-        mu, spks = self.forward(token, embedding)
+    def inference(self, token, embedding, decoder, n_timesteps=10, streaming=False, finalize=True):
+        """``CausalMaskedDiffWithXvec.inference`` without prompt (flow.py:437-511): tokens -> latents [B,80,2T']."""
+        mu, spks = self.forward(token, embedding, finalize=finalize, streaming=streaming)
         mask = torch.ones(mu.shape[0], 1, mu.shape[2], device=mu.device)
         feat, _ = decoder(mu=mu, mask=mask, spks=spks, cond=torch.zeros_like(mu), n_timesteps=n_timesteps, streaming=streaming)
         return feat.float(), None

@@ -97,7 +97,7 @@ def load():
         lib.ls_front_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_front_destroy.argtypes = [vp]
         lib.ls_front_destroy.restype = None
-        lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+        lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
         lib.ls_debug_set_buffer.argtypes = [vp, i64]
         lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
@@ -222,12 +222,12 @@ class FrontHandle:
         if h and _lib is not None:
             _lib.ls_front_destroy(h)
 
-    def encode(self, tokens, embedding):
+    def encode(self, tokens, embedding, n_context=0, streaming=False):
         B, T = tokens.shape
-        mu = torch.empty(B, self.out_dim, 2 * T, device=tokens.device, dtype=torch.float32)
+        mu = torch.empty(B, self.out_dim, 2 * (T - n_context), device=tokens.device, dtype=torch.float32)
         spks = torch.empty(B, self.out_dim, device=tokens.device, dtype=torch.float32)
-        check(load().ls_front_encode(self._h, ptr(tokens), ptr(embedding), ptr(mu), ptr(spks), B, T,
-                                     current_stream_ptr(self.device)), "ls_front_encode")
+        check(load().ls_front_encode(self._h, ptr(tokens), ptr(embedding), ptr(mu), ptr(spks), B, T, int(n_context),
+                                     int(bool(streaming)), current_stream_ptr(self.device)), "ls_front_encode")
         return mu, spks
 
 

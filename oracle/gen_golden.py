@@ -129,6 +129,12 @@ def main():
             out[f"enc_{name}_lens"] = np.array(lens)
             out[f"enc_{name}_h"] = h.numpy()
             print("conformer", name, h.shape, float(h.abs().mean()))
+        # non-final streaming chunk: look-ahead context = last 3 tokens, block-causal attention (flow.py:482-489)
+        tok = synth.token_inputs(5, 60)[0]
+        x = torch.nn.functional.embedding(tok, csd["input_embedding.weight"])
+        h, _ = enc(x[:, :-3], torch.tensor([60]), context=x[:, -3:], streaming=True)
+        out["enc_c_h"] = h.numpy()
+        print("conformer c (context + streaming)", h.shape, float(h.abs().mean()))
         np.savez_compressed(os.path.join(OUT, "conformer_golden.npz"), **out)
 
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----

@@ -295,7 +295,7 @@ def rel_pos_emb(T, d):
     return pe.unsqueeze(0)
 
 
-def rel_attention(sd, p, x, pos_emb, key_mask, heads):
+def rel_attention(sd, p, x, pos_emb, key_mask, heads, chunk=0):
     """RelPositionMultiHeadedAttention.forward (transformer/attention.py:249-330) + forward_attention (:84-127).
     x [B,T,d]; key_mask [B,T] bool; bd[i,j] = (q_i + v) . p[T-1-i+j] (the rel_shift of :225-247 in closed form)."""
     B, T, d = x.shape
@@ -312,24 +312,29 @@ def rel_attention(sd, p, x, pos_emb, key_mask, heads):
     bd = torch.gather(bd_full, 3, idx.expand(B, heads, T, T))
     scores = (ac + bd) / math.sqrt(dk)
     dead = ~key_mask.view(B, 1, 1, T)
+    if chunk > 0:  # add_optional_chunk_mask (utils/mask.py:161-236): key j visible to query i iff j < (i/chunk+1)*chunk
+        pos = torch.arange(T, device=x.device)
+        vis = pos.unsqueeze(0) < ((torch.div(pos, chunk, rounding_mode="trunc") + 1) * chunk).unsqueeze(1)
+        dead = dead | ~vis.view(1, 1, T, T)
     attn = torch.softmax(scores.masked_fill(dead, float("-inf")), dim=-1).masked_fill(dead, 0.0)
     o = torch.matmul(attn, v).transpose(1, 2).reshape(B, T, d)
     return F.linear(o, sd[p + ".linear_out.weight"], sd[p + ".linear_out.bias"])
 
 
-def conformer_layer(sd, p, x, pos_emb, key_mask, heads):
+def conformer_layer(sd, p, x, pos_emb, key_mask, heads, chunk=0):
     """ConformerEncoderLayer.forward (transformer/encoder_layer.py:109-) for normalize_before, no macaron, no conv
     module (config.yaml:73-88): x += attn(LN(x)); x += FF(LN(x)), FF = w_2(swish(w_1(.)))."""
     n = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm_mha.weight"], sd[p + ".norm_mha.bias"], 1e-5)
-    x = x + rel_attention(sd, p + ".self_attn", n, pos_emb, key_mask, heads)
+    x = x + rel_attention(sd, p + ".self_attn", n, pos_emb, key_mask, heads, chunk)
     n = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm_ff.weight"], sd[p + ".norm_ff.bias"], 1e-5)
     h = F.silu(F.linear(n, sd[p + ".feed_forward.w_1.weight"], sd[p + ".feed_forward.w_1.bias"]))
     return x + F.linear(h, sd[p + ".feed_forward.w_2.weight"], sd[p + ".feed_forward.w_2.bias"])
 
 
-def upsample_conformer_encode(sd, xs, lens, heads=8, prefix="encoder."):
-    """UpsampleConformerEncoder.forward (upsample_encoder.py:266-318), non-streaming, no look-ahead context
-    (the finalize=True call of flow.py:480-481).  xs [B,T,512] (embedded tokens), lens [B] -> ([B,2T,512], 2*lens)."""
+def upsample_conformer_encode(sd, xs, lens, heads=8, prefix="encoder.", context=None, streaming=False, chunk=25):
+    """UpsampleConformerEncoder.forward (upsample_encoder.py:266-318).  xs [B,T,512] (embedded tokens), lens [B] ->
+    ([B,2T,512], 2*lens).  ``context`` [B,3,512]: the look-ahead tokens of a non-final chunk (flow.py:482-489), else the
+    input is right-padded with zeros; ``streaming``: block-causal attention, chunk 25 tokens then 50 frames."""
     P = prefix
     B, T, d = xs.shape
     key_mask = torch.arange(T, device=xs.device).unsqueeze(0) < lens.unsqueeze(1)
@@ -341,13 +346,17 @@ def upsample_conformer_encode(sd, xs, lens, heads=8, prefix="encoder."):
 
     x, pos = embed(P + "embed", xs)
     # PreLookaheadLayer (upsample_encoder.py:66-107) without context: right-pad 3, conv k=4, leaky_relu, causal conv k=3
-    y = F.pad(x.transpose(1, 2), (0, 3))
+    if context is not None:  # context goes through the same embed (offset only moves the unused pos_emb)
+        ctx, _ = embed(P + "embed", context)
+        y = torch.cat([x, ctx], dim=1).transpose(1, 2)
+    else:
+        y = F.pad(x.transpose(1, 2), (0, 3))
     y = F.leaky_relu(F.conv1d(y, sd[P + "pre_lookahead_layer.conv1.weight"], sd[P + "pre_lookahead_layer.conv1.bias"]))
     y = F.conv1d(F.pad(y, (2, 0)), sd[P + "pre_lookahead_layer.conv2.weight"], sd[P + "pre_lookahead_layer.conv2.bias"])
     x = y.transpose(1, 2) + x
     i = 0
     while f"{P}encoders.{i}.norm_mha.weight" in sd:
-        x = conformer_layer(sd, f"{P}encoders.{i}", x, pos, key_mask, heads)
+        x = conformer_layer(sd, f"{P}encoders.{i}", x, pos, key_mask, heads, chunk if streaming else 0)
         i += 1
     # Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5
     y = F.interpolate(x.transpose(1, 2), scale_factor=2.0, mode="nearest")
@@ -357,19 +366,23 @@ def upsample_conformer_encode(sd, xs, lens, heads=8, prefix="encoder."):
     x, pos = embed(P + "up_embed", y.transpose(1, 2))
     i = 0
     while f"{P}up_encoders.{i}.norm_mha.weight" in sd:
-        x = conformer_layer(sd, f"{P}up_encoders.{i}", x, pos, key_mask, heads)
+        x = conformer_layer(sd, f"{P}up_encoders.{i}", x, pos, key_mask, heads, 2 * chunk if streaming else 0)
         i += 1
     x = F.layer_norm(x, (d,), sd[P + "after_norm.weight"], sd[P + "after_norm.bias"], 1e-5)
     return x, lens2
 
 
-def tokens_to_mu(sd, token, embedding):
-    """CausalMaskedDiffWithXvec.inference front half (flow.py:461-489) for one utterance, finalize=True, no prompt:
-    (mu [1,80,2T], spks [1,80])."""
+def tokens_to_mu(sd, token, embedding, finalize=True, streaming=False, pre_lookahead_len=3):
+    """CausalMaskedDiffWithXvec.inference front half (flow.py:461-489) for one utterance, no prompt:
+    (mu [1,80,2T], spks [1,80]); finalize=False: the last 3 tokens are look-ahead context only (T shrinks by 3)."""
     spks = F.linear(F.normalize(embedding, dim=1), sd["spk_embed_affine_layer.weight"], sd["spk_embed_affine_layer.bias"])
     x = F.embedding(torch.clamp(token, min=0), sd["input_embedding.weight"])
     lens = torch.tensor([token.shape[1]])
-    h, _ = upsample_conformer_encode(sd, x, lens)
+    if finalize:
+        h, _ = upsample_conformer_encode(sd, x, lens, streaming=streaming)
+    else:
+        h, _ = upsample_conformer_encode(sd, x[:, :-pre_lookahead_len], lens, context=x[:, -pre_lookahead_len:],
+                                         streaming=streaming)
     mu = F.linear(h, sd["encoder_proj.weight"], sd["encoder_proj.bias"])
     return mu.transpose(1, 2).contiguous(), spks
 

@@ -75,3 +75,19 @@ def test_tokens_to_waveform(front):
     e, s = O.rel_l2(lat.cpu(), lat_ref), O.snr_db(wav.cpu(), wav_ref)
     print(f"tokens -> waveform (fp32): latent rel-L2 {e:.3e}, waveform SNR {s:.1f} dB")
     assert e < 1e-4 and s > 80.0
+
+
+def test_non_final_streaming_chunk_vs_reference_golden(front):
+    """finalize=False (3 look-ahead context tokens) + streaming=True (block-causal attention) against the unmodified
+    reference encoder's output (golden case c) and the oracle."""
+    g, sd, f = front
+    tok, emb = synth.token_inputs(5, 60)
+    mu, spks = f(tok.to(DEV), emb.to(DEV), finalize=False, streaming=True)
+    h = torch.from_numpy(g["enc_c_h"])
+    mu_ref = torch.nn.functional.linear(h, sd["encoder_proj.weight"], sd["encoder_proj.bias"]).transpose(1, 2)
+    e = O.rel_l2(mu.cpu(), mu_ref)
+    print(f"front mu (context + streaming) vs reference golden: rel-L2 {e:.3e}")
+    assert mu.shape == (1, 80, 114) and e < 1e-4
+    with torch.inference_mode():
+        mo, _ = O.tokens_to_mu(sd, tok, emb, finalize=False, streaming=True)
+    assert O.rel_l2(mu.cpu(), mo) < 1e-4

@@ -118,3 +118,14 @@ def test_conformer_encoder_matches_reference(golden_dir, case):
     for b, n in enumerate(lens):
         assert int(l2[b]) == 2 * n
         assert O.rel_l2(h[b, :2 * n], ref[b, :2 * n]) < 1e-5
+
+
+def test_conformer_encoder_context_and_streaming_matches_reference(golden_dir):
+    """Non-final chunk: 3 look-ahead context tokens + block-causal attention (chunk 25 tokens / 50 frames)."""
+    g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
+    sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
+    x = torch.nn.functional.embedding(synth.token_inputs(5, 60)[0], sd["input_embedding.weight"])
+    with torch.inference_mode():
+        h, l2 = O.upsample_conformer_encode(sd, x[:, :-3], torch.tensor([60]), context=x[:, -3:], streaming=True)
+    assert h.shape == (1, 114, 512)
+    assert O.rel_l2(h, torch.from_numpy(g["enc_c_h"])) < 1e-5
