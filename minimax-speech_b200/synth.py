@@ -230,6 +230,30 @@ def conformer_encoder_state_dict(seed=7, d=512, heads=8, ff=2048, num_blocks=6, 
     return sd
 
 
+def speaker_encoder_state_dict(seed=13, mel_dim=80, model_dim=512, output_dim=192, num_blocks=6, **_):
+    """Keys/shapes of LearnableSpeakerEncoder (llm/llm.py:34-96; AttentionBlock: transformer/arch_util.py:80-123).
+    Test initialisation (the reference zero-initialises proj_out; here every tensor is non-trivial)."""
+    sd = {}
+
+    def conv(name, n, c):
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (n, c, 1), 1.0 / math.sqrt(c))
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 1.0 / math.sqrt(c))
+
+    conv("init", model_dim, mel_dim)
+    for i in range(num_blocks):
+        sd[f"attn.{i}.norm.weight"] = _uniform(seed, f"attn.{i}.norm.weight", (model_dim,), 0.2).add(1.0)
+        sd[f"attn.{i}.norm.bias"] = _uniform(seed, f"attn.{i}.norm.bias", (model_dim,), 0.1)
+        conv(f"attn.{i}.qkv", 3 * model_dim, model_dim)
+        conv(f"attn.{i}.proj_out", model_dim, model_dim)
+    sd["output_proj.weight"] = _uniform(seed, "output_proj.weight", (output_dim, model_dim), 1.0 / math.sqrt(model_dim))
+    sd["output_proj.bias"] = _uniform(seed, "output_proj.bias", (output_dim,), 1.0 / math.sqrt(model_dim))
+    return sd
+
+
+def reference_mel(index, frames, mel_dim=80):
+    return _normal(8000 + index, "mel", (1, mel_dim, frames), 1.0)
+
+
 def token_inputs(index, n_tokens, vocab=6561, spk_dim=192):
     """Synthetic FSQ tokens (25 Hz) and a speaker embedding."""
     r = _rng(7000 + index, "tokens")

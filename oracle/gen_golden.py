@@ -21,6 +21,7 @@ import minimax_speech_b200.synth as synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 EST_SEED, DAC_SEED = 7, 11
 ENC_SEED = 7
+SPK_SEED = 13
 
 
 def est_inputs(lengths, seed):
@@ -136,6 +137,18 @@ def main():
         out["enc_c_h"] = h.numpy()
         print("conformer c (context + streaming)", h.shape, float(h.abs().mean()))
         np.savez_compressed(os.path.join(OUT, "conformer_golden.npz"), **out)
+
+        # ---- speaker encoder: the unmodified LearnableSpeakerEncoder
+        spk = R.build_reference_speaker_encoder()
+        ssd = synth.speaker_encoder_state_dict(SPK_SEED)
+        spk.load_state_dict(ssd, strict=True)
+        out = {"weights_seed": SPK_SEED, "weights_checksum": synth.checksum(ssd)}
+        for name, frames in [("a", 150), ("b", 37)]:
+            mel = torch.cat([synth.reference_mel(i, frames) for i in range(2)], 0)
+            out[f"spk_{name}_frames"] = frames
+            out[f"spk_{name}_y"] = spk(mel).numpy()
+            print("speaker", name, out[f"spk_{name}_y"].shape)
+        np.savez_compressed(os.path.join(OUT, "speaker_golden.npz"), **out)
 
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
         import json

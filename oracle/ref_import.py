@@ -187,3 +187,23 @@ def build_reference_flow(estimator_kwargs=None):
 def build_reference_dac(cfg=None):
     dm = load_dac_module()
     return dm.DACVAE(**(cfg or DAC_CFG_X2)).eval()
+
+
+def build_reference_speaker_encoder():
+    """The unmodified LearnableSpeakerEncoder (speech/cosyvoice/llm/llm.py:34-96); cosyvoice.transformer.xtransformers
+    (only used by other classes of arch_util) is stubbed."""
+    import importlib
+    import types
+    install_stubs()
+    if "cosyvoice.transformer.xtransformers" not in sys.modules:
+        xt = types.ModuleType("cosyvoice.transformer.xtransformers")
+
+        class _Absent:
+            def __init__(self, *a, **k):
+                raise RuntimeError("xtransformers is stubbed")
+
+        xt.ContinuousTransformerWrapper = _Absent
+        xt.RelativePositionBias = _Absent
+        sys.modules["cosyvoice.transformer.xtransformers"] = xt
+    llm = importlib.import_module("cosyvoice.llm.llm")
+    return llm.LearnableSpeakerEncoder(mel_dim=80, model_dim=512, output_dim=192, num_blocks=6, num_heads=8).eval()

@@ -388,6 +388,28 @@ def tokens_to_mu(sd, token, embedding, finalize=True, streaming=False, pre_looka
 
 
 # --------------------------------------------------------------------------------------
+# speaker encoder: llm/llm.py:34-96, transformer/arch_util.py:80-123
+# --------------------------------------------------------------------------------------
+def speaker_encode(sd, mel, heads=8):
+    """LearnableSpeakerEncoder.forward: mel [B,80,T] -> L2-normalised embedding [B,192] (first-frame pooling)."""
+    h = F.conv1d(mel, sd["init.weight"], sd["init.bias"])
+    i = 0
+    while f"attn.{i}.norm.weight" in sd:
+        p = f"attn.{i}"
+        B, C, T = h.shape
+        n = F.group_norm(h, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-5)  # normalization(): 32 groups
+        qkv = F.conv1d(n, sd[p + ".qkv.weight"], sd[p + ".qkv.bias"])
+        ch = C // heads
+        q, k, v = qkv.reshape(B * heads, 3 * ch, T).split(ch, dim=1)  # QKVAttentionLegacy: head-major [q|k|v] blocks
+        w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) / math.sqrt(ch), dim=-1)
+        a = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
+        h = h + F.conv1d(a, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+        i += 1
+    out = F.linear(h[:, :, 0], sd["output_proj.weight"], sd["output_proj.bias"])
+    return F.normalize(out, p=2, dim=1)
+
+
+# --------------------------------------------------------------------------------------
 # Parity metrics (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------
 

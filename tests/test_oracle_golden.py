@@ -129,3 +129,15 @@ def test_conformer_encoder_context_and_streaming_matches_reference(golden_dir):
         h, l2 = O.upsample_conformer_encode(sd, x[:, :-3], torch.tensor([60]), context=x[:, -3:], streaming=True)
     assert h.shape == (1, 114, 512)
     assert O.rel_l2(h, torch.from_numpy(g["enc_c_h"])) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_speaker_encoder_matches_reference(golden_dir, case):
+    """oracle.speaker_encode against the unmodified LearnableSpeakerEncoder."""
+    g = np.load(os.path.join(golden_dir, "speaker_golden.npz"))
+    sd = synth.speaker_encoder_state_dict(int(g["weights_seed"]))
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    mel = torch.cat([synth.reference_mel(i, int(g[f"spk_{case}_frames"])) for i in range(2)], 0)
+    with torch.inference_mode():
+        y = O.speaker_encode(sd, mel)
+    assert O.rel_l2(y, torch.from_numpy(g[f"spk_{case}_y"])) < 1e-5
