@@ -110,6 +110,10 @@ struct ls_front {
   std::unique_ptr<ls::FrontEngineF32> eng32;
 };
 
+struct ls_speaker {
+  std::unique_ptr<ls::SpeakerEngineF32> eng32;
+};
+
 extern "C" {
 
 int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out) {
@@ -128,6 +132,23 @@ int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embeddi
     ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
     h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
                      (cudaStream_t)stream);
+  });
+}
+
+int32_t ls_speaker_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_speaker** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_speaker_create_fp32: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_speaker>();
+    h->eng32 = std::make_unique<ls::SpeakerEngineF32>(w, device);
+    *out = h.release();
+  });
+}
+void ls_speaker_destroy(ls_speaker* h) { delete h; }
+int32_t ls_speaker_encode(ls_speaker* h, const float* mel, float* embedding, int32_t B, int32_t T, int32_t n_refs, void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && mel && embedding, "ls_speaker_encode: null argument");
+    h->eng32->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
   });
 }
 

@@ -1,6 +1,7 @@
 // fp32 mode of the hot path: see f32_path.h.  Plain CUDA-core kernels in the reference's NCT layout, one per
 // reference op, no fusion, accurate libm (no fast-math intrinsics).  Reference lines next to each kernel.
 #include <cmath>
+#include <utility>
 
 #include "f32_path.h"
 
@@ -384,6 +385,94 @@ __global__ void normalize_rows_kernel(const float* __restrict__ x, float* __rest
   }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) y[(size_t)r * K + k] = x[(size_t)r * K + k] / sh;
+}
+
+// ---- speaker encoder: llm/llm.py:34-96, transformer/arch_util.py:21-123 --------------------
+// GroupNorm32 (arch_util.py:21-41): statistics over (C/G channels x T) of one (b, group) -- contiguous in NCT --
+// eps 1e-5, per-channel affine.  One block per (group, b); two passes (mean, then centred variance).
+__global__ void __launch_bounds__(256) group_norm_nct_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                             const float* __restrict__ be, float* __restrict__ y, int C,
+                                                             int T, int G) {
+  const int grp = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  const size_t n = (size_t)cpg * T;
+  const float* xb = x + ((size_t)b * C + (size_t)grp * cpg) * T;
+  float* yb = y + ((size_t)b * C + (size_t)grp * cpg) * T;
+  __shared__ float red[8];
+  __shared__ float stat;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // red / stat of the previous reduction have been consumed
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      stat = t;
+    }
+    __syncthreads();
+    return stat;
+  };
+  float a = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) a += xb[i];
+  const float mean = block_sum(a) / (float)n;
+  float q = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const float d = xb[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(block_sum(q) / (float)n + 1e-5f);
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const int c = grp * cpg + (int)(i / T);
+    yb[i] = (xb[i] - mean) * rstd * g[c] + be[c];
+  }
+}
+// QKVAttentionLegacy (arch_util.py:44-77) on qkv [B, H*3*64, T]: heads are split BEFORE q/k/v (head h owns channels
+// [192h, 192h+192) = [q | k | v]); weight = softmax((q*s) . (k*s)), s = 64^-1/4, over all T keys (no mask); a = weight . v
+// -> [B, H*64, T].  One thread per (b, h, query).
+__global__ void __launch_bounds__(kTB) qkv_legacy_attention_kernel(const float* __restrict__ qkv, float* __restrict__ o, int H,
+                                                                   int T) {
+  const int i = blockIdx.x * kTB + threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  if (i >= T) return;
+  const float* q = qkv + ((size_t)b * H + h) * 192 * T;
+  const float* k = q + (size_t)64 * T;
+  const float* v = q + (size_t)128 * T;
+  const float sc = 1.0f / sqrtf(sqrtf(64.0f));
+  float qr[64], acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) qr[d] = q[(size_t)d * T + i] * sc, acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < T; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s = fmaf(qr[d], k[(size_t)d * T + j] * sc, s);
+    const float m_new = fmaxf(m, s);
+    const float corr = expf(m - m_new);
+    const float p = expf(s - m_new);
+    l = l * corr + p;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = fmaf(p, v[(size_t)d * T + j], acc[d] * corr);
+    m = m_new;
+  }
+  const float inv = 1.0f / l;
+  float* ob = o + ((size_t)b * H + h) * 64 * T;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) ob[(size_t)d * T + i] = acc[d] * inv;
+}
+// y[b,c] = x[b,c,0]   (first-position pooling, llm.py:88)
+__global__ void first_frame_kernel(const float* __restrict__ x, float* __restrict__ y, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i * T];
+}
+// y = mean over N stacked embeddings [N][B*K] (flow.py:355, several reference clips)
+__global__ void mean_stack_kernel(const float* __restrict__ x, float* __restrict__ y, int N, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int k = 0; k < N; ++k) a += x[(size_t)k * n + i];
+  y[i] = a / (float)N;
 }
 
 inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
@@ -899,6 +988,59 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
   F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x, w_.ptr("encoder.after_norm.weight"), w_.ptr("encoder.after_norm.bias"),
              an, d_, T2, 0, (const float*)nullptr, (const float*)nullptr);
   conv1d(an, nullptr, w_.ptr("encoder_proj.weight"), w_.ptr("encoder_proj.bias"), mu, nullptr, B, d_, T2, out_, 1, 1, 0, -1.f, s);
+}
+
+// ---------------------------------------------------------------------------------------------- speaker encoder (f-4)
+SpeakerEngineF32::SpeakerEngineF32(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  upload_all(w, &w_);
+  mel_ = (int)w_.shape("init.weight")[1];
+  d_ = (int)w_.shape("init.weight")[0];
+  out_ = (int)w_.shape("output_proj.weight")[0];
+  require(d_ == heads_ * 64 && d_ % groups_ == 0, "fp32 speaker encoder: expected 8 heads of 64 channels", LS_ERR_UNSUPPORTED);
+  while (w_.has("attn." + std::to_string(n_blocks_) + ".norm.weight")) ++n_blocks_;
+}
+
+// LearnableSpeakerEncoder.forward (llm.py:70-96): init conv -> AttentionBlocks (x + proj_out(attn(qkv(GroupNorm(x))))) ->
+// first frame -> output_proj -> L2 normalise.  n_refs > 1: mel is [n_refs][B,mel,T]; the embeddings are averaged and
+// normalised again (CausalMaskedDiffWithXvec.get_speaker_embedding, flow.py:336-366).
+void SpeakerEngineF32::encode(const float* mel, float* emb, int B, int T, int n_refs, cudaStream_t s) {
+  require(B > 0 && T > 0 && n_refs > 0, "B, T, n_refs must be positive");
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  const int R = B * n_refs;  // every clip is an independent row of the batch
+  const size_t n = (size_t)R * d_ * T;
+  float* h = scratch_.get(n, s);
+  conv1d(mel, nullptr, w_.ptr("init.weight"), w_.ptr("init.bias"), h, nullptr, R, mel_, T, d_, 1, 1, 0, -1.f, s);
+  float* nrm = scratch_.get(n, s);
+  float* qkv = scratch_.get(3 * n, s);
+  float* att = scratch_.get(n, s);
+  float* prj = scratch_.get(n, s);
+  float* h2 = scratch_.get(n, s);
+  for (int i = 0; i < n_blocks_; ++i) {
+    const std::string p = "attn." + std::to_string(i);
+    F32_LAUNCH(group_norm_nct_kernel, dim3(groups_, R), 256, s, h, w_.ptr(p + ".norm.weight"), w_.ptr(p + ".norm.bias"), nrm, d_, T,
+               groups_);
+    conv1d(nrm, nullptr, w_.ptr(p + ".qkv.weight"), w_.ptr(p + ".qkv.bias"), qkv, nullptr, R, d_, T, 3 * d_, 1, 1, 0, -1.f, s);
+    F32_LAUNCH(qkv_legacy_attention_kernel, grid_t(T, heads_, R), kTB, s, qkv, att, heads_, T);
+    conv1d(att, nullptr, w_.ptr(p + ".proj_out.weight"), w_.ptr(p + ".proj_out.bias"), prj, nullptr, R, d_, T, d_, 1, 1, 0, -1.f, s);
+    ew(h, prj, h2, n, EW_ADD, s);
+    std::swap(h, h2);
+  }
+  float* pooled = scratch_.get((size_t)R * d_, s);
+  F32_LAUNCH(first_frame_kernel, blocks((size_t)R * d_), 256, s, h, pooled, T, (size_t)R * d_);
+  float* proj = scratch_.get((size_t)R * out_, s);
+  F32_LAUNCH(linear_rows_kernel, dim3((out_ + 127) / 128, R), 128, s, pooled, w_.ptr("output_proj.weight"), w_.ptr("output_proj.bias"),
+             proj, R, d_, out_, 0, 0);
+  if (n_refs == 1) {
+    F32_LAUNCH(normalize_rows_kernel, R, 128, s, proj, emb, out_);
+    return;
+  }
+  float* each = scratch_.get((size_t)R * out_, s);
+  F32_LAUNCH(normalize_rows_kernel, R, 128, s, proj, each, out_);
+  float* avg = scratch_.get((size_t)B * out_, s);
+  F32_LAUNCH(mean_stack_kernel, blocks((size_t)B * out_), 256, s, each, avg, n_refs, (size_t)B * out_);
+  F32_LAUNCH(normalize_rows_kernel, B, 128, s, avg, emb, out_);
 }
 
 }  // namespace ls

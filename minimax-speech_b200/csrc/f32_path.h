@@ -112,4 +112,21 @@ class FrontEngineF32 {
   F32Scratch scratch_;
 };
 
+// LearnableSpeakerEncoder (speech/cosyvoice/llm/llm.py:34-96): reference mel [B,80,T] -> L2-normalised
+// speaker embedding [B,192] (the `embedding` input of the front half).  fp32 mode; equal-length clips.
+class SpeakerEngineF32 {
+ public:
+  SpeakerEngineF32(const Weights& w, int device);
+  // mel [n_refs][B,mel,T] -> emb [B,out]; n_refs > 1 averages the per-clip embeddings (flow.py:336-366)
+  void encode(const float* mel, float* emb, int B, int T, int n_refs, cudaStream_t s);
+  int mel_dim() const { return mel_; }
+  int out_dim() const { return out_; }
+  int device() const { return device_; }
+
+ private:
+  int device_ = 0, mel_ = 80, d_ = 512, out_ = 192, heads_ = 8, groups_ = 32, n_blocks_ = 0;
+  F32Weights w_;
+  F32Scratch scratch_;
+};
+
 }  // namespace ls

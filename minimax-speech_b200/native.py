@@ -16,6 +16,7 @@ OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32", "ls_dac_encode",
            "ls_front_create_fp32", "ls_front_destroy", "ls_front_encode",
+           "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
            "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
@@ -98,6 +99,10 @@ def load():
         lib.ls_front_destroy.argtypes = [vp]
         lib.ls_front_destroy.restype = None
         lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.ls_speaker_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_speaker_destroy.argtypes = [vp]
+        lib.ls_speaker_destroy.restype = None
+        lib.ls_speaker_encode.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
         lib.ls_debug_set_buffer.argtypes = [vp, i64]
         lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
@@ -229,6 +234,33 @@ class FrontHandle:
         check(load().ls_front_encode(self._h, ptr(tokens), ptr(embedding), ptr(mu), ptr(spks), B, T, int(n_context),
                                      int(bool(streaming)), current_stream_ptr(self.device)), "ls_front_encode")
         return mu, spks
+
+
+class SpeakerHandle:
+    """Owns an ls_speaker*: LearnableSpeakerEncoder (fp32 mode)."""
+
+    def __init__(self, state_dict, device):
+        lib = load()
+        self.device = torch.device(device)
+        arr, keep = tensor_table(state_dict)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ls_speaker_create_fp32(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_speaker_create_fp32")
+        self._h = h
+        self.out_dim = int(state_dict["output_proj.weight"].shape[0])
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ls_speaker_destroy(h)
+
+    def encode(self, mel):
+        """mel [n_refs, B, 80, T] (contiguous) -> [B, out_dim]"""
+        n_refs, B, _, T = mel.shape
+        emb = torch.empty(B, self.out_dim, device=mel.device, dtype=torch.float32)
+        check(load().ls_speaker_encode(self._h, ptr(mel), ptr(emb), B, T, n_refs, current_stream_ptr(self.device)),
+              "ls_speaker_encode")
+        return emb
 
 
 class DacHandle:

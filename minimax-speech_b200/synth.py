@@ -262,6 +262,30 @@ def token_inputs(index, n_tokens, vocab=6561, spk_dim=192):
     return tok, emb
 
 
+PIPE_EST = dict(n_blocks=1, num_mid_blocks=1)
+
+
+def pipeline_inputs(case):
+    """Inputs of the two whole-pipeline golden cases (oracle/gen_golden.py pipeline_golden and the tests)."""
+    if case == "a":  # given x-vector, 8 prompt tokens / 16 prompt frames, final chunk
+        tok, emb = token_inputs(30, 30)
+        ptok, _ = token_inputs(31, 8)
+        pfeat = dac_latents(32, 16).transpose(1, 2).contiguous()
+        return dict(token=tok, prompt_token=ptok, prompt_feat=pfeat, embedding=emb, reference_mels=None, streaming=False,
+                    finalize=True)
+    tok, _ = token_inputs(40, 53)  # two reference clips -> speaker encoder; non-final streaming chunk
+    ptok, _ = token_inputs(41, 10)
+    pfeat = dac_latents(42, 20).transpose(1, 2).contiguous()
+    mels = torch.stack([reference_mel(50 + i, 40) for i in range(2)], dim=1)  # [1,2,80,40]
+    return dict(token=tok, prompt_token=ptok, prompt_feat=pfeat, embedding=None, reference_mels=mels, streaming=True,
+                finalize=False)
+
+
+def pipeline_state_dicts():
+    return (conformer_encoder_state_dict(7), estimator_state_dict(7, init="test", **PIPE_EST),
+            speaker_encoder_state_dict(13))
+
+
 def audio_clip(index, samples):
     """Synthetic mono audio in (-1, 1): a few sinusoids plus noise, deterministic per index."""
     t = torch.arange(samples, dtype=torch.float32) / 24000.0

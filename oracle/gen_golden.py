@@ -38,7 +38,37 @@ def est_inputs(lengths, seed):
     return x, mask, mu, t, spks, cond
 
 
+def pipeline_golden():
+    """The unmodified CausalMaskedDiffWithXvec.inference (flow.py:437-511): prompt tokens + prompt latents + speaker encoder."""
+    with torch.inference_mode():
+        m = R.build_reference_pipeline(synth.PIPE_EST)
+        fsd, esd, ssd = synth.pipeline_state_dicts()
+        full = dict(fsd)
+        full.update({"decoder.estimator." + k: v for k, v in esd.items()})
+        full.update({"speaker_encoder." + k: v for k, v in ssd.items()})
+        missing, unexpected = m.load_state_dict(full, strict=False)
+        assert not unexpected and not missing, (missing[:5], unexpected[:5])
+        out = {"weights_checksum": synth.checksum(fsd) + synth.checksum(esd) + synth.checksum(ssd)}
+        import json
+        with open(os.path.join(OUT, "pipeline_keys.json"), "w") as f:  # the reference pipeline's state_dict schema
+            json.dump({k: list(v.shape) for k, v in m.state_dict().items()}, f, indent=0, sort_keys=True)
+        for case in ("a", "b"):
+            a = synth.pipeline_inputs(case)
+            n = lambda t: torch.tensor([t.shape[1]], dtype=torch.int32)
+            kw = {}
+            if a["reference_mels"] is not None:
+                kw = dict(reference_mels=a["reference_mels"], reference_mel_masks=torch.ones(1, 2, a["reference_mels"].shape[-1]))
+            feat, _ = m.inference(a["token"], n(a["token"]), a["prompt_token"], n(a["prompt_token"]), a["prompt_feat"],
+                                  n(a["prompt_feat"]), embedding=a["embedding"], streaming=a["streaming"], finalize=a["finalize"],
+                                  **kw)
+            out[f"pipe_{case}_y"] = feat.numpy()
+            print("pipeline", case, feat.shape, float(feat.abs().mean()))
+        np.savez_compressed(os.path.join(OUT, "pipeline_golden.npz"), **out)
+
+
 def main():
+    if "--pipeline-only" in sys.argv:
+        return pipeline_golden()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     with torch.inference_mode():
@@ -149,6 +179,8 @@ def main():
             out[f"spk_{name}_y"] = spk(mel).numpy()
             print("speaker", name, out[f"spk_{name}_y"].shape)
         np.savez_compressed(os.path.join(OUT, "speaker_golden.npz"), **out)
+
+        pipeline_golden()
 
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
         import json

@@ -207,3 +207,24 @@ def build_reference_speaker_encoder():
         sys.modules["cosyvoice.transformer.xtransformers"] = xt
     llm = importlib.import_module("cosyvoice.llm.llm")
     return llm.LearnableSpeakerEncoder(mel_dim=80, model_dim=512, output_dim=192, num_blocks=6, num_heads=8).eval()
+
+
+def build_reference_pipeline(estimator_kwargs=None):
+    """The unmodified CausalMaskedDiffWithXvec (speech/cosyvoice/flow/flow.py:201-511) per speech/config.yaml:61-116 with its
+    own UpsampleConformerEncoder, CausalConditionalCFM and LearnableSpeakerEncoder (use_speaker_encoder=True)."""
+    import importlib
+    build_reference_speaker_encoder()  # installs the xtransformers stub before cosyvoice.llm.llm is imported
+    um = importlib.import_module("cosyvoice.transformer.upsample_encoder")
+    fl = importlib.import_module("cosyvoice.flow.flow")
+    enc = um.UpsampleConformerEncoder(
+        input_size=512, output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+        positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True, input_layer="linear",
+        pos_enc_layer_type="rel_pos_espnet", selfattention_layer_type="rel_selfattn", use_cnn_module=False,
+        macaron_style=False, static_chunk_size=25)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints its config
+        m = fl.CausalMaskedDiffWithXvec(input_size=512, output_size=80, spk_embed_dim=192, output_type="mel", vocab_size=6561,
+                                        input_frame_rate=25, only_mask_loss=True, token_latent_ratio=2, pre_lookahead_len=3,
+                                        use_speaker_encoder=True, encoder=enc, decoder=build_reference_flow(estimator_kwargs))
+    return m.eval()

@@ -409,6 +409,29 @@ def speaker_encode(sd, mel, heads=8):
     return F.normalize(out, p=2, dim=1)
 
 
+def flow_inference(sd_flow, sd_est, noise, token, prompt_token, prompt_feat, embedding=None, reference_mels=None, sd_spk=None,
+                   streaming=False, finalize=False, n_timesteps=10, pre_lookahead_len=3):
+    """CausalMaskedDiffWithXvec.inference (flow/flow.py:437-511), batch 1: speaker embedding (given, or from reference
+    mels [1,80,T] / [1,N,80,T] through the speaker encoder, flow.py:336-366), [prompt_token | token] -> mu, cond = prompt_feat
+    on the first frames, CFM solve (10 steps), the prompt frames cut off.  -> latents [1,80,2*T_token(-6)]."""
+    if reference_mels is not None:
+        if reference_mels.dim() == 4:
+            embs = [speaker_encode(sd_spk, reference_mels[:, i]) for i in range(reference_mels.shape[1])]
+            embedding = torch.stack(embs, dim=1).mean(dim=1)
+        else:
+            embedding = speaker_encode(sd_spk, reference_mels)
+    elif embedding is None:
+        embedding = torch.zeros(1, sd_flow["spk_embed_affine_layer.weight"].shape[1])
+    tok = torch.cat([prompt_token, token], dim=1)
+    mu, spks = tokens_to_mu(sd_flow, tok, embedding, finalize=finalize, streaming=streaming, pre_lookahead_len=pre_lookahead_len)
+    mel_len1 = prompt_feat.shape[1]
+    cond = torch.zeros_like(mu)
+    cond[:, :, :mel_len1] = prompt_feat.transpose(1, 2)
+    mask = torch.ones(1, 1, mu.shape[2])
+    feat = cfm_forward(sd_est, noise, mu, mask, n_timesteps, 1.0, spks, cond, streaming=streaming)
+    return feat[:, :, mel_len1:]
+
+
 # --------------------------------------------------------------------------------------
 # Parity metrics (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------

@@ -127,3 +127,24 @@ def test_latent_extraction_sharding_and_record_format(tmp_path):
                           "latent_shape", "original_path"}
     assert saved["compression_ratio"] == 480 and saved["original_samples"] == 1600 and saved["latent_shape"] == [80, 4]
     assert saved["mu"].shape == (80, 4) and float(saved["mu"].abs().max()) <= 1.0  # clamped to [-1, 1] before encoding
+
+
+def test_pipeline_state_dict_schema_matches_reference(golden_dir):
+    """The CausalMaskedDiffWithXvec drop-in (front half + speaker encoder + CFM) exposes the unmodified reference module's
+    state_dict keys and shapes, and loads such a checkpoint strictly."""
+    keys = json.load(open(os.path.join(golden_dir, "pipeline_keys.json")))
+    from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder
+    from minimax_speech_b200.front import CausalMaskedDiffWithXvec
+    est = CausalConditionalDecoder(**synth.PIPE_EST)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    m = CausalMaskedDiffWithXvec(use_speaker_encoder=True, decoder=cfm)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == keys
+    fsd, esd, ssd = synth.pipeline_state_dicts()
+    full = dict(fsd)
+    full.update({"decoder.estimator." + k: v for k, v in esd.items()})
+    full.update({"speaker_encoder." + k: v for k, v in ssd.items()})
+    m.load_state_dict(full, strict=True)
+    assert torch.equal(m.state_dict()["speaker_encoder.attn.3.qkv.weight"], ssd["attn.3.qkv.weight"])
+    with pytest.raises(RuntimeError):
+        m.inference(torch.zeros(1, 8, dtype=torch.int64), None, torch.zeros(1, 0, dtype=torch.int64), None,
+                    torch.zeros(1, 0, 80), None, finalize=True)  # CPU tensors are rejected, not emulated

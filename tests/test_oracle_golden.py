@@ -141,3 +141,20 @@ def test_speaker_encoder_matches_reference(golden_dir, case):
     with torch.inference_mode():
         y = O.speaker_encode(sd, mel)
     assert O.rel_l2(y, torch.from_numpy(g[f"spk_{case}_y"])) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_flow_inference_matches_reference(golden_dir, case):
+    """oracle.flow_inference against the unmodified CausalMaskedDiffWithXvec.inference (flow.py:437-511): prompt tokens,
+    prompt latents as cond, x-vector (a) or two reference clips through the speaker encoder + non-final streaming chunk (b)."""
+    g = np.load(os.path.join(golden_dir, "pipeline_golden.npz"))
+    fsd, esd, ssd = synth.pipeline_state_dicts()
+    ck = synth.checksum(fsd) + synth.checksum(esd) + synth.checksum(ssd)
+    assert abs(ck - float(g["weights_checksum"])) < 1e-6 * abs(ck)
+    a = synth.pipeline_inputs(case)
+    with torch.inference_mode():
+        y = O.flow_inference(fsd, esd, synth.fixed_noise(), a["token"], a["prompt_token"], a["prompt_feat"], embedding=a["embedding"],
+                             reference_mels=a["reference_mels"], sd_spk=ssd, streaming=a["streaming"], finalize=a["finalize"])
+    ref = torch.from_numpy(g[f"pipe_{case}_y"])
+    assert y.shape == ref.shape
+    assert O.rel_l2(y, ref) < 1e-5
