@@ -59,6 +59,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float c, floa
   }
 }
 
+template <bool kBias>
 __global__ void __launch_bounds__(kAttnThreads, kCtasPerSm)
 attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapOut,
             const __grid_constant__ AttnParams p) {
@@ -223,6 +224,18 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_f);
       if (j < 4) TLS(17 + 6 * j);
+      if (kBias) {  // relative-position term: this row's 64 consecutive entries of its (skewed) bias row
+        const int qc = qi < p.T ? qi : p.T - 1;
+        const float* br = p.bias + ((long long)b * p.H + h) * p.bias_bh + (long long)qc * p.bias_ld + (p.T - 1 - qc) + j * kKV;
+#pragma unroll
+        for (int cc = 0; cc < kChunks; ++cc)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int jj = cc * 32 + i;
+            const float bv = (j * kKV + jj < p.T) ? __ldg(br + jj) : 0.f;
+            s[cc][i] = __float_as_uint(__uint_as_float(s[cc][i]) + bv);
+          }
+      }
       const int nvalid = limit - j * kKV;  // valid keys of this row in this tile (may be <= 0 for streaming rows)
       if (nvalid < kKV) {  // masked keys: -inf scores (exp2 -> 0); only the last key tile of a row pays for this
 #pragma unroll
@@ -338,7 +351,8 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -368,7 +382,8 @@ cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cud
     e.out = p.out, e.B = p.B, e.T = p.T, e.H = p.H;
     hit = &e;
   }
-  return launch_pdl(attn_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, hit->map, pp);
+  if (p.bias) return launch_pdl(attn_kernel<true>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, hit->map, pp);
+  return launch_pdl(attn_kernel<false>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, stream, 1, mapQKV, hit->map, pp);
 }
 
 }  // namespace ls

@@ -8,6 +8,7 @@
 #include "engine_common.h"
 #include "f32_path.h"
 #include "flow_engine.h"
+#include "front_engine.h"
 #include "profiler.h"
 
 namespace ls {
@@ -107,7 +108,8 @@ struct ls_dac {
 };
 
 struct ls_front {
-  std::unique_ptr<ls::FrontEngineF32> eng32;
+  std::unique_ptr<ls::FrontEngine> eng;       // tensor-core path
+  std::unique_ptr<ls::FrontEngineF32> eng32;  // fp32 mode
 };
 
 struct ls_speaker {
@@ -125,13 +127,24 @@ int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_
     *out = h.release();
   });
 }
+int32_t ls_front_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_front_create: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_front>();
+    h->eng = std::make_unique<ls::FrontEngine>(w, device);
+    *out = h.release();
+  });
+}
 void ls_front_destroy(ls_front* h) { delete h; }
 int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
                         int32_t T, int32_t n_context, int32_t streaming, void* stream) {
   return ls::guarded([&] {
     ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
-    h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
-                     (cudaStream_t)stream);
+    if (h->eng) h->eng->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
+                               (cudaStream_t)stream);
+    else h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
+                          (cudaStream_t)stream);
   });
 }
 

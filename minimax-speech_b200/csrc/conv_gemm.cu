@@ -611,6 +611,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         } else if (act == ACT_GELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[i] = gelu_erf(x[i]);
+        } else if (act == ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.0f + __expf(-x[i]));
+        } else if (act == ACT_LRELU001) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = x[i] > 0.f ? x[i] : 0.01f * x[i];
         }
       };
       // statistics of this thread's 64 columns (4 chunks), merged chunk by chunk (Chan), then across the 4 column

@@ -43,7 +43,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4 };
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4,
+                 ACT_SILU = 5, ACT_LRELU001 = 6 /* F.leaky_relu's default slope 0.01 */ };
 enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 };
 enum Out1Mode : int { OUT1_NONE = 0, OUT1_LN = 1, OUT1_COPY = 2, OUT1_SNAKE = 3 };
 
@@ -116,6 +117,10 @@ struct AttnParams {
   int chunk;            // >0: block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
   float scale_log2e;    // softmax scale * log2(e)
   __nv_bfloat16* out;   // [B][T][H*64]
+  // optional additive score term (the conformer's relative-position term, front_engine.cu): score(i, j) gets
+  // bias[(b*H + h)*bias_bh + i*bias_ld + (T-1-i) + j] before the softmax scale; nullptr = none
+  const float* bias;
+  long long bias_ld, bias_bh;
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps, or nullptr
 };
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);

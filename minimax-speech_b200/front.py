@@ -1,9 +1,9 @@
 """Token -> mu front half of ``CausalMaskedDiffWithXvec.inference`` (speech/cosyvoice/flow/flow.py:437-511; SURVEY.md
 section 8 row f-1): speaker-embedding normalise + ``spk_embed_affine_layer``, ``input_embedding``, the
 ``UpsampleConformerEncoder`` (transformer/upsample_encoder.py) and ``encoder_proj``.  Parameters are registered under the
-reference's state_dict keys, so the flow checkpoint loads unchanged.  fp32 mode only in this round (CUDA-core kernels of
-csrc/f32_path.cu): equal-length batches, no prompt; final chunks (finalize=True) and non-final chunks (3 look-ahead
-context tokens), optional block-causal streaming attention.  ``CausalMaskedDiffWithXvec`` is the drop-in for the reference's
+reference's state_dict keys, so the flow checkpoint loads unchanged.  ``precision="bf16"`` (default): tensor-core path
+(csrc/front_engine.cu); ``"fp32"``: CUDA-core kernels of csrc/f32_path.cu.  Equal-length batches; final chunks
+(finalize=True) and non-final chunks (3 look-ahead context tokens), optional block-causal streaming attention.  ``CausalMaskedDiffWithXvec`` is the drop-in for the reference's
 pipeline class: the same ``inference`` signature (prompt tokens, prompt latents, x-vector or reference mels)."""
 import torch
 import torch.nn as nn
@@ -18,10 +18,9 @@ _FRONT_PREFIXES = ("input_embedding.", "encoder.", "encoder_proj.", "spk_embed_a
 
 class TokenToMu(nn.Module):
     def __init__(self, input_size=512, output_size=80, spk_embed_dim=192, vocab_size=6561, attention_heads=8,
-                 linear_units=2048, num_blocks=6, weight_seed=7, precision="fp32", **_ignored):
+                 linear_units=2048, num_blocks=6, weight_seed=7, precision="bf16", **_ignored):
         super().__init__()
-        if precision != "fp32":
-            raise NotImplementedError("the token -> mu front half runs in fp32 mode only (tensor-core path: not built yet)")
+        precision = native.check_precision(precision)
         if input_size != attention_heads * 64:
             raise NotImplementedError("head dim 64 only (config.yaml:73-88: 512 / 8)")
         self.precision, self.output_size, self.spk_embed_dim, self.vocab_size = precision, output_size, spk_embed_dim, vocab_size
@@ -39,9 +38,9 @@ class TokenToMu(nn.Module):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
-        if self._handle is None or self._handle.device != device:
+        if self._handle is None or self._handle.device != device or self._handle.precision != self.precision:
             sd = {k: v for k, v in self.state_dict().items() if k.startswith(_FRONT_PREFIXES)}
-            self._handle = native.FrontHandle(sd, device)
+            self._handle = native.FrontHandle(sd, device, self.precision)
         return self._handle
 
     pre_lookahead_len = 3
@@ -78,13 +77,13 @@ class CausalMaskedDiffWithXvec(TokenToMu):
     def __init__(self, input_size=512, output_size=80, spk_embed_dim=192, output_type="mel", vocab_size=6561, input_frame_rate=25,
                  only_mask_loss=True, token_latent_ratio=2, pre_lookahead_len=3, use_speaker_encoder=False,
                  freeze_speaker_encoder=False, max_conditioning_inputs=2, speaker_encoder_path=None, encoder=None, decoder=None,
-                 **_ignored):
+                 precision="bf16", **_ignored):
         if decoder is None:
             raise ValueError("decoder (a CausalConditionalCFM) is required")
         if pre_lookahead_len != TokenToMu.pre_lookahead_len:
             raise NotImplementedError("pre_lookahead_len = 3 only (config.yaml:70)")
         super().__init__(input_size=input_size, output_size=output_size, spk_embed_dim=spk_embed_dim, vocab_size=vocab_size,
-                         **(encoder or {}))
+                         precision=precision, **(encoder or {}))
         self.input_size, self.input_frame_rate, self.token_latent_ratio = input_size, input_frame_rate, token_latent_ratio
         self.use_speaker_encoder = use_speaker_encoder
         self.decoder = decoder

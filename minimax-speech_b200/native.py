@@ -15,7 +15,7 @@ OUT_NONE, OUT_F32, OUT_BF16 = range(3)
 OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32", "ls_dac_encode",
-           "ls_front_create_fp32", "ls_front_destroy", "ls_front_encode",
+           "ls_front_create", "ls_front_create_fp32", "ls_front_destroy", "ls_front_encode",
            "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
@@ -95,6 +95,7 @@ def load():
         lib.ls_dac_hop_length.argtypes = [vp]
         lib.ls_dac_decode.argtypes = [vp, vp, vp, vp, i32, i32, vp]
         lib.ls_dac_encode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+        lib.ls_front_create.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_front_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_front_destroy.argtypes = [vp]
         lib.ls_front_destroy.restype = None
@@ -210,15 +211,17 @@ class FlowHandle:
 
 
 class FrontHandle:
-    """Owns an ls_front*: the token -> mu front half (fp32 mode)."""
+    """Owns an ls_front*: the token -> mu front half (tensor-core path or fp32 mode)."""
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, precision="bf16"):
         lib = load()
         self.device = torch.device(device)
+        self.precision = check_precision(precision)
         arr, keep = tensor_table(state_dict)
         h = C.c_void_p()
+        create = lib.ls_front_create_fp32 if self.precision == "fp32" else lib.ls_front_create
         with torch.cuda.device(self.device):
-            check(lib.ls_front_create_fp32(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_front_create_fp32")
+            check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_front_create")
         self._h = h
         self.out_dim = int(state_dict["encoder_proj.weight"].shape[0])
 

@@ -25,7 +25,18 @@ torch.set_num_threads(os.cpu_count() or 1)
 def front(golden_dir):
     g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
     sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
+    f = TokenToMu(precision="fp32")
+    f.load_state_dict(sd)
+    return g, sd, f
+
+
+@pytest.fixture(scope="module")
+def front_tc(golden_dir):
+    """The tensor-core path (bf16 operands, fp32 accumulate): north_star's 1e-2 bar."""
+    g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
+    sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
     f = TokenToMu()
+    assert f.precision == "bf16"
     f.load_state_dict(sd)
     return g, sd, f
 
@@ -91,3 +102,60 @@ def test_non_final_streaming_chunk_vs_reference_golden(front):
     with torch.inference_mode():
         mo, _ = O.tokens_to_mu(sd, tok, emb, finalize=False, streaming=True)
     assert O.rel_l2(mu.cpu(), mo) < 1e-4
+
+
+# ---- tensor-core path ---------------------------------------------------------------------------------------------------
+def _mu_ref(g, sd, key):
+    h = torch.from_numpy(g[key])
+    return torch.nn.functional.linear(h, sd["encoder_proj.weight"], sd["encoder_proj.bias"]).transpose(1, 2)
+
+
+def test_tc_mu_vs_reference_golden(front_tc):
+    g, sd, f = front_tc
+    tok, emb = synth.token_inputs(0, int(g["enc_a_lens"][0]))
+    mu, spks = f(tok.to(DEV), emb.to(DEV))
+    e = O.rel_l2(mu.cpu(), _mu_ref(g, sd, "enc_a_h"))
+    print(f"tensor-core front mu vs reference golden: rel-L2 {e:.3e}")
+    assert mu.shape == (1, 80, 80) and e < 1e-2
+    with torch.inference_mode():
+        _, sr = O.tokens_to_mu(sd, tok, emb)
+    assert O.rel_l2(spks.cpu(), sr) < 1e-5
+
+
+def test_tc_non_final_streaming_chunk_vs_reference_golden(front_tc):
+    g, sd, f = front_tc
+    tok, emb = synth.token_inputs(5, 60)
+    mu, _ = f(tok.to(DEV), emb.to(DEV), finalize=False, streaming=True)
+    e = O.rel_l2(mu.cpu(), _mu_ref(g, sd, "enc_c_h"))
+    print(f"tensor-core front mu (context + streaming) vs reference golden: rel-L2 {e:.3e}")
+    assert mu.shape == (1, 80, 114) and e < 1e-2
+
+
+@pytest.mark.parametrize("n_tokens,batch", [(37, 3), (250, 16), (129, 2)])
+def test_tc_batch_vs_oracle_and_batch_invariance(front_tc, n_tokens, batch):
+    """Several utterances in one call == each alone (bit-exact), and against the oracle; 250 tokens x 16 = BASELINE configs[1]."""
+    g, sd, f = front_tc
+    toks, embs = zip(*[synth.token_inputs(20 + b, n_tokens) for b in range(batch)])
+    tok, emb = torch.cat(toks, 0), torch.cat(embs, 0)
+    mu, spks = f(tok.to(DEV), emb.to(DEV))
+    assert mu.shape == (batch, 80, 2 * n_tokens)
+    for b in (0, batch - 1):
+        with torch.inference_mode():
+            mr, sr = O.tokens_to_mu(sd, tok[b:b + 1], emb[b:b + 1])
+        e = O.rel_l2(mu[b:b + 1].cpu(), mr)
+        print(f"tensor-core front, {n_tokens} tokens x {batch}, utterance {b} vs oracle: rel-L2 {e:.3e}")
+        assert e < 1e-2 and O.rel_l2(spks[b:b + 1].cpu(), sr) < 1e-5
+    one, _ = f(tok[1:2].to(DEV), emb[1:2].to(DEV))
+    assert torch.equal(one, mu[1:2])
+
+
+def test_tc_streaming_batch_vs_oracle(front_tc):
+    g, sd, f = front_tc
+    toks, embs = zip(*[synth.token_inputs(70 + b, 103) for b in range(2)])
+    tok, emb = torch.cat(toks, 0), torch.cat(embs, 0)
+    mu, _ = f(tok.to(DEV), emb.to(DEV), finalize=False, streaming=True)
+    with torch.inference_mode():
+        mr, _ = O.tokens_to_mu(sd, tok[1:2], emb[1:2], finalize=False, streaming=True)
+    e = O.rel_l2(mu[1:2].cpu(), mr)
+    print(f"tensor-core front, streaming non-final chunk x 2 vs oracle: rel-L2 {e:.3e}")
+    assert mu.shape == (2, 80, 200) and e < 1e-2

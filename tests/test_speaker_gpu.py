@@ -55,7 +55,7 @@ def pipeline():
     fsd, esd, ssd = synth.pipeline_state_dicts()
     est = CausalConditionalDecoder(precision="fp32", **synth.PIPE_EST)
     cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
-    m = CausalMaskedDiffWithXvec(use_speaker_encoder=True, decoder=cfm)
+    m = CausalMaskedDiffWithXvec(use_speaker_encoder=True, decoder=cfm, precision="fp32")
     full = dict(fsd)
     full.update({"decoder.estimator." + k: v for k, v in esd.items()})
     full.update({"speaker_encoder." + k: v for k, v in ssd.items()})
@@ -89,3 +89,24 @@ def test_inference_without_speaker_information(pipeline):
     with torch.inference_mode():
         ref = O.flow_inference(fsd, esd, synth.fixed_noise(), a["token"], a["prompt_token"], a["prompt_feat"], finalize=True)
     assert O.rel_l2(feat.cpu(), ref) < 1e-4
+
+
+def test_inference_tensor_core_path(golden_dir):
+    """The default (bf16 tensor-core) front half + estimator against the reference's golden pipeline outputs: 1e-2 bar."""
+    g = np.load(os.path.join(golden_dir, "pipeline_golden.npz"))
+    fsd, esd, ssd = synth.pipeline_state_dicts()
+    est = CausalConditionalDecoder(**synth.PIPE_EST)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    m = CausalMaskedDiffWithXvec(use_speaker_encoder=True, decoder=cfm)
+    full = dict(fsd)
+    full.update({"decoder.estimator." + k: v for k, v in esd.items()})
+    full.update({"speaker_encoder." + k: v for k, v in ssd.items()})
+    m.load_state_dict(full, strict=True)
+    for case in ("a", "b"):
+        a = synth.pipeline_inputs(case)
+        dv = lambda t: None if t is None else t.to(DEV)  # noqa: E731
+        feat, _ = m.inference(dv(a["token"]), None, dv(a["prompt_token"]), None, dv(a["prompt_feat"]), None, embedding=dv(a["embedding"]),
+                              reference_mels=dv(a["reference_mels"]), streaming=a["streaming"], finalize=a["finalize"])
+        e = O.rel_l2(feat.cpu(), torch.from_numpy(g[f"pipe_{case}_y"]))
+        print(f"CausalMaskedDiffWithXvec.inference {case} (tensor-core path) vs reference golden: rel-L2 {e:.3e}")
+        assert e < 1.5e-2
