@@ -66,9 +66,31 @@ class TokenToMu(nn.Module):
         return feat.float(), None
 
 
+class UpsampleConformerEncoder:
+    """Constructor-argument holder with the signature of ``cosyvoice.transformer.upsample_encoder.UpsampleConformerEncoder``
+    (upsample_encoder.py:110-180), so that speech/config.yaml:73-88 can name this class for the ``encoder:`` entry of the
+    drop-in ``CausalMaskedDiffWithXvec``.  The parameters live on the pipeline module (keys ``encoder.*``); only the
+    configuration of config.yaml is built (rel-pos self-attention, linear input layer, no macaron / CNN module)."""
+
+    def __init__(self, input_size=512, output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+                 positional_dropout_rate=0.1, attention_dropout_rate=0.1, input_layer="linear", pos_enc_layer_type="rel_pos_espnet",
+                 normalize_before=True, static_chunk_size=25, use_dynamic_chunk=False, global_cmvn=None,
+                 use_dynamic_left_chunk=False, positionwise_conv_kernel_size=1, macaron_style=False,
+                 selfattention_layer_type="rel_selfattn", activation_type="swish", use_cnn_module=False, cnn_module_kernel=15,
+                 causal=False, cnn_module_norm="batch_norm", key_bias=True, gradient_checkpointing=False):
+        if (input_size != output_size or input_layer != "linear" or pos_enc_layer_type != "rel_pos_espnet" or not normalize_before
+                or macaron_style or use_cnn_module or selfattention_layer_type != "rel_selfattn" or activation_type != "swish"
+                or static_chunk_size != 25 or not key_bias or global_cmvn is not None):
+            raise NotImplementedError("B200 token encoder covers config.yaml:73-88's UpsampleConformerEncoder only")
+        self.kwargs = dict(input_size=input_size, attention_heads=attention_heads, linear_units=linear_units, num_blocks=num_blocks)
+
+    def output_size(self):
+        return self.kwargs["input_size"]
+
+
 class CausalMaskedDiffWithXvec(TokenToMu):
     """Drop-in for ``cosyvoice.flow.flow.CausalMaskedDiffWithXvec`` (speech/cosyvoice/flow/flow.py:201-511), inference only:
-    same constructor keywords as speech/config.yaml:61-116 (``encoder`` = the encoder's keyword dict or None, ``decoder`` = a
+    same constructor keywords as speech/config.yaml:61-116 (``encoder`` = an ``UpsampleConformerEncoder`` holder, its keyword dict or None, ``decoder`` = a
     ``CausalConditionalCFM``), same ``inference(...)`` signature and return value, same state_dict keys
     (``input_embedding.*``, ``encoder.*``, ``encoder_proj.*``, ``spk_embed_affine_layer.*``, ``speaker_encoder.*``,
     ``decoder.estimator.*``), so the reference's flow checkpoint loads with ``load_state_dict`` unchanged.  ``forward`` (the
@@ -82,8 +104,11 @@ class CausalMaskedDiffWithXvec(TokenToMu):
             raise ValueError("decoder (a CausalConditionalCFM) is required")
         if pre_lookahead_len != TokenToMu.pre_lookahead_len:
             raise NotImplementedError("pre_lookahead_len = 3 only (config.yaml:70)")
+        enc = dict(encoder.kwargs if isinstance(encoder, UpsampleConformerEncoder) else (encoder or {}))
+        if enc.pop("input_size", input_size) != input_size:
+            raise ValueError("encoder input_size must equal the pipeline's input_size")
         super().__init__(input_size=input_size, output_size=output_size, spk_embed_dim=spk_embed_dim, vocab_size=vocab_size,
-                         precision=precision, **(encoder or {}))
+                         precision=precision, **enc)
         self.input_size, self.input_frame_rate, self.token_latent_ratio = input_size, input_frame_rate, token_latent_ratio
         self.use_speaker_encoder = use_speaker_encoder
         self.decoder = decoder

@@ -159,3 +159,50 @@ def test_tc_streaming_batch_vs_oracle(front_tc):
     e = O.rel_l2(mu[1:2].cpu(), mr)
     print(f"tensor-core front, streaming non-final chunk x 2 vs oracle: rel-L2 {e:.3e}")
     assert mu.shape == (2, 80, 200) and e < 1e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("fp32", 1e-4)])
+def test_edge_cases_vs_oracle(golden_dir, precision, tol):
+    """One token; a non-final chunk that leaves one token (4 = 1 + 3 context); negative ids clamp to 0 (flow.py:476);
+    the all-zero speaker embedding stays zero through the normalise (flow.py:465-466)."""
+    sd = synth.conformer_encoder_state_dict(7)
+    f = TokenToMu(precision=precision)
+    f.load_state_dict(sd)
+    cases = []
+    tok, emb = synth.token_inputs(90, 1)
+    cases.append((tok, emb, True))
+    tok, emb = synth.token_inputs(91, 4)
+    cases.append((tok, emb, False))
+    tok, emb = synth.token_inputs(92, 9)
+    tok = tok.clone()
+    tok[0, 2], tok[0, 5] = -1, -7
+    cases.append((tok, torch.zeros_like(emb), True))
+    for tok, emb, fin in cases:
+        mu, spks = f(tok.to(DEV), emb.to(DEV), finalize=fin)
+        with torch.inference_mode():
+            mr, sr = O.tokens_to_mu(sd, tok, emb, finalize=fin)
+        assert mu.shape == mr.shape and torch.isfinite(mu).all()
+        assert O.rel_l2(mu.cpu(), mr) < tol and O.rel_l2(spks.cpu(), sr) < 1e-5
+    with pytest.raises(ValueError):
+        f(torch.zeros(1, 3, dtype=torch.int64, device=DEV), emb.to(DEV), finalize=False)  # nothing left after the context
+
+
+def test_yaml_style_construction():
+    """speech/config.yaml:60-116 with the class paths swapped: encoder holder + CFM passed as constructor arguments."""
+    from minimax_speech_b200.front import CausalMaskedDiffWithXvec, UpsampleConformerEncoder
+    enc = UpsampleConformerEncoder(output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+                                   positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True,
+                                   input_layer="linear", pos_enc_layer_type="rel_pos_espnet", selfattention_layer_type="rel_selfattn",
+                                   input_size=512, use_cnn_module=False, macaron_style=False, static_chunk_size=25)
+    est = CausalConditionalDecoder(**synth.PIPE_EST)
+    cfm = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    m = CausalMaskedDiffWithXvec(input_size=512, output_size=80, spk_embed_dim=192, output_type="mel", vocab_size=6561,
+                                 input_frame_rate=25, only_mask_loss=True, token_latent_ratio=2, pre_lookahead_len=3,
+                                 use_speaker_encoder=False, freeze_speaker_encoder=True, speaker_encoder_path=None, encoder=enc,
+                                 decoder=cfm)
+    tok, emb = synth.token_inputs(3, 20)
+    feat, _ = m.inference(tok.to(DEV), torch.tensor([20]), torch.zeros(1, 0, dtype=torch.int64, device=DEV), torch.tensor([0]),
+                          torch.zeros(1, 0, 80, device=DEV), torch.tensor([0]), embedding=emb.to(DEV), finalize=True)
+    assert feat.shape == (1, 80, 40) and torch.isfinite(feat).all()
+    with pytest.raises(NotImplementedError):
+        UpsampleConformerEncoder(input_size=512, output_size=512, macaron_style=True)
