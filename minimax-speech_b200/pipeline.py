@@ -51,32 +51,96 @@ def shard_utterances(lengths, world_size):
     return [sorted(s) for s in shards]
 
 
-def gather_waveforms(wav, n_samples, index, dst=0, group=None):
+def gather_plan(shards, n_samples_all):
+    """Host-side description of a gather, known on every rank before the step (the shard assignment is computed from the
+    utterance lengths, so every rank knows what every other rank will contribute): per rank (sample counts, utterance ids).
+    ``shards``: per-rank lists of utterance ids (``shard_utterances``); ``n_samples_all[i]``: valid samples of utterance i."""
+    return [([int(n_samples_all[i]) for i in s], [int(i) for i in s]) for s in shards]
+
+
+class PlannedGather:
+    """``gather_waveforms`` with a plan and persistent staging buffers: nothing is allocated, exchanged as metadata or read back
+    per call, so the host thread keeps launching the next step (allocating the padded buffers per step makes the caching
+    allocator wait on the communication stream's use of the previous ones).  The returned views alias the receive buffer and
+    are overwritten by the next call."""
+
+    def __init__(self, plan, device, dst=0, group=None):
+        import torch.distributed as dist
+        self.plan, self.dst, self.group = plan, dst, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if len(plan) != self.world:
+            raise ValueError("gather plan must have one entry per rank")
+        self.bmax = max(len(p[0]) for p in plan)
+        self.smax = max([n for p in plan for n in p[0]] + [1])
+        self.pad = torch.zeros(self.bmax, self.smax, device=device, dtype=torch.float32)
+        self.out = torch.empty(self.world, self.bmax, self.smax, device=device, dtype=torch.float32) if self.rank == dst else None
+        self.nccl = dist.get_backend(group) == "nccl"
+
+    def __call__(self, wav):
+        import torch.distributed as dist
+        b, S = wav.shape[0], min(wav.shape[-1], self.smax)
+        if b != len(self.plan[self.rank][0]):
+            raise ValueError("gather plan does not describe this rank's contribution")
+        self.pad[:b, :S].copy_(wav[:, 0, :S])
+        if self.nccl:
+            dist.gather(self.pad, list(self.out.unbind(0)) if self.rank == self.dst else None, dst=self.dst, group=self.group)
+        else:
+            bufs = [torch.zeros_like(self.pad) for _ in range(self.world)] if self.rank == self.dst else None
+            dist.gather(self.pad, bufs, dst=self.dst, group=self.group)
+            if self.rank == self.dst:
+                self.out.copy_(torch.stack(bufs))
+        if self.rank != self.dst:
+            return None
+        return {uid: self.out[r, i, :n] for r, (counts, ids) in enumerate(self.plan) for i, (n, uid) in enumerate(zip(counts, ids))}
+
+
+def gather_waveforms(wav, n_samples, index, dst=0, group=None, plan=None):
     """Variable-length gather to ``dst``: every rank contributes ``wav [b,1,S_r]`` with per-item valid sample
     counts ``n_samples`` and global utterance ids ``index``.  Returns {utterance id: 1-D tensor} on ``dst``.
-    One collective for the payload (padded all_gather over NCCL/NVLink, or gloo on CPU) plus a tiny metadata one."""
+    One collective for the payload (padded gather over NCCL/NVLink, or gloo on CPU).  With ``plan`` (``gather_plan``) the
+    sizes are host knowledge and the call neither exchanges metadata nor reads anything back from the device, so the host
+    keeps launching the next step; without it a tiny metadata all_gather and a read-back of the counts come first."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = wav.device
+    b = wav.shape[0]
+
+    def exchange(pad, bmax, width):
+        out = torch.empty(world, bmax, width, device=dev, dtype=torch.float32) if rank == dst else None
+        if dist.get_backend(group) == "nccl":
+            dist.gather(pad, list(out.unbind(0)) if rank == dst else None, dst=dst, group=group)
+        else:
+            bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+            dist.gather(pad, bufs, dst=dst, group=group)
+            if rank == dst:
+                out = torch.stack(bufs)
+        return out
+
+    if plan is not None:
+        if len(plan) != world or list(plan[rank][1]) != [int(i) for i in index] or len(plan[rank][0]) != b:
+            raise ValueError("gather plan does not describe this rank's contribution")
+        bmax = max(len(p[0]) for p in plan)
+        smax = max([n for p in plan for n in p[0]] + [1])
+        if wav.shape[-1] > smax:
+            wav = wav[..., :smax]
+        pad = torch.zeros(bmax, smax, device=dev, dtype=torch.float32)
+        pad[:b, :wav.shape[-1]] = wav[:, 0, :]
+        out = exchange(pad, bmax, smax)
+        if rank != dst:
+            return None
+        return {uid: out[r, i, :n] for r, (counts, ids) in enumerate(plan) for i, (n, uid) in enumerate(zip(counts, ids))}
+
     meta = torch.tensor([wav.shape[0], wav.shape[-1]], device=dev, dtype=torch.int64)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
     bmax = int(max(m[0] for m in metas))
     smax = int(max(m[1] for m in metas))
     pad = torch.zeros(bmax, smax + 2, device=dev, dtype=torch.float32)
-    b = wav.shape[0]
     pad[:b, :wav.shape[-1]] = wav[:, 0, :]
     pad[:b, smax] = torch.as_tensor(n_samples, device=dev, dtype=torch.float32)
     pad[:b, smax + 1] = torch.as_tensor(index, device=dev, dtype=torch.float32)
-    out = torch.empty(world, bmax, smax + 2, device=dev, dtype=torch.float32) if rank == dst else None
-    if dist.get_backend(group) == "nccl":
-        dist.gather(pad, list(out.unbind(0)) if rank == dst else None, dst=dst, group=group)
-    else:
-        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
-        dist.gather(pad, bufs, dst=dst, group=group)
-        if rank == dst:
-            out = torch.stack(bufs)
+    out = exchange(pad, bmax, smax + 2)
     if rank != dst:
         return None
     res = {}

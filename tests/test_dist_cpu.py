@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from minimax_speech_b200.pipeline import gather_waveforms, shard_utterances, utterance_cost
+from minimax_speech_b200.pipeline import gather_plan, gather_waveforms, shard_utterances, utterance_cost
 
 
 def _free_port():
@@ -21,7 +21,7 @@ def _signal(uid, n):
     return torch.arange(n, dtype=torch.float32) * 1e-4 + float(uid)
 
 
-def _worker(rank, world, port, lengths, hop, ret):
+def _worker(rank, world, port, lengths, hop, ret, planned=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -30,7 +30,8 @@ def _worker(rank, world, port, lengths, hop, ret):
         wav = torch.zeros(len(mine), 1, smax)
         for j, i in enumerate(mine):
             wav[j, 0, :lengths[i] * hop] = _signal(i, lengths[i] * hop)
-        res = gather_waveforms(wav, [lengths[i] * hop for i in mine], mine, dst=0)
+        plan = gather_plan(shard_utterances(lengths, world), [n * hop for n in lengths]) if planned else None
+        res = gather_waveforms(wav, [lengths[i] * hop for i in mine], mine, dst=0, plan=plan)
         if rank == 0:
             ok = sorted(res) == list(range(len(lengths)))
             for i, w in res.items():
@@ -42,13 +43,18 @@ def _worker(rank, world, port, lengths, hop, ret):
         dist.destroy_process_group()
 
 
-def test_gather_waveforms_world2_gloo():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("planned", [False, True])
+def test_gather_waveforms_world2_gloo(planned):
+    """planned: sizes from the host-side gather plan (no metadata collective, no device read-back)."""
     rng = random.Random(0)
     lengths = [rng.randint(2, 30) for _ in range(9)]  # odd count: ranks hold different numbers of utterances
     ctx = mp.get_context("spawn")
     ret = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, 48, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, 48, ret, planned)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
