@@ -97,7 +97,10 @@ int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* 
  * (speech/cosyvoice/flow/flow.py:461-489): speaker-embedding normalise + affine, input embedding,
  * UpsampleConformerEncoder (speech/cosyvoice/transformer/upsample_encoder.py:266-318), encoder_proj.
  * ls_front_create: tensor-core path (bf16 operands, fp32 accumulate and residual stream); ls_front_create_fp32: fp32 mode.
- * Equal-length batches; prompt tokens are simply part of `tokens` (flow.py:471-475 concatenates them).
+ * token_len (device int32 [B], or NULL = every utterance has T tokens): token counts of a right-padded batch -- padded
+ * token rows are embedded as zeros and masked as attention keys exactly as the reference's encoder does with `xs_lens`
+ * (flow.py:475-476, upsample_encoder.py:293-301); mu is zero past 2 * token_len.  Prompt tokens are simply part of
+ * `tokens` (flow.py:471-475 concatenates them).
  * tokens [B,T] int64 (25 Hz FSQ ids), embedding [B,192] -> mu [B,80,2(T - n_context)], spks [B,80] (the inputs of
  * ls_flow_solve).  n_context = 0: final chunk (finalize = True); n_context = 3: the last 3 tokens are look-ahead context
  * only (flow.py:482-489).  streaming != 0: block-causal attention (25 tokens / 50 frames, upsample_encoder.py:297,312). */
@@ -106,7 +109,7 @@ int32_t ls_front_create(const ls_tensor* weights, int32_t n_weights, int32_t dev
 int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out);
 void ls_front_destroy(ls_front* h);
 int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
-                        int32_t T, int32_t n_context, int32_t streaming, void* stream);
+                        int32_t T, int32_t n_context, int32_t streaming, const int32_t* token_len, void* stream);
 
 /* ---- speaker encoder: LearnableSpeakerEncoder.forward (speech/cosyvoice/llm/llm.py:34-96, blocks:
  * speech/cosyvoice/transformer/arch_util.py:21-123) and the averaging over several reference clips of

@@ -138,13 +138,13 @@ int32_t ls_front_create(const ls_tensor* weights, int32_t n_weights, int32_t dev
 }
 void ls_front_destroy(ls_front* h) { delete h; }
 int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embedding, float* mu, float* spks, int32_t B,
-                        int32_t T, int32_t n_context, int32_t streaming, void* stream) {
+                        int32_t T, int32_t n_context, int32_t streaming, const int32_t* token_len, void* stream) {
   return ls::guarded([&] {
     ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
     if (h->eng) h->eng->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
-                               (cudaStream_t)stream);
+                               token_len, (cudaStream_t)stream);
     else h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
-                          (cudaStream_t)stream);
+                          token_len, (cudaStream_t)stream);
   });
 }
 

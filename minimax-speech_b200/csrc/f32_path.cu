@@ -297,8 +297,9 @@ __global__ void reparam_kernel(const float* __restrict__ x, const float* __restr
 
 // ---- token -> mu front half -------------------------------------------------------------
 // x[b,c,t] = E[clamp(tok[b,t], 0)][c]   (flow/flow.py:476: input_embedding(torch.clamp(token, min=0)))
+// rows past the utterance's token count are zero (flow.py:475-476: input_embedding(token) * mask)
 __global__ void embed_tokens_kernel(const long long* __restrict__ tok, const float* __restrict__ E, float* __restrict__ x, int d,
-                                    int T, int vocab, size_t n) {
+                                    int T, int vocab, size_t n, const int* __restrict__ lens) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t = (int)(i % T);
@@ -306,7 +307,20 @@ __global__ void embed_tokens_kernel(const long long* __restrict__ tok, const flo
   const size_t b = i / ((size_t)T * d);
   long long id = tok[b * T + t];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  x[i] = E[(size_t)id * d + c];
+  x[i] = (lens && t >= lens[b]) ? 0.f : E[(size_t)id * d + c];
+}
+// y[b,c,t] = 0 for t >= lens[b]
+__global__ void zero_tail_nct_kernel(float* __restrict__ y, const int* __restrict__ lens, int C, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if ((int)(i % T) >= lens[i / ((size_t)C * T)]) y[i] = 0.f;
+}
+// lens0[b] = min(token_len[b], T) (keys at 25 Hz), lens1[b] = 2 * lens0[b] (keys and valid frames at 50 Hz)
+__global__ void front_lens_kernel(const int* __restrict__ token_len, int* __restrict__ lens0, int* __restrict__ lens1, int B, int T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int l = max(0, min(token_len[b], T));
+  lens0[b] = l, lens1[b] = 2 * l;
 }
 __global__ void scale_kernel(float* __restrict__ x, float sc, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,10 +342,12 @@ __global__ void rel_pos_emb_kernel(float* __restrict__ pe, int T, int d) {
 __global__ void __launch_bounds__(kTB) rel_attention_nct_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                 const float* __restrict__ v, const float* __restrict__ pp,
                                                                 const float* __restrict__ bu, const float* __restrict__ bv,
-                                                                float* __restrict__ o, int H, int T, int len, int chunk) {
+                                                                float* __restrict__ o, int H, int T, int len, int chunk,
+                                                                const int* __restrict__ lens) {
   const int i = blockIdx.x * kTB + threadIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
   if (i >= T) return;
+  if (lens) len = min(len, lens[b]);  // key-padding mask of a mixed-length batch (attention.py:84-127)
   if (chunk > 0) len = min(len, (i / chunk + 1) * chunk);  // block-causal (utils/mask.py:127-158)
   const size_t base = ((size_t)b * H + h) * 64 * T;
   const int inner = H * 64;
@@ -882,7 +898,8 @@ FrontEngineF32::FrontEngineF32(const Weights& w, int device) : device_(device) {
 }
 
 // ConformerEncoderLayer (normalize_before, no macaron, no conv module): x += attn(LN(x)); x += w_2(swish(w_1(LN(x))))
-float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, int B, int T, int chunk, cudaStream_t s) {
+float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, int B, int T, int chunk, const int* lens,
+                             cudaStream_t s) {
   const size_t n = (size_t)B * d_ * T;
   const int P = 2 * T - 1;
   float* nrm = scratch_.get(n, s);
@@ -900,7 +917,7 @@ float* FrontEngineF32::layer(const std::string& p, float* x, const float* pe, in
              d_, d_, 0, 0);
   float* att = scratch_.get(n, s);
   F32_LAUNCH(rel_attention_nct_kernel, grid_t(T, heads_, B), kTB, s, q, k, v, pp, w_.ptr(a + ".pos_bias_u"), w_.ptr(a + ".pos_bias_v"),
-             att, heads_, T, T, chunk);
+             att, heads_, T, T, chunk, lens);
   float* o = scratch_.get(n, s);
   conv1d(att, nullptr, w_.ptr(a + ".linear_out.weight"), w_.ptr(a + ".linear_out.bias"), o, nullptr, B, d_, T, d_, 1, 1, 0, -1.f, s);
   float* x1 = scratch_.get(n, s);
@@ -937,7 +954,7 @@ float* FrontEngineF32::embed(const std::string& p, const float* x, int B, int T,
 // n_context tokens are look-ahead context only (the finalize = False call, flow.py:482-489); streaming: block-causal
 // attention with chunk_ tokens at 25 Hz and 2*chunk_ frames at 50 Hz.
 void FrontEngineF32::encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T_all,
-                            int n_context, bool streaming, cudaStream_t s) {
+                            int n_context, bool streaming, const int* token_len, cudaStream_t s) {
   const int T = T_all - n_context;
   require(B > 0 && T > 0 && (n_context == 0 || n_context == 3), "B, T must be positive; context is 0 or 3 tokens");
   LS_CUDA(cudaSetDevice(device_));
@@ -949,7 +966,14 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
              w_.ptr("spk_embed_affine_layer.bias"), spks, B, spk_, out_, 0, 0);
   const size_t n_all = (size_t)B * d_ * T_all, n = (size_t)B * d_ * T;
   float* x0 = scratch_.get(n_all, s);
-  F32_LAUNCH(embed_tokens_kernel, blocks(n_all), 256, s, tokens, w_.ptr("input_embedding.weight"), x0, d_, T_all, vocab_, n_all);
+  int *lens0 = nullptr, *lens1 = nullptr;
+  if (token_len) {
+    lens0 = reinterpret_cast<int*>(scratch_.get((size_t)2 * B + 8, s));
+    lens1 = lens0 + B;
+    F32_LAUNCH(front_lens_kernel, (B + 127) / 128, 128, s, token_len, lens0, lens1, B, T_all - n_context);
+  }
+  F32_LAUNCH(embed_tokens_kernel, blocks(n_all), 256, s, tokens, w_.ptr("input_embedding.weight"), x0, d_, T_all, vocab_, n_all,
+             token_len);
   // embed (Linear, LayerNorm, scale) is position-independent: tokens and context go through it together
   float* pe_all = nullptr;
   float* xe = embed("encoder.embed", x0, B, T_all, &pe_all, s);
@@ -973,7 +997,7 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
     x = r;
   }
   const int chunk = streaming ? chunk_ : 0;
-  for (int i = 0; i < n_blocks_; ++i) x = layer("encoder.encoders." + std::to_string(i), x, pe, B, T, chunk, s);
+  for (int i = 0; i < n_blocks_; ++i) x = layer("encoder.encoders." + std::to_string(i), x, pe, B, T, chunk, lens0, s);
   // Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5
   const int T2 = 2 * T;
   const size_t n2 = (size_t)B * d_ * T2;
@@ -983,11 +1007,12 @@ void FrontEngineF32::encode(const long long* tokens, const float* embedding, flo
   conv1d(up, nullptr, w_.ptr("encoder.up_layer.conv.weight"), w_.ptr("encoder.up_layer.conv.bias"), uc, nullptr, B, d_, T2, d_, 5, 1, 4,
          -1.f, s);
   x = embed("encoder.up_embed", uc, B, T2, &pe, s);
-  for (int i = 0; i < n_up_; ++i) x = layer("encoder.up_encoders." + std::to_string(i), x, pe, B, T2, 2 * chunk, s);
+  for (int i = 0; i < n_up_; ++i) x = layer("encoder.up_encoders." + std::to_string(i), x, pe, B, T2, 2 * chunk, lens1, s);
   float* an = scratch_.get(n2, s);
   F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x, w_.ptr("encoder.after_norm.weight"), w_.ptr("encoder.after_norm.bias"),
              an, d_, T2, 0, (const float*)nullptr, (const float*)nullptr);
   conv1d(an, nullptr, w_.ptr("encoder_proj.weight"), w_.ptr("encoder_proj.bias"), mu, nullptr, B, d_, T2, out_, 1, 1, 0, -1.f, s);
+  if (lens1) F32_LAUNCH(zero_tail_nct_kernel, blocks((size_t)B * out_ * T2), 256, s, mu, lens1, out_, T2, (size_t)B * out_ * T2);
 }
 
 // ---------------------------------------------------------------------------------------------- speaker encoder (f-4)

@@ -92,20 +92,21 @@ class DacEngineF32 {
 
 // token -> mu front half of CausalMaskedDiffWithXvec.inference (flow/flow.py:437-511): input
 // embedding, UpsampleConformerEncoder (rel-pos conformer layers at 25 Hz, x2 upsample, conformer layers at 50 Hz),
-// encoder_proj, speaker-embedding affine.  fp32 mode only; equal-length batches; finalize = True or a non-final chunk
+// encoder_proj, speaker-embedding affine.  fp32 mode; right-padded batches; finalize = True or a non-final chunk
 // (3 look-ahead context tokens), optional block-causal streaming attention.
 class FrontEngineF32 {
  public:
   FrontEngineF32(const Weights& w, int device);
   // tokens [B,T_all] int64 (device), embedding [B,spk_dim] -> mu [B,80,2(T_all - n_context)], spks [B,80]
+  // token_len (device, nullable): per-utterance token counts of a right-padded batch
   void encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T_all, int n_context,
-              bool streaming, cudaStream_t s);
+              bool streaming, const int* token_len, cudaStream_t s);
   int out_dim() const { return out_; }
   int spk_dim() const { return spk_; }
   int device() const { return device_; }
 
  private:
-  float* layer(const std::string& p, float* x, const float* pe, int B, int T, int chunk, cudaStream_t s);
+  float* layer(const std::string& p, float* x, const float* pe, int B, int T, int chunk, const int* lens, cudaStream_t s);
   float* embed(const std::string& p, const float* x, int B, int T, float** pe, cudaStream_t s);
   int device_ = 0, d_ = 512, vocab_ = 6561, out_ = 80, spk_ = 192, heads_ = 8, n_blocks_ = 0, n_up_ = 0, chunk_ = 25;
   F32Weights w_;

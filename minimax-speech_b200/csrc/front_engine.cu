@@ -10,12 +10,23 @@ namespace {
 constexpr int kD = 512;  // encoder width (config.yaml:73-88); the small kernels below are written for it
 
 // e[r][:] = table[clamp(tok[r], 0, vocab-1)][:]   (flow.py:476: input_embedding(torch.clamp(token, min=0)))
+// rows past the utterance's token count are zero (flow.py:475-476: input_embedding(token) * mask)
 __global__ void __launch_bounds__(64) front_gather_kernel(const long long* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
-                                                          __nv_bfloat16* __restrict__ e, int vocab) {
+                                                          __nv_bfloat16* __restrict__ e, int vocab, int T_all,
+                                                          const int* __restrict__ lens) {
   const size_t r = blockIdx.x;
   long long id = tok[r];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  reinterpret_cast<uint4*>(e + r * kD)[threadIdx.x] = reinterpret_cast<const uint4*>(table + (size_t)id * kD)[threadIdx.x];
+  uint4 v = reinterpret_cast<const uint4*>(table + (size_t)id * kD)[threadIdx.x];
+  if (lens && (int)(r % T_all) >= lens[r / T_all]) v = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(e + r * kD)[threadIdx.x] = v;
+}
+// lens0[b] = min(token_len[b], T) (keys at 25 Hz), lens1[b] = 2 * lens0[b] (keys and valid frames at 50 Hz)
+__global__ void front_lens_kernel(const int* __restrict__ token_len, int* __restrict__ lens0, int* __restrict__ lens1, int B, int T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int l = max(0, min(token_len[b], T));
+  lens0[b] = l, lens1[b] = 2 * l;
 }
 
 // LayerNorm over the 512 channels of a row (eps 1e-5), times `scale` (the rel-pos encoding's sqrt(d) input scale,
@@ -279,7 +290,7 @@ void FrontEngine::ensure_workspace(int B, int T_all, int T) {
   o_pp_ = take(Pcap * kD * 2);
   o_pph_ = take(Pcap * kD * 2);
   o_bd_ = take(((size_t)cap_bd_ + 4096) * 4);
-  o_spk_ = take(4096);
+  o_spk_ = take(4096);  // int lens0[512] | lens1[512]
   LS_CUDA(cudaMalloc(&ws_base_, off));
   LS_CUDA(cudaMemset(ws_base_, 0, off));
 }
@@ -322,7 +333,7 @@ const FrontEngine::Plan& FrontEngine::plan_for(int B, int T_all, int T) {
 }
 
 void FrontEngine::encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T_all,
-                         int n_context, bool streaming, cudaStream_t s) {
+                         int n_context, bool streaming, const int* token_len, cudaStream_t s) {
   const int T = T_all - n_context, T2 = 2 * T;
   require(B > 0 && T > 0 && (n_context == 0 || n_context == 3), "B, T must be positive; context is 0 or 3 tokens");
   LS_CUDA(cudaSetDevice(device_));
@@ -364,7 +375,7 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
     LS_CUDA(cudaGetLastError());
   };
   // ConformerEncoderLayer (encoder_layer.py:109-, normalize_before, no macaron, no conv module) on the residual stream xr
-  auto layer = [&](const LayerW& L, const Plan::Level& lv, float* xr, int chunk) {
+  auto layer = [&](const LayerW& L, const Plan::Level& lv, float* xr, int chunk, const int* lens) {
     const int Tl = lv.T;
     const long long R = (long long)B * Tl;
     ln(xr, L.g_mha, L.b_mha, 1.0f, nullptr, nb, R);
@@ -398,7 +409,7 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
     }
     {
       AttnParams ap{};
-      ap.B = B, ap.T = Tl, ap.H = heads_, ap.lengths = nullptr, ap.chunk = chunk;
+      ap.B = B, ap.T = Tl, ap.H = heads_, ap.lengths = lens, ap.chunk = chunk;
       ap.scale_log2e = 0.125f * 1.4426950408889634f;
       ap.out = att;
       ap.bias = bd, ap.bias_ld = lv.Ppad, ap.bias_bh = (long long)Tl * lv.Ppad;
@@ -426,7 +437,16 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
   front_spk_kernel<<<B, 128, 0, s>>>(embedding, f32(spk_w_), f32(spk_b_), spks, spk_, out_);
   LS_CUDA(cudaGetLastError());
   count_launch();
-  front_gather_kernel<<<(unsigned)((size_t)B * T_all), 64, 0, s>>>(tokens, arena_.ptr<__nv_bfloat16>(emb_table_), hb, vocab_);
+  int *lens0 = nullptr, *lens1 = nullptr;
+  if (token_len) {  // right-padded batch: key bounds of the two frame rates
+    require(B <= 512, "at most 512 utterances per call with token lengths");
+    lens0 = ws<int>(o_spk_), lens1 = lens0 + 512;
+    count_launch();
+    front_lens_kernel<<<(B + 127) / 128, 128, 0, s>>>(token_len, lens0, lens1, B, T);
+    LS_CUDA(cudaGetLastError());
+  }
+  front_gather_kernel<<<(unsigned)((size_t)B * T_all), 64, 0, s>>>(tokens, arena_.ptr<__nv_bfloat16>(emb_table_), hb, vocab_, T_all,
+                                                                   token_len);
   LS_CUDA(cudaGetLastError());
   const float sqrt_d = sqrtf((float)kD);
   {  // LinearNoSubsampling (subsampling.py:69-113) on tokens and context alike: Linear, LayerNorm, x sqrt(d)
@@ -450,7 +470,7 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
   }
   const int chunk = streaming ? chunk_ : 0;
   rel_pos(T);
-  for (const LayerW& L : layers_) layer(L, pl.lv[0], xr, chunk);
+  for (const LayerW& L : layers_) layer(L, pl.lv[0], xr, chunk, lens0);
   {  // Upsample1D (upsample_encoder.py:37-63): nearest x2, left-pad 4, conv k=5; then up_embed
     count_launch();
     front_upsample2_kernel<<<blocks((size_t)B * T2 * kD), 256, 0, s>>>(xr, nb, T, (size_t)B * T2 * kD);
@@ -464,14 +484,14 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
     ln(y, up_embed_.g, up_embed_.b, sqrt_d, x, nb, (long long)B * T2);
   }
   rel_pos(T2);
-  for (const LayerW& L : up_layers_) layer(L, pl.lv[1], x, 2 * chunk);
+  for (const LayerW& L : up_layers_) layer(L, pl.lv[1], x, 2 * chunk, lens1);
   ln(x, g_after_, b_after_, 1.0f, nullptr, nb, (long long)B * T2);
   {
     ConvGemmParams p{};
     p.out0 = y, p.out0_dtype = OUT_F32;
     conv(pl.lv[1].nb, proj_, B, T2, 0, p);
   }
-  LS_CUDA(launch_unpack_nct(y, mu, B, out_, T2, nullptr, s));
+  LS_CUDA(launch_unpack_nct(y, mu, B, out_, T2, lens1, s));  // frames past 2 * token_len are zero
 }
 
 }  // namespace ls

@@ -14,14 +14,15 @@ namespace ls {
 // Time-major activations [B][T][512]: fp32 residual stream, bf16 GEMM operands.  Every linear / convolution is a
 // conv_gemm launch; self-attention is the estimator's flash-attention kernel with the relative-position term
 // bd[i, j] = (q_i + v) . p[T-1-i+j] (attention.py:225-247's rel_shift in closed form) added to the scores from a
-// [B][H][T][2T-1] matrix that one conv_gemm launch per head writes.  Equal-length batches (as FrontEngineF32).
+// [B][H][T][2T-1] matrix that one conv_gemm launch per head writes.  Right-padded batches through per-utterance key bounds.
 class FrontEngine {
  public:
   FrontEngine(const Weights& w, int device);
   ~FrontEngine();
   // tokens [B,T_all] int64 (device), embedding [B,spk_dim] -> mu [B,80,2(T_all - n_context)], spks [B,80]
+  // token_len (device, nullable): per-utterance token counts of a right-padded batch (mu is zero past 2 * token_len)
   void encode(const long long* tokens, const float* embedding, float* mu, float* spks, int B, int T_all, int n_context,
-              bool streaming, cudaStream_t s);
+              bool streaming, const int* token_len, cudaStream_t s);
   int out_dim() const { return out_; }
   int spk_dim() const { return spk_; }
   int device() const { return device_; }

@@ -2,7 +2,7 @@
 section 8 row f-1): speaker-embedding normalise + ``spk_embed_affine_layer``, ``input_embedding``, the
 ``UpsampleConformerEncoder`` (transformer/upsample_encoder.py) and ``encoder_proj``.  Parameters are registered under the
 reference's state_dict keys, so the flow checkpoint loads unchanged.  ``precision="bf16"`` (default): tensor-core path
-(csrc/front_engine.cu); ``"fp32"``: CUDA-core kernels of csrc/f32_path.cu.  Equal-length batches; final chunks
+(csrc/front_engine.cu); ``"fp32"``: CUDA-core kernels of csrc/f32_path.cu.  Equal-length or right-padded batches; final chunks
 (finalize=True) and non-final chunks (3 look-ahead context tokens), optional block-causal streaming attention.  ``CausalMaskedDiffWithXvec`` is the drop-in for the reference's
 pipeline class: the same ``inference`` signature (prompt tokens, prompt latents, x-vector or reference mels)."""
 import torch
@@ -46,16 +46,25 @@ class TokenToMu(nn.Module):
     pre_lookahead_len = 3
 
     @torch.inference_mode()
-    def forward(self, token, embedding, finalize=True, streaming=False):
+    def forward(self, token, embedding, finalize=True, streaming=False, token_len=None):
         """token [B,T] int64, embedding [B,192] -> (mu [B,80,2T'], spks [B,80]): the ``mu`` / ``spks`` the reference hands to
-        ``self.decoder`` (flow.py:501-508).  finalize=False: the last 3 tokens are look-ahead context (T' = T - 3)."""
+        ``self.decoder`` (flow.py:501-508).  finalize=False: the last 3 tokens are look-ahead context (T' = T - 3).
+        token_len [B] (optional): token counts of a right-padded batch, handled like the reference encoder's ``xs_lens``
+        (zero embeddings and masked keys past the length); mu is zero past ``2 * token_len``."""
         n_ctx = 0 if finalize else self.pre_lookahead_len
         if token.dim() != 2 or token.shape[1] < 1 + n_ctx or token.dtype != torch.int64:
             raise ValueError(f"token must be an int64 tensor [B, T >= {1 + n_ctx}]")
         if tuple(embedding.shape) != (token.shape[0], self.spk_embed_dim):
             raise ValueError(f"embedding must be [{token.shape[0]}, {self.spk_embed_dim}]")
         dev = token.device
-        return self.handle(dev).encode(token.contiguous(), _as_f32(embedding, dev), n_ctx, streaming)
+        if token_len is not None:
+            token_len = torch.as_tensor(token_len).reshape(-1)
+            if token_len.numel() != token.shape[0] or int(token_len.min()) < 1 or int(token_len.max()) > token.shape[1]:
+                raise ValueError("token_len must hold one count in [1, T] per utterance")
+            if n_ctx:
+                raise NotImplementedError("right-padded batches of non-final chunks (the reference call is batch 1)")
+            token_len = token_len.to(device=dev, dtype=torch.int32).contiguous()
+        return self.handle(dev).encode(token.contiguous(), _as_f32(embedding, dev), n_ctx, streaming, token_len)
 
     @torch.inference_mode()
     def inference(self, token, embedding, decoder, n_timesteps=10, streaming=False, finalize=True):

@@ -99,7 +99,7 @@ def load():
         lib.ls_front_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_front_destroy.argtypes = [vp]
         lib.ls_front_destroy.restype = None
-        lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
         lib.ls_speaker_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_speaker_destroy.argtypes = [vp]
         lib.ls_speaker_destroy.restype = None
@@ -230,12 +230,13 @@ class FrontHandle:
         if h and _lib is not None:
             _lib.ls_front_destroy(h)
 
-    def encode(self, tokens, embedding, n_context=0, streaming=False):
+    def encode(self, tokens, embedding, n_context=0, streaming=False, token_len=None):
         B, T = tokens.shape
         mu = torch.empty(B, self.out_dim, 2 * (T - n_context), device=tokens.device, dtype=torch.float32)
         spks = torch.empty(B, self.out_dim, device=tokens.device, dtype=torch.float32)
         check(load().ls_front_encode(self._h, ptr(tokens), ptr(embedding), ptr(mu), ptr(spks), B, T, int(n_context),
-                                     int(bool(streaming)), current_stream_ptr(self.device)), "ls_front_encode")
+                                     int(bool(streaming)), ptr(token_len) if token_len is not None else None,
+                                     current_stream_ptr(self.device)), "ls_front_encode")
         return mu, spks
 
 

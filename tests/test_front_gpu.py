@@ -206,3 +206,33 @@ def test_yaml_style_construction():
     assert feat.shape == (1, 80, 40) and torch.isfinite(feat).all()
     with pytest.raises(NotImplementedError):
         UpsampleConformerEncoder(input_size=512, output_size=512, macaron_style=True)
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("fp32", 1e-4)])
+def test_padded_batch_vs_reference_golden(golden_dir, precision, tol):
+    """A right-padded batch (23 and 15 tokens; golden case b: the unmodified reference encoder run with xs_lens): valid frames
+    against the golden output, zeros past 2 * token_len, and the longest utterance equal to its own unpadded run."""
+    g = np.load(os.path.join(golden_dir, "conformer_golden.npz"))
+    sd = synth.conformer_encoder_state_dict(int(g["weights_seed"]))
+    f = TokenToMu(precision=precision)
+    f.load_state_dict(sd)
+    lens = [int(n) for n in g["enc_b_lens"]]
+    toks, embs = zip(*[synth.token_inputs(i, n) for i, n in enumerate(lens)])
+    tok = torch.zeros(len(lens), max(lens), dtype=torch.int64)
+    for b, t in enumerate(toks):
+        tok[b, :t.shape[1]] = t[0]
+    tok[1, lens[1]:] = 4321  # whatever sits in the padding must not matter
+    emb = torch.cat(embs, 0)
+    mu, spks = f(tok.to(DEV), emb.to(DEV), token_len=torch.tensor(lens))
+    ref = _mu_ref(g, sd, "enc_b_h")
+    for b, n in enumerate(lens):
+        e = O.rel_l2(mu[b:b + 1, :, :2 * n].cpu(), ref[b:b + 1, :, :2 * n])
+        print(f"padded batch ({precision}), utterance {b} ({n} tokens) vs reference golden: rel-L2 {e:.3e}")
+        assert e < tol
+        assert float(mu[b, :, 2 * n:].abs().max()) == 0.0 if 2 * n < mu.shape[2] else True
+    # (the shorter utterance differs from its own unpadded run, in the reference too: the pre-lookahead convolution reads
+    # the embedded padding rows, upsample_encoder.py:66-107; the longest utterance of a batch has no padding)
+    one, _ = f(toks[0].to(DEV), embs[0].to(DEV))
+    assert O.rel_l2(mu[0:1].cpu(), one.cpu()) < tol * 0.1
+    with pytest.raises(ValueError):
+        f(tok.to(DEV), emb.to(DEV), token_len=torch.tensor([23, 0]))
