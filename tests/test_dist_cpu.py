@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from minimax_speech_b200.pipeline import gather_plan, gather_waveforms, shard_utterances, utterance_cost
+from minimax_speech_b200.pipeline import PlannedGather, gather_plan, gather_waveforms, shard_utterances, utterance_cost
 
 
 def _free_port():
@@ -32,6 +32,13 @@ def _worker(rank, world, port, lengths, hop, ret, planned=False):
             wav[j, 0, :lengths[i] * hop] = _signal(i, lengths[i] * hop)
         plan = gather_plan(shard_utterances(lengths, world), [n * hop for n in lengths]) if planned else None
         res = gather_waveforms(wav, [lengths[i] * hop for i in mine], mine, dst=0, plan=plan)
+        if planned:  # the persistent-buffer form used by bench.py: same result, call after call
+            g = PlannedGather(plan, wav.device, dst=0)
+            for _ in range(2):
+                again = g(wav)
+                assert (again is None) == (rank != 0)
+                if rank == 0:
+                    assert sorted(again) == sorted(res) and all(torch.equal(again[i], res[i]) for i in res)
         if rank == 0:
             ok = sorted(res) == list(range(len(lengths)))
             for i, w in res.items():
