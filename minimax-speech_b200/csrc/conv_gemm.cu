@@ -438,7 +438,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the tile / k loops in uniform control flow (every value below is warp-uniform); one elected
+    // lane issues the MMAs and commits (see elect_one()).
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, false, false);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -447,10 +450,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       int n_it = 0, n_tile = 0;  // timeline aid
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
-        if (tile_skipped(p, tc)) continue;
+        if (__shfl_sync(0xffffffffu, (int)tile_skipped(p, tc), 0)) continue;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * acc_stride);
         for (int kb = 0; kb < p.kb_per_tap; ++kb) {
           for (int tap = 0; tap < p.taps; ++tap) {
             if (!halo || tap == 0) {
@@ -461,7 +464,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
             }
-            if (tl && n_it < 24) tl[8 + n_it] = clock64();
+            if (tl && n_it < 24 && lane == 0) tl[8 + n_it] = clock64();
             ++n_it;
             // tap t of the halo box = the same rows shifted down by t*dil: start address + t*dil*128 B, with the
             // swizzle phase of the first row in the descriptor's base-offset field
@@ -469,20 +472,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + (size_t)as * a_bytes) + (uint32_t)shift * 128u,
                                                         p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + (size_t)bs * b_bytes));
+            const bool a_done = !halo || tap == p.taps - 1;
+            // the last K block of a single-source launch may be partly padding (C = 48, 80, 96 ...): whole 16-wide
+            // K steps of zeros are not issued (an SS-mode MMA costs the same ~130 clk whatever it multiplies)
+            int nk = kBlockK / 16;
+            if (p.k_true > 0 && p.kb_split == p.kb_per_tap) nk = min(nk, (p.k_true - kb * kBlockK + 15) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
-            if (!p.b_resident) umma_commit(&b_empty[bs]);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                if (k < nk) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+              if (!p.b_resident) umma_commit(&b_empty[bs]);
+              if (a_done) umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
             if (++bs == p.b_stages) bs = 0, bph ^= 1;
-            if (!halo || tap == p.taps - 1) {
-              umma_commit(&a_empty[as]);
+            if (a_done) {
               if (++as == p.a_stages) as = 0, aph ^= 1;
             }
           }
         }
-        umma_commit(&tfull[acc]);
-        if (tl && n_it <= p.taps * p.kb_per_tap) tl[32] = clock64();
-        if (tl && n_tile < 8) tl[24 + n_tile] = clock64();  // (overlaps the late k-iteration stamps: fine for multi-tile runs)
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (tl && lane == 0 && n_it <= p.taps * p.kb_per_tap) tl[32] = clock64();
+        if (tl && lane == 0 && n_tile < 8) tl[24 + n_tile] = clock64();  // (overlaps the late k-iteration stamps: fine for multi-tile runs)
         ++n_tile;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;

@@ -150,6 +150,19 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of a CONVERGED warp (always the same one for the full mask).  The tcgen05.mma issue loops run with the whole
+// warp in uniform control flow and only the instructions themselves under this predicate: descriptors and TMEM addresses
+// then live in uniform registers.  Inside an `if (lane == 0)` region the compiler has to assume divergence and wraps
+// every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, which costs more than a small-N MMA itself.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // arrives on the mbarrier once every tcgen05 op previously issued by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

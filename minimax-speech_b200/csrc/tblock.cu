@@ -324,7 +324,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     }
   } else if (warp == kMmaWarp) {
     // ======================================================================== MMA issuer
-    if (lane == 0 && (!kPair || rank == 0)) {  // pair: the leader CTA issues every MMA of both CTAs
+    // The whole warp walks the phases in uniform control flow (every descriptor and TMEM address stays in uniform
+    // registers); one elected lane issues the MMAs and commits (see elect_one() in ptx.cuh).
+    if (!kPair || rank == 0) {  // pair: the leader CTA issues every MMA of both CTAs
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+#define TLM(i)                                 \
+  do {                                         \
+    if (tl && lane == 0) tl[(i)] = clock64();  \
+  } while (0)
       const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kTileM : kTileM, 128, false, false);
       const uint32_t idesc256 = make_idesc_bf16(2 * kTileM, 256, false, false);  // pair: one N = 256 MMA fills D
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
@@ -332,8 +339,11 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         else umma_bf16(d, ad, bd, idesc, acc);
       };
       auto commit = [&](uint64_t* bar) {  // MMA -> epilogue barriers exist in both CTAs
-        if (kPair) umma_commit_pair(bar);
-        else umma_commit(bar);
+        if (elect_one()) {
+          if (kPair) umma_commit_pair(bar);
+          else umma_commit(bar);
+        }
+        __syncwarp();
       };
       auto wait_epi = [&](uint64_t* bar, uint32_t parity) {  // epilogue -> MMA (pair: arrivals come from both CTAs)
         if (kPair) mbar_wait_cluster(bar, parity);
@@ -353,17 +363,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         if (kPair) mbar_wait_cluster(&full[s], ph);
         else mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (tl && n_full < 16) tl[112 + n_full] = clock64();
+        if (tl && lane == 0 && n_full < 16) tl[112 + n_full] = clock64();
         n_full += (ahead == 0);
         return make_smem_desc_sw128(smem_u32(sRing + s * kRingSlotBytes));
       };
       auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
-        for (int j = 0; j < n; ++j) {
-          if (kPair) umma_commit_pair(&empty[slot]);
-          else if (kCS > 1) umma_commit_mc(&empty[slot], kCtaMask);
-          else umma_commit(&empty[slot]);
-          if (++slot == kSlots) slot = 0, phase ^= 1;
+        if (elect_one()) {
+          int sl = slot;
+          for (int j = 0; j < n; ++j) {
+            if (kPair) umma_commit_pair(&empty[sl]);
+            else if (kCS > 1) umma_commit_mc(&empty[sl], kCtaMask);
+            else umma_commit(&empty[sl]);
+            if (++sl == kSlots) sl = 0;
+          }
         }
+        __syncwarp();
+        for (int j = 0; j < n; ++j)
+          if (++slot == kSlots) slot = 0, phase ^= 1;
       };
       auto wait_drained = [&](int i) {  // the epilogue has finished with the latest fill of H[i]
         const uint32_t f = i ? fills1 : fills0;
@@ -377,23 +393,25 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       // H[i] = A3 (128 x 256, K-major in smem) . Wchunk^T, weights from 4 ring slots
       auto gemm_from_a3 = [&](int i) {
         wait_drained(i);
-        const uint32_t d = tmem_base + kTmemH + (uint32_t)i * 128;
+        const uint32_t d = tmem_u + kTmemH + (uint32_t)i * 128;
         for (int kb = 0; kb < kC / 64; ++kb) {
           // pair: a slot holds two K blocks of this CTA's 64 weight rows (8 KB each)
           const uint64_t bdesc = slot_desc(0) + (kPair ? (uint64_t)((kb & 1) * (8192 >> 4)) : 0);
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA3 + kb * kSlotBytes));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma(d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) mma(d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          }
           if (!kPair || (kb & 1)) release(1);
         }
         commit(&h_full[i]);
         if (i) fills1 += 1;
         else fills0 += 1;
       };
-      const uint32_t dD = tmem_base + kTmemD;
-      TL(0);
+      const uint32_t dD = tmem_u + kTmemD;
+      TLM(0);
       for (int g = group0; g < n_groups; g += group_step) {
-        if (group_skipped(g)) continue;
+        if (__shfl_sync(0xffffffffu, (int)group_skipped(g), 0)) continue;
         if (g != group0) tl = nullptr;
         if (!head) {
         // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
@@ -401,49 +419,57 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           const uint64_t adesc = slot_desc(0);
           const uint64_t b0 = slot_desc(1);
           if (kPair) {  // b0 = this CTA's 128 rows of Wo: the pair's operand is all 256
-            if (kb == 0) TL(1);
+            if (kb == 0) TLM(1);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, (kb | k) != 0 ? 1u : 0u);
+            }
             release(2);
             continue;
           }
           const uint64_t b1 = slot_desc(2);
-          if (kb == 0) TL(1);
+          if (kb == 0) TLM(1);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            mma(dD, adesc + 2 * k, b0 + 2 * k, acc);
-            mma(dD + 128, adesc + 2 * k, b1 + 2 * k, acc);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              mma(dD, adesc + 2 * k, b0 + 2 * k, acc);
+              mma(dD + 128, adesc + 2 * k, b1 + 2 * k, acc);
+            }
           }
           release(3);
         }
         commit(d_full);
-        TL(2);
+        TLM(2);
         // ---- FF: H[c&1] = n3 . W1[c]^T ; D += gelu(H[c&1]) . W2[:, c]^T
         wait_epi(a3_ready, a3_cnt & 1);  // n3 in A3, u' written back to D
         a3_cnt += 1;
         tc_fence_after();
-        TL(3);
+        TLM(3);
         gemm_from_a3(0);
         gemm_from_a3(1);
         for (int c = 0; c < kFF / 128; ++c) {
           const int i = c & 1;
           wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
-          TL(4 + c);
+          TLM(4 + c);
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
             const uint64_t b0 = slot_desc(0);
             if (kPair) {  // this CTA's 128 rows of W2[:, chunk]: one N = 256 MMA per K step
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, 1u);
+                for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, 1u);
+              }
               release(1);
               continue;
             }
             const uint64_t b1 = slot_desc(1);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              mma(dD, adesc + 2 * k, b0 + 2 * k, 1u);
-              mma(dD + 128, adesc + 2 * k, b1 + 2 * k, 1u);
+              for (int k = 0; k < 4; ++k) {
+                mma(dD, adesc + 2 * k, b0 + 2 * k, 1u);
+                mma(dD + 128, adesc + 2 * k, b1 + 2 * k, 1u);
+              }
             }
             release(2);
           }
@@ -451,22 +477,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (c + 2 < kFF / 128) gemm_from_a3(i);
         }
         commit(d_full);
-        TL(12);
+        TLM(12);
         }  // !head
         // ---- tail: D drained by the epilogue (and, tail 0 / 2, the LayerNorm output written to A3)
         wait_epi(a3_ready, a3_cnt & 1);
         a3_cnt += 1;
         tc_fence_after();
-        TL(13);
+        TLM(13);
         if (do_qkv)
           for (int c = 0; c < kQKV / 128; ++c) {
             gemm_from_a3(c & 1);
-            TL(14 + c);
+            TLM(14 + c);
           }
-        TL(26);
+        TLM(26);
       }
     }
   } else {
+#undef TLM
     // ======================================================================== epilogue warps
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int cg = (warp - kFirstEpiWarp) >> 2;  // column group: 64 of D's 256 columns, 32 of an H chunk's 128
