@@ -130,66 +130,86 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
   if (nkv == 0) {
     // fall through to the common exit (TMEM is released there)
   } else if (warp == kSoftmaxWarps) {
-    if (lane == 0) {
-      // ------------------------------------------------ control thread: TMA loads + MMA issue
+    {
+      // ------------------------------------------------ control warp: TMA loads + MMA issue.  The whole warp walks the
+      // loop in uniform control flow (descriptors, coordinates and TMEM addresses stay in uniform registers); one elected
+      // lane issues (see elect_one() in ptx.cuh).
+      const uint32_t tmem_su = __shfl_sync(0xffffffffu, tmem_s, 0);
+      const uint32_t tmem_ou = __shfl_sync(0xffffffffu, tmem_o, 0);
+      const int nkv_u = __shfl_sync(0xffffffffu, nkv, 0);
       const int inner = p.H * kD;
       const int colq = h * kD, colk = inner + h * kD, colv = 2 * inner + h * kD;
-      mbar_arrive_expect_tx(bar_q, kTile);  // (the tensor map's boxes have kKV rows: the Q tile takes 128 / kKV loads)
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, kTile);  // (the tensor map's boxes have kKV rows: the Q tile takes 128 / kKV loads)
 #pragma unroll
-      for (int i = 0; i < kQ / kKV; ++i) tma_load_3d(sQ + i * kKVTile, &mapQKV, bar_q, colq, q0 + i * kKV, b);
-      mbar_arrive_expect_tx(&bar_k[0], kKVTile);
-      tma_load_3d(sK, &mapQKV, &bar_k[0], colk, 0, b);
-      mbar_arrive_expect_tx(bar_v, kKVTile);
-      tma_load_3d(sV, &mapQKV, bar_v, colv, 0, b);
-      if (nkv > 1) {
-        mbar_arrive_expect_tx(&bar_k[1], kKVTile);
-        tma_load_3d(sK + kKVTile, &mapQKV, &bar_k[1], colk, kKV, b);
+        for (int i = 0; i < kQ / kKV; ++i) tma_load_3d(sQ + i * kKVTile, &mapQKV, bar_q, colq, q0 + i * kKV, b);
+        mbar_arrive_expect_tx(&bar_k[0], kKVTile);
+        tma_load_3d(sK, &mapQKV, &bar_k[0], colk, 0, b);
+        mbar_arrive_expect_tx(bar_v, kKVTile);
+        tma_load_3d(sV, &mapQKV, bar_v, colv, 0, b);
+        if (nkv_u > 1) {
+          mbar_arrive_expect_tx(&bar_k[1], kKVTile);
+          tma_load_3d(sK + kKVTile, &mapQKV, &bar_k[1], colk, kKV, b);
+        }
       }
+      __syncwarp();
       const uint32_t idesc_s = make_idesc_bf16(kQ, kKV, false, false);
       const uint32_t idesc_o = make_idesc_bf16(kQ, kD, false, true);  // B = V tile, MN-major
       const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ));
       auto issue_s = [&](int j) {
         const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + (j & 1) * kKVTile));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(bar_s);
+          for (int k = 0; k < kD / 16; ++k) umma_bf16(tmem_su, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
       };
-      TL(1);
+      if (lane == 0) TL(1);
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k[0], 0);
       tc_fence_after();
-      TL(2);
+      if (lane == 0) TL(2);
       issue_s(0);
       const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t dp1 = make_smem_desc_sw128(smem_u32(sP + kTile));
       const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV));
-      for (int j = 0; j < nkv; ++j) {
+      for (int j = 0; j < nkv_u; ++j) {
         // the softmax warps hold S(j) in registers: the next scores can be computed while they work on this tile
         mbar_wait(bar_f, j & 1);
         tc_fence_after();
-        if (j + 1 < nkv) {
+        if (j + 1 < nkv_u) {
           mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(j + 1);
         }
-        if (j + 2 < nkv) {  // S(j) has retired (the softmax warps read it): K buffer j&1 is free
-          mbar_arrive_expect_tx(&bar_k[j & 1], kKVTile);
-          tma_load_3d(sK + (j & 1) * kKVTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
+        if (j + 2 < nkv_u) {  // S(j) has retired (the softmax warps read it): K buffer j&1 is free
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bar_k[j & 1], kKVTile);
+            tma_load_3d(sK + (j & 1) * kKVTile, &mapQKV, &bar_k[j & 1], colk, (j + 2) * kKV, b);
+          }
+          __syncwarp();
         }
         mbar_wait(bar_p, j & 1);  // P(j) written, O rescaled where needed
         tc_fence_after();
-        if (j < 4) TL(3 + 2 * j);
+        if (j < 4 && lane == 0) TL(3 + 2 * j);
         mbar_wait(bar_v, j & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kKV / 16; ++kk)  // V rows of 16 keys are 2048 B apart (>> 4 = 128 in the descriptor)
-          umma_bf16(tmem_o, (kk < 4 ? dp0 : dp1) + 2 * (kk & 3), dv0 + 128 * kk, idesc_o, (j | kk) != 0 ? 1u : 0u);
-        umma_commit(bar_o);
-        if (j < 4) TL(4 + 2 * j);
-        if (j + 1 < nkv) {
+          for (int kk = 0; kk < kKV / 16; ++kk)  // V rows of 16 keys are 2048 B apart (>> 4 = 128 in the descriptor)
+            umma_bf16(tmem_ou, (kk < 4 ? dp0 : dp1) + 2 * (kk & 3), dv0 + 128 * kk, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          umma_commit(bar_o);
+        }
+        __syncwarp();
+        if (j < 4 && lane == 0) TL(4 + 2 * j);
+        if (j + 1 < nkv_u) {
           mbar_wait(bar_o, j & 1);  // P(j) V(j) retired: the V buffer is free
-          mbar_arrive_expect_tx(bar_v, kKVTile);
-          tma_load_3d(sV, &mapQKV, bar_v, colv, (j + 1) * kKV, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_v, kKVTile);
+            tma_load_3d(sV, &mapQKV, bar_v, colv, (j + 1) * kKV, b);
+          }
+          __syncwarp();
         }
       }
     }

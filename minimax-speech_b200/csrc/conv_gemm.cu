@@ -401,6 +401,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int b_seq = 0, p_tile = 0;
+      int a_seq = 0;
+      // Resident weights leave the weight producers idle after the first tile: the activation boxes are then shared
+      // round-robin by ALL producer warps (one load per ~2 k clk and warp was what bounded the thin DAC layers once the MMA
+      // issue loop had been fixed).  Safe while producers <= ring stages (see above); every producer tracks the ring.
+      const bool a_share = p.b_resident && p.a_stages >= kProducerWarps;
       const uint32_t a_tx = (uint32_t)p.a_box_rows * 128u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
@@ -411,8 +416,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         ++p_tile;
         for (int kb = 0; kb < p.kb_per_tap; ++kb) {
           for (int tap = 0; tap < p.taps; ++tap) {
-            if (warp == 0) {
-              if (!halo || tap == 0) {
+            if (!halo || tap == 0) {
+              if (warp == (a_share ? a_seq : 0)) {
                 const int trow = t0 - p.pad + (halo ? 0 : tap * p.dil);
                 mbar_wait(&a_empty[as], aph ^ 1);
                 uint8_t* sa = smem_a + (size_t)as * a_bytes;
@@ -421,9 +426,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                   tma_load_3d(sa, &mapA0, &a_full[as], kb * kBlockK, trow, tc.b);
                 else
                   tma_load_3d(sa, &mapA1, &a_full[as], (kb - p.kb_split) * kBlockK, trow, tc.b);
-                if (++as == p.a_stages) as = 0, aph ^= 1;
               }
-            } else if (!p.b_resident || p_tile == 1) {  // resident weights: fetched with the CTA's first tile only
+              if (++a_seq == kProducerWarps) a_seq = 0;
+              if (++as == p.a_stages) as = 0, aph ^= 1;
+            }
+            if (warp != 0 && (!p.b_resident || p_tile == 1)) {  // resident weights: fetched with the CTA's first tile only
               if (b_seq == warp - 1) {
                 if (!p.b_resident) mbar_wait(&b_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
@@ -454,6 +461,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * acc_stride);
+        if (halo && p.b_resident && n_tile > 0) {
+          // Resident weights + halo box (the thin DAC layers): nothing to wait for inside a K block.  The lean form of the
+          // loop below -- the issuing lane is bound by its own instruction latencies, every per-tap instruction counts
+          // (DAC conv7 at C = 48: 362 us with this loop, 512 us through the general one).
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            int nk = kBlockK / 16;
+            if (p.k_true > 0 && p.kb_split == p.kb_per_tap) nk = min(nk, (p.k_true - kb * kBlockK + 15) >> 4);
+            const uint32_t a_addr = smem_u32(smem_a + (size_t)as * a_bytes);
+            const uint32_t b_addr = smem_u32(smem_b) + (uint32_t)(kb * p.taps) * (uint32_t)b_bytes;
+            if (tl && n_it < 24 && lane == 0) tl[8 + n_it] = clock64();
+            n_it += p.taps;
+            if (elect_one()) {
+              for (int tap = 0; tap < p.taps; ++tap) {
+                const int shift = tap * p.dil;
+                const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)shift * 128u, p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
+                const uint64_t bdesc = make_smem_desc_sw128(b_addr + (uint32_t)tap * (uint32_t)b_bytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  if (k < nk) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
+            if (++as == p.a_stages) as = 0, aph ^= 1;
+          }
+        } else if (halo) {
+          // Halo box: the taps of a K block read ONE activation box, so the only waits inside a K block are for weight
+          // boxes (none once the weights are resident).  All its taps are issued under ONE election -- the per-tap loop
+          // overhead (barrier bookkeeping, election, warp sync) was several times the cost of the small-N MMAs it wrapped
+          // (DAC conv7 at C = 96, streamed weights: 595 -> 524 us).
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            int nk = kBlockK / 16;
+            if (p.k_true > 0 && p.kb_split == p.kb_per_tap) nk = min(nk, (p.k_true - kb * kBlockK + 15) >> 4);
+            const uint32_t a_addr = smem_u32(smem_a + (size_t)as * a_bytes);
+            const bool wait_b = !p.b_resident || n_tile == 0;
+            if (tl && n_it < 24 && lane == 0) tl[8 + n_it] = clock64();
+            n_it += p.taps;
+            if (elect_one()) {
+              int bl = bs;
+              uint32_t bphl = bph;
+              for (int tap = 0; tap < p.taps; ++tap) {
+                if (wait_b) {
+                  mbar_wait(&b_full[bl], bphl);
+                  tc_fence_after();
+                }
+                const int shift = tap * p.dil;
+                const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)shift * 128u, p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + (size_t)bl * b_bytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  if (k < nk) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+                if (!p.b_resident) umma_commit(&b_empty[bl]);
+                if (++bl == p.b_stages) bl = 0, bphl ^= 1;
+              }
+              umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
+            for (int tap = 0; tap < p.taps; ++tap)
+              if (++bs == p.b_stages) bs = 0, bph ^= 1;
+            if (++as == p.a_stages) as = 0, aph ^= 1;
+          }
+        } else
         for (int kb = 0; kb < p.kb_per_tap; ++kb) {
           for (int tap = 0; tap < p.taps; ++tap) {
             if (!halo || tap == 0) {
