@@ -246,13 +246,18 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     // less than the MMA warp consumes, but different warps overlap.  kProducerWarps threads walk the same fixed load
     // sequence of a tile; warp w issues the loads whose sequence number is w mod kProducerWarps.  (Separate warps, not
     // lanes of one warp: a lane blocked in mbarrier.try_wait suspends its whole warp.)
-    if (lane < kProducerLanes) {
-      const int issuer = warp * kProducerLanes + lane;
+    // kProducerLanes == 1 (default): the whole warp walks the load sequence in uniform control flow and one elected lane
+    // issues, so the tensor-map pointer, coordinates and barrier addresses stay in uniform registers (inside a
+    // single-lane region every UTMALDG is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, on the critical path
+    // between "slot free" and "load issued").
+    constexpr bool kWarpIssue = kProducerLanes == 1;
+    if (kWarpIssue || lane < kProducerLanes) {
+      const int issuer = warp * kProducerLanes + (kWarpIssue ? 0 : lane);
       const int per_tile = kPair ? (head ? 24 : (do_qkv ? 72 : 48)) : (head ? 48 : (do_qkv ? 136 : 88));
       long long seq0 = 0;  // sequence number of the tile's first load (slot = seq % kSlots, use = seq / kSlots)
       for (int g = group0; g < n_groups; g += group_step) {
         const int row0 = (g * kCS + rank) * kTileM;
-        if (group_skipped(g)) continue;
+        if (kWarpIssue ? __shfl_sync(0xffffffffu, (int)group_skipped(g), 0) != 0 : group_skipped(g)) continue;
         for (int i = issuer; i < per_tile; i += kIssuers) {
           // decode load i of the tile: (tensor map, column, row), in exactly the order the MMA warp consumes them
           const CUtensorMap* m;
@@ -305,9 +310,11 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           const int slot = (int)(seq % kSlots);
           const uint32_t use = (uint32_t)(seq / kSlots);
           mbar_wait(&empty[slot], (use & 1) ^ 1);
-          if (tl && seq < 48) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
+          if (tl && seq < 48 && (!kWarpIssue || lane == 0)) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
           uint8_t* dst = sRing + slot * kRingSlotBytes;
-          if (kPair) {
+          if (kWarpIssue && !elect_one()) {
+            // (the other lanes only keep the warp's control flow uniform)
+          } else if (kPair) {
             // this CTA's half of the box (own rows for att), completion signalled on the LEADER's barrier
             const uint32_t fb = cluster_addr(&full[slot], 0);
             mbar_arrive_expect_tx_cluster(fb, kRingSlotBytes);
@@ -318,6 +325,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
             else tma_load_2d(dst, m, &full[slot], c0, c1);
           }
+          if (kWarpIssue) __syncwarp();
         }
         seq0 += per_tile;
       }
