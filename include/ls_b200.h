@@ -113,10 +113,11 @@ int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embeddi
 
 /* ---- speaker encoder: LearnableSpeakerEncoder.forward (speech/cosyvoice/llm/llm.py:34-96, blocks:
  * speech/cosyvoice/transformer/arch_util.py:21-123) and the averaging over several reference clips of
- * CausalMaskedDiffWithXvec.get_speaker_embedding (speech/cosyvoice/flow/flow.py:336-366).  fp32 mode; equal-length clips.
+ * CausalMaskedDiffWithXvec.get_speaker_embedding (speech/cosyvoice/flow/flow.py:336-366).  Equal-length clips.
  * mel [n_refs][B,80,T] -> embedding [B,192], L2-normalised (the `embedding` input of ls_front_encode). */
 typedef struct ls_speaker ls_speaker;
-int32_t ls_speaker_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_speaker** out);
+int32_t ls_speaker_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_speaker** out);      /* tensor cores */
+int32_t ls_speaker_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_speaker** out); /* fp32 mode */
 void ls_speaker_destroy(ls_speaker* h);
 int32_t ls_speaker_encode(ls_speaker* h, const float* mel, float* embedding, int32_t B, int32_t T, int32_t n_refs,
                           void* stream);

@@ -113,7 +113,8 @@ struct ls_front {
 };
 
 struct ls_speaker {
-  std::unique_ptr<ls::SpeakerEngineF32> eng32;
+  std::unique_ptr<ls::SpeakerEngine> eng;        // tensor-core path
+  std::unique_ptr<ls::SpeakerEngineF32> eng32;   // fp32 mode
 };
 
 extern "C" {
@@ -157,11 +158,21 @@ int32_t ls_speaker_create_fp32(const ls_tensor* weights, int32_t n_weights, int3
     *out = h.release();
   });
 }
+int32_t ls_speaker_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_speaker** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_speaker_create: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_speaker>();
+    h->eng = std::make_unique<ls::SpeakerEngine>(w, device);
+    *out = h.release();
+  });
+}
 void ls_speaker_destroy(ls_speaker* h) { delete h; }
 int32_t ls_speaker_encode(ls_speaker* h, const float* mel, float* embedding, int32_t B, int32_t T, int32_t n_refs, void* stream) {
   return ls::guarded([&] {
     ls::require(h && mel && embedding, "ls_speaker_encode: null argument");
-    h->eng32->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
+    if (h->eng) h->eng->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
+    else h->eng32->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
   });
 }
 

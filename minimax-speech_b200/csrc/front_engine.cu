@@ -494,4 +494,246 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
   LS_CUDA(launch_unpack_nct(y, mu, B, out_, T2, lens1, s));  // frames past 2 * token_len are zero
 }
 
+// ------------------------------------------------------------------------------------------------ speaker encoder (f-4)
+namespace {
+
+// GroupNorm32 (arch_util.py:21-41) on the time-major fp32 residual stream [R][T][512]: statistics over (16 channels x T
+// frames) of one (clip, group), eps 1e-5, per-channel affine; bf16 output (the operand of the qkv GEMM).
+// One block per (group, clip); thread = (row phase, float4 of the group's 16 channels).
+__global__ void __launch_bounds__(256) spk_group_norm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                             const float* __restrict__ be, __nv_bfloat16* __restrict__ y, int T) {
+  const int grp = blockIdx.x, r = blockIdx.y;
+  const int q4 = threadIdx.x & 3, ph = threadIdx.x >> 2;  // 64 row phases
+  const float* xb = x + (size_t)r * T * kD + grp * 16 + q4 * 4;
+  __shared__ float red[8];
+  __shared__ float stat;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      stat = t;
+    }
+    __syncthreads();
+    return stat;
+  };
+  const float n = 16.0f * (float)T;
+  float a = 0.f;
+  for (int t = ph; t < T; t += 64) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + (size_t)t * kD);
+    a += v.x + v.y + v.z + v.w;
+  }
+  const float mean = block_sum(a) / n;
+  float q = 0.f;
+  for (int t = ph; t < T; t += 64) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + (size_t)t * kD);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  const float rstd = rsqrtf(block_sum(q) / n + 1e-5f);
+  const float4 gm = *reinterpret_cast<const float4*>(g + grp * 16 + q4 * 4);
+  const float4 bt = *reinterpret_cast<const float4*>(be + grp * 16 + q4 * 4);
+  __nv_bfloat16* yb = y + (size_t)r * T * kD + grp * 16 + q4 * 4;
+  for (int t = ph; t < T; t += 64) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + (size_t)t * kD);
+    const uint2 o = make_uint2(pack_bf16x2((v.x - mean) * rstd * gm.x + bt.x, (v.y - mean) * rstd * gm.y + bt.y),
+                               pack_bf16x2((v.z - mean) * rstd * gm.z + bt.z, (v.w - mean) * rstd * gm.w + bt.w));
+    *reinterpret_cast<uint2*>(yb + (size_t)t * kD) = o;
+  }
+}
+
+// first-frame pooling (llm.py:88), output_proj, L2 normalise; n_refs > 1: mean of the per-clip unit vectors, normalised
+// again (flow.py:336-366).  h is [n_refs][B][T][512]; one block per utterance b.
+__global__ void __launch_bounds__(256) spk_head_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ emb, int B, int T,
+                                                       int n_refs, int N) {
+  const int b = blockIdx.x;
+  __shared__ float v[256];    // this clip's projection (N <= 256)
+  __shared__ float acc[256];  // sum of the unit vectors
+  __shared__ float red[8];
+  __shared__ float nrm;
+  auto block_norm = [&](float x2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      nrm = fmaxf(sqrtf(t), 1e-12f);
+    }
+    __syncthreads();
+    return nrm;
+  };
+  acc[threadIdx.x] = 0.f;
+  for (int i = 0; i < n_refs; ++i) {
+    const float* row = h + ((size_t)i * B + b) * T * kD;  // frame 0 of clip (i, b)
+    float y = 0.f;
+    if (threadIdx.x < N) {
+      y = bias[threadIdx.x];
+      for (int k = 0; k < kD; ++k) y = fmaf(row[k], w[(size_t)threadIdx.x * kD + k], y);
+    }
+    v[threadIdx.x] = y;
+    const float nn = block_norm(threadIdx.x < N ? y * y : 0.f);
+    acc[threadIdx.x] += v[threadIdx.x] / nn;
+    __syncthreads();
+  }
+  if (n_refs == 1) {
+    if (threadIdx.x < N) emb[(size_t)b * N + threadIdx.x] = acc[threadIdx.x];
+    return;
+  }
+  const float m = acc[threadIdx.x] / (float)n_refs;
+  const float nn = block_norm(threadIdx.x < N ? m * m : 0.f);
+  if (threadIdx.x < N) emb[(size_t)b * N + threadIdx.x] = m / nn;
+}
+
+}  // namespace
+
+struct SpeakerEngine::Plan {
+  CUtensorMap mel, nb, att, qkv_attn;
+};
+
+SpeakerEngine::~SpeakerEngine() {
+  if (ws_base_) cudaFree(ws_base_);
+}
+
+SpeakerEngine::SpeakerEngine(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LS_CUDA(cudaGetDeviceProperties(&prop, device));
+  require(prop.major == 10, "this library only runs on sm_100 (B200) devices", LS_ERR_UNSUPPORTED);
+  num_sms_ = prop.multiProcessorCount;
+  const ls_tensor& wi = w.get("init.weight");
+  require(wi.ndim == 3 && wi.shape[0] == kD && wi.shape[2] == 1 && wi.shape[1] % 8 == 0, "speaker encoder: expected Conv1d(mel, 512, 1)",
+          LS_ERR_UNSUPPORTED);
+  mel_ = (int)wi.shape[1];
+  init_ = pack_dense(arena_, wi, &w.get("init.bias"));
+  const ls_tensor& wo = w.get("output_proj.weight");
+  out_ = (int)wo.shape[0];
+  require(wo.ndim == 2 && wo.shape[1] == kD && out_ <= 256, "speaker encoder: unexpected output_proj", LS_ERR_UNSUPPORTED);
+  out_w_ = arena_.put_f32(wo.data, (size_t)out_ * kD);
+  out_b_ = arena_.put_f32(w.get("output_proj.bias", {out_}).data, out_);
+  for (int i = 0; w.has("attn." + std::to_string(i) + ".norm.weight"); ++i) {
+    const std::string p = "attn." + std::to_string(i);
+    BlockW bw;
+    {  // qkv conv rows are head-major [q_h | k_h | v_h] (QKVAttentionLegacy, arch_util.py:57-60) -> Q | K | V column blocks
+      const ls_tensor& wq = w.get(p + ".qkv.weight", {3 * kD, kD, 1});
+      const ls_tensor& bq = w.get(p + ".qkv.bias", {3 * kD});
+      std::vector<float> cat((size_t)3 * kD * kD), bias((size_t)3 * kD);
+      for (int part = 0; part < 3; ++part)
+        for (int hh = 0; hh < heads_; ++hh)
+          for (int d = 0; d < 64; ++d) {
+            const size_t src = (size_t)hh * 192 + part * 64 + d, dst = (size_t)part * kD + hh * 64 + d;
+            std::memcpy(cat.data() + dst * kD, wq.data + src * kD, (size_t)kD * 4);
+            bias[dst] = bq.data[src];
+          }
+      ls_tensor tw{}, tb{};
+      tw.name = wq.name, tw.data = cat.data(), tw.ndim = 2, tw.shape[0] = 3 * kD, tw.shape[1] = kD;
+      tb.name = wq.name, tb.data = bias.data(), tb.ndim = 1, tb.shape[0] = 3 * kD;
+      bw.qkv = pack_dense(arena_, tw, &tb);
+    }
+    bw.proj = pack_dense(arena_, w.get(p + ".proj_out.weight", {kD, kD, 1}), &w.get(p + ".proj_out.bias"));
+    bw.g = arena_.put_f32(w.get(p + ".norm.weight", {kD}).data, kD);
+    bw.b = arena_.put_f32(w.get(p + ".norm.bias", {kD}).data, kD);
+    blocks_.push_back(bw);
+  }
+  arena_.upload();
+  finalize_dense(arena_, init_);
+  for (BlockW& bw : blocks_) finalize_dense(arena_, bw.qkv), finalize_dense(arena_, bw.proj);
+}
+
+const SpeakerEngine::Plan& SpeakerEngine::plan_for(int R, int T) {
+  const long long rows = (long long)R * T;
+  if (rows > cap_rows_) {
+    LS_CUDA(cudaDeviceSynchronize());
+    if (ws_base_) cudaFree(ws_base_);
+    ws_base_ = nullptr;
+    plans_.clear();
+    cap_rows_ = rows;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = off;
+      off = (off + bytes + 1023) & ~size_t(1023);
+      return o;
+    };
+    const size_t n = (size_t)rows + 256;
+    o_h_ = take(n * kD * 4), o_nb_ = take(n * kD * 2), o_qkv_ = take(n * 3 * kD * 2), o_att_ = take(n * kD * 2);
+    o_mel_ = take(n * (size_t)mel_ * 2), o_emb_ = take(4096);
+    LS_CUDA(cudaMalloc(&ws_base_, off));
+    LS_CUDA(cudaMemset(ws_base_, 0, off));
+  }
+  auto key = std::make_pair(R, T);
+  auto it = plans_.find(key);
+  if (it != plans_.end()) return *it->second;
+  auto pl = std::make_unique<Plan>();
+  require(make_act_map(&pl->mel, ws_base_ + o_mel_, mel_, T, R, mel_, (long long)T * mel_, 128) &&
+              make_act_map(&pl->nb, ws_base_ + o_nb_, kD, T, R, kD, (long long)T * kD, 128) &&
+              make_act_map(&pl->att, ws_base_ + o_att_, kD, T, R, kD, (long long)T * kD, 128) &&
+              make_act_map(&pl->qkv_attn, ws_base_ + o_qkv_, 3 * kD, T, R, 3 * kD, (long long)T * 3 * kD, ATTN_KV),
+          "cuTensorMapEncodeTiled failed for a speaker-encoder buffer", LS_ERR_CUDA);
+  const Plan& ref = *pl;
+  plans_[key] = std::move(pl);
+  return ref;
+}
+
+// LearnableSpeakerEncoder.forward (llm.py:70-96): init conv -> AttentionBlocks (x + proj_out(attn(qkv(GroupNorm(x))))) ->
+// first frame -> output_proj -> L2 normalise (-> mean over reference clips -> normalise)
+void SpeakerEngine::encode(const float* mel, float* emb, int B, int T, int n_refs, cudaStream_t s) {
+  require(B > 0 && T > 0 && n_refs > 0, "B, T, n_refs must be positive");
+  LS_CUDA(cudaSetDevice(device_));
+  const int R = B * n_refs;  // every clip is an independent batch row
+  const Plan& pl = plan_for(R, T);
+  auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
+  float* h = ws<float>(o_h_);
+  __nv_bfloat16* nb = ws<__nv_bfloat16>(o_nb_);
+  __nv_bfloat16* qkv = ws<__nv_bfloat16>(o_qkv_);
+  __nv_bfloat16* att = ws<__nv_bfloat16>(o_att_);
+  auto conv = [&](const CUtensorMap& a, const PackedLinear& w, ConvGemmParams p) {
+    p.B = R, p.M = T, p.N = w.N, p.block_n = w.block_n;
+    p.taps = 1, p.dil = 1, p.pad = 0;
+    p.kb_per_tap = (w.K + 63) / 64, p.kb_split = p.kb_per_tap;
+    p.lengths = nullptr, p.m_len_mul = 1, p.m_len_add = 0, p.skip_halo = 0;
+    p.bias = w.bias, p.chan_mod = w.N, p.n_store = w.N;
+    p.out_ld = w.N, p.out_shift = 0, p.out_bstride = (long long)T * w.N, p.out_alloc = (long long)T * w.N, p.out_valid_mul = w.N;
+    p.k_true = w.K, p.tag = 0, p.halo_mode = 0;
+    LS_CUDA(launch_conv_gemm(a, a, w.map, p, num_sms_, s));
+  };
+  LS_CUDA(launch_pack_nct(mel, ws<__nv_bfloat16>(o_mel_), R, mel_, T, (long long)mel_ * T, mel_, 0, nullptr, s));
+  {
+    ConvGemmParams p{};
+    p.out0 = h, p.out0_dtype = OUT_F32;
+    conv(pl.mel, init_, p);
+  }
+  for (const BlockW& bw : blocks_) {
+    count_launch();
+    spk_group_norm_kernel<<<dim3(groups_, R), 256, 0, s>>>(h, f32(bw.g), f32(bw.b), nb, T);
+    LS_CUDA(cudaGetLastError());
+    {
+      ConvGemmParams p{};
+      p.out1 = qkv, p.out1_mode = OUT1_COPY;
+      conv(pl.nb, bw.qkv, p);
+    }
+    {
+      AttnParams ap{};
+      ap.B = R, ap.T = T, ap.H = heads_, ap.lengths = nullptr, ap.chunk = 0;
+      ap.scale_log2e = 0.125f * 1.4426950408889634f;  // (q 64^-1/4) . (k 64^-1/4)
+      ap.out = att;
+      LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
+    }
+    {
+      ConvGemmParams p{};
+      p.addend = h, p.addend_dtype = OUT_F32, p.out0 = h, p.out0_dtype = OUT_F32;
+      conv(pl.att, bw.proj, p);
+    }
+  }
+  count_launch();
+  spk_head_kernel<<<B, 256, 0, s>>>(h, f32(out_w_), f32(out_b_), emb, B, T, n_refs, out_);
+  LS_CUDA(cudaGetLastError());
+}
+
 }  // namespace ls

@@ -57,4 +57,37 @@ class FrontEngine {
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
 };
 
+// LearnableSpeakerEncoder (speech/cosyvoice/llm/llm.py:34-96) on the tensor cores: the 1x1 convolutions
+// (init, qkv, proj_out) are conv_gemm launches, QKVAttentionLegacy is the estimator's flash-attention kernel (the head-major
+// [q|k|v] rows of the qkv weight are permuted to Q | K | V column blocks at load; its scale 64^-1/4 on q and k is the
+// kernel's 1/8 on the product), GroupNorm32 is a small kernel over the fp32 residual stream.  Equal-length clips.
+class SpeakerEngine {
+ public:
+  SpeakerEngine(const Weights& w, int device);
+  ~SpeakerEngine();
+  // mel [n_refs][B,mel,T] -> emb [B,out]; n_refs > 1 averages the per-clip embeddings (flow.py:336-366)
+  void encode(const float* mel, float* emb, int B, int T, int n_refs, cudaStream_t s);
+  int device() const { return device_; }
+
+ private:
+  struct BlockW {
+    PackedLinear qkv, proj;
+    size_t g, b;
+  };
+  struct Plan;
+  const Plan& plan_for(int R, int T);
+  template <typename T>
+  T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
+
+  int device_ = 0, num_sms_ = 148, mel_ = 80, out_ = 192, heads_ = 8, groups_ = 32;
+  Arena arena_;
+  PackedLinear init_;
+  size_t out_w_ = 0, out_b_ = 0;
+  std::vector<BlockW> blocks_;
+  uint8_t* ws_base_ = nullptr;
+  long long cap_rows_ = 0;
+  size_t o_h_ = 0, o_nb_ = 0, o_qkv_ = 0, o_att_ = 0, o_mel_ = 0, o_emb_ = 0;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans_;
+};
+
 }  // namespace ls

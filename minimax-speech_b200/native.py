@@ -16,7 +16,7 @@ OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp32", "ls_dac_create_fp32", "ls_dac_encode",
            "ls_front_create", "ls_front_create_fp32", "ls_front_destroy", "ls_front_encode",
-           "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
+           "ls_speaker_create", "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
            "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
@@ -100,6 +100,7 @@ def load():
         lib.ls_front_destroy.argtypes = [vp]
         lib.ls_front_destroy.restype = None
         lib.ls_front_encode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.ls_speaker_create.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_speaker_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
         lib.ls_speaker_destroy.argtypes = [vp]
         lib.ls_speaker_destroy.restype = None
@@ -241,15 +242,17 @@ class FrontHandle:
 
 
 class SpeakerHandle:
-    """Owns an ls_speaker*: LearnableSpeakerEncoder (fp32 mode)."""
+    """Owns an ls_speaker*: LearnableSpeakerEncoder (tensor-core path or fp32 mode)."""
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, precision="fp32"):
         lib = load()
         self.device = torch.device(device)
+        self.precision = check_precision(precision)
         arr, keep = tensor_table(state_dict)
         h = C.c_void_p()
+        create = lib.ls_speaker_create_fp32 if self.precision == "fp32" else lib.ls_speaker_create
         with torch.cuda.device(self.device):
-            check(lib.ls_speaker_create_fp32(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_speaker_create_fp32")
+            check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_speaker_create")
         self._h = h
         self.out_dim = int(state_dict["output_proj.weight"].shape[0])
 

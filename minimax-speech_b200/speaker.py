@@ -1,7 +1,8 @@
 """Drop-in for ``cosyvoice.llm.llm.LearnableSpeakerEncoder`` (speech/cosyvoice/llm/llm.py:34-96; SURVEY.md section 8 row
 f-4): reference mel-spectrogram -> L2-normalised speaker embedding, the ``embedding`` input of the flow front half.  Same
 constructor and ``forward(x, mask=None)`` signature, same state_dict keys (``init.*``, ``attn.{i}.norm|qkv|proj_out.*``,
-``output_proj.*``).  fp32 mode (CUDA-core kernels of csrc/f32_path.cu): it runs once per speaker."""
+``output_proj.*``).  ``precision="fp32"`` (default; CUDA-core kernels of csrc/f32_path.cu -- it runs once per speaker) or
+``"bf16"`` (tensor cores: conv_gemm + the flash-attention kernel, csrc/front_engine.cu)."""
 import torch
 import torch.nn as nn
 
@@ -11,8 +12,9 @@ from .flow import _as_f32, _register_tree
 
 class LearnableSpeakerEncoder(nn.Module):
     def __init__(self, mel_dim=80, model_dim=512, output_dim=192, num_blocks=6, num_heads=8, dropout=0.0, mean_pooling=False,
-                 weight_seed=13):
+                 weight_seed=13, precision="fp32"):
         super().__init__()
+        self.precision = native.check_precision(precision)  # "bf16": tensor-core path (csrc/front_engine.cu SpeakerEngine)
         if mean_pooling:
             raise NotImplementedError("first-position pooling only (the reference's default, llm.py:47,88)")
         if model_dim != num_heads * 64 or model_dim % 32:
@@ -30,8 +32,8 @@ class LearnableSpeakerEncoder(nn.Module):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("the B200 hot path runs on CUDA tensors only (no CPU fallback)")
-        if self._handle is None or self._handle.device != device:
-            self._handle = native.SpeakerHandle(self.state_dict(), device)
+        if self._handle is None or self._handle.device != device or self._handle.precision != self.precision:
+            self._handle = native.SpeakerHandle(self.state_dict(), device, self.precision)
         return self._handle
 
     @torch.inference_mode()

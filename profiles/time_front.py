@@ -50,5 +50,9 @@ mel = torch.cat([synth.reference_mel(i, 300) for i in range(B)], 0).to(DEV)
 mss = timeit(lambda: spk(mel), n=3, warm=1)
 out["speaker_fp32_ms"] = mss
 print(f"speaker encoder (fp32 mode) {B} x 300 mel frames: {mss:.2f} ms")
+spk_tc = LearnableSpeakerEncoder(precision="bf16")
+mst = timeit(lambda: spk_tc(mel), n=5, warm=3)
+out["speaker_bf16_ms"] = mst
+print(f"speaker encoder (tensor cores) {B} x 300 mel frames: {mst:.3f} ms")
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/time_front.json", "w"), indent=1)

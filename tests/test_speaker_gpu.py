@@ -110,3 +110,24 @@ def test_inference_tensor_core_path(golden_dir):
         e = O.rel_l2(feat.cpu(), torch.from_numpy(g[f"pipe_{case}_y"]))
         print(f"CausalMaskedDiffWithXvec.inference {case} (tensor-core path) vs reference golden: rel-L2 {e:.3e}")
         assert e < 1.5e-2
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_speaker_embedding_tensor_core_path(golden_dir, case):
+    """precision="bf16": conv_gemm + the flash-attention kernel (qkv rows permuted from head-major to Q | K | V), 1e-2 bar."""
+    g = np.load(os.path.join(golden_dir, "speaker_golden.npz"))
+    sd = synth.speaker_encoder_state_dict(int(g["weights_seed"]))
+    enc = LearnableSpeakerEncoder(precision="bf16")
+    enc.load_state_dict(sd)
+    mel = torch.cat([synth.reference_mel(i, int(g[f"spk_{case}_frames"])) for i in range(2)], 0)
+    y = enc(mel.to(DEV))
+    e = O.rel_l2(y.cpu(), torch.from_numpy(g[f"spk_{case}_y"]))
+    print(f"speaker embedding {case} (tensor-core path) vs reference golden: rel-L2 {e:.3e}")
+    assert y.shape == (2, 192) and e < 1e-2
+    assert torch.allclose(y.norm(dim=1).cpu(), torch.ones(2), atol=1e-5)
+    assert torch.equal(enc(mel[1:2].to(DEV)), y[1:2])  # batch == per-clip
+    mels = torch.stack([mel, mel.flip(0)], dim=1)  # [2, 2 refs, 80, T]
+    ym = enc.encode_references(mels.to(DEV))
+    with torch.inference_mode():
+        ref = torch.nn.functional.normalize(torch.stack([O.speaker_encode(sd, mels[:, i]) for i in range(2)], 1).mean(1), dim=1)
+    assert O.rel_l2(ym.cpu(), ref) < 1e-2
