@@ -123,7 +123,7 @@ class CausalMaskedDiffWithXvec(TokenToMu):
         self.decoder = decoder
         if use_speaker_encoder:
             self.speaker_encoder = LearnableSpeakerEncoder(mel_dim=80, model_dim=512, output_dim=spk_embed_dim, num_blocks=6,
-                                                           num_heads=8)
+                                                           num_heads=8, precision=precision)
             if speaker_encoder_path is not None:  # flow.py:270-305: the speaker_encoder.* entries of an LLM checkpoint
                 ck = torch.load(speaker_encoder_path, map_location="cpu")
                 sd = ck["state_dict"] if "state_dict" in ck else {k: v for k, v in ck.items() if k not in ("epoch", "step")}

@@ -1,8 +1,8 @@
 """Drop-in for ``cosyvoice.llm.llm.LearnableSpeakerEncoder`` (speech/cosyvoice/llm/llm.py:34-96; SURVEY.md section 8 row
 f-4): reference mel-spectrogram -> L2-normalised speaker embedding, the ``embedding`` input of the flow front half.  Same
 constructor and ``forward(x, mask=None)`` signature, same state_dict keys (``init.*``, ``attn.{i}.norm|qkv|proj_out.*``,
-``output_proj.*``).  ``precision="fp32"`` (default; CUDA-core kernels of csrc/f32_path.cu -- it runs once per speaker) or
-``"bf16"`` (tensor cores: conv_gemm + the flash-attention kernel, csrc/front_engine.cu)."""
+``output_proj.*``).  ``precision="bf16"`` (default): tensor cores (conv_gemm + the flash-attention kernel, csrc/front_engine.cu);
+``"fp32"``: CUDA-core kernels of csrc/f32_path.cu."""
 import torch
 import torch.nn as nn
 
@@ -12,7 +12,7 @@ from .flow import _as_f32, _register_tree
 
 class LearnableSpeakerEncoder(nn.Module):
     def __init__(self, mel_dim=80, model_dim=512, output_dim=192, num_blocks=6, num_heads=8, dropout=0.0, mean_pooling=False,
-                 weight_seed=13, precision="fp32"):
+                 weight_seed=13, precision="bf16"):
         super().__init__()
         self.precision = native.check_precision(precision)  # "bf16": tensor-core path (csrc/front_engine.cu SpeakerEngine)
         if mean_pooling:

@@ -45,7 +45,7 @@ f32 = TokenToMu(precision="fp32")
 ms32 = timeit(lambda: f32(tok, emb), n=2, warm=1)
 out["front_fp32_ms"] = ms32
 print(f"front (fp32 mode)   {B} x {T} tokens: {ms32:.2f} ms")
-spk = LearnableSpeakerEncoder()
+spk = LearnableSpeakerEncoder(precision="fp32")
 mel = torch.cat([synth.reference_mel(i, 300) for i in range(B)], 0).to(DEV)
 mss = timeit(lambda: spk(mel), n=3, warm=1)
 out["speaker_fp32_ms"] = mss

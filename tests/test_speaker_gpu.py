@@ -25,7 +25,7 @@ torch.set_num_threads(os.cpu_count() or 1)
 def test_speaker_embedding_vs_reference_golden(golden_dir, case):
     g = np.load(os.path.join(golden_dir, "speaker_golden.npz"))
     sd = synth.speaker_encoder_state_dict(int(g["weights_seed"]))
-    enc = LearnableSpeakerEncoder()
+    enc = LearnableSpeakerEncoder(precision="fp32")
     enc.load_state_dict(sd)
     mel = torch.cat([synth.reference_mel(i, int(g[f"spk_{case}_frames"])) for i in range(2)], 0)
     y = enc(mel.to(DEV))
@@ -41,7 +41,7 @@ def test_speaker_embedding_vs_reference_golden(golden_dir, case):
 def test_several_reference_clips_vs_oracle():
     """[B, N, 80, T]: per-clip embeddings averaged and normalised again (flow.py:336-366)."""
     sd = synth.speaker_encoder_state_dict(13)
-    enc = LearnableSpeakerEncoder()
+    enc = LearnableSpeakerEncoder(precision="fp32")
     enc.load_state_dict(sd)
     mels = torch.stack([torch.cat([synth.reference_mel(60 + 3 * b + i, 29) for b in range(2)], 0) for i in range(3)], dim=1)
     y = enc.encode_references(mels.to(DEV))
@@ -117,7 +117,8 @@ def test_speaker_embedding_tensor_core_path(golden_dir, case):
     """precision="bf16": conv_gemm + the flash-attention kernel (qkv rows permuted from head-major to Q | K | V), 1e-2 bar."""
     g = np.load(os.path.join(golden_dir, "speaker_golden.npz"))
     sd = synth.speaker_encoder_state_dict(int(g["weights_seed"]))
-    enc = LearnableSpeakerEncoder(precision="bf16")
+    enc = LearnableSpeakerEncoder()
+    assert enc.precision == "bf16"
     enc.load_state_dict(sd)
     mel = torch.cat([synth.reference_mel(i, int(g[f"spk_{case}_frames"])) for i in range(2)], 0)
     y = enc(mel.to(DEV))
