@@ -148,3 +148,22 @@ def test_pipeline_state_dict_schema_matches_reference(golden_dir):
     with pytest.raises(RuntimeError):
         m.inference(torch.zeros(1, 8, dtype=torch.int64), None, torch.zeros(1, 0, dtype=torch.int64), None,
                     torch.zeros(1, 0, 80), None, finalize=True)  # CPU tensors are rejected, not emulated
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/ls_b200.h must compile as C99 (no torch / C++ types in the signatures), and a
+    C translation unit that only includes it must link against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "ls_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "use.c"
+    src.write_text('#include "ls_b200.h"\nint main(void) { return ls_abi_version() == LS_ABI_VERSION ? 0 : 1; }\n')
+    lib = build.build()
+    exe = tmp_path / "use"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), lib, "-o", str(exe),
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
