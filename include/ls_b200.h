@@ -18,8 +18,13 @@
  * Tensor layouts at the boundary are the reference's: float32, NCT contiguous
  * (x/mu/cond [rows,80,T], mask [rows,1,T], spks [rows,80], t [rows], latents z [B,80,L],
  * waveform [B,1,L*hop]).  Unless stated otherwise pointers are DEVICE pointers valid on `stream`.
- * Calls on one handle must be serialised by the caller (one handle per stream/thread, like one
- * TensorRT execution context); different handles are independent.
+ * One handle = one workspace (like one TensorRT execution context): calls on the same handle are serialised by the
+ * library -- host threads by a per-handle mutex, streams by an event the next call waits for when the handle moves to
+ * another stream -- so concurrent use is safe but does not overlap; use one handle per concurrent session.  Different
+ * handles are independent.  The hot calls do not synchronise the device and allocate only when a shape larger than any
+ * seen before arrives (stream-ordered cudaMallocAsync).  A mask that is not a prefix (right-padding) mask is detected on
+ * the device and reported by the NEXT call on the handle (LS_ERR_INVALID): validating it in the call itself would cost a
+ * host synchronisation.
  */
 #ifndef LS_B200_H
 #define LS_B200_H
@@ -129,7 +134,29 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
                            int64_t noise_stride, const float* t_span_host, int32_t n_timesteps, float temperature,
                            float cfg_rate, float* wav_host, int32_t B, int32_t T, void* stream);
 
-/* Number of kernel launches issued by this library since load (all handles, all threads). */
+/* lengths[b] = number of non-zero entries of mask[b,0,:] (device pointers; the glue between ls_flow_solve and
+ * ls_dac_decode -- the reference builds the same information with make_pad_mask, speech/cosyvoice/flow/flow.py:478). */
+int32_t ls_mask_to_lengths(const float* mask, int32_t* lengths, int32_t B, int32_t T, void* stream);
+
+/* ---- CUDA-graph replay of one fixed shape: the n_timesteps loop of ConditionalCFM.solve_euler
+ * (speech/cosyvoice/flow/flow_matching.py:103) plus, when dac != NULL, DACVAE.decode, captured once as a CUDA graph
+ * (programmatic-dependent-launch edges kept) over buffers owned by the ls_graph object and replayed with one
+ * cudaGraphLaunch: the form for launch-bound small batches (one 10 s utterance is ~1800 kernels of a few microseconds).
+ * Tensor-core handles only; n_timesteps <= 64.  The caller writes the inputs into the static buffers (ls_graph_buffer:
+ * 0 mu [B,80,T], 1 mask [B,1,T], 2 spks [B,80], 3 cond [B,80,T]), launches, and reads 4 latents [B,80,T] and 5 waveform
+ * [B,1,T*hop] (NULL without a dac handle).  The flow / dac handles must outlive the graph; a launch re-captures by itself
+ * when a larger eager call on the same handles has reallocated their workspace in between. */
+typedef struct ls_graph ls_graph;
+int32_t ls_graph_create(ls_flow* flow, ls_dac* dac, const float* noise_dev, int64_t noise_stride, const float* t_span_host,
+                        int32_t n_timesteps, float temperature, float cfg_rate, int32_t streaming, int32_t B, int32_t T,
+                        void* stream, ls_graph** out);
+void* ls_graph_buffer(ls_graph* g, int32_t which);
+int32_t ls_graph_launch(ls_graph* g, void* stream);
+int64_t ls_graph_kernel_count(const ls_graph* g); /* kernels inside one replay */
+void ls_graph_destroy(ls_graph* g);
+
+/* Number of kernel launches issued by this library since load (all handles, all threads; a graph replay counts the
+ * kernels it contains). */
 int64_t ls_launch_count(void);
 
 /* Per-kernel timing for bench.py's roofline figures: between ls_profile_begin() and ls_profile_end() every launch

@@ -369,13 +369,9 @@ attn_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ 
 }  // namespace
 
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> optin0{0}, optin1{0};  // one bit per device
+  if (cudaError_t e = smem_optin_once(optin0, reinterpret_cast<const void*>(attn_kernel<false>), kAttnSmem); e != cudaSuccess) return e;
+  if (cudaError_t e = smem_optin_once(optin1, reinterpret_cast<const void*>(attn_kernel<true>), kAttnSmem); e != cudaSuccess) return e;
   if (p.B <= 0 || p.T <= 0) return cudaSuccess;
   dim3 grid((p.T + kQ - 1) / kQ, p.H, p.B);
   const double bh = (double)p.B * p.H;

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <mutex>
+#include <vector>
 
 #include "dac_enc_engine.h"
 #include "dac_engine.h"
@@ -74,9 +75,54 @@ static int32_t guarded(F&& f) {
   }
 }
 
+// Calls that reach one handle are serialised: a per-handle mutex orders the host threads, and when the handle is used on
+// a different stream than its previous call the new stream first waits for an event recorded at the end of that call
+// (the handle's workspace, plans and staging buffers are shared state).  Different handles stay independent.  While a
+// stream is being captured into a CUDA graph nothing is recorded or waited for (the capture owns the ordering).
+struct StreamSerial {
+  std::mutex mu;
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
+  ~StreamSerial() {
+    if (ev) cudaEventDestroy(ev);
+  }
+};
+class SerialScope {
+ public:
+  SerialScope(StreamSerial& ss, int device, cudaStream_t s) : ss_(ss), s_(s) {
+    ss_.mu.lock();
+    try {
+      LS_CUDA(cudaSetDevice(device));
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      LS_CUDA(cudaStreamIsCapturing(s, &st));
+      capturing_ = st != cudaStreamCaptureStatusNone;
+      if (!capturing_) {
+        if (!ss_.ev) LS_CUDA(cudaEventCreateWithFlags(&ss_.ev, cudaEventDisableTiming));
+        if (ss_.used && ss_.last != s) LS_CUDA(cudaStreamWaitEvent(s, ss_.ev, 0));
+      }
+    } catch (...) {
+      ss_.mu.unlock();
+      throw;
+    }
+  }
+  ~SerialScope() {
+    if (!capturing_ && ss_.ev && cudaEventRecord(ss_.ev, s_) == cudaSuccess) ss_.last = s_, ss_.used = true;
+    ss_.mu.unlock();
+  }
+  SerialScope(const SerialScope&) = delete;
+  SerialScope& operator=(const SerialScope&) = delete;
+
+ private:
+  StreamSerial& ss_;
+  cudaStream_t s_;
+  bool capturing_ = false;
+};
+
 }  // namespace ls
 
 struct ls_flow {
+  ls::StreamSerial serial;
   std::unique_ptr<ls::FlowEngine> eng;        // bf16 tensor-core path (default)
   std::unique_ptr<ls::FlowEngineF32> eng32;   // fp32 mode (ls_flow_create_fp32)
   int feat() const { return eng ? eng->feat() : eng32->feat(); }
@@ -96,6 +142,8 @@ struct ls_flow {
   size_t stage_bytes = 0;
 };
 struct ls_dac {
+  ls::StreamSerial serial;
+  int device() const { return eng ? eng->device() : enc ? enc->device() : eng32->device(); }
   std::unique_ptr<ls::DacEngine> eng;       // tensor-core decoder (state dict holds decoder.* / de_conv_pre.*)
   std::unique_ptr<ls::DacEncEngine> enc;    // tensor-core encoder (state dict holds encoder.* / en_conv_post.*)
   std::unique_ptr<ls::DacEngineF32> eng32;  // fp32 mode: both directions
@@ -108,11 +156,15 @@ struct ls_dac {
 };
 
 struct ls_front {
+  ls::StreamSerial serial;
+  int device() const { return eng ? eng->device() : eng32->device(); }
   std::unique_ptr<ls::FrontEngine> eng;       // tensor-core path
   std::unique_ptr<ls::FrontEngineF32> eng32;  // fp32 mode
 };
 
 struct ls_speaker {
+  ls::StreamSerial serial;
+  int device() const { return eng ? eng->device() : eng32->device(); }
   std::unique_ptr<ls::SpeakerEngine> eng;        // tensor-core path
   std::unique_ptr<ls::SpeakerEngineF32> eng32;   // fp32 mode
 };
@@ -142,6 +194,7 @@ int32_t ls_front_encode(ls_front* h, const int64_t* tokens, const float* embeddi
                         int32_t T, int32_t n_context, int32_t streaming, const int32_t* token_len, void* stream) {
   return ls::guarded([&] {
     ls::require(h && tokens && embedding && mu && spks, "ls_front_encode: null argument");
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     if (h->eng) h->eng->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
                                token_len, (cudaStream_t)stream);
     else h->eng32->encode(reinterpret_cast<const long long*>(tokens), embedding, mu, spks, B, T, n_context, streaming != 0,
@@ -171,6 +224,7 @@ void ls_speaker_destroy(ls_speaker* h) { delete h; }
 int32_t ls_speaker_encode(ls_speaker* h, const float* mel, float* embedding, int32_t B, int32_t T, int32_t n_refs, void* stream) {
   return ls::guarded([&] {
     ls::require(h && mel && embedding, "ls_speaker_encode: null argument");
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     if (h->eng) h->eng->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
     else h->eng32->encode(mel, embedding, B, T, n_refs, (cudaStream_t)stream);
   });
@@ -220,6 +274,7 @@ int32_t ls_flow_estimator_forward(ls_flow* h, const float* x, const float* mask,
                                   int32_t streaming, void* stream) {
   return ls::guarded([&] {
     ls::require(h && x && mask && mu && t && spks && cond && out, "ls_flow_estimator_forward: null argument");
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     h->estimator_forward(x, mask, mu, t, spks, cond, out, rows, T, streaming != 0, (cudaStream_t)stream);
   });
 }
@@ -230,6 +285,7 @@ int32_t ls_flow_solve(ls_flow* h, const float* mu, const float* mask, const floa
                       void* stream) {
   return ls::guarded([&] {
     ls::require(h && mu && mask && spks && cond && noise && t_span_host && out, "ls_flow_solve: null argument");
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     h->solve(mu, mask, spks, cond, noise, noise_stride, t_span_host, n_timesteps, temperature, cfg_rate, streaming != 0,
              out, B, T, (cudaStream_t)stream);
   });
@@ -263,6 +319,7 @@ int32_t ls_dac_decode(ls_dac* h, const float* z, const int32_t* lengths, float* 
                       void* stream) {
   return ls::guarded([&] {
     ls::require(h && z && wav, "ls_dac_decode: null argument");
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     h->decode(z, lengths, wav, B, L, (cudaStream_t)stream);
   });
 }
@@ -273,6 +330,7 @@ int32_t ls_dac_encode(ls_dac* h, const float* audio, const float* noise, float* 
     ls::require(h && audio && z && m && logs, "ls_dac_encode: null argument");
     ls::require(h->enc != nullptr || h->eng32 != nullptr, "ls_dac_encode: this handle holds no encoder weights",
                 LS_ERR_WEIGHTS);
+    ls::SerialScope scope(h->serial, h->device(), (cudaStream_t)stream);
     if (h->enc) h->enc->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
     else h->eng32->encode(audio, noise, z, m, logs, B, S, (cudaStream_t)stream);
   });
@@ -293,12 +351,14 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
     const size_t n_wav = (size_t)B * T * hop;
     // staging layout: mu | cond | latent | mask | spks | lengths(int) | wav
     const size_t need = (3 * n_mu + n_mask + n_spk + (size_t)B + n_wav) * sizeof(float) + 7 * 256;
-    LS_CUDA(cudaSetDevice(flow->device()));
-    if (need > flow->stage_bytes) {
-      LS_CUDA(cudaStreamSynchronize(s));
-      if (flow->stage) cudaFree(flow->stage);
-      flow->stage = nullptr;
-      LS_CUDA(cudaMalloc(&flow->stage, need));
+    ls::SerialScope scope_f(flow->serial, flow->device(), s);
+    ls::SerialScope scope_d(dac->serial, dac->device(), s);
+    if (need > flow->stage_bytes) {  // stream-ordered growth: no synchronisation
+      uint8_t* st = reinterpret_cast<uint8_t*>(flow->stage);
+      ls::ws_release(st, s);
+      flow->stage = nullptr, flow->stage_bytes = 0;
+      ls::ws_alloc(st, need, s);
+      flow->stage = reinterpret_cast<float*>(st);
       flow->stage_bytes = need;
     }
     auto al = [](size_t n) { return (n + 63) & ~size_t(63); };
@@ -321,6 +381,151 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
     LS_CUDA(cudaStreamSynchronize(s));
   });
 }
+
+int32_t ls_mask_to_lengths(const float* mask, int32_t* lengths, int32_t B, int32_t T, void* stream) {
+  return ls::guarded([&] {
+    ls::require(mask && lengths && B > 0 && T > 0, "ls_mask_to_lengths: bad argument");
+    LS_CUDA(ls::launch_mask_to_lengths(mask, lengths, B, T, 1, (cudaStream_t)stream));
+  });
+}
+
+}  // extern "C"
+
+// ---- CUDA-graph replay of one fixed-shape solve (+ decode) --------------------------------------------------------
+// The n-step solve is ~1800 PDL-chained launches (flow_matching.py:103 is the loop); for small batches the step is
+// launch-bound, so the whole sequence is captured once per shape over buffers owned by this object and replayed with
+// one cudaGraphLaunch.  The graph bakes the engines' workspace addresses: if a larger call on the same handles made a
+// workspace grow in between (ws_generation changed) the sequence is captured again at the next launch.
+struct ls_graph {
+  ls_flow* flow = nullptr;
+  ls_dac* dac = nullptr;  // may be null: solve only
+  int B = 0, T = 0, n_steps = 0, streaming = 0;
+  float temperature = 1.f, cfg_rate = 0.f;
+  const float* noise = nullptr;
+  long long noise_stride = 0;
+  std::vector<float> t_span;
+  uint8_t* buf = nullptr;
+  float *mu = nullptr, *mask = nullptr, *spks = nullptr, *cond = nullptr, *lat = nullptr, *wav = nullptr;
+  int32_t* len = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long gen_flow = 0, gen_dac = 0;
+  long long launches = 0;  // kernels per replay
+
+  void run(cudaStream_t s) {
+    flow->solve(mu, mask, spks, cond, noise, noise_stride, t_span.data(), n_steps, temperature, cfg_rate, streaming != 0, lat, B,
+                T, s);
+    if (dac) {
+      LS_CUDA(ls::launch_mask_to_lengths(mask, len, B, T, 1, s));
+      dac->decode(lat, len, wav, B, T, s);
+    }
+  }
+  void drop() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr, graph = nullptr;
+  }
+  void capture(cudaStream_t s) {
+    drop();
+    run(s);  // eager pass: workspace growth, plans, per-device attribute opt-ins all happen outside the capture
+    const long long before = ls::g_launch_count.load();
+    LS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    try {
+      run(s);
+    } catch (...) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(s, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    LS_CUDA(cudaStreamEndCapture(s, &graph));
+    launches = ls::g_launch_count.load() - before;
+    LS_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    gen_flow = flow->eng ? flow->eng->ws_generation() : 0;
+    gen_dac = dac && dac->eng ? dac->eng->ws_generation() : 0;
+  }
+  bool current() const {
+    return exec && gen_flow == (flow->eng ? flow->eng->ws_generation() : 0) &&
+           gen_dac == (dac && dac->eng ? dac->eng->ws_generation() : 0);
+  }
+  ~ls_graph() {
+    drop();
+    if (buf) cudaFree(buf);
+  }
+};
+
+extern "C" {
+
+int32_t ls_graph_create(ls_flow* flow, ls_dac* dac, const float* noise_dev, int64_t noise_stride, const float* t_span_host,
+                        int32_t n_timesteps, float temperature, float cfg_rate, int32_t streaming, int32_t B, int32_t T,
+                        void* stream, ls_graph** out) {
+  return ls::guarded([&] {
+    ls::require(flow && noise_dev && t_span_host && out, "ls_graph_create: null argument");
+    ls::require(flow->eng != nullptr && (!dac || dac->eng != nullptr), "ls_graph_create: tensor-core handles only (fp32 mode is not graphed)",
+                LS_ERR_UNSUPPORTED);
+    ls::require(B > 0 && T > 0 && n_timesteps > 0 && n_timesteps <= 64, "ls_graph_create: need B, T > 0 and 1 <= n_timesteps <= 64");
+    cudaStream_t s = (cudaStream_t)stream;
+    auto g = std::make_unique<ls_graph>();
+    g->flow = flow, g->dac = dac, g->B = B, g->T = T, g->n_steps = n_timesteps, g->streaming = streaming;
+    g->temperature = temperature, g->cfg_rate = cfg_rate, g->noise = noise_dev, g->noise_stride = noise_stride;
+    g->t_span.assign(t_span_host, t_span_host + n_timesteps + 1);
+    const int F = flow->feat();
+    const size_t n_mu = (size_t)B * F * T, n_mask = (size_t)B * T, n_spk = (size_t)B * F;
+    const size_t n_wav = dac ? (size_t)B * T * dac->hop() : 0;
+    auto al = [](size_t n) { return (n + 63) & ~size_t(63); };
+    const size_t floats = 3 * al(n_mu) + al(n_mask) + al(n_spk) + al((size_t)B) + al(n_wav);
+    ls::SerialScope scope_f(flow->serial, flow->device(), s);
+    std::unique_ptr<ls::SerialScope> scope_d;
+    if (dac) scope_d = std::make_unique<ls::SerialScope>(dac->serial, dac->device(), s);
+    LS_CUDA(cudaMalloc(&g->buf, floats * sizeof(float)));
+    LS_CUDA(cudaMemsetAsync(g->buf, 0, floats * sizeof(float), s));
+    float* f = reinterpret_cast<float*>(g->buf);
+    g->mu = f, f += al(n_mu);
+    g->cond = f, f += al(n_mu);
+    g->lat = f, f += al(n_mu);
+    g->mask = f, f += al(n_mask);
+    g->spks = f, f += al(n_spk);
+    g->len = reinterpret_cast<int32_t*>(f), f += al((size_t)B);
+    g->wav = dac ? f : nullptr;
+    // the capture pass needs a valid mask: all frames valid until the caller writes the real one
+    std::vector<float> ones(n_mask, 1.0f);
+    LS_CUDA(cudaMemcpyAsync(g->mask, ones.data(), n_mask * 4, cudaMemcpyHostToDevice, s));
+    LS_CUDA(cudaStreamSynchronize(s));  // (`ones` leaves scope; creation is not a hot call)
+    g->capture(s);
+    *out = g.release();
+  });
+}
+
+void* ls_graph_buffer(ls_graph* g, int32_t which) {
+  if (!g) return nullptr;
+  switch (which) {
+    case 0: return g->mu;
+    case 1: return g->mask;
+    case 2: return g->spks;
+    case 3: return g->cond;
+    case 4: return g->lat;
+    case 5: return g->wav;
+    default: return nullptr;
+  }
+}
+
+int32_t ls_graph_launch(ls_graph* g, void* stream) {
+  return ls::guarded([&] {
+    ls::require(g != nullptr, "ls_graph_launch: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ls::SerialScope scope_f(g->flow->serial, g->flow->device(), s);
+    std::unique_ptr<ls::SerialScope> scope_d;
+    if (g->dac) scope_d = std::make_unique<ls::SerialScope>(g->dac->serial, g->dac->device(), s);
+    g->flow->eng->check_sticky();
+    if (!g->current()) g->capture(s);
+    LS_CUDA(cudaGraphLaunch(g->exec, s));
+    ls::g_launch_count.fetch_add(g->launches, std::memory_order_relaxed);
+  });
+}
+
+int64_t ls_graph_kernel_count(const ls_graph* g) { return g ? g->launches : 0; }
+
+void ls_graph_destroy(ls_graph* g) { delete g; }
 
 int32_t ls_debug_set_buffer(void* dev_ptr, int64_t bytes) {
   ls::g_debug_buffer = reinterpret_cast<long long*>(dev_ptr);

@@ -892,12 +892,8 @@ cudaError_t launch_instance(int grid, size_t smem, cudaStream_t stream, const CU
                             const CUtensorMap& mapW, const CUtensorMap& mapO0, const CUtensorMap& mapO1,
                             const ConvGemmParams& pp, int tmem_cols, int acc_stride) {
   auto* kernel = conv_gemm_kernel<kAct, kOut0, kOut1, kAdd, kTemb>;
-  static bool attr_done = false;  // one flag per instance
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> optin{0};  // per instance, one bit per device
+  if (cudaError_t e = smem_optin_once(optin, reinterpret_cast<const void*>(kernel), 227 * 1024); e != cudaSuccess) return e;
   return launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, stream, 1, mapA0, mapA1, mapW, mapO0, mapO1, pp, tmem_cols,
                     acc_stride);
 }
@@ -968,31 +964,35 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
                  rows * kt * 2.0 + (double)p.taps * p.N * kt * 2.0 + rows * (p.n_store < p.N ? p.n_store : p.N) * out_b);
   count_launch();
-  // dense outputs go out through TMA stores (see store_chunk_tma); tensor maps cached per (buffer, shape)
+  // dense outputs go out through TMA stores (see store_chunk_tma); tensor maps cached per (buffer, shape).  The cache
+  // hands maps out BY VALUE: an insertion may evict (clear) the table, so no pointer into it survives a second lookup.
   static thread_local std::unordered_map<std::string, CUtensorMap> out_maps;
-  auto out_map = [&](const void* base, int elem_bytes) -> const CUtensorMap* {
+  auto out_map = [&](const void* base, int elem_bytes, CUtensorMap* dst) -> bool {
     char key[96];
     snprintf(key, sizeof key, "%p/%d/%d/%d/%d", base, elem_bytes, p.N, p.M, p.B);
     auto it = out_maps.find(key);
     if (it == out_maps.end()) {
       CUtensorMap m;
-      if (!make_out_map(&m, base, elem_bytes, p.N, p.M, p.B)) return nullptr;
+      if (!make_out_map(&m, base, elem_bytes, p.N, p.M, p.B)) return false;
       if (out_maps.size() > 4096) out_maps.clear();
       it = out_maps.emplace(key, m).first;
     }
-    return &it->second;
+    *dst = it->second;
+    return true;
   };
   const bool dense = p.out_ld == p.N && p.out_shift == 0 && p.n_store == p.N && p.out_bstride == (long long)p.M * p.N &&
                      p.out_alloc == (long long)p.M * p.N && (p.out_valid_mul % p.N) == 0 && p.N % 16 == 0 &&
                      (p.out0_dtype != OUT_NONE || p.out1_mode != OUT1_NONE) && conv_tma_out_enabled();
-  const CUtensorMap* mo0 = &mapW;  // placeholders when unused
-  const CUtensorMap* mo1 = &mapW;
+  CUtensorMap mo0v = mapW, mo1v = mapW;  // placeholders when unused
   pp.tma_out = 0;
   if (dense) {
-    const CUtensorMap* a = p.out0_dtype != OUT_NONE ? out_map(p.out0, p.out0_dtype == OUT_F32 ? 4 : 2) : &mapW;
-    const CUtensorMap* b = p.out1_mode != OUT1_NONE ? out_map(p.out1, 2) : &mapW;
-    if (a && b) mo0 = a, mo1 = b, pp.tma_out = 1;
+    const bool a = p.out0_dtype == OUT_NONE || out_map(p.out0, p.out0_dtype == OUT_F32 ? 4 : 2, &mo0v);
+    const bool b = p.out1_mode == OUT1_NONE || out_map(p.out1, 2, &mo1v);
+    if (a && b) pp.tma_out = 1;
+    else mo0v = mapW, mo1v = mapW;
   }
+  const CUtensorMap* mo0 = &mo0v;
+  const CUtensorMap* mo1 = &mo1v;
   const int add = p.addend ? p.addend_dtype : OUT_NONE;
   const int temb = p.temb ? 1 : 0;
 #define LS_CONV_CASE(A, O0, O1, AD, TE)                                                                          \

@@ -195,12 +195,10 @@ DacEncEngine::DacEncEngine(const Weights& w, int device) : device_(device) {
   }
 }
 
-void DacEncEngine::ensure_workspace(int B, int S) {
+void DacEncEngine::ensure_workspace(int B, int S, cudaStream_t s) {
   const long long samples = (long long)B * S;
   if (samples <= cap_samples_) return;
-  LS_CUDA(cudaDeviceSynchronize());
-  if (ws_base_) cudaFree(ws_base_);
-  ws_base_ = nullptr;
+  ws_release(ws_base_, s);
   plans_.clear();
   cap_samples_ = samples;
   // widest activation in elements per input sample: stage i holds (S / prod strides) x (dim0 * 2^i)
@@ -217,8 +215,7 @@ void DacEncEngine::ensure_workspace(int B, int S) {
   o_sA_ = take(elems * 2);
   o_sB_ = take(elems * 2);
   o_y_ = take((size_t)(samples / hop_ + 1) * latent_ * 4);
-  LS_CUDA(cudaMalloc(&ws_base_, off));
-  LS_CUDA(cudaMemset(ws_base_, 0, off));
+  ws_alloc(ws_base_, off, s);
 }
 
 const DacEncEngine::Plan& DacEncEngine::plan_for(int B, int S) {
@@ -251,7 +248,7 @@ void DacEncEngine::encode(const float* audio, const float* noise, float* z, floa
                           cudaStream_t s) {
   require(B > 0 && S > 0 && S % hop_ == 0, "audio length must be a positive multiple of the hop (pad first, model.py:455-462)");
   LS_CUDA(cudaSetDevice(device_));
-  ensure_workspace(B, S);
+  ensure_workspace(B, S, s);
   const Plan& pl = plan_for(B, S);
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
   const bool halo = conv_halo_enabled();

@@ -31,7 +31,7 @@ class DacEncEngine {
     PackedLinear down;     // 3-tap polyphase form over the [L/s][s*cin] view of the input
   };
   struct Plan;
-  void ensure_workspace(int B, int S);
+  void ensure_workspace(int B, int S, cudaStream_t s);
   const Plan& plan_for(int B, int S);
   template <typename T>
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }

@@ -173,12 +173,10 @@ DacEngine::DacEngine(const Weights& w, int device) : device_(device) {
   }
 }
 
-void DacEngine::ensure_workspace(int B, int L) {
+void DacEngine::ensure_workspace(int B, int L, cudaStream_t s) {
   const long long frames = (long long)B * L;
   if (frames <= cap_frames_ && B <= cap_b_) return;
-  LS_CUDA(cudaDeviceSynchronize());
-  if (ws_base_) cudaFree(ws_base_);
-  ws_base_ = nullptr;
+  ws_release(ws_base_, s);
   plans_.clear();
   cap_frames_ = std::max(frames, cap_frames_);
   cap_b_ = std::max(B, cap_b_);
@@ -202,8 +200,8 @@ void DacEngine::ensure_workspace(int B, int L) {
   o_sA_[1] = take(F * per_frame * 2);
   o_sB_ = take(F * per_frame * 2);
   o_len_ = take((size_t)cap_b_ * 4);
-  LS_CUDA(cudaMalloc(&ws_base_, off));
-  LS_CUDA(cudaMemset(ws_base_, 0, off));
+  ws_alloc(ws_base_, off, s);
+  ++ws_generation_;
 }
 
 const DacEngine::Plan& DacEngine::plan_for(int B, int L) {
@@ -236,7 +234,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
   require(B > 0 && L > 0, "B and L must be positive");
   require((long long)L * hop_ < (1ll << 31), "utterance too long");
   LS_CUDA(cudaSetDevice(device_));
-  ensure_workspace(B, L);
+  ensure_workspace(B, L, s);
   const Plan& pl = plan_for(B, L);
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
   const bool halo = conv_halo_enabled();

@@ -20,12 +20,13 @@ class DacEngine {
   int hop() const { return hop_; }
   int latent_dim() const { return latent_; }
   int device() const { return device_; }
+  unsigned long long ws_generation() const { return ws_generation_; }
 
  private:
   struct UnitW;
   struct StageW;
   struct Plan;
-  void ensure_workspace(int B, int L);
+  void ensure_workspace(int B, int L, cudaStream_t s);
   const Plan& plan_for(int B, int L);
   template <typename T>
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
@@ -41,6 +42,7 @@ class DacEngine {
   uint8_t* ws_base_ = nullptr;
   long long cap_frames_ = 0;  // B*L capacity
   int cap_b_ = 0;
+  unsigned long long ws_generation_ = 0;
   size_t o_zt_ = 0, o_a0_ = 0, o_x_ = 0, o_sA_[2] = {0, 0}, o_sB_ = 0, o_len_ = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans_;
 };

@@ -114,74 +114,93 @@ __global__ void unpack_nct_kernel(const float* __restrict__ src, float* __restri
   }
 }
 
+// lengths[b] = number of non-zero mask entries; a mask that is not a prefix (right-padding) mask -- a non-zero entry after
+// a zero -- raises *bad_flag (optional: a sticky flag the engine reports at its next call, so that validating the mask
+// costs no host synchronisation on the hot call)
 __global__ void mask_to_lengths_kernel(const float* __restrict__ mask, int* __restrict__ lengths, int B, int T,
-                                       int dup) {
+                                       int dup, int* bad_flag) {
   const int b = blockIdx.x;
-  __shared__ int cnt;
-  if (threadIdx.x == 0) cnt = 0;
+  __shared__ int cnt, bad;
+  if (threadIdx.x == 0) cnt = 0, bad = 0;
   __syncthreads();
-  int local = 0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) local += mask[(long long)b * T + t] != 0.f ? 1 : 0;
+  int local = 0, local_bad = 0;
+  const float* m = mask + (long long)b * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const bool on = m[t] != 0.f;
+    local += on ? 1 : 0;
+    if (on && t > 0 && m[t - 1] == 0.f) local_bad = 1;
+  }
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, local);
+  local_bad = __any_sync(0xffffffffu, local_bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&cnt, local);
+    if (local_bad) bad = 1;
+  }
   __syncthreads();
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     for (int d = 0; d < dup; ++d) lengths[d * B + b] = cnt;
-}
-
-// ---- timestep conditioning: one block per time value ----
-// out[o] = act_in(in)[:] . W[o][:] + bias[o], warp per output row, fp32
-__device__ void block_gemv(const float* __restrict__ W, const float* __restrict__ bias, const float* in_smem,
-                           float* out, int n_out, int n_in) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int o = warp; o < n_out; o += nwarps) {
-    const float* w = W + (long long)o * n_in;
-    float acc = 0.f;
-    for (int k = lane; k < n_in; k += 32) acc = fmaf(__ldg(w + k), in_smem[k], acc);
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) out[o] = acc + bias[o];
+    if (bad && bad_flag) *bad_flag = 1;
   }
 }
 
-__global__ void __launch_bounds__(1024) time_embed_kernel(const TimeEmbedParams p) {
-  extern __shared__ float sm[];
-  float* emb = sm;                 // [in_dim]
-  float* h1 = emb + p.in_dim;      // [hid]
-  float* h2 = h1 + p.hid;          // [hid]
-  const int it = blockIdx.x;
-  const float t = p.t[it];
-  const int half = p.in_dim / 2;
-  for (int i = threadIdx.x; i < half; i += blockDim.x) {
-    const float a = (1000.0f * t) * p.freqs[i];  // scale * x * emb  (matcha decoder.py:27)
-    emb[i] = sinf(a);
-    emb[half + i] = cosf(a);
+// ---- timestep conditioning (matcha decoder.py:14-29 SinusoidalPosEmb, :73-117 TimestepEmbedding, :49 ResnetBlock1D.mlp)
+// Three GEMV stages over ALL time values of a solve at once, each a grid of (output rows / 8, nt) blocks of 8 warps with
+// one output row per warp -- the weights (19 MB fp32) are streamed by ~450 blocks per time value instead of by one
+// 1024-thread block per time value (634 us per solve before, launch-latency-sized now).
+//   stage 0: in = [sin(1000 t f_i) | cos(1000 t f_i)]         out = W1 in + b1
+//   stage 1: in = SiLU(prev)                                  out = W2 in + b2
+//   stage 2: in = Mish(prev)                                  out[r] = Wr[r] in + br[r]   (every resnet's Linear, stacked)
+constexpr int kTimeInline = 64;  // time values carried in the kernel parameters (keeps the solve capturable in a CUDA graph)
+struct TimeStage {
+  const float* t;         // [nt] device, or nullptr: t_inline
+  float t_inline[kTimeInline];
+  const float* freqs;     // stage 0
+  const float* in;        // stages 1, 2: [nt][n_in]
+  const float* W;         // [n_out][n_in]
+  const float* bias;      // [n_out]
+  float* out;             // [nt][n_out]
+  int n_in, n_out;
+};
+template <int kStage>
+__global__ void __launch_bounds__(256) time_stage_kernel(const TimeStage p) {
+  extern __shared__ float vin[];  // [n_in]
+  const int it = blockIdx.y;
+  if (kStage == 0) {
+    const float t = p.t ? p.t[it] : p.t_inline[it];
+    const int half = p.n_in / 2;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+      const float a = (1000.0f * t) * p.freqs[i];  // scale * x * emb  (matcha decoder.py:27)
+      vin[i] = sinf(a);
+      vin[half + i] = cosf(a);
+    }
+  } else {
+    const float* src = p.in + (long long)it * p.n_in;
+    for (int i = threadIdx.x; i < p.n_in; i += blockDim.x) {
+      const float x = src[i];
+      if (kStage == 1) {
+        vin[i] = x / (1.0f + expf(-x));  // SiLU
+      } else {
+        const float sp = x > 20.f ? x : log1pf(expf(x));  // Mish feeding every resnet's Linear
+        vin[i] = x * tanhf(sp);
+      }
+    }
   }
   __syncthreads();
-  block_gemv(p.w1, p.b1, emb, h1, p.hid, p.in_dim);
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.hid; i += blockDim.x) {
-    const float x = h1[i];
-    h1[i] = x / (1.0f + expf(-x));  // SiLU
-  }
-  __syncthreads();
-  block_gemv(p.w2, p.b2, h1, h2, p.hid, p.hid);
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.hid; i += blockDim.x) {  // Mish feeding every resnet's Linear
-    const float x = h2[i];
-    const float sp = x > 20.f ? x : log1pf(expf(x));
-    h2[i] = x * tanhf(sp);
-  }
-  __syncthreads();
-  for (int r = 0; r < p.n_res; ++r)
-    block_gemv(p.wr + (long long)r * p.out_dim * p.hid, p.br + (long long)r * p.out_dim, h2,
-               p.out + ((long long)it * p.n_res + r) * p.out_dim, p.out_dim, p.hid);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (o >= p.n_out) return;
+  const float* w = p.W + (long long)o * p.n_in;
+  float acc = 0.f;
+  for (int k = lane; k < p.n_in; k += 32) acc = fmaf(__ldg(w + k), vin[k], acc);
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) p.out[(long long)it * p.n_out + o] = acc + p.bias[o];
 }
 
 }  // namespace
 
 cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,
                             int ld, int c_off, const int* lengths, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * (4.0 + 2.0));
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   pack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, src_bstride, ld, c_off, lengths);
   count_launch();
@@ -189,14 +208,14 @@ cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, 
 }
 cudaError_t launch_pack_bcast(const float* src, __nv_bfloat16* dst, int B, int C, int T, int ld, int c_off,
                               const int* lengths, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * 4.0 + (double)B * C * T * 2.0);
   dim3 grid((unsigned)(((long long)T * C + 255) / 256), B);
   pack_bcast_kernel<<<grid, 256, 0, s>>>(src, dst, C, T, ld, c_off, lengths);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, int c_off, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * 2.0);
   dim3 grid((unsigned)(((long long)T * C + 255) / 256), B);
   pack_zero_kernel<<<grid, 256, 0, s>>>(dst, C, T, ld, c_off);
   count_launch();
@@ -204,7 +223,7 @@ cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, in
 }
 cudaError_t launch_init_state(const float* noise, int noise_ld, float temperature, float* x_state,
                               __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)C * T * 4.0 + (double)B * C * T * (4.0 + 2.0 * 2.0));
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   init_state_kernel<<<grid, block, 0, s>>>(noise, noise_ld, temperature, x_state, xin, B, C, T, ld, lengths);
   count_launch();
@@ -212,7 +231,7 @@ cudaError_t launch_init_state(const float* noise, int noise_ld, float temperatur
 }
 cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin, int B, int C, int T, int ld,
                              float dt, float cfg_rate, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * (2 * 4.0 + 4.0 + 4.0 + 2 * 2.0));
   const long long n4 = (long long)B * T * C / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
@@ -222,25 +241,44 @@ cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin,
   return cudaGetLastError();
 }
 cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T, const int* lengths, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * (4.0 + 4.0));
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   unpack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, lengths);
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
-  mask_to_lengths_kernel<<<B, 256, 0, s>>>(mask, lengths, B, T, dup);
+cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s, int* bad_flag) {
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * T * 4.0);
+  mask_to_lengths_kernel<<<B, 256, 0, s>>>(mask, lengths, B, T, dup, bad_flag);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_time_embed(const TimeEmbedParams& p, cudaStream_t s) {
-  ProfScope prof(s, PK_ELEMENTWISE, 0.0, 0.0);
   if (p.nt <= 0) return cudaSuccess;
-  const size_t smem = (size_t)(p.in_dim + 2 * p.hid) * sizeof(float);
-  time_embed_kernel<<<p.nt, 1024, smem, s>>>(p);
-  count_launch();
-  return cudaGetLastError();
+  if (p.t == nullptr && p.nt > kTimeInline) return cudaErrorInvalidValue;
+  const double w_bytes = 4.0 * ((double)p.hid * p.in_dim + (double)p.hid * p.hid + (double)p.n_res * p.out_dim * p.hid);
+  TimeStage st{};
+  st.t = p.t;
+  if (!p.t)
+    for (int i = 0; i < p.nt; ++i) st.t_inline[i] = p.t_host[i];
+  auto run = [&](auto kernel, int n_in, int n_out, double flops, double bytes) -> cudaError_t {
+    ProfScope prof(s, PK_ELEMENTWISE, flops, bytes);
+    st.n_in = n_in, st.n_out = n_out;
+    kernel<<<dim3((n_out + 7) / 8, p.nt), 256, (size_t)n_in * sizeof(float), s>>>(st);
+    count_launch();
+    return cudaGetLastError();
+  };
+  (void)w_bytes;
+  // h1 [nt][hid] and h2 [nt][hid] live behind the output (the caller's buffer has room: see TimeEmbedParams::scratch)
+  st.freqs = p.freqs, st.W = p.w1, st.bias = p.b1, st.out = p.scratch;
+  cudaError_t e = run(time_stage_kernel<0>, p.in_dim, p.hid, 2.0 * p.nt * p.hid * p.in_dim, 4.0 * p.hid * (p.in_dim + 1.0 + p.nt));
+  if (e != cudaSuccess) return e;
+  st.in = p.scratch, st.W = p.w2, st.bias = p.b2, st.out = p.scratch + (long long)p.nt * p.hid;
+  e = run(time_stage_kernel<1>, p.hid, p.hid, 2.0 * p.nt * p.hid * p.hid, 4.0 * p.hid * (p.hid + 1.0 + 2.0 * p.nt));
+  if (e != cudaSuccess) return e;
+  st.in = p.scratch + (long long)p.nt * p.hid, st.W = p.wr, st.bias = p.br, st.out = p.out;
+  const int n_out = p.n_res * p.out_dim;
+  return run(time_stage_kernel<2>, p.hid, n_out, 2.0 * p.nt * n_out * p.hid, 4.0 * n_out * (p.hid + 1.0 + p.nt) + 4.0 * p.nt * p.hid);
 }
 
 }  // namespace ls

@@ -92,6 +92,26 @@ class Arena {
   size_t bytes_ = 0;
 };
 
+// Stream-ordered workspace (re)allocation: growth happens with cudaFreeAsync / cudaMallocAsync on the calling stream --
+// no device-wide synchronisation, nothing another handle or stream has to wait for ("no device-wide syncs").
+// The C-ABI layer orders calls that reach one handle from different streams (StreamSerial in c_api.cu), so the old
+// block's last users are ordered before the free.  Growth cannot be captured into a CUDA graph: run the call once
+// outside capture with the largest shapes first.
+inline void ws_release(uint8_t*& base, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  LS_CUDA(cudaStreamIsCapturing(s, &st));
+  require(st == cudaStreamCaptureStatusNone,
+          "workspace growth during stream capture: run the call once outside capture with these shapes first");
+  if (base) LS_CUDA(cudaFreeAsync(base, s));
+  base = nullptr;
+}
+inline void ws_alloc(uint8_t*& base, size_t bytes, cudaStream_t s) {
+  void* p = nullptr;
+  LS_CUDA(cudaMallocAsync(&p, bytes, s));
+  base = reinterpret_cast<uint8_t*>(p);
+  LS_CUDA(cudaMemsetAsync(base, 0, bytes, s));
+}
+
 // One dense contraction's weights in kernel layout: bf16 [taps*N][K] (K contiguous) + its TMA map.
 struct PackedLinear {
   size_t w_off = 0, bias_off = 0;

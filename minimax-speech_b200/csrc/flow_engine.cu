@@ -85,6 +85,17 @@ struct FlowEngine::Plan {
 
 FlowEngine::~FlowEngine() {
   if (ws_base_) cudaFree(ws_base_);
+  if (bad_mask_host_) cudaFreeHost(bad_mask_host_);
+}
+
+// A non-prefix mask is detected on the device (mask_to_lengths_kernel) and reported here, at the next call on the
+// handle: validating it on the hot call would cost a host synchronisation per call.
+void FlowEngine::check_sticky() {
+  if (bad_mask_host_ && *bad_mask_host_) {
+    *bad_mask_host_ = 0;
+    throw EngineError(LS_ERR_INVALID, "an earlier call on this handle was given a mask that is not a prefix (right-padding) "
+                                      "mask; its result is undefined");
+  }
 }
 
 FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
@@ -93,6 +104,9 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
   LS_CUDA(cudaGetDeviceProperties(&prop, device));
   require(prop.major == 10, "this library only runs on sm_100 (B200) devices", LS_ERR_UNSUPPORTED);
   num_sms_ = prop.multiProcessorCount;
+  LS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&bad_mask_host_), sizeof(int), cudaHostAllocMapped));
+  *bad_mask_host_ = 0;
+  LS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&bad_mask_dev_), bad_mask_host_, 0));
 
   const ls_tensor& l1 = w.get("time_mlp.linear_1.weight");
   hid_ = (int)l1.shape[0];
@@ -237,12 +251,10 @@ FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
 }
 
 // ------------------------------------------------------------------------------------------------
-void FlowEngine::ensure_workspace(int B2, int T, int nt) {
+void FlowEngine::ensure_workspace(int B2, int T, int nt, cudaStream_t s) {
   const long long rows = (long long)B2 * T;
   if (rows <= cap_rows_ && nt <= cap_nt_ && B2 <= cap_b2_) return;
-  LS_CUDA(cudaDeviceSynchronize());
-  if (ws_base_) cudaFree(ws_base_);
-  ws_base_ = nullptr;
+  ws_release(ws_base_, s);
   plans_.clear();
   cap_rows_ = std::max(rows, cap_rows_);
   cap_nt_ = std::max(nt, cap_nt_);
@@ -270,9 +282,10 @@ void FlowEngine::ensure_workspace(int B2, int T, int nt) {
   o_len_ = take((size_t)cap_b2_ * 4);
   o_t_ = take((size_t)cap_nt_ * 4);
   o_temb_ = take((size_t)cap_nt_ * groups_.size() * C_ * 4);
-  LS_CUDA(cudaMalloc(&ws_base_, off));
-  LS_CUDA(cudaMemset(ws_base_, 0, off));
+  o_tscr_ = take((size_t)cap_nt_ * 2 * hid_ * 4);
+  ws_alloc(ws_base_, off, s);
   ws_bytes_ = off;
+  ++ws_generation_;
 }
 
 const FlowEngine::Plan& FlowEngine::plan_for(int B2, int T) {
@@ -485,9 +498,9 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   (void)inner;
 }
 
-void FlowEngine::time_embed(const float* t_dev, int nt, cudaStream_t s) {
+void FlowEngine::time_embed(const float* t_dev, const float* t_host, int nt, cudaStream_t s) {
   TimeEmbedParams tp{};
-  tp.t = t_dev, tp.freqs = arena_.ptr<float>(freqs_);
+  tp.t = t_dev, tp.t_host = t_host, tp.scratch = ws<float>(o_tscr_), tp.freqs = arena_.ptr<float>(freqs_);
   tp.w1 = arena_.ptr<float>(w1_), tp.b1 = arena_.ptr<float>(b1_);
   tp.w2 = arena_.ptr<float>(w2_), tp.b2 = arena_.ptr<float>(b2_);
   tp.wr = arena_.ptr<float>(wr_), tp.br = arena_.ptr<float>(br_);
@@ -501,16 +514,17 @@ void FlowEngine::estimator_forward(const float* x, const float* mask, const floa
                                    cudaStream_t s) {
   require(rows > 0 && T > 0, "rows and T must be positive");
   LS_CUDA(cudaSetDevice(device_));
-  ensure_workspace(rows, T, rows);
+  check_sticky();
+  ensure_workspace(rows, T, rows, s);
   int* lengths = ws<int>(o_len_);
   __nv_bfloat16* xin = ws<__nv_bfloat16>(o_xin_);
-  LS_CUDA(launch_mask_to_lengths(mask, lengths, rows, T, 1, s));
+  LS_CUDA(launch_mask_to_lengths(mask, lengths, rows, T, 1, s, bad_mask_dev_));
   const long long bs = (long long)feat_ * T;
   LS_CUDA(launch_pack_nct(x, xin, rows, feat_, T, bs, in_ch_, 0, lengths, s));
   LS_CUDA(launch_pack_nct(mu, xin, rows, feat_, T, bs, in_ch_, feat_, lengths, s));
   LS_CUDA(launch_pack_bcast(spks, xin, rows, feat_, T, in_ch_, 2 * feat_, lengths, s));
   LS_CUDA(launch_pack_nct(cond, xin, rows, feat_, T, bs, in_ch_, 3 * feat_, lengths, s));
-  time_embed(t, rows, s);
+  time_embed(t, nullptr, rows, s);
   run_estimator(rows, T, ws<float>(o_temb_), (long long)groups_.size() * C_, streaming, s);
   LS_CUDA(launch_unpack_nct(ws<float>(o_v_), out, rows, feat_, T, lengths, s));
 }
@@ -521,8 +535,9 @@ void FlowEngine::solve(const float* mu, const float* mask, const float* spks, co
   require(B > 0 && T > 0 && n_steps > 0, "B, T and n_timesteps must be positive");
   require(noise_stride >= T, "noise buffer shorter than T (reference: rand_noise holds 15000 frames)");
   LS_CUDA(cudaSetDevice(device_));
+  check_sticky();
   const int B2 = 2 * B;
-  ensure_workspace(B2, T, n_steps);
+  ensure_workspace(B2, T, n_steps, s);
   int* lengths = ws<int>(o_len_);
   __nv_bfloat16* xin = ws<__nv_bfloat16>(o_xin_);
   float* x_state = ws<float>(o_x_);
@@ -539,9 +554,11 @@ void FlowEngine::solve(const float* mu, const float* mask, const float* spks, co
       if (step < n_steps) dt = t_span[step + 1] - t;
     }
   }
-  LS_CUDA(cudaMemcpyAsync(ws<float>(o_t_), t_host_.data(), (size_t)n_steps * 4, cudaMemcpyHostToDevice, s));
+  // up to 64 time values travel inside the kernel parameters (no host -> device copy: the solve stays capturable)
+  const bool t_inline = n_steps <= 64;
+  if (!t_inline) LS_CUDA(cudaMemcpyAsync(ws<float>(o_t_), t_host_.data(), (size_t)n_steps * 4, cudaMemcpyHostToDevice, s));
 
-  LS_CUDA(launch_mask_to_lengths(mask, lengths, B, T, 2, s));
+  LS_CUDA(launch_mask_to_lengths(mask, lengths, B, T, 2, s, bad_mask_dev_));
   const long long bs = (long long)feat_ * T;
   // conditional half rows [0,B): [x | mu | spks | cond]; unconditional half rows [B,2B): [x | 0 | 0 | 0]
   LS_CUDA(launch_pack_nct(mu, xin, B, feat_, T, bs, in_ch_, feat_, lengths, s));
@@ -549,7 +566,7 @@ void FlowEngine::solve(const float* mu, const float* mask, const float* spks, co
   LS_CUDA(launch_pack_nct(cond, xin, B, feat_, T, bs, in_ch_, 3 * feat_, lengths, s));
   LS_CUDA(launch_pack_zero(xin + (long long)B * T * in_ch_, B, 3 * feat_, T, in_ch_, feat_, s));
   LS_CUDA(launch_init_state(noise, (int)noise_stride, temperature, x_state, xin, B, feat_, T, in_ch_, lengths, s));
-  time_embed(ws<float>(o_t_), n_steps, s);
+  time_embed(t_inline ? nullptr : ws<float>(o_t_), t_host_.data(), n_steps, s);
   const long long per_t = (long long)groups_.size() * C_;
   for (int k = 0; k < n_steps; ++k) {
     run_estimator(B2, T, ws<float>(o_temb_) + k * per_t, 0, streaming, s);

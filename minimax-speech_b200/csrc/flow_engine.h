@@ -18,6 +18,10 @@ class FlowEngine {
              bool streaming, float* out, int B, int T, cudaStream_t s);
   int feat() const { return feat_; }
   int device() const { return device_; }
+  // changes whenever the workspace was reallocated (CUDA graphs captured over it must be captured again)
+  unsigned long long ws_generation() const { return ws_generation_; }
+  // throws if an earlier call saw a non-prefix mask (detected on the device, reported without a synchronisation)
+  void check_sticky();
 
  private:
   struct ResnetW;
@@ -25,10 +29,10 @@ class FlowEngine {
   struct GroupW;
   struct Plan;
 
-  void ensure_workspace(int B2, int T, int nt);
+  void ensure_workspace(int B2, int T, int nt, cudaStream_t s);
   const Plan& plan_for(int B2, int T);
   void run_estimator(int B2, int T, const float* temb, long long temb_bstride, bool streaming, cudaStream_t s);
-  void time_embed(const float* t_dev, int nt, cudaStream_t s);
+  void time_embed(const float* t_dev, const float* t_host, int nt, cudaStream_t s);
   template <typename T>
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
 
@@ -46,9 +50,12 @@ class FlowEngine {
   long long cap_rows_ = 0;
   int cap_nt_ = 0, cap_b2_ = 0;
   size_t o_xin_ = 0, o_hA_ = 0, o_hB_ = 0, o_skip_ = 0, o_nrm_ = 0, o_qkv_ = 0, o_att_ = 0, o_ff_ = 0, o_u_ = 0,
-         o_r_ = 0, o_v_ = 0, o_x_ = 0, o_len_ = 0, o_t_ = 0, o_temb_ = 0;
+         o_r_ = 0, o_v_ = 0, o_x_ = 0, o_len_ = 0, o_t_ = 0, o_temb_ = 0, o_tscr_ = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans_;
   std::vector<float> t_host_, dt_host_;
+  unsigned long long ws_generation_ = 0;
+  int* bad_mask_host_ = nullptr;  // mapped pinned flag written by mask_to_lengths_kernel
+  int* bad_mask_dev_ = nullptr;
 };
 
 }  // namespace ls

@@ -259,15 +259,13 @@ FrontEngine::FrontEngine(const Weights& w, int device) : device_(device) {
       for (PackedLinear* pl : {&L.qkv, &L.pos, &L.out, &L.ff1, &L.ff2}) finalize_dense(arena_, *pl);
 }
 
-void FrontEngine::ensure_workspace(int B, int T_all, int T) {
+void FrontEngine::ensure_workspace(int B, int T_all, int T, cudaStream_t s) {
   const int T2 = 2 * T;
   const long long rows = (long long)B * std::max(T2, T_all);
   const int Ppad = round_up(2 * T2 - 1, 128);
   const long long bd = (long long)B * heads_ * T2 * Ppad;
   if (rows <= cap_rows_ && bd <= cap_bd_) return;
-  LS_CUDA(cudaDeviceSynchronize());
-  if (ws_base_) cudaFree(ws_base_);
-  ws_base_ = nullptr;
+  ws_release(ws_base_, s);
   plans_.clear();
   cap_rows_ = std::max(rows, cap_rows_), cap_bd_ = std::max(bd, cap_bd_);
   size_t off = 0;
@@ -291,8 +289,7 @@ void FrontEngine::ensure_workspace(int B, int T_all, int T) {
   o_pph_ = take(Pcap * kD * 2);
   o_bd_ = take(((size_t)cap_bd_ + 4096) * 4);
   o_spk_ = take(4096);  // int lens0[512] | lens1[512]
-  LS_CUDA(cudaMalloc(&ws_base_, off));
-  LS_CUDA(cudaMemset(ws_base_, 0, off));
+  ws_alloc(ws_base_, off, s);
 }
 
 const FrontEngine::Plan& FrontEngine::plan_for(int B, int T_all, int T) {
@@ -337,7 +334,7 @@ void FrontEngine::encode(const long long* tokens, const float* embedding, float*
   const int T = T_all - n_context, T2 = 2 * T;
   require(B > 0 && T > 0 && (n_context == 0 || n_context == 3), "B, T must be positive; context is 0 or 3 tokens");
   LS_CUDA(cudaSetDevice(device_));
-  ensure_workspace(B, T_all, T);
+  ensure_workspace(B, T_all, T, s);
   const Plan& pl = plan_for(B, T_all, T);
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
   const bool halo = conv_halo_enabled();
@@ -647,12 +644,10 @@ SpeakerEngine::SpeakerEngine(const Weights& w, int device) : device_(device) {
   for (BlockW& bw : blocks_) finalize_dense(arena_, bw.qkv), finalize_dense(arena_, bw.proj);
 }
 
-const SpeakerEngine::Plan& SpeakerEngine::plan_for(int R, int T) {
+const SpeakerEngine::Plan& SpeakerEngine::plan_for(int R, int T, cudaStream_t s) {
   const long long rows = (long long)R * T;
   if (rows > cap_rows_) {
-    LS_CUDA(cudaDeviceSynchronize());
-    if (ws_base_) cudaFree(ws_base_);
-    ws_base_ = nullptr;
+    ws_release(ws_base_, s);
     plans_.clear();
     cap_rows_ = rows;
     size_t off = 0;
@@ -664,8 +659,7 @@ const SpeakerEngine::Plan& SpeakerEngine::plan_for(int R, int T) {
     const size_t n = (size_t)rows + 256;
     o_h_ = take(n * kD * 4), o_nb_ = take(n * kD * 2), o_qkv_ = take(n * 3 * kD * 2), o_att_ = take(n * kD * 2);
     o_mel_ = take(n * (size_t)mel_ * 2), o_emb_ = take(4096);
-    LS_CUDA(cudaMalloc(&ws_base_, off));
-    LS_CUDA(cudaMemset(ws_base_, 0, off));
+    ws_alloc(ws_base_, off, s);
   }
   auto key = std::make_pair(R, T);
   auto it = plans_.find(key);
@@ -687,7 +681,7 @@ void SpeakerEngine::encode(const float* mel, float* emb, int B, int T, int n_ref
   require(B > 0 && T > 0 && n_refs > 0, "B, T, n_refs must be positive");
   LS_CUDA(cudaSetDevice(device_));
   const int R = B * n_refs;  // every clip is an independent batch row
-  const Plan& pl = plan_for(R, T);
+  const Plan& pl = plan_for(R, T, s);
   auto f32 = [&](size_t off) { return arena_.ptr<float>(off); };
   float* h = ws<float>(o_h_);
   __nv_bfloat16* nb = ws<__nv_bfloat16>(o_nb_);

@@ -37,7 +37,7 @@ class FrontEngine {
     size_t g, b;
   };
   struct Plan;
-  void ensure_workspace(int B, int T_all, int T);
+  void ensure_workspace(int B, int T_all, int T, cudaStream_t s);
   const Plan& plan_for(int B, int T_all, int T);
   template <typename T>
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
@@ -75,7 +75,7 @@ class SpeakerEngine {
     size_t g, b;
   };
   struct Plan;
-  const Plan& plan_for(int R, int T);
+  const Plan& plan_for(int R, int T, cudaStream_t s);
   template <typename T>
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
 

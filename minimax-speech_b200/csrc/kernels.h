@@ -43,6 +43,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and handles can be created on
+// any device of the process: the opt-in is tracked per (kernel instance, device) in a bit mask owned by the caller
+// (one static mask per kernel instance).  Racing threads may both set the attribute; that is idempotent.
+inline cudaError_t smem_optin_once(std::atomic<unsigned long long>& done_mask, const void* func, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  done_mask.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
+}
+
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4,
                  ACT_SILU = 5, ACT_LRELU001 = 6 /* F.leaky_relu's default slope 0.01 */ };
 enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 };
@@ -180,11 +195,15 @@ cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin,
                              float dt, float cfg_rate, cudaStream_t s);
 // time-major fp32 [B][T][C] -> NCT fp32 [B][C][T], rows >= len zeroed
 cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T, const int* lengths, cudaStream_t s);
-// lengths[b] = number of non-zero entries of mask[b][0][:]
-cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s);
+// lengths[d*B + b] = number of non-zero entries of mask[b][0][:] for d < dup; *bad_flag (device-visible, optional) is set
+// when a mask is not a prefix mask
+cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s,
+                                   int* bad_flag = nullptr);
 // timestep conditioning for nt time values: sinusoidal embedding -> MLP -> per-resnet projections
 struct TimeEmbedParams {
-  const float* t;        // [nt] device
+  const float* t;        // [nt] device, or nullptr: the values come from t_host (nt <= 64) inside the kernel parameters
+  const float* t_host;   // [nt] host (only read when t == nullptr)
+  float* scratch;        // device, 2 * nt * hid floats (the two hidden layers of the MLP)
   const float* freqs;    // [in_dim/2]
   const float* w1; const float* b1;   // [hid][in_dim]
   const float* w2; const float* b2;   // [hid][hid]

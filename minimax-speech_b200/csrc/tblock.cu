@@ -784,12 +784,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
 
 cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream) {
   if (p.R <= 0 || p.T <= 0 || p.vec == nullptr) return cudaErrorInvalidValue;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> optin{0};  // one bit per device
+  if (cudaError_t e = smem_optin_once(optin, reinterpret_cast<const void*>(tblock_kernel), kSmemBytes); e != cudaSuccess) return e;
   const int n_tiles = (p.R + kTileM - 1) / kTileM;
   const int n_groups = (n_tiles + kCS - 1) / kCS;
   static int max_clusters = 0;

@@ -9,7 +9,7 @@ class instead.  The encoder (``encode``) is out of scope (SURVEY.md section 8f-3
 import torch
 import torch.nn as nn
 
-from . import native, synth
+from . import native, ops, synth
 from .flow import _as_f32, _register_tree
 
 
@@ -53,6 +53,10 @@ class DACVAEDecoder(nn.Module):
     def decode(self, z, lengths=None):
         """``lengths`` (optional int tensor [B]): valid latent frames per item of a right-padded batch; each item
         is then decoded exactly as if alone (the reference decodes one utterance per call)."""
+        return self.run(z, lengths)
+
+    def run(self, z, lengths=None):
+        """``decode`` without the inference_mode decorator (the form torch.compile traces)."""
         dev = z.device
         if z.dim() != 3 or z.shape[1] != self.latent_dim or z.shape[2] < 1:
             raise ValueError(f"z must be [B, {self.latent_dim}, L >= 1], got {tuple(z.shape)}")
@@ -60,7 +64,7 @@ class DACVAEDecoder(nn.Module):
             if lengths.numel() != z.shape[0]:
                 raise ValueError(f"lengths must have {z.shape[0]} entries")
             lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
-        return self.handle(dev).decode(_as_f32(z, dev), lengths)
+        return torch.ops.ls_b200.dac_decode(self.handle(dev).key, _as_f32(z, dev), lengths, self.hop_length)
 
     forward = decode
 

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import native, synth
+from . import native, ops, synth
 
 
 class _Holder(nn.Module):
@@ -48,12 +48,28 @@ def _as_f32(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-def _check_prefix_mask(mask):
+def _check_prefix_mask(mask, sync_ok=False):
     """The kernels take per-utterance lengths; the reference always builds prefix masks
-    (``~make_pad_mask(len)``, flow.py:478,493)."""
+    (``~make_pad_mask(len)``, flow.py:478,493).  A CPU mask is checked here.  A CUDA mask is checked on the device by the
+    tensor-core engine itself (mask_to_lengths_kernel raises a sticky flag that the next call on the handle reports):
+    reading the verdict back here would synchronise the host with the stream at the top of every call.  ``sync_ok``
+    (the fp32 validation mode) checks CUDA masks here anyway."""
+    if mask.is_cuda and not sync_ok:
+        return
     m = mask != 0
     if bool((m[..., 1:] & ~m[..., :-1]).any()):
         raise ValueError("mask must be a prefix (right-padding) mask")
+
+
+@torch.compiler.assume_constant_result
+def _t_span_values(n_timesteps, scheduler):
+    """The Euler time grid as a tuple of Python floats holding the reference's fp32 values (flow_matching.py:56-58 /
+    340-342: ``linspace`` then ``1 - cos(t * 0.5 * pi)``, all in fp32).  Constant for given arguments, so
+    torch.compile folds it."""
+    t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)
+    if scheduler == "cosine":
+        t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
+    return tuple(float(v) for v in t_span)
 
 
 class CausalConditionalDecoder(nn.Module):
@@ -91,6 +107,10 @@ class CausalConditionalDecoder(nn.Module):
 
     @torch.inference_mode()
     def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
+        return self.run(x, mask, mu, t, spks, cond, streaming)
+
+    def run(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
+        """``forward`` without the inference_mode decorator (the form torch.compile traces)."""
         dev = x.device
         if x.dim() != 3 or x.shape[1] != self.out_channels or x.shape[2] < 1:
             raise ValueError(f"x must be [rows, {self.out_channels}, T >= 1], got {tuple(x.shape)}")
@@ -100,12 +120,13 @@ class CausalConditionalDecoder(nn.Module):
         if tuple(mu.shape) != (rows, F, T) or tuple(cond.shape) != (rows, F, T) or tuple(mask.shape) != (rows, 1, T) \
                 or tuple(spks.shape) != (rows, F):
             raise ValueError("estimator inputs: x, mu, cond [rows,80,T], mask [rows,1,T], spks [rows,80]")
-        _check_prefix_mask(mask)
+        _check_prefix_mask(mask, self.precision == "fp32")
         t = t.reshape(-1).expand(rows) if t.numel() == 1 else t
         if t.numel() != rows:
             raise ValueError(f"t must have {rows} entries")
-        out = self.handle(dev).estimator_forward(_as_f32(x, dev), _as_f32(mask, dev), _as_f32(mu, dev),
-                                                 _as_f32(t, dev), _as_f32(spks, dev), _as_f32(cond, dev), streaming)
+        out = torch.ops.ls_b200.estimator_forward(self.handle(dev).key, _as_f32(x, dev), _as_f32(mask, dev),
+                                                  _as_f32(mu, dev), _as_f32(t, dev), _as_f32(spks, dev),
+                                                  _as_f32(cond, dev), bool(streaming))
         return out.to(x.dtype)
 
 
@@ -122,10 +143,8 @@ class ConditionalCFM(nn.Module):
 
     # -- helpers ------------------------------------------------------------------------------
     def _t_span(self, n_timesteps):
-        t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)  # schedule kept in fp32
-        if self.t_scheduler == "cosine":
-            t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
-        return t_span
+        """fp32 tensor of the schedule; ``_t_span_values`` is the same thing as Python floats."""
+        return torch.tensor(_t_span_values(int(n_timesteps), self.t_scheduler), dtype=torch.float32)
 
     def _check_inputs(self, mu, mask, spks, cond, n_timesteps):
         """Shapes are validated here: past this point only raw pointers and sizes cross the C ABI."""
@@ -148,14 +167,15 @@ class ConditionalCFM(nn.Module):
         B, F, T = mu.shape
         if z.dim() != 3 or z.shape[1] != F or z.shape[2] < T:
             raise ValueError(f"noise must be [1, {F}, >= {T}], got {tuple(z.shape)}")
-        _check_prefix_mask(mask)
+        _check_prefix_mask(mask, self.estimator.precision == "fp32")
         if z.shape[0] != 1:
             raise NotImplementedError("per-utterance noise: pass z with a single leading row shared by the batch")
         spks = torch.zeros(B, F, device=dev) if spks is None else spks
         cond = torch.zeros_like(mu) if cond is None else cond
         h = self.estimator.handle(dev)
-        return h.solve(_as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev), _as_f32(cond, dev), z[0],
-                       t_span.numpy(), 1.0, self.inference_cfg_rate, streaming)
+        return torch.ops.ls_b200.flow_solve(h.key, _as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev),
+                                            _as_f32(cond, dev), z[0], [float(v) for v in t_span], 1.0,
+                                            float(self.inference_cfg_rate), bool(streaming))
 
     # -- reference surface --------------------------------------------------------------------
     @torch.inference_mode()
@@ -175,11 +195,11 @@ class ConditionalCFM(nn.Module):
         z_cache = torch.concat([z[:, :, :prompt_len], z[:, :, -34:]], dim=2)
         mu_cache = torch.concat([mu[:, :, :prompt_len], mu[:, :, -34:]], dim=2)
         cache = torch.stack([z_cache, mu_cache.to(z_cache)], dim=-1)
-        return self._solve(z, self._t_span(n_timesteps), mu, mask, spks, cond), cache
+        return self._solve(z, _t_span_values(int(n_timesteps), self.t_scheduler), mu, mask, spks, cond), cache
 
     def solve_euler(self, x, t_span, mu, mask, spks, cond, streaming=False):
         """flow_matching.py:74-126; ``x`` is the initial noise."""
-        return self._solve(_as_f32(x, mu.device), t_span.detach().float().cpu(), mu, mask, spks, cond, streaming)
+        return self._solve(_as_f32(x, mu.device), t_span.detach().float().cpu().tolist(), mu, mask, spks, cond, streaming)
 
     def forward_estimator(self, x, mask, mu, t, spks, cond, streaming=False):
         """flow_matching.py:128-155 (nn.Module branch)."""
@@ -208,16 +228,21 @@ class CausalConditionalCFM(ConditionalCFM):
     @torch.inference_mode()
     def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False):
         """flow_matching.py:323-348 -> ``(latent [B,80,T] fp32, None)``; B >= 1 (per-utterance semantics)."""
+        return self.run(mu, mask, n_timesteps, temperature, spks, cond, streaming)
+
+    def run(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False):
+        """``forward`` without the inference_mode decorator (the form torch.compile traces)."""
         dev = mu.device
         self._check_inputs(mu, mask, spks, cond, n_timesteps)
         B, F, T = mu.shape
         if T > self.rand_noise.shape[2]:
             raise ValueError(f"T={T} exceeds the fixed-noise buffer ({self.rand_noise.shape[2]} frames)")
-        _check_prefix_mask(mask)
+        _check_prefix_mask(mask, self.estimator.precision == "fp32")
         spks = torch.zeros(B, F, device=dev) if spks is None else spks
         cond = torch.zeros_like(mu) if cond is None else cond
         h = self.estimator.handle(dev)
-        out = h.solve(_as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev), _as_f32(cond, dev),
-                      self._noise_on(dev)[0], self._t_span(n_timesteps).numpy(), temperature,
-                      self.inference_cfg_rate, streaming)
+        out = torch.ops.ls_b200.flow_solve(h.key, _as_f32(mu, dev), _as_f32(mask, dev), _as_f32(spks, dev),
+                                           _as_f32(cond, dev), self._noise_on(dev)[0],
+                                           list(_t_span_values(int(n_timesteps), self.t_scheduler)), float(temperature),
+                                           float(self.inference_cfg_rate), bool(streaming))
         return out, None

@@ -19,7 +19,8 @@ EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create
            "ls_speaker_create", "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
-           "ls_dac_decode", "ls_synthesize_host", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
+           "ls_dac_decode", "ls_synthesize_host", "ls_mask_to_lengths", "ls_graph_create", "ls_graph_buffer",
+           "ls_graph_launch", "ls_graph_kernel_count", "ls_graph_destroy", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
 
 
 class LsTensor(C.Structure):
@@ -64,14 +65,19 @@ def lib_path():
 
 
 def load():
-    """Load (building first if the .so is missing or stale and nvcc is present)."""
+    """Load the library, building it first when the .so is missing or was built from other sources (content hash of
+    csrc/ + the header, see build.is_stale).  LS_NO_REBUILD=1 loads a stale library as is, with a warning."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
         path = _build.LIB
-        if not os.path.exists(path):
-            _build.build()
+        if _build.is_stale():
+            if os.path.exists(path) and os.environ.get("LS_NO_REBUILD") == "1":
+                import warnings
+                warnings.warn(f"{path} was not built from the current csrc/ (LS_NO_REBUILD=1: loading it anyway)")
+            else:
+                _build.build()
         try:
             lib = C.CDLL(path)
         except OSError as e:
@@ -106,6 +112,15 @@ def load():
         lib.ls_speaker_destroy.restype = None
         lib.ls_speaker_encode.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
+        lib.ls_mask_to_lengths.argtypes = [vp, vp, i32, i32, vp]
+        lib.ls_graph_create.argtypes = [vp, vp, vp, i64, vp, i32, f32, f32, i32, i32, i32, vp, C.POINTER(vp)]
+        lib.ls_graph_buffer.argtypes = [vp, i32]
+        lib.ls_graph_buffer.restype = vp
+        lib.ls_graph_launch.argtypes = [vp, vp]
+        lib.ls_graph_kernel_count.argtypes = [vp]
+        lib.ls_graph_kernel_count.restype = i64
+        lib.ls_graph_destroy.argtypes = [vp]
+        lib.ls_graph_destroy.restype = None
         lib.ls_debug_set_buffer.argtypes = [vp, i64]
         lib.ls_profile_end.argtypes = [C.POINTER(ProfileEntry), i32]
         lib.ls_test_tblock.argtypes = [vp] * 10 + [i32, i32, i32, vp]
@@ -186,6 +201,8 @@ class FlowHandle:
         with torch.cuda.device(self.device):
             check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_flow_create")
         self._h = h
+        from . import ops
+        self.key = ops.register_handle(self)  # the handle argument of torch.ops.ls_b200.*
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -203,7 +220,7 @@ class FlowHandle:
     def solve(self, mu, mask, spks, cond, noise, t_span, temperature, cfg_rate, streaming=False):
         B, F, T = mu.shape
         out = torch.empty(B, F, T, device=mu.device, dtype=torch.float32)
-        ts = np.ascontiguousarray(t_span, dtype=np.float32)
+        ts = np.ascontiguousarray(t_span, dtype=np.float32)  # (a list of Python floats holding fp32 values round-trips)
         check(load().ls_flow_solve(self._h, ptr(mu), ptr(mask), ptr(spks), ptr(cond), ptr(noise),
                                    noise.stride(-2), C.c_void_p(ts.ctypes.data), len(ts) - 1, float(temperature),
                                    float(cfg_rate), int(bool(streaming)), ptr(out), B, T,
@@ -281,6 +298,8 @@ class DacHandle:
         with torch.cuda.device(self.device):
             check(create(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_dac_create")
         self._h = h
+        from . import ops
+        self.key = ops.register_handle(self)
         self.hop_length = int(lib.ls_dac_hop_length(h))
         self.latent_dim = 80
         for k, v in state_dict.items():
@@ -308,12 +327,89 @@ class DacHandle:
         return wav
 
 
+def mask_to_lengths(mask):
+    """mask [B,1,T] float32 (device) -> int32 [B]: valid frames per utterance."""
+    B, _, T = mask.shape
+    out = torch.empty(B, device=mask.device, dtype=torch.int32)
+    check(load().ls_mask_to_lengths(ptr(mask), ptr(out), B, T, current_stream_ptr(mask.device)), "ls_mask_to_lengths")
+    return out
+
+
+def _host_f32(name, t, shape):
+    """Host buffers cross the C ABI as raw pointers: they must be CPU, float32, contiguous and of the expected shape
+    (anything else would be copied as raw bytes)."""
+    if not isinstance(t, torch.Tensor) or t.device.type != "cpu":
+        raise ValueError(f"{name} must be a CPU tensor (host buffer), got {getattr(t, 'device', type(t))}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
 def synthesize_host(flow, dac, mu, mask, spks, cond, noise_dev, t_span, temperature, cfg_rate, wav_out):
     """End-to-end call on HOST tensors (pinned preferred): copies, solve, decode and read-back inside."""
-    B, _, T = mu.shape
+    if mu.dim() != 3:
+        raise ValueError(f"mu must be [B, F, T], got {tuple(mu.shape)}")
+    B, F, T = mu.shape
+    mu = _host_f32("mu", mu, (B, F, T))
+    mask = _host_f32("mask", mask, (B, 1, T))
+    spks = _host_f32("spks", spks, (B, F))
+    cond = _host_f32("cond", cond, (B, F, T))
+    if not isinstance(wav_out, torch.Tensor) or wav_out.device.type != "cpu" or wav_out.dtype != torch.float32 or \
+            not wav_out.is_contiguous() or tuple(wav_out.shape) != (B, 1, T * dac.hop_length):
+        raise ValueError(f"wav_out must be a contiguous float32 CPU tensor [{B}, 1, {T * dac.hop_length}]")
+    if noise_dev.device.type != "cuda" or noise_dev.dtype != torch.float32 or noise_dev.stride(-1) != 1:
+        raise ValueError("noise must be a float32 CUDA tensor with a contiguous last dim")
     ts = np.ascontiguousarray(t_span, dtype=np.float32)
     check(load().ls_synthesize_host(flow._h, dac._h, ptr(mu), ptr(mask), ptr(spks), ptr(cond), ptr(noise_dev),
                                     noise_dev.stride(-2), C.c_void_p(ts.ctypes.data), len(ts) - 1,
                                     float(temperature), float(cfg_rate), ptr(wav_out), B, T,
                                     current_stream_ptr(flow.device)), "ls_synthesize_host")
     return wav_out
+
+
+class GraphHandle:
+    """Owns an ls_graph*: one (B, T, n_timesteps) solve (+ decode) captured as a CUDA graph over static buffers."""
+
+    def __init__(self, flow, dac, noise_dev, t_span, temperature, cfg_rate, streaming, B, T):
+        lib = load()
+        self.flow, self.dac, self.noise = flow, dac, noise_dev  # keep the handles and the noise buffer alive
+        self.device = flow.device
+        ts = np.ascontiguousarray(t_span, dtype=np.float32)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ls_graph_create(flow._h, dac._h if dac is not None else None, ptr(noise_dev), noise_dev.stride(-2),
+                                      C.c_void_p(ts.ctypes.data), len(ts) - 1, float(temperature), float(cfg_rate),
+                                      int(bool(streaming)), B, T, current_stream_ptr(self.device), C.byref(h)),
+                  "ls_graph_create")
+        self._h = h
+        F = 80
+        hop = dac.hop_length if dac is not None else 0
+        shapes = [(B, F, T), (B, 1, T), (B, F), (B, F, T), (B, F, T), (B, 1, T * hop)]
+        self.buffers = []
+        for i, shp in enumerate(shapes):
+            p = lib.ls_graph_buffer(h, i)
+            self.buffers.append(_wrap_device_f32(p, shp, self.device) if p else None)
+        self.kernels = int(lib.ls_graph_kernel_count(h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ls_graph_destroy(h)
+
+    def launch(self):
+        check(load().ls_graph_launch(self._h, current_stream_ptr(self.device)), "ls_graph_launch")
+
+
+class _CudaArray:
+    """__cuda_array_interface__ view of library-owned device memory (no copy, no ownership)."""
+
+    def __init__(self, p, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(p), False), "version": 3,
+                                         "strides": None}
+
+
+def _wrap_device_f32(p, shape, device):
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArray(p, shape), device=device)

@@ -12,13 +12,18 @@ class Synthesizer:
 
     def __init__(self, cfm, dac):
         self.cfm, self.dac = cfm, dac
+        self._graphs = {}
 
     @torch.inference_mode()
     def __call__(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, streaming=False):
-        lat, _ = self.cfm(mu=mu, mask=mask, n_timesteps=n_timesteps, temperature=temperature, spks=spks, cond=cond,
-                          streaming=streaming)
-        lengths = mask[:, 0, :].ne(0).sum(-1).to(torch.int32)
-        return self.dac.decode(lat, lengths)
+        return self.run(mu, mask, spks, cond, n_timesteps, temperature, streaming)
+
+    def run(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, streaming=False):
+        """``__call__`` without the inference_mode decorator: three ``torch.ops.ls_b200`` calls and nothing else on the
+        device (the form ``torch.compile(fullgraph=True)`` traces)."""
+        lat, _ = self.cfm.run(mu, mask, n_timesteps, temperature, spks, cond, streaming)
+        lengths = torch.ops.ls_b200.mask_to_lengths(mask.to(dtype=torch.float32).contiguous())
+        return self.dac.run(lat, lengths)
 
     @torch.inference_mode()
     def synthesize_host(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, wav_out=None, device=None):
@@ -32,6 +37,28 @@ class Synthesizer:
         return native.synthesize_host(flow_h, dac_h, mu, mask, spks, cond, self.cfm._noise_on(device)[0],
                                       self.cfm._t_span(n_timesteps).numpy(), temperature,
                                       self.cfm.inference_cfg_rate, wav_out)
+
+    @torch.inference_mode()
+    def graphed(self, mu, mask, spks, cond, n_timesteps=10, temperature=1.0, streaming=False):
+        """The same result as ``__call__`` through a CUDA graph captured once per (B, T, n_timesteps, temperature,
+        streaming): ~1800 kernel launches become one cudaGraphLaunch (the form for launch-bound small batches, e.g.
+        one 10 s utterance).  Inputs are copied into the graph's static buffers; the returned waveform is a view of
+        its static output buffer, overwritten by the next call with the same shape."""
+        dev = mu.device
+        B, _, T = mu.shape
+        key = (str(dev), B, T, int(n_timesteps), float(temperature), bool(streaming))
+        g = self._graphs.get(key)
+        if g is None:
+            if self.cfm.estimator.precision != "bf16" or self.dac.precision != "bf16":
+                raise NotImplementedError("CUDA-graph replay covers the tensor-core path (precision='bf16')")
+            g = native.GraphHandle(self.cfm.estimator.handle(dev), self.dac.handle(dev), self.cfm._noise_on(dev)[0],
+                                   self.cfm._t_span(n_timesteps).numpy(), temperature, self.cfm.inference_cfg_rate,
+                                   streaming, B, T)
+            self._graphs[key] = g
+        g_mu, g_mask, g_spks, g_cond, _, g_wav = g.buffers
+        g_mu.copy_(mu), g_mask.copy_(mask), g_spks.copy_(spks), g_cond.copy_(cond)
+        g.launch()
+        return g_wav
 
 
 def utterance_cost(frames):
@@ -138,16 +165,19 @@ def gather_waveforms(wav, n_samples, index, dst=0, group=None, plan=None):
     smax = int(max(m[1] for m in metas))
     pad = torch.zeros(bmax, smax + 2, device=dev, dtype=torch.float32)
     pad[:b, :wav.shape[-1]] = wav[:, 0, :]
-    pad[:b, smax] = torch.as_tensor(n_samples, device=dev, dtype=torch.float32)
-    pad[:b, smax + 1] = torch.as_tensor(index, device=dev, dtype=torch.float32)
+    # counts and ids travel bit-cast as int32 inside the float payload (a float32 VALUE would round above 2^24)
+    pad_i = pad.view(torch.int32)
+    pad_i[:b, smax] = torch.as_tensor(n_samples, device=dev, dtype=torch.int32)
+    pad_i[:b, smax + 1] = torch.as_tensor(index, device=dev, dtype=torch.int32)
     out = exchange(pad, bmax, smax + 2)
     if rank != dst:
         return None
     res = {}
+    out_i = out.view(torch.int32)
     for r in range(world):
         for i in range(int(metas[r][0])):
-            n = int(out[r, i, smax])
-            res[int(out[r, i, smax + 1])] = out[r, i, :n]
+            n = int(out_i[r, i, smax])
+            res[int(out_i[r, i, smax + 1])] = out[r, i, :n]
     return res
 
 

@@ -23,6 +23,7 @@ ESTIMATOR_CFG = dict(in_channels=320, out_channels=80, channels=256, n_blocks=4,
                      num_heads=8, head_dim=64, static_chunk_size=50)  # speech/config.yaml:105-116
 DAC_CFG = dict(latent_dim=80, decoder_dim=1536, decoder_rates=(5, 4, 4, 3, 2), d_out=1,
                sample_rate=24000)  # dac-vae/configs/configx2.yml
+TRAINED_GAIN = 1.5  # weight_g multiplier of init="trained" (DAC): activations of O(10) at the Snake inputs
 CFG_RATE = 0.7  # speech/config.yaml:99
 NOISE_FRAMES = 50 * 300  # flow_matching.py:321
 
@@ -100,7 +101,8 @@ def estimator_state_dict(seed=1986, init="reference", in_channels=320, out_chann
 def dac_decoder_state_dict(seed=0, init="reference", latent_dim=80, decoder_dim=1536,
                            decoder_rates=(5, 4, 4, 3, 2), d_out=1, **_):
     """Keys/shapes of the ``decoder.*`` + ``de_conv_pre.*`` part of ``DACVAE.state_dict()``."""
-    test = init == "test"
+    trained = init == "trained"  # "test" + the regime of a trained checkpoint: Snake alpha = O(1), activations = O(10)
+    test = init == "test" or trained
     sd = {}
 
     def wn(name, w_shape, fan_in, n_bias, transpose=False):
@@ -108,13 +110,18 @@ def dac_decoder_state_dict(seed=0, init="reference", latent_dim=80, decoder_dim=
         g = v.reshape(w_shape[0], -1).norm(dim=1).reshape(w_shape[0], 1, 1)
         if test:
             g = g * _uniform(seed, name + ".weight_g", (w_shape[0], 1, 1), 0.3).add(1.0)
+        if trained:
+            g = g * TRAINED_GAIN
         sd[name + ".bias"] = (_uniform(seed, name + ".bias", (n_bias,), 1.0 / math.sqrt(fan_in)) if test
                               else torch.zeros(n_bias))
         sd[name + ".weight_g"] = g
         sd[name + ".weight_v"] = v
 
     def snake(name, c):
-        sd[name + ".alpha"] = _normal(seed, name + ".alpha", (1, c, 1), math.sqrt(2.0 / (c + 1)))
+        if trained:  # alpha in [0.5, 2]: |alpha * x| reaches tens of radians (the range-reduction regime of sin)
+            sd[name + ".alpha"] = _uniform(seed, name + ".alpha", (1, c, 1), 0.75).add(1.25)
+        else:
+            sd[name + ".alpha"] = _normal(seed, name + ".alpha", (1, c, 1), math.sqrt(2.0 / (c + 1)))
 
     def conv(name, cout, cin, k):  # WNConv1d shadow adds the trailing ".0" (dac-vae/model.py:509-514)
         wn(name + ".0", (cout, cin, k), cin * k, cout)

@@ -66,9 +66,63 @@ def pipeline_golden():
         np.savez_compressed(os.path.join(OUT, "pipeline_golden.npz"), **out)
 
 
+NC_SEED_1, NC_SEED_2 = 501, 502   # torch.manual_seed before each non-causal forward (its z = torch.randn_like(mu))
+DAC_TRAINED_SEED = 21
+
+
+def extra_golden():
+    """Round-2 fixtures (own files: the round-1 fixtures stay byte-identical).
+
+    cfm_nc_golden.npz     the non-causal twin ``ConditionalCFM.forward`` (flow_matching.py:39-72) called twice on the
+                          unmodified reference: prompt_len = 20 with an empty cache, then with the returned cache
+                          (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
+    dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
+                          Snake alpha in [0.5, 2], activations of O(10), |alpha * x| up to ~25 rad), layers.py:18-33.
+    """
+    os.makedirs(OUT, exist_ok=True)
+    with torch.inference_mode():
+        sd = synth.estimator_state_dict(EST_SEED, init="test")
+        cfm = R.build_reference_flow()
+        cfm.estimator.load_state_dict(sd, strict=True)
+        nc_forward = type(cfm).__mro__[1].forward  # ConditionalCFM.forward, the parent's (non-causal) method
+        assert type(cfm).__mro__[1].__name__ == "ConditionalCFM"
+        out = {"weights_seed": EST_SEED, "weights_checksum": synth.checksum(sd), "prompt_len": 20, "steps": 3}
+        cache = torch.zeros(1, 80, 0, 2)
+        for i, (T, seed) in enumerate([(70, NC_SEED_1), (90, NC_SEED_2)], 1):
+            mu, mask, spks, cond = synth.batch_inputs([T], first_index=70 + i)
+            torch.manual_seed(seed)
+            z = torch.randn_like(mu)  # what the forward below draws (same seed, same shape)
+            torch.manual_seed(seed)
+            y, cache = nc_forward(cfm, mu.clone(), mask, 3, temperature=0.8, spks=spks, cond=cond, prompt_len=20, cache=cache)
+            out[f"nc_{i}_T"], out[f"nc_{i}_index"] = T, 70 + i
+            out[f"nc_{i}_z"], out[f"nc_{i}_y"], out[f"nc_{i}_cache"] = z.numpy(), y.numpy(), cache.numpy()
+            print("cfm non-causal", i, y.shape, cache.shape, float(y.abs().mean()))
+        np.savez_compressed(os.path.join(OUT, "cfm_nc_golden.npz"), **out)
+
+        sd = synth.dac_decoder_state_dict(DAC_TRAINED_SEED, init="trained")
+        dac = R.build_reference_dac()
+        missing, unexpected = dac.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith(("encoder.", "en_conv_post.")) for k in missing), (missing[:5], unexpected)
+        out = {"weights_seed": DAC_TRAINED_SEED, "weights_checksum": synth.checksum(sd)}
+        peak = [0.0]
+        for n, m in dac.named_modules():
+            if m.__class__.__name__ == "Snake1d" and n.startswith("decoder"):
+                m.register_forward_hook(lambda mod, inp, o: peak.__setitem__(0, max(peak[0], float((inp[0].abs() * mod.alpha.abs()).max()))))
+        for name, frames, idx in [("a", 20, 3), ("b", 5, 4)]:
+            z = synth.dac_latents(idx, frames)
+            y = dac.decode(z)
+            out[f"dac_{name}_frames"], out[f"dac_{name}_index"], out[f"dac_{name}_y"] = frames, idx, y.numpy()
+            print("dac trained-scale", name, y.shape, float(y.abs().max()), float(y.abs().mean()))
+        out["max_abs_alpha_x"] = peak[0]
+        print("max |alpha * x| at a Snake input:", peak[0])
+        np.savez_compressed(os.path.join(OUT, "dac_trained_golden.npz"), **out)
+
+
 def main():
     if "--pipeline-only" in sys.argv:
         return pipeline_golden()
+    if "--extra-only" in sys.argv:
+        return extra_golden()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     with torch.inference_mode():
@@ -181,6 +235,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, "speaker_golden.npz"), **out)
 
         pipeline_golden()
+        extra_golden()
 
         # ---- key schema of the reference state_dicts (drop-in modules must expose exactly these) ----
         import json

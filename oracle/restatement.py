@@ -185,6 +185,26 @@ def cfm_forward(sd, noise, mu, mask, n_timesteps, temperature=1.0, spks=None, co
     return solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate, streaming, heads, chunk)
 
 
+def cfm_forward_cached(sd, z, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, prompt_len=0, cache=None,
+                       cfg_rate=0.7, heads=8, chunk=50):
+    """The non-causal twin ``ConditionalCFM.forward`` flow_matching.py:39-72 (batch 1): ``z`` is the injected
+    ``torch.randn_like(mu)`` sample (before temperature); the first ``cache.shape[2]`` frames of z and mu are replaced by
+    the cached prompt + overlap frames (:60-64), the new cache is [z | mu] over the first ``prompt_len`` and the last 34
+    frames (:65-67).  Returns (latent, cache [1,80,prompt_len+34,2]); ``mu`` is NOT modified in place here."""
+    z = z.to(mu.dtype) * temperature
+    mu = mu.clone()
+    if cache is not None and cache.shape[2] != 0:
+        n = cache.shape[2]
+        z = z.clone()
+        z[:, :, :n] = cache[:, :, :, 0]
+        mu[:, :, :n] = cache[:, :, :, 1]
+    z_cache = torch.cat([z[:, :, :prompt_len], z[:, :, -34:]], dim=2)
+    mu_cache = torch.cat([mu[:, :, :prompt_len], mu[:, :, -34:]], dim=2)
+    new_cache = torch.stack([z_cache, mu_cache], dim=-1)
+    t_span = cosine_t_span(n_timesteps, mu.dtype).to(mu.device)
+    return solve_euler(sd, z, t_span, mu, mask, spks, cond, cfg_rate, False, heads, chunk), new_cache
+
+
 # --------------------------------------------------------------------------------------
 # DAC-VAE decoder
 # --------------------------------------------------------------------------------------

@@ -98,12 +98,24 @@ def test_config3_32steps_30s_batch32(models):
     for b in (5, 31):
         e = O.rel_l2(lat[b].cpu(), _single(cfm, mu, mask, spks, cond, b, T, 32))
         assert e < 1e-5, (b, e)
-    # oracle at full length, 2 steps (the per-step arithmetic is the same for every step count)
-    y2 = _single(cfm, mu, mask, spks, cond, 2, T, 2)
+    # the whole 32-step solve of one 30 s utterance of the batch against the CPU oracle (bf16 rounding accumulates over
+    # the Euler steps: this is the configuration the 1e-2 bar is about)
     with torch.inference_mode():
-        ref = O.cfm_forward(esd, synth.fixed_noise(), mu[2:3], mask[2:3], 2, 1.0, spks[2:3], cond[2:3])
-    e = O.rel_l2(y2[None], ref)
-    print(f"config 3 shape (T = 1500), 2 steps: latent rel-L2 {e:.3e}")
+        ref = O.cfm_forward(esd, synth.fixed_noise(), mu[2:3], mask[2:3], 32, 1.0, spks[2:3], cond[2:3])
+    e = O.rel_l2(lat[2:3].cpu(), ref)
+    print(f"config 3 (T = 1500, 32 steps, utterance 2 of the batch): latent rel-L2 {e:.3e}")
+    assert e < LATENT_TOL
+
+
+def test_config3_32steps_vs_oracle_6s(models):
+    """32 Euler steps + CFG against the oracle at a second length (T = 300), a separate call at batch 1."""
+    esd, dsd, cfm, dac = models
+    mu, mask, spks, cond = synth.batch_inputs([300], first_index=340)
+    y = _single(cfm, mu, mask, spks, cond, 0, 300, 32)
+    with torch.inference_mode():
+        ref = O.cfm_forward(esd, synth.fixed_noise(), mu, mask, 32, 1.0, spks, cond)
+    e = O.rel_l2(y[None], ref)
+    print(f"config 3 step count at T = 300: latent rel-L2 {e:.3e}")
     assert e < LATENT_TOL
 
 

@@ -158,3 +158,35 @@ def test_flow_inference_matches_reference(golden_dir, case):
     ref = torch.from_numpy(g[f"pipe_{case}_y"])
     assert y.shape == ref.shape
     assert O.rel_l2(y, ref) < 1e-5
+
+
+# ---- round-2 fixtures: the non-causal ConditionalCFM.forward (prompt / overlap cache) and a trained-scale DAC ----
+def test_noncausal_cfm_cache_path_matches_reference(golden_dir):
+    """flow_matching.py:39-72 on the unmodified reference: first call with an empty cache, second call reusing the
+    returned cache (its z and mu frames overwrite the head of the new call's z and mu)."""
+    g = np.load(os.path.join(golden_dir, "cfm_nc_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    cache = None
+    for i in (1, 2):
+        T = int(g[f"nc_{i}_T"])
+        mu, mask, spks, cond = synth.batch_inputs([T], first_index=int(g[f"nc_{i}_index"]))
+        with torch.inference_mode():
+            y, cache = O.cfm_forward_cached(sd, torch.from_numpy(g[f"nc_{i}_z"]), mu, mask, int(g["steps"]), 0.8, spks, cond,
+                                            prompt_len=int(g["prompt_len"]), cache=cache)
+        assert tuple(cache.shape) == (1, 80, int(g["prompt_len"]) + 34, 2)
+        assert torch.equal(cache, torch.from_numpy(g[f"nc_{i}_cache"]))
+        assert O.rel_l2(y, torch.from_numpy(g[f"nc_{i}_y"])) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_dac_trained_scale_matches_reference(golden_dir, case):
+    """Snake alpha in [0.5, 2] and activations of O(10) (the regime of a trained checkpoint, layers.py:18-33)."""
+    g = np.load(os.path.join(golden_dir, "dac_trained_golden.npz"))
+    sd = synth.dac_decoder_state_dict(int(g["weights_seed"]), init="trained")
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    assert float(g["max_abs_alpha_x"]) > 10.0  # the fixture really is in the large-argument regime of sin
+    z = synth.dac_latents(int(g[f"dac_{case}_index"]), int(g[f"dac_{case}_frames"]))
+    with torch.inference_mode():
+        y = O.dac_decode(sd, z)
+    assert O.snr_db(y, torch.from_numpy(g[f"dac_{case}_y"])) > 90.0

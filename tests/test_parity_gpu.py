@@ -152,3 +152,49 @@ def test_end_to_end_latents_to_waveform(flow, dac):
         wav_ref = O.dac_decode(dsd, lat_ref)
     print(f"e2e latent rel-L2 {O.rel_l2(lat.cpu(), lat_ref):.3e}  waveform SNR {O.snr_db(wav, wav_ref):.1f} dB")
     assert O.rel_l2(lat.cpu(), lat_ref) < LATENT_TOL
+
+
+# ---- round 2: non-causal ConditionalCFM.forward (prompt / overlap cache), trained-scale DAC ----
+def test_noncausal_cfm_cache_path_vs_reference_golden(golden_dir):
+    """The non-causal twin (flow_matching.py:39-72) with prompt_len = 20: first call with an empty cache, second call
+    with the returned cache reused; injected noise = the z the reference drew."""
+    from minimax_speech_b200.flow import ConditionalCFM
+    g = np.load(os.path.join(golden_dir, "cfm_nc_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test")
+    est = CausalConditionalDecoder()
+    est.load_state_dict(sd)
+    cfm = ConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    cache = None
+    for i in (1, 2):
+        T = int(g[f"nc_{i}_T"])
+        mu, mask, spks, cond = synth.batch_inputs([T], first_index=int(g[f"nc_{i}_index"]))
+        mu_dev = mu.to(DEV)
+        y, cache = cfm(mu_dev, mask.to(DEV), int(g["steps"]), temperature=0.8, spks=spks.to(DEV), cond=cond.to(DEV),
+                       prompt_len=int(g["prompt_len"]), cache=cache, noise=torch.from_numpy(g[f"nc_{i}_z"]))
+        ref_cache = torch.from_numpy(g[f"nc_{i}_cache"])
+        assert tuple(cache.shape) == tuple(ref_cache.shape)
+        assert torch.equal(cache.cpu(), ref_cache)  # bookkeeping only: exact
+        if i == 2:  # like the reference, the call overwrote the head of the caller's mu with the cached frames (:62-64)
+            assert torch.equal(mu_dev[:, :, :54].cpu(), torch.from_numpy(g["nc_1_cache"])[:, :, :, 1])
+        e = O.rel_l2(y.cpu(), torch.from_numpy(g[f"nc_{i}_y"]))
+        print(f"non-causal cfm call {i} rel-L2 {e:.3e}")
+        assert e < LATENT_TOL
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_dac_trained_scale_vs_reference_golden(golden_dir, case):
+    """Snake at trained scale: alpha in [0.5, 2], |alpha * x| up to ~25 rad (layers.py:18-33) on the tensor-core path."""
+    g = np.load(os.path.join(golden_dir, "dac_trained_golden.npz"))
+    sd = synth.dac_decoder_state_dict(int(g["weights_seed"]), init="trained")
+    dec = DACVAEDecoder()
+    dec.load_state_dict(sd)
+    z = synth.dac_latents(int(g[f"dac_{case}_index"]), int(g[f"dac_{case}_frames"]))
+    y = dec.decode(z.to(DEV)).cpu()
+    s = O.snr_db(y, torch.from_numpy(g[f"dac_{case}_y"]))
+    print(f"dac trained-scale {case} SNR {s:.1f} dB")
+    assert s > SNR_MIN_DB
+    dec32 = DACVAEDecoder(precision="fp32")
+    dec32.load_state_dict(sd)
+    s32 = O.snr_db(dec32.decode(z.to(DEV)).cpu(), torch.from_numpy(g[f"dac_{case}_y"]))
+    print(f"dac trained-scale {case} fp32 mode SNR {s32:.1f} dB")
+    assert s32 > 80.0
