@@ -61,6 +61,12 @@ int32_t ls_device_check(int32_t device, int32_t* sm_count, int32_t* cc_major, in
 
 /* ---- flow: CausalConditionalDecoder estimator + Euler/CFG solve ---- */
 int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);
+/* fp16-operand mode: the same tensor-core kernels at the same speed with fp16 instead of bf16 GEMM operands (weights and
+ * activations; accumulation, residual stream, LayerNorm, softmax statistics stay fp32).  fp16 is the format of the
+ * reference's own half-precision path (speech/cosyvoice/cli/model.py:41-43 `.half()`; the TensorRT fp16 flag,
+ * speech/cosyvoice/utils/file_utils.py:63-64,75); three more mantissa bits than bf16: a single estimator call is 1.5e-3
+ * from the fp32 reference instead of 1.2e-2 (the bf16 rounding of the weights alone is 8.6e-3). */
+int32_t ls_flow_create_fp16(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);
 /* fp32 mode (north_star: latents within 1e-4 of the fp32 reference): the same handle type and calls, computed end to
  * end in fp32 on the CUDA cores with unfused kernels.  A validation mode, one to two orders of magnitude slower. */
 int32_t ls_flow_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out);

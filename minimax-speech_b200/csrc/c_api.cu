@@ -254,6 +254,15 @@ int32_t ls_flow_create(const ls_tensor* weights, int32_t n_weights, int32_t devi
     *out = h.release();
   });
 }
+int32_t ls_flow_create_fp16(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_flow_create_fp16: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_flow>();
+    h->eng = std::make_unique<ls::FlowEngine>(w, device, true);
+    *out = h.release();
+  });
+}
 int32_t ls_flow_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_flow** out) {
   return ls::guarded([&] {
     ls::require(weights && out && n_weights > 0, "ls_flow_create_fp32: null argument");
@@ -409,6 +418,7 @@ struct ls_graph {
   int32_t* len = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  cudaStream_t cap = nullptr;  // private capture stream
   unsigned long long gen_flow = 0, gen_dac = 0;
   long long launches = 0;  // kernels per replay
 
@@ -428,17 +438,19 @@ struct ls_graph {
   void capture(cudaStream_t s) {
     drop();
     run(s);  // eager pass: workspace growth, plans, per-device attribute opt-ins all happen outside the capture
+    // the capture runs on a private stream: the caller's stream may be the legacy default stream, which cannot be captured
+    if (!cap) LS_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     const long long before = ls::g_launch_count.load();
-    LS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    LS_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     try {
-      run(s);
+      run(cap);
     } catch (...) {
       cudaGraph_t g = nullptr;
-      cudaStreamEndCapture(s, &g);
+      cudaStreamEndCapture(cap, &g);
       if (g) cudaGraphDestroy(g);
       throw;
     }
-    LS_CUDA(cudaStreamEndCapture(s, &graph));
+    LS_CUDA(cudaStreamEndCapture(cap, &graph));
     launches = ls::g_launch_count.load() - before;
     LS_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     gen_flow = flow->eng ? flow->eng->ws_generation() : 0;
@@ -450,6 +462,7 @@ struct ls_graph {
   }
   ~ls_graph() {
     drop();
+    if (cap) cudaStreamDestroy(cap);
     if (buf) cudaFree(buf);
   }
 };

@@ -99,17 +99,17 @@ struct ChunkStore {
       for (int g = 0; g < 2; ++g) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (st == 2) {
-          v.x = pack_bf16x2(u[8 * g + 0], u[8 * g + 1]);
-          v.y = pack_bf16x2(u[8 * g + 2], u[8 * g + 3]);
-          v.z = pack_bf16x2(u[8 * g + 4], u[8 * g + 5]);
-          v.w = pack_bf16x2(u[8 * g + 6], u[8 * g + 7]);
+          v.x = LS_PACK_H2(u[8 * g + 0], u[8 * g + 1]);
+          v.y = LS_PACK_H2(u[8 * g + 2], u[8 * g + 3]);
+          v.z = LS_PACK_H2(u[8 * g + 4], u[8 * g + 5]);
+          v.w = LS_PACK_H2(u[8 * g + 6], u[8 * g + 7]);
         }
         d[g] = v;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (n + i < n_store) base[flat + i] = __float2bfloat16(st == 2 ? u[i] : 0.f);
+        if (n + i < n_store) reinterpret_cast<uint16_t*>(base)[flat + i] = LS_CVT_H_BITS(st == 2 ? u[i] : 0.f);
     }
   }
 };
@@ -199,9 +199,10 @@ __device__ __forceinline__ void apply_chunk(uint8_t* stg, int lane, const AddReg
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-        v[8 * u + 2 * k] += __low2float(h2);
-        v[8 * u + 2 * k + 1] += __high2float(h2);
+        float lo, hi;
+        LS_UNPACK_H2(w[k], lo, hi);
+        v[8 * u + 2 * k] += lo;
+        v[8 * u + 2 * k + 1] += hi;
       }
     }
   }
@@ -232,8 +233,8 @@ __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRo
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       *reinterpret_cast<uint4*>(stg + stg_b16(lane, u)) =
-          make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+          make_uint4(LS_PACK_H2(v[8 * u], v[8 * u + 1]), LS_PACK_H2(v[8 * u + 2], v[8 * u + 3]),
+                     LS_PACK_H2(v[8 * u + 4], v[8 * u + 5]), LS_PACK_H2(v[8 * u + 6], v[8 * u + 7]));
     __syncwarp();
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
@@ -270,8 +271,8 @@ __device__ __forceinline__ void store_chunk_tma(uint8_t* stg, int lane, const CU
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       *reinterpret_cast<uint4*>(sb + stg_b16(lane, u)) =
-          row_valid ? make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]))
+          row_valid ? make_uint4(LS_PACK_H2(v[8 * u], v[8 * u + 1]), LS_PACK_H2(v[8 * u + 2], v[8 * u + 3]),
+                                 LS_PACK_H2(v[8 * u + 4], v[8 * u + 5]), LS_PACK_H2(v[8 * u + 6], v[8 * u + 7]))
                     : make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
@@ -802,8 +803,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             for (int i = 0; i < 16 && n + i < p.n_store; ++i) {
               const float xv = stt == 2 ? x[i] : 0.f;
               if (out0_dtype == OUT_F32) out0f[flat + i] = xv;
-              else if (out0_dtype == OUT_BF16) out0h[flat + i] = __float2bfloat16(xv);
-              if (out1_mode == OUT1_COPY) out1[flat + i] = __float2bfloat16(xv);
+              else if (out0_dtype == OUT_BF16) reinterpret_cast<uint16_t*>(out0h)[flat + i] = LS_CVT_H_BITS(xv);
+              if (out1_mode == OUT1_COPY) reinterpret_cast<uint16_t*>(out1)[flat + i] = LS_CVT_H_BITS(xv);
             }
           }
         } else {
@@ -900,8 +901,11 @@ cudaError_t launch_instance(int grid, size_t smem, cudaStream_t stream, const CU
 
 }  // namespace
 
-cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
-                             const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
+                                    const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+#if !LS_HALF_FP16
+  if (p.fp16) return launch_conv_gemm_fp16(mapA0, mapA1, mapW, p, num_sms, stream);  // fp16-operand build of this file
+#endif
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.N % p.block_n || p.chan_mod % 16) return cudaErrorInvalidValue;
   if ((p.act == ACT_LN_MISH || p.out1_mode == OUT1_LN) && p.block_n != p.N) return cudaErrorInvalidValue;
   if (p.out1_mode == OUT1_LN && p.out0_dtype != OUT_F32) return cudaErrorInvalidValue;
@@ -1005,6 +1009,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_NONE, OUT_F32, 0)
   LS_CONV_CASE(ACT_NONE, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
+#if !LS_HALF_FP16  // (the fp16-operand build serves the flow estimator only)
   // DAC decoder: de_conv_pre | input conv, conv7 | transposed conv | conv1 + residual (x kept / last unit) | final conv
   LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_NONE, 0)
@@ -1012,6 +1017,7 @@ cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
   LS_CONV_CASE(ACT_LRELU, OUT_F32, OUT1_SNAKE, OUT_F32, 0)
   LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_F32, 0)
   LS_CONV_CASE(ACT_LRELU_TANH, OUT_F32, OUT1_NONE, OUT_NONE, 0)
+#endif
 #undef LS_CONV_CASE
   return launch_instance<-1, -1, -1, -1, -1>(grid, smem, stream, mapA0, mapA1, mapW, *mo0, *mo1, pp, tmem_cols, acc_stride);
 }

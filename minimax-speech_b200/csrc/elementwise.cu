@@ -8,9 +8,14 @@
 namespace ls {
 namespace {
 
+// 16-bit operand format of the destination: bf16 (default) or fp16 (the flow estimator's fp16-operand mode)
+__device__ __forceinline__ void store_h(__nv_bfloat16* dst, long long i, float v, int fp16) {
+  reinterpret_cast<uint16_t*>(dst)[i] = fp16 ? cvt_f16_bits(v) : cvt_bf16_bits(v);
+}
+
 // ---- NCT fp32 -> time-major bf16 (32x32 smem transpose tiles) ----
 __global__ void pack_nct_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int T,
-                                long long src_bstride, int ld, int c_off, const int* __restrict__ lengths) {
+                                long long src_bstride, int ld, int c_off, const int* __restrict__ lengths, int fp16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -23,18 +28,18 @@ __global__ void pack_nct_kernel(const float* __restrict__ src, __nv_bfloat16* __
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (t < T && c < C) dst[((long long)b * T + t) * ld + c_off + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    if (t < T && c < C) store_h(dst, ((long long)b * T + t) * ld + c_off + c, tile[threadIdx.x][i], fp16);
   }
 }
 
 __global__ void pack_bcast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int T,
-                                  int ld, int c_off, const int* __restrict__ lengths) {
+                                  int ld, int c_off, const int* __restrict__ lengths, int fp16) {
   const int b = blockIdx.y;
   const int len = lengths ? min(lengths[b], T) : T;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * C) return;
   const int t = (int)(idx / C), c = (int)(idx % C);
-  dst[((long long)b * T + t) * ld + c_off + c] = __float2bfloat16(t < len ? src[(long long)b * C + c] : 0.f);
+  store_h(dst, ((long long)b * T + t) * ld + c_off + c, t < len ? src[(long long)b * C + c] : 0.f, fp16);
 }
 
 __global__ void pack_zero_kernel(__nv_bfloat16* __restrict__ dst, int C, int T, int ld, int c_off) {
@@ -48,7 +53,7 @@ __global__ void pack_zero_kernel(__nv_bfloat16* __restrict__ dst, int C, int T, 
 // x_state[b][t][c] = noise[c][t]*temperature ; bf16 copies into xin rows b and B+b
 __global__ void init_state_kernel(const float* __restrict__ noise, int noise_ld, float temperature,
                                   float* __restrict__ x_state, __nv_bfloat16* __restrict__ xin, int B, int C, int T,
-                                  int ld, const int* __restrict__ lengths) {
+                                  int ld, const int* __restrict__ lengths, int fp16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -63,9 +68,8 @@ __global__ void init_state_kernel(const float* __restrict__ noise, int noise_ld,
     if (t < T && c < C) {
       const float v = tile[threadIdx.x][i];
       x_state[((long long)b * T + t) * C + c] = v;
-      const __nv_bfloat16 h = __float2bfloat16(v);
-      xin[((long long)b * T + t) * ld + c] = h;
-      xin[((long long)(B + b) * T + t) * ld + c] = h;
+      store_h(xin, ((long long)b * T + t) * ld + c, v, fp16);
+      store_h(xin, ((long long)(B + b) * T + t) * ld + c, v, fp16);
     }
   }
 }
@@ -73,7 +77,7 @@ __global__ void init_state_kernel(const float* __restrict__ noise, int noise_ld,
 // v: [2B][T][C] fp32 time-major (conditional rows first).  4 channels per thread.
 __global__ void cfg_euler_kernel(const float* __restrict__ v, float* __restrict__ x_state,
                                  __nv_bfloat16* __restrict__ xin, int B, int C, int T, int ld, float dt,
-                                 float cfg_rate) {
+                                 float cfg_rate, int fp16) {
   const long long n4 = (long long)B * T * C / 4;
   const long long half = (long long)B * T * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -90,8 +94,8 @@ __global__ void cfg_euler_kernel(const float* __restrict__ v, float* __restrict_
     const long long row = e / C;  // b*T + t
     const int c = (int)(e % C);
     uint2 h;
-    h.x = pack_bf16x2(x.x, x.y);
-    h.y = pack_bf16x2(x.z, x.w);
+    h.x = fp16 ? pack_f16x2(x.x, x.y) : pack_bf16x2(x.x, x.y);
+    h.y = fp16 ? pack_f16x2(x.z, x.w) : pack_bf16x2(x.z, x.w);
     *reinterpret_cast<uint2*>(xin + row * ld + c) = h;
     *reinterpret_cast<uint2*>(xin + (row + (long long)B * T) * ld + c) = h;
   }
@@ -199,18 +203,18 @@ __global__ void __launch_bounds__(256) time_stage_kernel(const TimeStage p) {
 }  // namespace
 
 cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,
-                            int ld, int c_off, const int* lengths, cudaStream_t s) {
+                            int ld, int c_off, const int* lengths, cudaStream_t s, int fp16) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * (4.0 + 2.0));
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  pack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, src_bstride, ld, c_off, lengths);
+  pack_nct_kernel<<<grid, block, 0, s>>>(src, dst, C, T, src_bstride, ld, c_off, lengths, fp16);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bcast(const float* src, __nv_bfloat16* dst, int B, int C, int T, int ld, int c_off,
-                              const int* lengths, cudaStream_t s) {
+                              const int* lengths, cudaStream_t s, int fp16) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * 4.0 + (double)B * C * T * 2.0);
   dim3 grid((unsigned)(((long long)T * C + 255) / 256), B);
-  pack_bcast_kernel<<<grid, 256, 0, s>>>(src, dst, C, T, ld, c_off, lengths);
+  pack_bcast_kernel<<<grid, 256, 0, s>>>(src, dst, C, T, ld, c_off, lengths, fp16);
   count_launch();
   return cudaGetLastError();
 }
@@ -222,21 +226,22 @@ cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, in
   return cudaGetLastError();
 }
 cudaError_t launch_init_state(const float* noise, int noise_ld, float temperature, float* x_state,
-                              __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s) {
+                              __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s,
+                              int fp16) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)C * T * 4.0 + (double)B * C * T * (4.0 + 2.0 * 2.0));
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  init_state_kernel<<<grid, block, 0, s>>>(noise, noise_ld, temperature, x_state, xin, B, C, T, ld, lengths);
+  init_state_kernel<<<grid, block, 0, s>>>(noise, noise_ld, temperature, x_state, xin, B, C, T, ld, lengths, fp16);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin, int B, int C, int T, int ld,
-                             float dt, float cfg_rate, cudaStream_t s) {
+                             float dt, float cfg_rate, cudaStream_t s, int fp16) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * C * T * (2 * 4.0 + 4.0 + 4.0 + 2 * 2.0));
   const long long n4 = (long long)B * T * C / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;
-  cfg_euler_kernel<<<grid, 256, 0, s>>>(v, x_state, xin, B, C, T, ld, dt, cfg_rate);
+  cfg_euler_kernel<<<grid, 256, 0, s>>>(v, x_state, xin, B, C, T, ld, dt, cfg_rate, fp16);
   count_launch();
   return cudaGetLastError();
 }

@@ -5,6 +5,9 @@
 // self-attention core is the flash kernel, everything row-local is fused into GEMM epilogues.
 #include <cmath>
 #include <memory>
+#include <mutex>
+
+#include <cuda_fp16.h>
 
 #include "engine_common.h"
 #include "flow_engine.h"
@@ -12,11 +15,20 @@
 namespace ls {
 namespace {
 
+// 16-bit operand format of a handle: bf16, or fp16 (ls_flow_create_fp16: same kernels, compiled for fp16 operands)
+bool g_pack_fp16 = false;  // set for the duration of a constructor (host-side weight packing only)
+inline __nv_bfloat16 to_h16(float x) {
+  if (!g_pack_fp16) return __float2bfloat16(x);
+  const __half h = __float2half_rn(x);
+  __nv_bfloat16 out;
+  std::memcpy(&out, &h, 2);
+  return out;
+}
 void to_bf16(const float* src, __nv_bfloat16* dst, size_t n) {
-  for (size_t i = 0; i < n; ++i) dst[i] = __float2bfloat16(src[i]);
+  for (size_t i = 0; i < n; ++i) dst[i] = to_h16(src[i]);
 }
 
-// weight [N][K] (linear) or [N][K][taps] (conv1d) -> bf16 [taps][N][K]
+// weight [N][K] (linear) or [N][K][taps] (conv1d) -> 16-bit [taps][N][K]
 PackedLinear pack_linear(Arena& a, const ls_tensor& w, const ls_tensor* bias) {
   PackedLinear pl;
   pl.N = (int)w.shape[0];
@@ -28,7 +40,7 @@ PackedLinear pack_linear(Arena& a, const ls_tensor& w, const ls_tensor* bias) {
   for (int t = 0; t < pl.taps; ++t)
     for (int n = 0; n < pl.N; ++n)
       for (int k = 0; k < pl.K; ++k)
-        dst[((size_t)t * pl.N + n) * pl.K + k] = __float2bfloat16(w.data[((size_t)n * pl.K + k) * pl.taps + t]);
+        dst[((size_t)t * pl.N + n) * pl.K + k] = to_h16(w.data[((size_t)n * pl.K + k) * pl.taps + t]);
   if (bias) {
     require(bias->shape[0] == pl.N, std::string("bias shape mismatch for ") + w.name, LS_ERR_WEIGHTS);
     pl.bias_off = a.put_f32(bias->data, pl.N);
@@ -98,7 +110,10 @@ void FlowEngine::check_sticky() {
   }
 }
 
-FlowEngine::FlowEngine(const Weights& w, int device) : device_(device) {
+FlowEngine::FlowEngine(const Weights& w, int device, bool fp16) : device_(device), fp16_(fp16 ? 1 : 0) {
+  static std::mutex pack_mu;  // g_pack_fp16 is process-wide: constructors are serialised
+  std::lock_guard<std::mutex> pack_lock(pack_mu);
+  g_pack_fp16 = fp16;
   LS_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   LS_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -363,7 +378,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
     p.p1_a = e.p1_a, p.p1_b = e.p1_b, p.n_store = w.N;
     p.out_ld = w.N, p.out_shift = 0, p.out_bstride = (long long)T * w.N, p.out_alloc = (long long)T * w.N;
     p.out_valid_mul = w.N;
-    p.k_true = w.K, p.tag = 0, p.zero_skipped = e.zero_skipped;
+    p.k_true = w.K, p.tag = 0, p.zero_skipped = e.zero_skipped, p.fp16 = fp16_;
     p.halo_mode = halo ? conv_halo_mode() : 0;
     LS_CUDA(launch_conv_gemm(a0, a1 ? *a1 : a0, w.map, p, num_sms_, s));
   };
@@ -400,7 +415,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
     auto attention = [&]() {
       AttnParams ap{};
       ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
-      ap.scale_log2e = 0.125f * 1.4426950408889634f;
+      ap.scale_log2e = 0.125f * 1.4426950408889634f, ap.fp16 = fp16_;
       ap.out = ws<__nv_bfloat16>(o_att_);
       LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
     };
@@ -409,7 +424,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       // every later QKV comes out of the previous block's launch
       {
         TBlockParams tp{};
-        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2;
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2, tp.fp16 = fp16_;
         TBlockMaps tm;
         tm.att = pl.att_flat, tm.wo = g.tb[0].m_out, tm.w1 = g.tb[0].m_ff1, tm.w2 = g.tb[0].m_ff2;  // unused in head mode
         tm.wqkv = g.tb[0].m_qkv, tm.u = pl.u_flat, tm.qkv_out = pl.qkv_flat, tm.tail_out = pl.tail_hB;
@@ -420,7 +435,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         attention();
         const bool last = j + 1 == n_blocks_;
         TBlockParams tp{};
-        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(t.vec), tp.tail_mode = last ? 1 : 0;
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(t.vec), tp.tail_mode = last ? 1 : 0, tp.fp16 = fp16_;
         TBlockMaps tm;
         tm.att = pl.att_flat, tm.wo = t.m_out, tm.w1 = t.m_ff1, tm.w2 = t.m_ff2;
         tm.wqkv = last ? t.m_qkv : g.tb[j + 1].m_qkv;
@@ -440,7 +455,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       {
         AttnParams ap{};
         ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
-        ap.scale_log2e = 0.125f * 1.4426950408889634f;
+        ap.scale_log2e = 0.125f * 1.4426950408889634f, ap.fp16 = fp16_;
         ap.out = ws<__nv_bfloat16>(o_att_);
         LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
       }
@@ -520,10 +535,10 @@ void FlowEngine::estimator_forward(const float* x, const float* mask, const floa
   __nv_bfloat16* xin = ws<__nv_bfloat16>(o_xin_);
   LS_CUDA(launch_mask_to_lengths(mask, lengths, rows, T, 1, s, bad_mask_dev_));
   const long long bs = (long long)feat_ * T;
-  LS_CUDA(launch_pack_nct(x, xin, rows, feat_, T, bs, in_ch_, 0, lengths, s));
-  LS_CUDA(launch_pack_nct(mu, xin, rows, feat_, T, bs, in_ch_, feat_, lengths, s));
-  LS_CUDA(launch_pack_bcast(spks, xin, rows, feat_, T, in_ch_, 2 * feat_, lengths, s));
-  LS_CUDA(launch_pack_nct(cond, xin, rows, feat_, T, bs, in_ch_, 3 * feat_, lengths, s));
+  LS_CUDA(launch_pack_nct(x, xin, rows, feat_, T, bs, in_ch_, 0, lengths, s, fp16_));
+  LS_CUDA(launch_pack_nct(mu, xin, rows, feat_, T, bs, in_ch_, feat_, lengths, s, fp16_));
+  LS_CUDA(launch_pack_bcast(spks, xin, rows, feat_, T, in_ch_, 2 * feat_, lengths, s, fp16_));
+  LS_CUDA(launch_pack_nct(cond, xin, rows, feat_, T, bs, in_ch_, 3 * feat_, lengths, s, fp16_));
   time_embed(t, nullptr, rows, s);
   run_estimator(rows, T, ws<float>(o_temb_), (long long)groups_.size() * C_, streaming, s);
   LS_CUDA(launch_unpack_nct(ws<float>(o_v_), out, rows, feat_, T, lengths, s));
@@ -561,16 +576,16 @@ void FlowEngine::solve(const float* mu, const float* mask, const float* spks, co
   LS_CUDA(launch_mask_to_lengths(mask, lengths, B, T, 2, s, bad_mask_dev_));
   const long long bs = (long long)feat_ * T;
   // conditional half rows [0,B): [x | mu | spks | cond]; unconditional half rows [B,2B): [x | 0 | 0 | 0]
-  LS_CUDA(launch_pack_nct(mu, xin, B, feat_, T, bs, in_ch_, feat_, lengths, s));
-  LS_CUDA(launch_pack_bcast(spks, xin, B, feat_, T, in_ch_, 2 * feat_, lengths, s));
-  LS_CUDA(launch_pack_nct(cond, xin, B, feat_, T, bs, in_ch_, 3 * feat_, lengths, s));
+  LS_CUDA(launch_pack_nct(mu, xin, B, feat_, T, bs, in_ch_, feat_, lengths, s, fp16_));
+  LS_CUDA(launch_pack_bcast(spks, xin, B, feat_, T, in_ch_, 2 * feat_, lengths, s, fp16_));
+  LS_CUDA(launch_pack_nct(cond, xin, B, feat_, T, bs, in_ch_, 3 * feat_, lengths, s, fp16_));
   LS_CUDA(launch_pack_zero(xin + (long long)B * T * in_ch_, B, 3 * feat_, T, in_ch_, feat_, s));
-  LS_CUDA(launch_init_state(noise, (int)noise_stride, temperature, x_state, xin, B, feat_, T, in_ch_, lengths, s));
+  LS_CUDA(launch_init_state(noise, (int)noise_stride, temperature, x_state, xin, B, feat_, T, in_ch_, lengths, s, fp16_));
   time_embed(t_inline ? nullptr : ws<float>(o_t_), t_host_.data(), n_steps, s);
   const long long per_t = (long long)groups_.size() * C_;
   for (int k = 0; k < n_steps; ++k) {
     run_estimator(B2, T, ws<float>(o_temb_) + k * per_t, 0, streaming, s);
-    LS_CUDA(launch_cfg_euler(ws<float>(o_v_), x_state, xin, B, feat_, T, in_ch_, dt_host_[k], cfg_rate, s));
+    LS_CUDA(launch_cfg_euler(ws<float>(o_v_), x_state, xin, B, feat_, T, in_ch_, dt_host_[k], cfg_rate, s, fp16_));
   }
   LS_CUDA(launch_unpack_nct(x_state, out, B, feat_, T, lengths, s));
 }

@@ -9,7 +9,8 @@ namespace ls {
 
 class FlowEngine {
  public:
-  FlowEngine(const Weights& w, int device);
+  // fp16: the 16-bit GEMM operands (weights and activations) are fp16 instead of bf16; same kernels, same speed
+  FlowEngine(const Weights& w, int device, bool fp16 = false);
   ~FlowEngine();
   void estimator_forward(const float* x, const float* mask, const float* mu, const float* t, const float* spks,
                          const float* cond, float* out, int rows, int T, bool streaming, cudaStream_t s);
@@ -37,6 +38,7 @@ class FlowEngine {
   T* ws(size_t off) const { return reinterpret_cast<T*>(ws_base_ + off); }
 
   int device_ = 0, num_sms_ = 148;
+  int fp16_ = 0;
   bool fused_blocks_ = false;
   int C_ = 256, in_ch_ = 320, feat_ = 80, heads_ = 8, hid_ = 1024, n_blocks_ = 4, n_mid_ = 12, chunk_ = 50;
   Arena arena_;

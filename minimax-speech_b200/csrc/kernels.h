@@ -101,6 +101,7 @@ struct ConvGemmParams {
   long long out_ld, out_shift, out_bstride, out_alloc, out_valid_mul;
   // accounting only (profiler): true K per tap and which engine launched it (0 flow, 1 DAC)
   int k_true, tag;
+  int fp16;           // 1: the 16-bit operands and outputs of this launch are fp16 instead of bf16 (flow estimator only)
   // A-operand staging.  halo_mode 1: the caller's activation maps have boxes of 128 + (taps-1)*dil rows and the
   // kernel fetches each K block of the input ONCE, reading tap t through a descriptor shifted by t*dil rows;
   // halo_mode 0: 128-row boxes fetched per tap.  The remaining fields are filled in by launch_conv_gemm.
@@ -121,6 +122,8 @@ __host__ __device__ constexpr int ls_conv_a_stage_bytes(int box_rows) { return (
 // Tensor maps are created on the host (tma_host.cpp helpers) and passed by value.
 cudaError_t launch_conv_gemm(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_gemm_fp16(const CUtensorMap& mapA0, const CUtensorMap& mapA1, const CUtensorMap& mapW,
+                                  const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 // Flash attention forward over a packed [B][T][3*H*64] bf16 QKV tensor (Q | K | V column blocks).
 #ifndef ATTN_KV
@@ -137,8 +140,11 @@ struct AttnParams {
   const float* bias;
   long long bias_ld, bias_bh;
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps, or nullptr
+  long long timeline_entries;
+  int fp16;             // 1: Q / K / V and the output are fp16 instead of bf16
 };
 cudaError_t launch_attention(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);
+cudaError_t launch_attention_fp16(const CUtensorMap& mapQKV, const AttnParams& p, cudaStream_t stream);
 
 // Fused row-local tail of a transformer block (tblock.cu): out-proj + residual + LayerNorm + FF1 + GELU + FF2 +
 // residual, then either the next block's LayerNorm + QKV projection (tail_mode 0) or a masked bf16 copy of the
@@ -166,6 +172,7 @@ struct TBlockParams {
   int tail_mode;       // 0: u updated in place + next block's QKV written; 1: masked bf16 copy of u'' written;
                        // 2: "head" of a block group: only LayerNorm(u; g1n, be1n) + QKV (att, Wo, W1, W2 unused)
   long long* timeline; // development aid (ls_debug_set_buffer): [grid][64] clock64 stamps of the first tile, or nullptr
+  int fp16;            // 1: every 16-bit operand / output is fp16 instead of bf16
 };
 // Every global tensor is reached through TMA (loads and stores), 128-row boxes, 128-byte swizzle:
 struct TBlockMaps {
@@ -176,23 +183,25 @@ struct TBlockMaps {
   CUtensorMap tail_out;  // bf16 [R][256]  u'' masked                      (box 64 x 128)   tail_mode 1
 };
 cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_tblock_fp16(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream);
 
 // ---- bandwidth kernels (elementwise.cu) ----
 // NCT fp32 [B][C][T] -> time-major bf16 dst[b][t][c_off + c], dst row stride ld; rows >= len zeroed.
 cudaError_t launch_pack_nct(const float* src, __nv_bfloat16* dst, int B, int C, int T, long long src_bstride,
-                            int ld, int c_off, const int* lengths, cudaStream_t s);
+                            int ld, int c_off, const int* lengths, cudaStream_t s, int fp16 = 0);
 // broadcast a per-batch vector [B][C] over time into dst[b][t][c_off + c]
 cudaError_t launch_pack_bcast(const float* src, __nv_bfloat16* dst, int B, int C, int T, int ld, int c_off,
-                              const int* lengths, cudaStream_t s);
+                              const int* lengths, cudaStream_t s, int fp16 = 0);
 // zero dst[b][t][c_off .. c_off+C)
 cudaError_t launch_pack_zero(__nv_bfloat16* dst, int B, int C, int T, int ld, int c_off, cudaStream_t s);
 // x_state[b][t][c] = noise[c][t] * temperature (noise row stride noise_ld); also writes bf16 copies into
 // xin rows b and B+b (channel offset 0).
 cudaError_t launch_init_state(const float* noise, int noise_ld, float temperature, float* x_state,
-                              __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s);
+                              __nv_bfloat16* xin, int B, int C, int T, int ld, const int* lengths, cudaStream_t s,
+                              int fp16 = 0);
 // CFG combine + Euler update (flow_matching.py:118-120): x += dt*((1+w) v[b] - w v[B+b]); refresh bf16 copies.
 cudaError_t launch_cfg_euler(const float* v, float* x_state, __nv_bfloat16* xin, int B, int C, int T, int ld,
-                             float dt, float cfg_rate, cudaStream_t s);
+                             float dt, float cfg_rate, cudaStream_t s, int fp16 = 0);
 // time-major fp32 [B][T][C] -> NCT fp32 [B][C][T], rows >= len zeroed
 cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T, const int* lengths, cudaStream_t s);
 // lengths[d*B + b] = number of non-zero entries of mask[b][0][:] for d < dup; *bad_flag (device-visible, optional) is set

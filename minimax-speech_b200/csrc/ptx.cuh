@@ -4,7 +4,12 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#ifndef LS_HALF_FP16
+#define LS_HALF_FP16 0
+#endif
 
 namespace ls {
 
@@ -178,6 +183,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand comes from tensor memory (lane = row; 16-bit elements, two consecutive K
+// elements per 32-bit column, so one K = 16 step reads 8 columns starting at tmem_a) -- no shared-memory read for A.
+// A is K-major by construction (the instruction descriptor's A-major bit must be 0).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // same, arriving on the barrier at this smem offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -328,8 +345,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 // bits: [4,6) D fmt (1=f32), [7,10) A fmt (1=bf16), [10,13) B fmt, 15 A MN-major, 16 B MN-major,
 //       [17,23) N>>3, [24,29) M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+// A / B format: 1 = bf16, 0 = fp16 (kind::f16 runs both at the same rate).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major,
+                                                       bool fp16 = LS_HALF_FP16 != 0) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -412,13 +431,62 @@ __device__ __forceinline__ float mish_f(float x) {
   const float n = w * (w + 2.0f);
   return x * __fdividef(n, n + 2.0f);
 }
+// snake(x) = x + sin^2(alpha x) / alpha  (dac-vae/layers.py:18-33).  MUFU.SIN loses absolute accuracy as |alpha x| grows
+// (trained checkpoints: alpha = O(1), activations = O(10)); sin^2 has period pi, so LS_SNAKE_REDUCE=1 first reduces the
+// argument to [-pi/2, pi/2] with a two-term Cody-Waite split of pi (4 extra instructions).  Measured on the trained-scale
+// fixture (|alpha x| up to 24 rad, tests/golden/dac_trained_golden.npz): 32.4 / 34.1 dB without, 32.4 / 33.7 dB with the
+// reduction -- __sinf is NOT what limits the SNR there (the bf16 operands are; fp32 mode: 103 dB) -- and the reduction
+// costs 0.7 ms per 160 audio-seconds of decode, so it is off by default.
+#ifndef LS_SNAKE_REDUCE
+#define LS_SNAKE_REDUCE 0
+#endif
 __device__ __forceinline__ float snake_f(float x, float alpha, float inv_alpha) {
-  const float s = __sinf(alpha * x);
+  float r = alpha * x;
+#if LS_SNAKE_REDUCE
+  const float k = rintf(r * 0.31830988618379067f);
+  r = fmaf(k, -3.14159274101257324f, r);    // float(pi)
+  r = fmaf(k, 8.74227765734758577e-8f, r);  // float(pi) - pi
+#endif
+  const float s = __sinf(r);
   return fmaf(inv_alpha, s * s, x);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint16_t cvt_bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16(x)); }
+__device__ __forceinline__ uint16_t cvt_f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
+  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  lo = __low2float(h2), hi = __high2float(h2);
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
+  const __half2 h2 = *reinterpret_cast<const __half2*>(&w);
+  lo = __low2float(h2), hi = __high2float(h2);
+}
+
+// The tensor-core kernels (conv_gemm.cu, tblock.cu, attention.cu) are compiled twice: once with bf16 operands and once
+// (the *_fp16.cu wrappers, LS_HALF_FP16 = 1) with fp16 operands -- same 16-bit layouts, same speed, 8x finer rounding.
+// fp16 is the format of the reference's own half-precision / TensorRT estimator (speech/cosyvoice/cli/model.py:41-43,
+// utils/file_utils.py:63-64); measured on one estimator call the bf16 rounding of the weights alone costs 8.6e-3 of
+// relative L2, fp16 operands 1.5e-3 in total (profiles/attrib_precision.py).  These macros are what differs.
+#ifndef LS_HALF_FP16
+#define LS_HALF_FP16 0
+#endif
+#if LS_HALF_FP16
+#define LS_PACK_H2 pack_f16x2
+#define LS_CVT_H_BITS cvt_f16_bits
+#define LS_UNPACK_H2 unpack_f16x2
+#define LS_FN(name) name##_fp16
+#else
+#define LS_PACK_H2 pack_bf16x2
+#define LS_CVT_H_BITS cvt_bf16_bits
+#define LS_UNPACK_H2 unpack_bf16x2
+#define LS_FN(name) name
+#endif
 
 }  // namespace ls

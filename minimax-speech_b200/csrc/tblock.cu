@@ -39,7 +39,10 @@ constexpr bool kPair = TBLOCK_PAIR != 0;
 // HALF AS MANY instructions of the same 16 KB: 128 own rows of Wo / W2 (the pair's N = 256 operand), or two K blocks of a
 // 64-row half of a W1 / Wqkv chunk (3-D box), per instruction.
 constexpr int kRingSlotBytes = kSlotBytes;
-constexpr int kSlots = 5;
+#ifndef TBLOCK_SLOTS
+#define TBLOCK_SLOTS 5
+#endif
+constexpr int kSlots = TBLOCK_SLOTS;
 #ifndef TBLOCK_PRODUCER_WARPS
 #define TBLOCK_PRODUCER_WARPS 3
 #endif
@@ -128,10 +131,10 @@ __device__ __forceinline__ void store_row_chunks(uint8_t* row_base, int sw, int 
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
     uint4 v;
-    v.x = pack_bf16x2(y[8 * q4 + 0], y[8 * q4 + 1]);
-    v.y = pack_bf16x2(y[8 * q4 + 2], y[8 * q4 + 3]);
-    v.z = pack_bf16x2(y[8 * q4 + 4], y[8 * q4 + 5]);
-    v.w = pack_bf16x2(y[8 * q4 + 6], y[8 * q4 + 7]);
+    v.x = LS_PACK_H2(y[8 * q4 + 0], y[8 * q4 + 1]);
+    v.y = LS_PACK_H2(y[8 * q4 + 2], y[8 * q4 + 3]);
+    v.z = LS_PACK_H2(y[8 * q4 + 4], y[8 * q4 + 5]);
+    v.w = LS_PACK_H2(y[8 * q4 + 6], y[8 * q4 + 7]);
     *reinterpret_cast<uint4*>(row_base + (((chunk0 + q4) ^ sw) << 4)) = v;
   }
 }
@@ -190,7 +193,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       if (!tile_all_padding(p, (g * kCS + r) * kTileM)) return false;
     return true;
   };
-  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 128 : nullptr;
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 256 : nullptr;
 #define TL(i)                         \
   do {                                \
     if (tl) tl[(i)] = clock64();      \
@@ -399,12 +402,15 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         }
       };
       // H[i] = A3 (128 x 256, K-major in smem) . Wchunk^T, weights from 4 ring slots
-      auto gemm_from_a3 = [&](int i) {
+      auto gemm_from_a3 = [&](int i, int tlb = -1) {  // tlb >= 0: detailed timeline stamps of this call (development aid)
+        if (tl && tlb >= 0 && lane == 0) tl[tlb] = clock64();
         wait_drained(i);
+        if (tl && tlb >= 0 && lane == 0) tl[tlb + 1] = clock64();
         const uint32_t d = tmem_u + kTmemH + (uint32_t)i * 128;
         for (int kb = 0; kb < kC / 64; ++kb) {
           // pair: a slot holds two K blocks of this CTA's 64 weight rows (8 KB each)
           const uint64_t bdesc = slot_desc(0) + (kPair ? (uint64_t)((kb & 1) * (8192 >> 4)) : 0);
+          if (tl && tlb >= 0 && lane == 0) tl[tlb + 2 + kb] = clock64();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA3 + kb * kSlotBytes));
           if (elect_one()) {
 #pragma unroll
@@ -413,6 +419,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (!kPair || (kb & 1)) release(1);
         }
         commit(&h_full[i]);
+        if (tl && tlb >= 0 && lane == 0) tl[tlb + 6] = clock64();
         if (i) fills1 += 1;
         else fills0 += 1;
       };
@@ -458,11 +465,13 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         gemm_from_a3(1);
         for (int c = 0; c < kFF / 128; ++c) {
           const int i = c & 1;
+          if (c == 4) TLM(128);
           wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
           TLM(4 + c);
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
             const uint64_t b0 = slot_desc(0);
+            if (c == 4) TLM(129 + 2 * kb2);
             if (kPair) {  // this CTA's 128 rows of W2[:, chunk]: one N = 256 MMA per K step
               if (elect_one()) {
 #pragma unroll
@@ -472,6 +481,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
               continue;
             }
             const uint64_t b1 = slot_desc(1);
+            if (c == 4) TLM(130 + 2 * kb2);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -482,7 +492,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             release(2);
           }
           commit(&ah_free[i]);
-          if (c + 2 < kFF / 128) gemm_from_a3(i);
+          if (c == 4) TLM(133);
+          if (c + 2 < kFF / 128) gemm_from_a3(i, c == 4 ? 134 : -1);
         }
         commit(d_full);
         TLM(12);
@@ -494,7 +505,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         TLM(13);
         if (do_qkv)
           for (int c = 0; c < kQKV / 128; ++c) {
-            gemm_from_a3(c & 1);
+            gemm_from_a3(c & 1, c == 6 ? 144 : -1);
             TLM(14 + c);
           }
         TLM(26);
@@ -616,13 +627,16 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       // ------------------------------------------------ FF1 chunks: AH[i] = gelu(H[i] + b1)
       for (int c = 0; c < (head ? 0 : kFF / 128); ++c) {
         const int i = c & 1;
+        if (c == 4) TLE(160);
         mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
         if (i) h_cnt1 += 1;
         else h_cnt0 += 1;
         tc_fence_after();
+        if (c == 4) TLE(161);
         float y[32];
         tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
         tmem_ld_wait();
+        if (c == 4) TLE(162);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 b1 = reinterpret_cast<const float4*>(sVec + V_B1 + c * 128 + cg * 32)[k];
@@ -631,12 +645,15 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           y[4 * k + 2] = gelu_fast(y[4 * k + 2] + b1.z);
           y[4 * k + 3] = gelu_fast(y[4 * k + 3] + b1.w);
         }
+        if (c == 4) TLE(163);
         const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
         if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
+        if (c == 4) TLE(164);
         if (i) ah_cnt1 += 1;
         else ah_cnt0 += 1;
         store_row_chunks(sAH + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
         warp_arrive(&ah_ready[i]);
+        if (c == 4) TLE(165);
         TLE(34 + c);
       }
 
@@ -745,24 +762,31 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         // -------------------------------------------- QKV chunks of the next block -> staging pair -> TMA store
         for (int c = 0; c < kQKV / 128; ++c) {
           const int i = c & 1;
+          if (c == 6) TLE(170);
           mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
           if (i) h_cnt1 += 1;
           else h_cnt0 += 1;
           tc_fence_after();
+          if (c == 6) TLE(171);
           float y[32];
           tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
           tmem_ld_wait();
           warp_arrive(&ah_ready[i]);  // H[i] is drained: the MMA warp may refill it
+          if (c == 6) TLE(172);
           // staging pair i is free: the leader waited for the store of chunk c-2 before the barrier of chunk c-1
           store_row_chunks(stage + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
           fence_proxy_async_smem();
+          if (c == 6) TLE(173);
           if (leader) bulk_wait_read<0>();  // store of chunk c-1 (issued a whole chunk ago) has left pair i^1
+          if (c == 6) TLE(174);
           epi_barrier();
+          if (c == 6) TLE(175);
           if (leader) {
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 0) * kSlotBytes, c * 128, row0);
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 1) * kSlotBytes, c * 128 + 64, row0);
             bulk_commit();
           }
+          if (c == 6) TLE(176);
           TLE(44 + c);
         }
       }
@@ -782,7 +806,10 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
 
 }  // namespace
 
-cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t LS_FN(launch_tblock)(const TBlockMaps& m, const TBlockParams& p, int num_sms, cudaStream_t stream) {
+#if !LS_HALF_FP16
+  if (p.fp16) return launch_tblock_fp16(m, p, num_sms, stream);  // fp16-operand build of this file
+#endif
   if (p.R <= 0 || p.T <= 0 || p.vec == nullptr) return cudaErrorInvalidValue;
   static std::atomic<unsigned long long> optin{0};  // one bit per device
   if (cudaError_t e = smem_optin_once(optin, reinterpret_cast<const void*>(tblock_kernel), kSmemBytes); e != cudaSuccess) return e;
@@ -810,7 +837,7 @@ cudaError_t launch_tblock(const TBlockMaps& m, const TBlockParams& p, int num_sm
                                           : rows * (kInner * 2.0 + kC * 4.0 + (p.tail_mode == 0 ? kC * 4.0 + kQKV * 2.0 : kC * 2.0))) +
                        macs * 2.0;
   TBlockParams pp = p;
-  pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 128 * 8) ? g_debug_buffer : nullptr;
+  pp.timeline = (g_debug_buffer && g_debug_bytes >= (long long)grid * 256 * 8) ? g_debug_buffer : nullptr;
   ProfScope prof(stream, PK_TBLOCK, 2.0 * rows * macs, bytes);
   count_launch();
   return launch_pdl(tblock_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, stream, kCS, m.att, m.wo, m.w1,

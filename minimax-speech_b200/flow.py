@@ -79,7 +79,7 @@ class CausalConditionalDecoder(nn.Module):
                  n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn="gelu", static_chunk_size=50,
                  num_decoding_left_chunks=-1, weight_seed=1986, precision="bf16"):
         super().__init__()
-        self.precision = native.check_precision(precision)
+        self.precision = native.check_precision(precision, fp16_ok=True)
         channels = tuple(channels)
         if channels != (256,) or attention_head_dim != 64 or act_fn != "gelu" or in_channels != 4 * out_channels:
             raise NotImplementedError("B200 estimator covers config.yaml's CausalConditionalDecoder: "

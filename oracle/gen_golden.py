@@ -73,7 +73,7 @@ DAC_TRAINED_SEED = 21
 def extra_golden():
     """Round-2 fixtures (own files: the round-1 fixtures stay byte-identical).
 
-    cfm_nc_golden.npz     the non-causal twin ``ConditionalCFM.forward`` (flow_matching.py:39-72) called twice on the
+    cfm_nc_golden.npz     the non-causal twin ``ConditionalCFM.forward`` (flow_matching.py:39-72) called twice (n_timesteps = 10, the value flow.py:192,506 pass) on the
                           unmodified reference: prompt_len = 20 with an empty cache, then with the returned cache
                           (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
     dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
@@ -86,14 +86,14 @@ def extra_golden():
         cfm.estimator.load_state_dict(sd, strict=True)
         nc_forward = type(cfm).__mro__[1].forward  # ConditionalCFM.forward, the parent's (non-causal) method
         assert type(cfm).__mro__[1].__name__ == "ConditionalCFM"
-        out = {"weights_seed": EST_SEED, "weights_checksum": synth.checksum(sd), "prompt_len": 20, "steps": 3}
+        out = {"weights_seed": EST_SEED, "weights_checksum": synth.checksum(sd), "prompt_len": 20, "steps": 10}
         cache = torch.zeros(1, 80, 0, 2)
         for i, (T, seed) in enumerate([(70, NC_SEED_1), (90, NC_SEED_2)], 1):
             mu, mask, spks, cond = synth.batch_inputs([T], first_index=70 + i)
             torch.manual_seed(seed)
             z = torch.randn_like(mu)  # what the forward below draws (same seed, same shape)
             torch.manual_seed(seed)
-            y, cache = nc_forward(cfm, mu.clone(), mask, 3, temperature=0.8, spks=spks, cond=cond, prompt_len=20, cache=cache)
+            y, cache = nc_forward(cfm, mu.clone(), mask, 10, temperature=0.8, spks=spks, cond=cond, prompt_len=20, cache=cache)
             out[f"nc_{i}_T"], out[f"nc_{i}_index"] = T, 70 + i
             out[f"nc_{i}_z"], out[f"nc_{i}_y"], out[f"nc_{i}_cache"] = z.numpy(), y.numpy(), cache.numpy()
             print("cfm non-causal", i, y.shape, cache.shape, float(y.abs().mean()))

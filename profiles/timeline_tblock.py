@@ -10,13 +10,13 @@ import profiles.time_kernels as tk
 
 DEV = torch.device("cuda:0")
 lib = native.load()
-buf = torch.zeros(148 * 128, dtype=torch.int64, device=DEV)
+buf = torch.zeros(148 * 256, dtype=torch.int64, device=DEV)
 R = int(os.environ.get("LS_R", "16000"))
 tk.tblock(R, 0)
 lib.ls_debug_set_buffer(native.ptr(buf), buf.numel() * 8)
 tk.tblock(R, 0)
 lib.ls_debug_set_buffer(None, 0)
-t = buf.view(148, 128).cpu()
+t = buf.view(148, 256).cpu()
 for cta in (0, 60, 124):
     r = t[cta]
     base = int(r[0])
@@ -26,3 +26,9 @@ for cta in (0, 60, 124):
     print("EPI :", " ".join(f"{i}={int(r[i]) - base}" for i in range(32, 56) if int(r[i])))
     print("LOAD slot-free time of loads 0..47:", [int(r[64 + i]) - base if int(r[64 + i]) else None for i in range(48)])
     print("MMA saw slots 0..15 full at:", [int(r[112 + i]) - base for i in range(16)])
+    d = lambda a, b: [int(r[i]) - base if int(r[i]) else None for i in range(a, b)]
+    print("MMA FF chunk 4: before AH wait, after, kb2=0 slot0/slot1, kb2=1 slot0/slot1... :", d(128, 134))
+    print("MMA FF1(6): before drained wait, after, kb0..3 slot seen, committed:", d(134, 141))
+    print("MMA QKV chunk 6: before drained wait, after, kb0..3 slot seen, committed:", d(144, 151))
+    print("EPI FF chunk 4: before h_full, after, ld done, gelu done, ah_free ok, arrived:", d(160, 166))
+    print("EPI QKV chunk 6: before h_full, after, ld+arrive, staged, bulk_wait_read, barrier, stores issued:", d(170, 177))

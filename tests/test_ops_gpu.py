@@ -3,6 +3,7 @@ asks for: fake kernels so the ops compose (opcheck, torch.compile fullgraph), no
 (a bad mask is reported by the next call), one handle safely shared by several streams."""
 import pytest
 import torch
+import torch._dynamo
 
 pytestmark = pytest.mark.gpu
 
@@ -67,7 +68,6 @@ def test_torch_compile_fullgraph_synthesizer(models):
     mu, mask, spks, cond = _inputs([64, 40])
     with torch.inference_mode():
         eager = syn(mu, mask, spks, cond, n_timesteps=3)
-    import torch._dynamo
     torch._dynamo.reset()
     seen = []
 
