@@ -59,6 +59,16 @@ constexpr int kCS = TBLOCK_CLUSTER;          // CTAs per cluster: each loads 1/k
 constexpr int kPartRows = 128 / kCS;         // weight rows per CTA per box
 constexpr int kPartBytes = kPartRows * 128;
 constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
+// Second weight ring (single-CTA form only): the four 16 KB boxes of W2[:, chunk] get slots of their own in the AH region,
+// which is idle in the FF phase now that the GELU output lives in tensor memory.  With one 5-slot ring the boxes of W2(c)
+// sat in it while the MMA warp waited for GELU(c), W1(c+2) could not be prefetched behind them, and every FF chunk paid a
+// TMA round trip (measured: 3.8 k clk per chunk against 2.8 k of MMA work).  The region doubles as the staging tile of the
+// residual-stream loads / stores outside the FF phase: its first use per tile waits for the epilogue's stage_free.
+#ifndef TBLOCK_RING_B
+#define TBLOCK_RING_B 0  // measured: 3.4 k instead of 3.8 k clk per FF chunk on the first tile of a CTA, but not yet correct for a CTA's later tiles
+#endif
+constexpr bool kRingB = TBLOCK_RING_B != 0 && !kPair && kCS == 1;
+constexpr int kSlotsB = 4;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstEpiWarp = kProducerWarps + 1;
@@ -175,7 +185,10 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint64_t* ah_ready = h_full + 2;   // [2] epilogue -> MMA: H[i] drained (and AH[i] written in the FF phase)
   uint64_t* ah_free = ah_ready + 2;  // [2] MMA -> epilogue: FF2 MMAs that read AH[i] have retired
   uint64_t* u_full = ah_free + 2;    // TMA -> epilogue: the u tile sits in the staging boxes (AH region + A3)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
+  uint64_t* full_b = u_full + 1;       // [kSlotsB] TMA -> MMA: W2 box r of the current FF chunk
+  uint64_t* empty_b = full_b + kSlotsB;  // [kSlotsB] MMA -> TMA
+  uint64_t* stage_free = empty_b + kSlotsB;  // epilogue -> TMA: the staging region may take this tile's W2 boxes
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,6 +233,11 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       mbar_init(&ah_free[i], 1);
     }
     mbar_init(u_full, 1);
+    for (int i = 0; i < kSlotsB; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    mbar_init(stage_free, 1);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -257,16 +275,26 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     if (kWarpIssue || lane < kProducerLanes) {
       const int issuer = warp * kProducerLanes + (kWarpIssue ? 0 : lane);
       const int per_tile = kPair ? (head ? 24 : (do_qkv ? 72 : 48)) : (head ? 48 : (do_qkv ? 136 : 88));
-      long long seq0 = 0;  // sequence number of the tile's first load (slot = seq % kSlots, use = seq / kSlots)
+      long long seq0 = 0;  // sequence number of the tile's first ring-A load (slot = seq % kSlots, use = seq / kSlots)
+      uint32_t tile_n = 0;  // tiles processed by this CTA (ring B: eight uses of every slot per tile)
       for (int g = group0; g < n_groups; g += group_step) {
         const int row0 = (g * kCS + rank) * kTileM;
         if (kWarpIssue ? __shfl_sync(0xffffffffu, (int)group_skipped(g), 0) != 0 : group_skipped(g)) continue;
-        for (int i = issuer; i < per_tile; i += kIssuers) {
+        // With the second ring, its loads all go through the LAST producer warp, in order: successive uses of one of its
+        // slots are then waited for by one thread, which can never be two uses ahead of the consumer (interleaved over
+        // several warps they could, and a parity wait cannot tell "two phases ahead" from "done"); the other warps
+        // share the ring-A loads.  It also keeps a W2 box from queueing behind a W1 box that waits for a ring-A slot.
+        const bool two_rings = kRingB && !head;
+        const bool b_warp = two_rings && warp == kProducerWarps - 1;
+        const int n_a = two_rings ? kIssuers - kProducerLanes : kIssuers;  // issuers of ring-A loads
+        for (int i = two_rings ? 0 : issuer; i < per_tile; i += two_rings ? 1 : kIssuers) {
           // decode load i of the tile: (tensor map, column, row), in exactly the order the MMA warp consumes them
           const CUtensorMap* m;
           int c0, c1;
           bool own_rows = false;
           int c2 = -1;  // >= 0: 3-D weight box (pair mode: 64 rows x 2 K blocks), third coordinate
+          int ring_b = -1, chunk_b = 0;  // >= 0: a W2 box of FF chunk chunk_b -> slot ring_b of the second ring
+          int a_idx = i;                 // index of this load among the tile's ring-A loads
           if (kPair) {
             auto chunk_half = [&](const CUtensorMap* wm, int chunk, int half) {  // W1 / Wqkv chunk: this CTA's 64 rows
               m = wm, c0 = 0, c1 = chunk * 128 + rank * kPartRows, c2 = half * 2;
@@ -303,34 +331,54 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             int c, r;
             if (j < 48) c = j >> 3, r = j & 7;
             else c = 6 + ((j - 48) >> 2), r = (j - 48) & 3;
-            if (r < 4) m = &mapW2, c0 = c * 128 + (r >> 1) * 64, c1 = (r & 1) * 128;
-            else m = &mapW1, c0 = (r - 4) * 64, c1 = (c + 2) * 128;
+            if (r < 4) {
+              m = &mapW2, c0 = c * 128 + (r >> 1) * 64, c1 = (r & 1) * 128;
+              if (kRingB) ring_b = r, chunk_b = c;
+            } else {
+              m = &mapW1, c0 = (r - 4) * 64, c1 = (c + 2) * 128;
+            }
+            if (kRingB) a_idx = i - (4 * c + (r < 4 ? r : 4));  // W2 boxes before this load travel in ring B
           } else {  // next block's QKV weight, 12 chunks of 128 rows
             const int j = i - 88;
             m = &mapWqkv, c0 = (j & 3) * 64, c1 = (j >> 2) * 128;
+            if (kRingB) a_idx = i - 32;
           }
-          const long long seq = seq0 + i;
-          const int slot = (int)(seq % kSlots);
-          const uint32_t use = (uint32_t)(seq / kSlots);
-          mbar_wait(&empty[slot], (use & 1) ^ 1);
-          if (tl && seq < 48 && (!kWarpIssue || lane == 0)) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
-          uint8_t* dst = sRing + slot * kRingSlotBytes;
+          if (two_rings && (ring_b >= 0 ? !b_warp : (b_warp || a_idx % n_a != issuer))) continue;  // another warp's load
+          uint64_t* full_bar;
+          uint8_t* dst;
+          if (ring_b >= 0) {
+            // second ring: slot r holds W2 box r of one chunk at a time; the first box of a tile waits for the epilogue to
+            // hand the staging region over, the others for the MMAs that read the slot's previous box
+            if (chunk_b == 0) mbar_wait(stage_free, tile_n & 1);
+            else mbar_wait(&empty_b[ring_b], (tile_n * 7 + (uint32_t)chunk_b - 1) & 1);
+            full_bar = &full_b[ring_b];
+            dst = sAH + ring_b * kSlotBytes;
+          } else {
+            const long long seq = seq0 + a_idx;
+            const int slot = (int)(seq % kSlots);
+            const uint32_t use = (uint32_t)(seq / kSlots);
+            mbar_wait(&empty[slot], (use & 1) ^ 1);
+            if (tl && seq < 48 && (!kWarpIssue || lane == 0)) tl[64 + seq] = clock64();  // load `seq` may start (its slot is free)
+            full_bar = &full[slot];
+            dst = sRing + slot * kRingSlotBytes;
+          }
           if (kWarpIssue && !elect_one()) {
             // (the other lanes only keep the warp's control flow uniform)
           } else if (kPair) {
             // this CTA's half of the box (own rows for att), completion signalled on the LEADER's barrier
-            const uint32_t fb = cluster_addr(&full[slot], 0);
+            const uint32_t fb = cluster_addr(full_bar, 0);
             mbar_arrive_expect_tx_cluster(fb, kRingSlotBytes);
             if (c2 >= 0) tma_load_3d_pair(dst, m, fb, c0, c1, c2);
             else tma_load_2d_pair(dst, m, fb, c0, c1);
           } else {
-            mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-            if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, &full[slot], c0, c1 + rank * kPartRows, kCtaMask);
-            else tma_load_2d(dst, m, &full[slot], c0, c1);
+            mbar_arrive_expect_tx(full_bar, kSlotBytes);
+            if (kCS > 1 && !own_rows) tma_load_2d_mc(dst + rank * kPartBytes, m, full_bar, c0, c1 + rank * kPartRows, kCtaMask);
+            else tma_load_2d(dst, m, full_bar, c0, c1);
           }
           if (kWarpIssue) __syncwarp();
         }
-        seq0 += per_tile;
+        seq0 += (kRingB && !head) ? per_tile - 32 : per_tile;
+        tile_n += 1;
       }
     }
   } else if (warp == kMmaWarp) {
@@ -424,9 +472,13 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         else fills0 += 1;
       };
       const uint32_t dD = tmem_u + kTmemD;
+      uint32_t tile_n = 0;  // tiles processed (second ring parities)
       TLM(0);
-      for (int g = group0; g < n_groups; g += group_step) {
-        if (__shfl_sync(0xffffffffu, (int)group_skipped(g), 0)) continue;
+      for (int g = group0; g < n_groups; g += group_step, ++tile_n) {
+        if (__shfl_sync(0xffffffffu, (int)group_skipped(g), 0)) {
+          --tile_n;
+          continue;
+        }
         if (g != group0) tl = nullptr;
         if (!head) {
         // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
@@ -469,10 +521,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
           TLM(4 + c);
           for (int kb2 = 0; kb2 < 2; ++kb2) {
+            // A = gelu(FF1 chunk c), packed 16-bit pairs in TENSOR MEMORY: the GELU epilogue wrote the pairs of column
+            // group cg over the first 16 of that group's 32 columns of H[i] (tcgen05.mma TS form: no shared-memory read
+            // for A, 73 instead of 102 clk per N = 128 MMA; profiles/micro/mma_bw.cu).  K step k of this 64-wide K block
+            // covers chunk columns [64 kb2 + 16 k, +16) = column group 2 kb2 + k / 2, packed columns 8 (k & 1) .. +8.
+            const uint32_t a_tm = tmem_u + kTmemH + (uint32_t)i * 128 + (uint32_t)kb2 * 64;
             const uint64_t adesc = make_smem_desc_sw128(smem_u32(sAH + i * 2 * kSlotBytes + kb2 * kSlotBytes));
-            const uint64_t b0 = slot_desc(0);
-            if (c == 4) TLM(129 + 2 * kb2);
             if (kPair) {  // this CTA's 128 rows of W2[:, chunk]: one N = 256 MMA per K step
+              const uint64_t b0 = slot_desc(0);
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16_pair(dD, adesc + 2 * k, b0 + 2 * k, idesc256, 1u);
@@ -480,18 +536,35 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
               release(1);
               continue;
             }
-            const uint64_t b1 = slot_desc(1);
+            uint64_t b0, b1;
+            if (kRingB) {  // W2 boxes 2 kb2 and 2 kb2 + 1 of this chunk sit in their own slots of the second ring
+              const uint32_t par = (tile_n * 8 + (uint32_t)c) & 1;
+              mbar_wait(&full_b[2 * kb2], par);
+              if (c == 4) TLM(129 + 2 * kb2);
+              mbar_wait(&full_b[2 * kb2 + 1], par);
+              tc_fence_after();
+              b0 = make_smem_desc_sw128(smem_u32(sAH + (2 * kb2) * kSlotBytes));
+              b1 = make_smem_desc_sw128(smem_u32(sAH + (2 * kb2 + 1) * kSlotBytes));
+            } else {
+              b0 = slot_desc(0);
+              if (c == 4) TLM(129 + 2 * kb2);
+              b1 = slot_desc(1);
+            }
             if (c == 4) TLM(130 + 2 * kb2);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                mma(dD, adesc + 2 * k, b0 + 2 * k, 1u);
-                mma(dD + 128, adesc + 2 * k, b1 + 2 * k, 1u);
+                const uint32_t a_k = a_tm + (uint32_t)(k >> 1) * 32 + (uint32_t)(k & 1) * 8;
+                umma_bf16_ts(dD, a_k, b0 + 2 * k, idesc, 1u);
+                umma_bf16_ts(dD + 128, a_k, b1 + 2 * k, idesc, 1u);
               }
+              // (the last chunk's boxes are not handed back: the next tile's first boxes wait for stage_free instead)
+              if (kRingB && c + 1 < kFF / 128) umma_commit(&empty_b[2 * kb2]), umma_commit(&empty_b[2 * kb2 + 1]);
             }
-            release(2);
+            if (kRingB) __syncwarp();
+            else release(2);
           }
-          commit(&ah_free[i]);
+          if (kPair) commit(&ah_free[i]);  // (single-CTA form: H[i] is reused in tensor-pipe order, nothing to signal)
           if (c == 4) TLM(133);
           if (c + 2 < kFF / 128) gemm_from_a3(i, c == 4 ? 134 : -1);
         }
@@ -610,6 +683,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         float mean, rstd;
         combine_groups(st, sRed, cg, row, mean, rstd);  // the barrier inside also orders every thread's u reads
         const float nmr = -mean * rstd;                 // before the A3 writes below (A3 held half of the u tile)
+        // every thread is done with the u tile and the previous tile's stores have left the staging region (the leader
+        // waited for them before loading u): it may take this tile's W2 boxes
+        if (kRingB && leader && !head) mbar_arrive(stage_free);
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int col = cg * 64 + ch * 32;
@@ -646,12 +722,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           y[4 * k + 3] = gelu_fast(y[4 * k + 3] + b1.w);
         }
         if (c == 4) TLE(163);
-        const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
-        if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
+        if (kPair) {
+          const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
+          if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
+          if (i) ah_cnt1 += 1;
+          else ah_cnt0 += 1;
+          store_row_chunks(sAH + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
+        } else {
+          // 32 values -> 16 packed pairs, written over the first 16 of this thread's own 32 columns of H[i]: the A
+          // operand of FF2 chunk c lives in tensor memory.  FF1 chunk c + 2 overwrites H[i] only after FF2 chunk c
+          // (tcgen05.mma instructions execute in issue order), so no "A consumed" barrier is needed.
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = LS_PACK_H2(y[2 * k], y[2 * k + 1]);
+          tmem_st16(trow + kTmemH + i * 128 + cg * 32, pk);
+          tmem_st_wait();
+        }
         if (c == 4) TLE(164);
-        if (i) ah_cnt1 += 1;
-        else ah_cnt0 += 1;
-        store_row_chunks(sAH + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
         warp_arrive(&ah_ready[i]);
         if (c == 4) TLE(165);
         TLE(34 + c);
