@@ -68,6 +68,21 @@ constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
 #define TBLOCK_RING_B 0  // measured: 3.4 k instead of 3.8 k clk per FF chunk on the first tile of a CTA, but not yet correct for a CTA's later tiles
 #endif
 constexpr bool kRingB = TBLOCK_RING_B != 0 && !kPair && kCS == 1;
+// FF2 with its A operand (the GELU output) in tensor memory -- the tcgen05 "TS" form: 73 instead of 102 clk per N = 128
+// MMA (profiles/micro/mma_bw.cu), no AH staging, no ah_free barrier.  Parity-green; in the same-box A/B of the whole
+// bench step it measured 38.5 against 37.8 ms of fused-block time, so it is off by default (the FF phase is bound by the
+// arrival of the weight boxes, not by the MMAs; the second ring above needs it).
+#ifndef TBLOCK_FF2_TS
+#define TBLOCK_FF2_TS TBLOCK_RING_B
+#endif
+constexpr bool kFf2Ts = TBLOCK_FF2_TS != 0 && !kPair;
+// TBLOCK_DETAIL_TL=1 adds per-sub-step clock64 stamps of FF chunk 4 / QKV chunk 6 (profiles/timeline_tblock.py); they cost
+// registers in the 96-register epilogue (spills), so product builds leave them out.
+#ifndef TBLOCK_DETAIL_TL
+#define TBLOCK_DETAIL_TL 0
+#endif
+constexpr bool kDetailTl = TBLOCK_DETAIL_TL != 0;
+static_assert(!kRingB || kFf2Ts, "the second ring lives in the AH region: it needs the TS form of FF2");
 constexpr int kSlotsB = 4;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -451,14 +466,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       };
       // H[i] = A3 (128 x 256, K-major in smem) . Wchunk^T, weights from 4 ring slots
       auto gemm_from_a3 = [&](int i, int tlb = -1) {  // tlb >= 0: detailed timeline stamps of this call (development aid)
-        if (tl && tlb >= 0 && lane == 0) tl[tlb] = clock64();
+        if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb] = clock64();
         wait_drained(i);
-        if (tl && tlb >= 0 && lane == 0) tl[tlb + 1] = clock64();
+        if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 1] = clock64();
         const uint32_t d = tmem_u + kTmemH + (uint32_t)i * 128;
         for (int kb = 0; kb < kC / 64; ++kb) {
           // pair: a slot holds two K blocks of this CTA's 64 weight rows (8 KB each)
           const uint64_t bdesc = slot_desc(0) + (kPair ? (uint64_t)((kb & 1) * (8192 >> 4)) : 0);
-          if (tl && tlb >= 0 && lane == 0) tl[tlb + 2 + kb] = clock64();
+          if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 2 + kb] = clock64();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA3 + kb * kSlotBytes));
           if (elect_one()) {
 #pragma unroll
@@ -467,7 +482,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (!kPair || (kb & 1)) release(1);
         }
         commit(&h_full[i]);
-        if (tl && tlb >= 0 && lane == 0) tl[tlb + 6] = clock64();
+        if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 6] = clock64();
         if (i) fills1 += 1;
         else fills0 += 1;
       };
@@ -517,7 +532,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         gemm_from_a3(1);
         for (int c = 0; c < kFF / 128; ++c) {
           const int i = c & 1;
-          if (c == 4) TLM(128);
+          if (kDetailTl && c == 4) TLM(128);
           wait_drained(i);  // AH[i] holds gelu(FF1 chunk c)
           TLM(4 + c);
           for (int kb2 = 0; kb2 < 2; ++kb2) {
@@ -540,23 +555,28 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             if (kRingB) {  // W2 boxes 2 kb2 and 2 kb2 + 1 of this chunk sit in their own slots of the second ring
               const uint32_t par = (tile_n * 8 + (uint32_t)c) & 1;
               mbar_wait(&full_b[2 * kb2], par);
-              if (c == 4) TLM(129 + 2 * kb2);
+              if (kDetailTl && c == 4) TLM(129 + 2 * kb2);
               mbar_wait(&full_b[2 * kb2 + 1], par);
               tc_fence_after();
               b0 = make_smem_desc_sw128(smem_u32(sAH + (2 * kb2) * kSlotBytes));
               b1 = make_smem_desc_sw128(smem_u32(sAH + (2 * kb2 + 1) * kSlotBytes));
             } else {
               b0 = slot_desc(0);
-              if (c == 4) TLM(129 + 2 * kb2);
+              if (kDetailTl && c == 4) TLM(129 + 2 * kb2);
               b1 = slot_desc(1);
             }
-            if (c == 4) TLM(130 + 2 * kb2);
+            if (kDetailTl && c == 4) TLM(130 + 2 * kb2);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t a_k = a_tm + (uint32_t)(k >> 1) * 32 + (uint32_t)(k & 1) * 8;
-                umma_bf16_ts(dD, a_k, b0 + 2 * k, idesc, 1u);
-                umma_bf16_ts(dD + 128, a_k, b1 + 2 * k, idesc, 1u);
+                if (kFf2Ts) {
+                  const uint32_t a_k = a_tm + (uint32_t)(k >> 1) * 32 + (uint32_t)(k & 1) * 8;
+                  umma_bf16_ts(dD, a_k, b0 + 2 * k, idesc, 1u);
+                  umma_bf16_ts(dD + 128, a_k, b1 + 2 * k, idesc, 1u);
+                } else {
+                  mma(dD, adesc + 2 * k, b0 + 2 * k, 1u);
+                  mma(dD + 128, adesc + 2 * k, b1 + 2 * k, 1u);
+                }
               }
               // (the last chunk's boxes are not handed back: the next tile's first boxes wait for stage_free instead)
               if (kRingB && c + 1 < kFF / 128) umma_commit(&empty_b[2 * kb2]), umma_commit(&empty_b[2 * kb2 + 1]);
@@ -564,9 +584,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             if (kRingB) __syncwarp();
             else release(2);
           }
-          if (kPair) commit(&ah_free[i]);  // (single-CTA form: H[i] is reused in tensor-pipe order, nothing to signal)
-          if (c == 4) TLM(133);
-          if (c + 2 < kFF / 128) gemm_from_a3(i, c == 4 ? 134 : -1);
+          if (!kFf2Ts) commit(&ah_free[i]);  // (TS form: H[i] is reused in tensor-pipe order, nothing to signal)
+          if (kDetailTl && c == 4) TLM(133);
+          if (c + 2 < kFF / 128) gemm_from_a3(i, kDetailTl && c == 4 ? 134 : -1);
         }
         commit(d_full);
         TLM(12);
@@ -578,7 +598,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         TLM(13);
         if (do_qkv)
           for (int c = 0; c < kQKV / 128; ++c) {
-            gemm_from_a3(c & 1, c == 6 ? 144 : -1);
+            gemm_from_a3(c & 1, kDetailTl && c == 6 ? 144 : -1);
             TLM(14 + c);
           }
         TLM(26);
@@ -703,16 +723,16 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       // ------------------------------------------------ FF1 chunks: AH[i] = gelu(H[i] + b1)
       for (int c = 0; c < (head ? 0 : kFF / 128); ++c) {
         const int i = c & 1;
-        if (c == 4) TLE(160);
+        if (kDetailTl && c == 4) TLE(160);
         mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
         if (i) h_cnt1 += 1;
         else h_cnt0 += 1;
         tc_fence_after();
-        if (c == 4) TLE(161);
+        if (kDetailTl && c == 4) TLE(161);
         float y[32];
         tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
         tmem_ld_wait();
-        if (c == 4) TLE(162);
+        if (kDetailTl && c == 4) TLE(162);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 b1 = reinterpret_cast<const float4*>(sVec + V_B1 + c * 128 + cg * 32)[k];
@@ -721,8 +741,8 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           y[4 * k + 2] = gelu_fast(y[4 * k + 2] + b1.z);
           y[4 * k + 3] = gelu_fast(y[4 * k + 3] + b1.w);
         }
-        if (c == 4) TLE(163);
-        if (kPair) {
+        if (kDetailTl && c == 4) TLE(163);
+        if (!kFf2Ts) {
           const uint32_t ahc = i ? ah_cnt1 : ah_cnt0;
           if (ahc >= 1) mbar_wait(&ah_free[i], (ahc - 1) & 1);  // FF2 of chunk c-2 has read AH[i]
           if (i) ah_cnt1 += 1;
@@ -738,9 +758,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           tmem_st16(trow + kTmemH + i * 128 + cg * 32, pk);
           tmem_st_wait();
         }
-        if (c == 4) TLE(164);
+        if (kDetailTl && c == 4) TLE(164);
         warp_arrive(&ah_ready[i]);
-        if (c == 4) TLE(165);
+        if (kDetailTl && c == 4) TLE(165);
         TLE(34 + c);
       }
 
@@ -849,31 +869,31 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         // -------------------------------------------- QKV chunks of the next block -> staging pair -> TMA store
         for (int c = 0; c < kQKV / 128; ++c) {
           const int i = c & 1;
-          if (c == 6) TLE(170);
+          if (kDetailTl && c == 6) TLE(170);
           mbar_wait(&h_full[i], (i ? h_cnt1 : h_cnt0) & 1);
           if (i) h_cnt1 += 1;
           else h_cnt0 += 1;
           tc_fence_after();
-          if (c == 6) TLE(171);
+          if (kDetailTl && c == 6) TLE(171);
           float y[32];
           tmem_ld32(trow + kTmemH + i * 128 + cg * 32, reinterpret_cast<uint32_t(&)[32]>(y));
           tmem_ld_wait();
           warp_arrive(&ah_ready[i]);  // H[i] is drained: the MMA warp may refill it
-          if (c == 6) TLE(172);
+          if (kDetailTl && c == 6) TLE(172);
           // staging pair i is free: the leader waited for the store of chunk c-2 before the barrier of chunk c-1
           store_row_chunks(stage + (i * 2 + (cg >> 1)) * kSlotBytes + row * 128, sw, (cg & 1) * 4, y);
           fence_proxy_async_smem();
-          if (c == 6) TLE(173);
+          if (kDetailTl && c == 6) TLE(173);
           if (leader) bulk_wait_read<0>();  // store of chunk c-1 (issued a whole chunk ago) has left pair i^1
-          if (c == 6) TLE(174);
+          if (kDetailTl && c == 6) TLE(174);
           epi_barrier();
-          if (c == 6) TLE(175);
+          if (kDetailTl && c == 6) TLE(175);
           if (leader) {
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 0) * kSlotBytes, c * 128, row0);
             tma_store_2d(&mapQkvOut, stage + (i * 2 + 1) * kSlotBytes, c * 128 + 64, row0);
             bulk_commit();
           }
-          if (c == 6) TLE(176);
+          if (kDetailTl && c == 6) TLE(176);
           TLE(44 + c);
         }
       }
