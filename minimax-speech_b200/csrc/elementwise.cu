@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels of the flow path: layout packing (the reference's einops.pack / rearrange copies,
 // flow/decoder.py:427-433), timestep conditioning (matcha decoder.py:14-29,73-117 + ResnetBlock1D.mlp :49),
 // CFG combine + Euler update (flow_matching.py:118-120) and the NCT <-> time-major boundary transposes.
+#include <algorithm>
+
 #include "kernels.h"
 #include "profiler.h"
 #include "ptx.cuh"
@@ -147,6 +149,92 @@ __global__ void mask_to_lengths_kernel(const float* __restrict__ mask, int* __re
   }
 }
 
+// ---- GroupNorm(8) + Mish of the non-causal ConditionalDecoder's blocks (matcha Block1D, decoder.py:32-43) on time-major
+// fp32 [B][T][C].  The statistics of a (batch row, group) run over (C/G channels x the row's valid frames), so they cannot
+// ride in the producing GEMM's epilogue (a tile sees 128 frames): one pass for the statistics, one to apply them.
+// Stats: one block per (group, batch row); per-thread Welford over its rows, merged with Chan's formula.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, float2* __restrict__ stats, int C,
+                                                              int T, int G, const int* __restrict__ lengths) {
+  const int grp = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;  // 32: one warp reads one frame's channels of the group (128 B)
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int t = warp; t < len; t += nw)
+    for (int c = lane; c < cpg; c += 32) {
+      const float v = x[((long long)b * T + t) * C + grp * cpg + c];
+      n += 1.f;
+      const float d = v - mean;
+      mean += d / n;
+      m2 = fmaf(d, v - mean, m2);
+    }
+  auto merge = [](float& na, float& ma, float& qa, float nb, float mb, float qb) {
+    const float nn = na + nb;
+    if (nn > 0.f) {
+      const float d = mb - ma;
+      ma += d * (nb / nn);
+      qa += qb + d * d * (na * nb / nn);
+      na = nn;
+    }
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    merge(n, mean, m2, nb, mb, qb);
+  }
+  __shared__ float sn[8], sm[8], sq[8];
+  if (lane == 0) sn[warp] = n, sm[warp] = mean, sq[warp] = m2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float na = sn[0], ma = sm[0], qa = sq[0];
+    for (int w = 1; w < nw; ++w) merge(na, ma, qa, sn[w], sm[w], sq[w]);
+    stats[b * G + grp] = make_float2(ma, na > 0.f ? rsqrtf(qa / na + 1e-5f) : 0.f);
+  }
+}
+// y = mish((x - mean) rstd gamma + beta) (+ temb[b][c]) (+ addend fp32) on valid frames, 0 on padding (what the next
+// convolution's x * mask makes of them); written as fp32 and / or in the 16-bit operand format.  4 channels per thread.
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ temb, long long temb_bstride,
+                                                              const float* __restrict__ addend, float* __restrict__ out_f32,
+                                                              __nv_bfloat16* __restrict__ out_h, int B, int C, int T, int G,
+                                                              const int* __restrict__ lengths, int fp16) {
+  const long long n4 = (long long)B * T * C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const long long row = e / C;
+    const int c = (int)(e - row * C);
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    const int len = lengths ? min(lengths[b], T) : T;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      const float2 st = stats[b * G + c / (C / G)];
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+      y.x = mish_f(fmaf((v.x - st.x) * st.y, gm.x, bt.x));
+      y.y = mish_f(fmaf((v.y - st.x) * st.y, gm.y, bt.y));
+      y.z = mish_f(fmaf((v.z - st.x) * st.y, gm.z, bt.z));
+      y.w = mish_f(fmaf((v.w - st.x) * st.y, gm.w, bt.w));
+      if (temb) {
+        const float4 tv = *reinterpret_cast<const float4*>(temb + (long long)b * temb_bstride + c);
+        y.x += tv.x, y.y += tv.y, y.z += tv.z, y.w += tv.w;
+      }
+      if (addend) {
+        const float4 a = reinterpret_cast<const float4*>(addend)[i];
+        y.x += a.x, y.y += a.y, y.z += a.z, y.w += a.w;
+      }
+    }
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = y;
+    if (out_h) {
+      uint2 h;
+      h.x = fp16 ? pack_f16x2(y.x, y.y) : pack_bf16x2(y.x, y.y);
+      h.y = fp16 ? pack_f16x2(y.z, y.w) : pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_h)[i] = h;
+    }
+  }
+}
+
 // ---- timestep conditioning (matcha decoder.py:14-29 SinusoidalPosEmb, :73-117 TimestepEmbedding, :49 ResnetBlock1D.mlp)
 // Three GEMV stages over ALL time values of a solve at once, each a grid of (output rows / 8, nt) blocks of 8 warps with
 // one output row per warp -- the weights (19 MB fp32) are streamed by ~450 blocks per time value instead of by one
@@ -255,6 +343,26 @@ cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T,
 cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s, int* bad_flag) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * T * 4.0);
   mask_to_lengths_kernel<<<B, 256, 0, s>>>(mask, lengths, B, T, dup, bad_flag);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_groupnorm_mish(const float* x, float2* stats, const float* gamma, const float* beta, const float* temb,
+                                  long long temb_bstride, const float* addend, float* out_f32, __nv_bfloat16* out_h, int B,
+                                  int C, int T, int G, const int* lengths, int fp16, cudaStream_t s) {
+  if (C % (4 * G) || (C / G) % 32) return cudaErrorInvalidValue;
+  const double elems = (double)B * T * C;
+  {
+    ProfScope prof(s, PK_ELEMENTWISE, 0.0, elems * 4.0);
+    groupnorm_stats_kernel<<<dim3(G, B), 256, 0, s>>>(x, stats, C, T, G, lengths);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  ProfScope prof(s, PK_ELEMENTWISE, 0.0, elems * (4.0 + (addend ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0) + (out_h ? 2.0 : 0.0)));
+  const long long n4 = (long long)B * T * C / 4;
+  int grid = (int)std::min<long long>((n4 + 255) / 256, 148 * 8);
+  groupnorm_apply_kernel<<<grid < 1 ? 1 : grid, 256, 0, s>>>(x, stats, gamma, beta, temb, temb_bstride, addend, out_f32, out_h, B,
+                                                            C, T, G, lengths, fp16);
   count_launch();
   return cudaGetLastError();
 }

@@ -120,6 +120,53 @@ __global__ void __launch_bounds__(kTB) layernorm_nct_kernel(const float* __restr
   }
 }
 
+// GroupNorm(G) -> Mish -> * mask (-> + vec[b,c]) on [B,C,T]: matcha Block1D (decoder.py:32-43), the block of the NON-causal
+// ConditionalDecoder (flow/decoder.py:88-291).  Statistics over the (C/G channels x valid frames) of one (b, group) -- the
+// frames of utterance b alone, as in one reference call per utterance -- two passes (mean, centred variance), eps 1e-5.
+__global__ void __launch_bounds__(256) group_norm_mish_nct_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                                  const float* __restrict__ be, float* __restrict__ y, int C,
+                                                                  int T, int G, const int* __restrict__ lens,
+                                                                  const float* __restrict__ vec) {
+  const int grp = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  const int len = min(lens[b], T);
+  const float* xb = x + ((size_t)b * C + (size_t)grp * cpg) * T;
+  float* yb = y + ((size_t)b * C + (size_t)grp * cpg) * T;
+  __shared__ float red[8];
+  __shared__ float stat;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // red / stat of the previous reduction have been consumed
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      stat = t;
+    }
+    __syncthreads();
+    return stat;
+  };
+  const int n = cpg * len;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) a += xb[(size_t)(i / len) * T + i % len];
+  const float mean = n ? block_sum(a) / (float)n : block_sum(0.f);
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float d = xb[(size_t)(i / len) * T + i % len] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf((n ? block_sum(q) / (float)n : block_sum(0.f)) + 1e-5f);
+  for (int i = threadIdx.x; i < cpg * T; i += 256) {
+    const int cl = i / T, t = i - cl * T, c = grp * cpg + cl;
+    float v = 0.f;
+    if (t < len) v = mish_exact((xb[i] - mean) * rstd * g[c] + be[c]);
+    if (vec) v += vec[(size_t)b * C + c];
+    yb[i] = v;
+  }
+}
+
 // diffusers Attention / AttnProcessor2_0 on q,k,v [R,H*64,T] with the additive mask of mask.py:161-236 +
 // common.py:160-168: key j visible iff j < len[r] (and, streaming, j < (i/chunk+1)*chunk); a query row with no
 // visible key sees every key (mask.py:233-235).  One thread per (r, h, query).
@@ -565,14 +612,26 @@ FlowEngineF32::FlowEngineF32(const Weights& w, int device) : device_(device) {
   feat_ = (int)w_.shape("final_proj.weight")[0];
   require(n_blocks_ > 0 && (int)w_.shape("down_blocks.0.1.0.attn1.to_q.weight")[0] == heads_ * 64,
           "fp32 estimator: expected 8 heads x 64", LS_ERR_UNSUPPORTED);
+  // CausalConditionalDecoder: LayerNorm at block.2 (after a Transpose); ConditionalDecoder: GroupNorm at block.1
+  causal_ = w_.has("final_block.block.2.weight");
+  conv_pad_ = causal_ ? 2 : 1;
+  require(causal_ || w_.has("final_block.block.1.weight"), "estimator state dict: neither block.2 (causal) nor block.1 norms",
+          LS_ERR_WEIGHTS);
 }
 
-// CausalBlock1D (decoder.py:65-78): conv3 causal on x*mask -> LayerNorm(C) -> Mish -> *mask (-> + addvec)
+// CausalBlock1D (decoder.py:65-78): conv3 causal on x*mask -> LayerNorm(C) -> Mish -> *mask (-> + addvec); for the
+// non-causal ConditionalDecoder, matcha's Block1D: conv3 pad 1 -> GroupNorm(8) over the utterance's frames -> Mish -> *mask
 float* FlowEngineF32::causal_block(const std::string& p, const float* x, int cin, const float* mask, const float* addvec,
                                    int R, int T, cudaStream_t s) {
   float* c = scratch_.get((size_t)R * C_ * T, s);
-  conv1d(x, mask, w_.ptr(p + ".block.0.weight"), w_.ptr(p + ".block.0.bias"), c, nullptr, R, cin, T, C_, 3, 1, 2, -1.f, s);
+  conv1d(x, mask, w_.ptr(p + ".block.0.weight"), w_.ptr(p + ".block.0.bias"), c, nullptr, R, cin, T, C_, 3, 1, conv_pad_, -1.f,
+         s);
   float* y = scratch_.get((size_t)R * C_ * T, s);
+  if (!causal_) {
+    F32_LAUNCH(group_norm_mish_nct_kernel, dim3(8, R), 256, s, c, w_.ptr(p + ".block.1.weight"), w_.ptr(p + ".block.1.bias"), y,
+               C_, T, 8, lens_, addvec);
+    return y;
+  }
   F32_LAUNCH(layernorm_nct_kernel, grid_t(T, 1, R), kTB, s, c, w_.ptr(p + ".block.2.weight"), w_.ptr(p + ".block.2.bias"), y,
              C_, T, 1, mask, addvec);
   return y;
@@ -639,6 +698,8 @@ void FlowEngineF32::run(const float* x, const float* mask, const float* mu, cons
   const int F = feat_;
   int* lens = reinterpret_cast<int*>(scratch_.get((size_t)R, s));
   F32_LAUNCH(mask_lengths_kernel, R, 256, s, mask, lens, T);
+  lens_ = lens;
+  if (!causal_) streaming = false;  // ConditionalDecoder.forward ignores the flag: full attention (decoder.py:241)
   // time embedding: sinusoid -> Linear -> SiLU -> Linear (matcha decoder.py:14-29, 73-117)
   const int tdim = (int)w_.shape("time_mlp.linear_1.weight")[1], thid = (int)w_.shape("time_mlp.linear_1.weight")[0];
   float* e0 = scratch_.get((size_t)R * tdim, s);
@@ -656,7 +717,8 @@ void FlowEngineF32::run(const float* x, const float* mask, const float* mu, cons
   float* h = group("down_blocks.0", h0, 4 * F, mask, temb, lens, R, T, streaming, s);
   float* skip = h;
   float* d = scratch_.get((size_t)R * C_ * T, s);
-  conv1d(h, mask, w_.ptr("down_blocks.0.2.weight"), w_.ptr("down_blocks.0.2.bias"), d, nullptr, R, C_, T, C_, 3, 1, 2, -1.f, s);
+  conv1d(h, mask, w_.ptr("down_blocks.0.2.weight"), w_.ptr("down_blocks.0.2.bias"), d, nullptr, R, C_, T, C_, 3, 1, conv_pad_, -1.f,
+         s);
   h = d;
   for (int i = 0; i < n_mid_; ++i) h = group("mid_blocks." + std::to_string(i), h, C_, mask, temb, lens, R, T, streaming, s);
   const size_t n_cat = (size_t)R * 2 * C_ * T;
@@ -664,7 +726,8 @@ void FlowEngineF32::run(const float* x, const float* mask, const float* mu, cons
   F32_LAUNCH(cat_channels_kernel, blocks(n_cat), 256, s, h, skip, cat, C_, C_, T, n_cat);
   h = group("up_blocks.0", cat, 2 * C_, mask, temb, lens, R, T, streaming, s);
   float* uo = scratch_.get((size_t)R * C_ * T, s);
-  conv1d(h, mask, w_.ptr("up_blocks.0.2.weight"), w_.ptr("up_blocks.0.2.bias"), uo, nullptr, R, C_, T, C_, 3, 1, 2, -1.f, s);
+  conv1d(h, mask, w_.ptr("up_blocks.0.2.weight"), w_.ptr("up_blocks.0.2.bias"), uo, nullptr, R, C_, T, C_, 3, 1, conv_pad_, -1.f,
+         s);
   float* fb = causal_block("final_block", uo, C_, mask, nullptr, R, T, s);
   conv1d(fb, mask, w_.ptr("final_proj.weight"), w_.ptr("final_proj.bias"), out, mask, R, C_, T, F, 1, 1, 0, -1.f, s);
 }

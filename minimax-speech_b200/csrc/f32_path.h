@@ -64,6 +64,9 @@ class FlowEngineF32 {
   float* causal_block(const std::string& p, const float* x, int cin, const float* mask, const float* addvec, int R,
                       int T, cudaStream_t s);
   int device_ = 0, feat_ = 80, C_ = 256, heads_ = 8, n_blocks_ = 0, n_mid_ = 0, chunk_ = 50;
+  bool causal_ = true;   // false: the non-causal ConditionalDecoder (Conv1d pad 1 + GroupNorm(8) blocks)
+  int conv_pad_ = 2;
+  const int* lens_ = nullptr;  // device lengths of the call in flight (GroupNorm statistics run over the valid frames)
   F32Weights w_;
   F32Scratch scratch_;
 };

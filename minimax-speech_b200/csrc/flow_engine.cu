@@ -55,6 +55,8 @@ void finalize_linear(const Arena& a, PackedLinear& pl) {
   pl.bias = pl.has_bias ? a.ptr<float>(pl.bias_off) : nullptr;
 }
 
+bool fused_blocks_check(int C, int inner) { return C == 256 && inner == 512; }
+
 int count_prefix(const Weights& w, const char* fmt) {
   int n = 0;
   char buf[160];
@@ -138,16 +140,22 @@ FlowEngine::FlowEngine(const Weights& w, int device, bool fp16) : device_(device
           "estimator configuration not covered: need channels=[256], head_dim 64, in_channels = 4*out_channels",
           LS_ERR_UNSUPPORTED);
 
+  // CausalConditionalDecoder keeps a LayerNorm at block.2 of every block (decoder.py:65-76), the non-causal
+  // ConditionalDecoder (decoder.py:88-291; matcha Block1D) a GroupNorm(8) at block.1
+  causal_ = w.has("final_block.block.2.weight");
+  require(causal_ || w.has("final_block.block.1.weight"), "estimator state dict: neither block.2 (causal) nor block.1 norms",
+          LS_ERR_WEIGHTS);
+  const std::string nk = causal_ ? ".block.2" : ".block.1";
   auto vec = [&](const std::string& name, int n) { return arena_.put_f32(w.get(name, {n}).data, n); };
   auto resnet = [&](const std::string& p, int cin) {
     ResnetW r;
     r.cin = cin;
     r.conv1 = pack_linear(arena_, w.get(p + ".block1.block.0.weight", {C_, cin, 3}), &w.get(p + ".block1.block.0.bias"));
-    r.ln1g = vec(p + ".block1.block.2.weight", C_);
-    r.ln1b = vec(p + ".block1.block.2.bias", C_);
+    r.ln1g = vec(p + ".block1" + nk + ".weight", C_);
+    r.ln1b = vec(p + ".block1" + nk + ".bias", C_);
     r.conv2 = pack_linear(arena_, w.get(p + ".block2.block.0.weight", {C_, C_, 3}), &w.get(p + ".block2.block.0.bias"));
-    r.ln2g = vec(p + ".block2.block.2.weight", C_);
-    r.ln2b = vec(p + ".block2.block.2.bias", C_);
+    r.ln2g = vec(p + ".block2" + nk + ".weight", C_);
+    r.ln2b = vec(p + ".block2" + nk + ".bias", C_);
     r.res = pack_linear(arena_, w.get(p + ".res_conv.weight", {C_, cin, 1}), &w.get(p + ".res_conv.bias"));
     return r;
   };
@@ -185,8 +193,10 @@ FlowEngine::FlowEngine(const Weights& w, int device, bool fp16) : device_(device
   down_conv_ = pack_linear(arena_, w.get("down_blocks.0.2.weight", {C_, C_, 3}), &w.get("down_blocks.0.2.bias"));
   up_conv_ = pack_linear(arena_, w.get("up_blocks.0.2.weight", {C_, C_, 3}), &w.get("up_blocks.0.2.bias"));
   final_conv_ = pack_linear(arena_, w.get("final_block.block.0.weight", {C_, C_, 3}), &w.get("final_block.block.0.bias"));
-  final_lng_ = vec("final_block.block.2.weight", C_);
-  final_lnb_ = vec("final_block.block.2.bias", C_);
+  final_lng_ = vec("final_block" + nk + ".weight", C_);
+  final_lnb_ = vec("final_block" + nk + ".bias", C_);
+  require(causal_ || fused_blocks_check(C_, inner), "the non-causal estimator needs the fused-block geometry (C = 256, 8 x 64)",
+          LS_ERR_UNSUPPORTED);
   final_proj_ = pack_linear(arena_, w.get("final_proj.weight", {feat_, C_, 1}), &w.get("final_proj.bias"));
 
   // timestep conditioning (fp32): sinusoid frequencies, time_mlp, one Linear per resnet
@@ -298,6 +308,10 @@ void FlowEngine::ensure_workspace(int B2, int T, int nt, cudaStream_t s) {
   o_t_ = take((size_t)cap_nt_ * 4);
   o_temb_ = take((size_t)cap_nt_ * groups_.size() * C_ * 4);
   o_tscr_ = take((size_t)cap_nt_ * 2 * hid_ * 4);
+  if (!causal_) {
+    o_raw_ = take(R * C_ * 4);                  // convolution output before GroupNorm (fp32)
+    o_gn_ = take((size_t)cap_b2_ * 8 * 8);      // (mean, rstd) per (batch row, group)
+  }
   ws_alloc(ws_base_, off, s);
   ws_bytes_ = off;
   ++ws_generation_;
@@ -358,6 +372,7 @@ struct Epi {
 
 void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_bstride, bool streaming,
                                cudaStream_t s) {
+  if (!causal_) streaming = false;  // ConditionalDecoder.forward ignores the flag: full attention (decoder.py:241)
   const Plan& pl = plan_for(B2, T);
   const int* lengths = ws<int>(o_len_);
   const int inner = heads_ * 64;
@@ -368,7 +383,8 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
     const CUtensorMap* a1 = am1 ? (w.taps > 1 ? &am1->k3 : &am1->k1) : nullptr;
     ConvGemmParams p{};
     p.B = B2, p.M = T, p.N = w.N, p.block_n = w.block_n;
-    p.taps = w.taps, p.dil = 1, p.pad = w.taps - 1;  // causal: left context only (decoder.py:59-62)
+    p.taps = w.taps, p.dil = 1;
+    p.pad = causal_ ? w.taps - 1 : (w.taps - 1) / 2;  // causal: left context only (decoder.py:59-62); else Conv1d(padding=1)
     p.kb_per_tap = (w.K + 63) / 64;
     p.kb_split = a1 ? a0_channels / 64 : p.kb_per_tap;
     p.lengths = lengths, p.m_len_mul = 1, p.m_len_add = 0, p.skip_halo = 0;
@@ -391,6 +407,32 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   // `a0`(+`a1`) = masked bf16 input; `tail` = bf16 buffer that receives the masked group output.
   auto group = [&](int gi, const ActMaps& a0, const ActMaps* a1, int a0_ch, void* tail) {
     const GroupW& g = groups_[gi];
+    if (!causal_) {
+      // matcha Block1D (decoder.py:32-43): conv3 (pad 1) -> GroupNorm(8) over the utterance's frames -> Mish -> mask.  The
+      // statistics span the whole utterance, so the convolution writes its raw fp32 output and two bandwidth kernels
+      // (statistics, apply) follow; the time-embedding add and the residual add ride in the apply pass.
+      float* raw = ws<float>(o_raw_);
+      float2* gst = ws<float2>(o_gn_);
+      {
+        Epi e;
+        e.out0 = raw, e.out0_dtype = OUT_F32, e.zero_skipped = 1;
+        gemm(a0, a1, a0_ch, g.res.conv1, e);
+      }
+      LS_CUDA(launch_groupnorm_mish(raw, gst, f32(g.res.ln1g), f32(g.res.ln1b), temb + (long long)gi * C_, temb_bstride, nullptr,
+                                    nullptr, ws<__nv_bfloat16>(o_hA_), B2, C_, T, 8, lengths, fp16_, s));
+      {  // res_conv(x*mask)
+        Epi e;
+        e.out0 = r, e.out0_dtype = OUT_F32, e.zero_skipped = 1;
+        gemm(a0, a1, a0_ch, g.res.res, e);
+      }
+      {
+        Epi e;
+        e.out0 = raw, e.out0_dtype = OUT_F32, e.zero_skipped = 1;
+        gemm(pl.hA, nullptr, 0, g.res.conv2, e);
+      }
+      LS_CUDA(launch_groupnorm_mish(raw, gst, f32(g.res.ln2g), f32(g.res.ln2b), nullptr, 0, r, u, nullptr, B2, C_, T, 8, lengths,
+                                    fp16_, s));
+    } else {
     {  // block1: conv3 -> LN -> Mish -> mask, then + Linear(Mish(temb))   (matcha decoder.py:57-58)
       Epi e;
       e.act = ACT_LN_MISH, e.ln_g = f32(g.res.ln1g), e.ln_b = f32(g.res.ln1b);
@@ -412,6 +454,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         e.out1 = ws<void>(o_nrm_), e.out1_mode = OUT1_LN, e.p1_a = f32(g.tb[0].n1g), e.p1_b = f32(g.tb[0].n1b);
       gemm(pl.hA, nullptr, 0, g.res.conv2, e);
     }
+    }  // causal
     auto attention = [&]() {
       AttnParams ap{};
       ap.B = B2, ap.T = T, ap.H = heads_, ap.lengths = lengths, ap.chunk = streaming ? chunk_ : 0;
@@ -424,7 +467,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       // every later QKV comes out of the previous block's launch
       {
         TBlockParams tp{};
-        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2, tp.fp16 = fp16_;
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2, tp.fp16 = fp16_, tp.no_skip = causal_ ? 0 : 1;
         TBlockMaps tm;
         tm.att = pl.att_flat, tm.wo = g.tb[0].m_out, tm.w1 = g.tb[0].m_ff1, tm.w2 = g.tb[0].m_ff2;  // unused in head mode
         tm.wqkv = g.tb[0].m_qkv, tm.u = pl.u_flat, tm.qkv_out = pl.qkv_flat, tm.tail_out = pl.tail_hB;
@@ -435,7 +478,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         attention();
         const bool last = j + 1 == n_blocks_;
         TBlockParams tp{};
-        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(t.vec), tp.tail_mode = last ? 1 : 0, tp.fp16 = fp16_;
+        tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(t.vec), tp.tail_mode = last ? 1 : 0, tp.fp16 = fp16_, tp.no_skip = causal_ ? 0 : 1;
         TBlockMaps tm;
         tm.att = pl.att_flat, tm.wo = t.m_out, tm.w1 = t.m_ff1, tm.w2 = t.m_ff2;
         tm.wqkv = last ? t.m_qkv : g.tb[j + 1].m_qkv;
@@ -488,7 +531,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   group(0, pl.xin, nullptr, 0, ws<void>(o_skip_));
   {
     Epi e;
-    e.out1 = ws<void>(o_hB_), e.out1_mode = OUT1_COPY;
+    e.out1 = ws<void>(o_hB_), e.out1_mode = OUT1_COPY, e.zero_skipped = causal_ ? 0 : 1;  // (non-causal: the next conv reads row `len`)
     gemm(pl.skip, nullptr, 0, down_conv_, e);
   }
   for (int i = 0; i < n_mid_; ++i) group(1 + i, pl.hB, nullptr, 0, ws<void>(o_hB_));
@@ -496,10 +539,16 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   group(1 + n_mid_, pl.hB, &pl.skip, C_, ws<void>(o_hB_));
   {
     Epi e;
-    e.out1 = ws<void>(o_hA_), e.out1_mode = OUT1_COPY;
+    e.out1 = ws<void>(o_hA_), e.out1_mode = OUT1_COPY, e.zero_skipped = causal_ ? 0 : 1;
     gemm(pl.hB, nullptr, 0, up_conv_, e);
   }
-  {  // final_block (decoder.py:494)
+  if (!causal_) {  // final_block = Block1D (decoder.py:195,290)
+    Epi e;
+    e.out0 = ws<float>(o_raw_), e.out0_dtype = OUT_F32, e.zero_skipped = 1;
+    gemm(pl.hA, nullptr, 0, final_conv_, e);
+    LS_CUDA(launch_groupnorm_mish(ws<float>(o_raw_), ws<float2>(o_gn_), f32(final_lng_), f32(final_lnb_), nullptr, 0, nullptr,
+                                  nullptr, ws<__nv_bfloat16>(o_hB_), B2, C_, T, 8, lengths, fp16_, s));
+  } else {  // final_block (decoder.py:494)
     Epi e;
     e.act = ACT_LN_MISH, e.ln_g = f32(final_lng_), e.ln_b = f32(final_lnb_);
     e.out1 = ws<void>(o_hB_), e.out1_mode = OUT1_COPY;

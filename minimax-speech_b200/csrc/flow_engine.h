@@ -39,6 +39,7 @@ class FlowEngine {
 
   int device_ = 0, num_sms_ = 148;
   int fp16_ = 0;
+  bool causal_ = true;  // false: the non-causal ConditionalDecoder (Conv1d pad 1 + GroupNorm(8) blocks)
   bool fused_blocks_ = false;
   int C_ = 256, in_ch_ = 320, feat_ = 80, heads_ = 8, hid_ = 1024, n_blocks_ = 4, n_mid_ = 12, chunk_ = 50;
   Arena arena_;
@@ -52,7 +53,7 @@ class FlowEngine {
   long long cap_rows_ = 0;
   int cap_nt_ = 0, cap_b2_ = 0;
   size_t o_xin_ = 0, o_hA_ = 0, o_hB_ = 0, o_skip_ = 0, o_nrm_ = 0, o_qkv_ = 0, o_att_ = 0, o_ff_ = 0, o_u_ = 0,
-         o_r_ = 0, o_v_ = 0, o_x_ = 0, o_len_ = 0, o_t_ = 0, o_temb_ = 0, o_tscr_ = 0;
+         o_r_ = 0, o_v_ = 0, o_x_ = 0, o_len_ = 0, o_t_ = 0, o_temb_ = 0, o_tscr_ = 0, o_raw_ = 0, o_gn_ = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans_;
   std::vector<float> t_host_, dt_host_;
   unsigned long long ws_generation_ = 0;

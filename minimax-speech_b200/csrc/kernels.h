@@ -173,6 +173,8 @@ struct TBlockParams {
                        // 2: "head" of a block group: only LayerNorm(u; g1n, be1n) + QKV (att, Wo, W1, W2 unused)
   long long* timeline; // development aid (ls_debug_set_buffer): [grid][64] clock64 stamps of the first tile, or nullptr
   int fp16;            // 1: every 16-bit operand / output is fp16 instead of bf16
+  int no_skip;         // 1: tiles that are padding only are processed too (their rows come out as zeros): the non-causal
+                       //    estimator's convolutions read the first padding row after an utterance
 };
 // Every global tensor is reached through TMA (loads and stores), 128-row boxes, 128-byte swizzle:
 struct TBlockMaps {
@@ -208,6 +210,12 @@ cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T,
 // when a mask is not a prefix mask
 cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s,
                                    int* bad_flag = nullptr);
+// GroupNorm(G) + Mish on time-major fp32 x [B][T][C] with per-row statistics over the valid frames (the non-causal
+// ConditionalDecoder's blocks): stats [B][G] scratch; then + temb[b] (optional) + addend (optional fp32, same layout);
+// fp32 and / or 16-bit outputs (either may be null); padding rows come out as 0 (+ temb + addend).
+cudaError_t launch_groupnorm_mish(const float* x, float2* stats, const float* gamma, const float* beta, const float* temb,
+                                  long long temb_bstride, const float* addend, float* out_f32, __nv_bfloat16* out_h, int B,
+                                  int C, int T, int G, const int* lengths, int fp16, cudaStream_t s);
 // timestep conditioning for nt time values: sinusoidal embedding -> MLP -> per-resnet projections
 struct TimeEmbedParams {
   const float* t;        // [nt] device, or nullptr: the values come from t_host (nt <= 64) inside the kernel parameters

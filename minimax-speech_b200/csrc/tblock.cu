@@ -108,7 +108,7 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 
 // true if every row of the tile is padding (t >= lengths[b])
 __device__ __forceinline__ bool tile_all_padding(const TBlockParams& p, int row0) {
-  if (p.lengths == nullptr) return false;
+  if (p.lengths == nullptr || p.no_skip) return false;
   const int last = min(row0 + kTileM, p.R) - 1;
   for (int b = row0 / p.T; b <= last / p.T; ++b) {
     const int t_start = max(row0, b * p.T) - b * p.T;

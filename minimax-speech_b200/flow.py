@@ -77,7 +77,7 @@ class CausalConditionalDecoder(nn.Module):
 
     def __init__(self, in_channels=320, out_channels=80, channels=(256,), dropout=0.0, attention_head_dim=64,
                  n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn="gelu", static_chunk_size=50,
-                 num_decoding_left_chunks=-1, weight_seed=1986, precision="bf16"):
+                 num_decoding_left_chunks=-1, weight_seed=1986, precision="bf16", _causal=True):
         super().__init__()
         self.precision = native.check_precision(precision, fp16_ok=True)
         channels = tuple(channels)
@@ -90,7 +90,8 @@ class CausalConditionalDecoder(nn.Module):
         self.static_chunk_size, self.num_decoding_left_chunks = static_chunk_size, num_decoding_left_chunks
         _register_tree(self, synth.estimator_state_dict(
             weight_seed, "reference", in_channels=in_channels, out_channels=out_channels, channels=256,
-            n_blocks=n_blocks, num_mid_blocks=num_mid_blocks, num_heads=num_heads, head_dim=attention_head_dim))
+            n_blocks=n_blocks, num_mid_blocks=num_mid_blocks, num_heads=num_heads, head_dim=attention_head_dim,
+            causal=_causal))
         self._handle = None
         self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
 
@@ -128,6 +129,26 @@ class CausalConditionalDecoder(nn.Module):
                                                   _as_f32(mu, dev), _as_f32(t, dev), _as_f32(spks, dev),
                                                   _as_f32(cond, dev), bool(streaming))
         return out.to(x.dtype)
+
+
+class ConditionalDecoder(CausalConditionalDecoder):
+    """The non-causal estimator, ``cosyvoice.flow.decoder.ConditionalDecoder`` (speech/cosyvoice/flow/decoder.py:88-291): the
+    same U-Net with matcha's ``Block1D`` blocks -- Conv1d(k 3, padding 1) -> GroupNorm(8) -> Mish -- in place of the causal
+    conv + LayerNorm ones, and full (never block-causal) attention.  Same ``forward(x, mask, mu, t, spks, cond)``, same
+    state_dict key schema as the reference class (GroupNorm parameters at ``block.1``).  GroupNorm statistics are taken over
+    each utterance's own frames (one reference call per utterance).  Covered geometry: ``channels=[256]`` (no down/up-sampling
+    level), 8 heads x 64, ``act_fn='gelu'`` -- config.yaml's estimator with the non-causal class swapped in."""
+
+    def __init__(self, in_channels=320, out_channels=80, channels=(256,), dropout=0.0, attention_head_dim=64, n_blocks=4,
+                 num_mid_blocks=12, num_heads=8, act_fn="gelu", weight_seed=1986, precision="bf16"):
+        if num_heads != 8:
+            raise NotImplementedError("B200 non-causal estimator: 8 heads x 64 (the fused transformer-block geometry)")
+        super().__init__(in_channels=in_channels, out_channels=out_channels, channels=channels, dropout=dropout,
+                         attention_head_dim=attention_head_dim, n_blocks=n_blocks, num_mid_blocks=num_mid_blocks,
+                         num_heads=num_heads, act_fn=act_fn, weight_seed=weight_seed, precision=precision, _causal=False)
+
+    def run(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
+        return super().run(x, mask, mu, t, spks, cond, False)  # the reference class ignores `streaming` (decoder.py:241)
 
 
 class ConditionalCFM(nn.Module):

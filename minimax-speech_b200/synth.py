@@ -43,8 +43,11 @@ def _uniform(seed, name, shape, bound):
 
 
 def estimator_state_dict(seed=1986, init="reference", in_channels=320, out_channels=80, channels=256,
-                         n_blocks=4, num_mid_blocks=12, num_heads=8, head_dim=64, **_):
-    """Keys/shapes of ``CausalConditionalDecoder.state_dict()`` for ``channels=[C]``."""
+                         n_blocks=4, num_mid_blocks=12, num_heads=8, head_dim=64, causal=True, **_):
+    """Keys/shapes of ``CausalConditionalDecoder.state_dict()`` for ``channels=[C]``; ``causal=False``: the non-causal
+    ``ConditionalDecoder`` (speech/cosyvoice/flow/decoder.py:88-291), whose blocks are Conv1d(pad 1) -> GroupNorm(8) ->
+    Mish (matcha Block1D): the norm parameters sit at ``block.1`` instead of ``block.2``."""
+    nk = "2" if causal else "1"
     C, inner, temb = channels, num_heads * head_dim, channels * 4
     test = init == "test"
     sd = {}
@@ -64,9 +67,9 @@ def estimator_state_dict(seed=1986, init="reference", in_channels=320, out_chann
     def resnet(p, cin):
         lin(p + ".mlp.1", C, temb)
         lin(p + ".block1.block.0", C, cin, k=3)
-        ln(p + ".block1.block.2", C)
+        ln(p + ".block1.block." + nk, C)
         lin(p + ".block2.block.0", C, C, k=3)
-        ln(p + ".block2.block.2", C)
+        ln(p + ".block2.block." + nk, C)
         lin(p + ".res_conv", C, cin, k=1)
 
     def tblock(p):
@@ -93,7 +96,7 @@ def estimator_state_dict(seed=1986, init="reference", in_channels=320, out_chann
         tblock(f"up_blocks.0.1.{j}")
     lin("up_blocks.0.2", C, C, k=3)
     lin("final_block.block.0", C, C, k=3)
-    ln("final_block.block.2", C)
+    ln("final_block.block." + nk, C)
     lin("final_proj", out_channels, C, k=1)
     return sd
 

@@ -76,6 +76,7 @@ def extra_golden():
     cfm_nc_golden.npz     the non-causal twin ``ConditionalCFM.forward`` (flow_matching.py:39-72) called twice (n_timesteps = 10, the value flow.py:192,506 pass) on the
                           unmodified reference: prompt_len = 20 with an empty cache, then with the returned cache
                           (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
+    est_nc_golden.npz     the non-causal ConditionalDecoder estimator (decoder.py:88-291), one call per utterance.
     dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
                           Snake alpha in [0.5, 2], activations of O(10), |alpha * x| up to ~25 rad), layers.py:18-33.
     """
@@ -98,6 +99,29 @@ def extra_golden():
             out[f"nc_{i}_z"], out[f"nc_{i}_y"], out[f"nc_{i}_cache"] = z.numpy(), y.numpy(), cache.numpy()
             print("cfm non-causal", i, y.shape, cache.shape, float(y.abs().mean()))
         np.savez_compressed(os.path.join(OUT, "cfm_nc_golden.npz"), **out)
+
+        # ---- the non-causal ConditionalDecoder (decoder.py:88-291): Conv1d(pad 1) + GroupNorm(8) blocks.  One reference
+        # call per utterance at its own length (the reference's solve_euler is batch 1): GroupNorm statistics run over the
+        # frames of that utterance only.
+        sd = synth.estimator_state_dict(EST_SEED + 2, init="test", causal=False)
+        est = R.build_reference_noncausal_estimator()
+        est.load_state_dict(sd, strict=True)
+        out = {"weights_seed": EST_SEED + 2, "weights_checksum": synth.checksum(sd)}
+        for name, lengths, seed in [("a", [96], 110), ("b", [130, 77], 111)]:
+            x, mask, mu, t, spks, cond = est_inputs(lengths, seed)
+            ys = []
+            for b, n in enumerate(lengths):
+                y = est(x[b:b + 1, :, :n], mask[b:b + 1, :, :n], mu[b:b + 1, :, :n], t[b:b + 1], spks[b:b + 1], cond[b:b + 1, :, :n])
+                yp = torch.zeros(1, 80, max(lengths))
+                yp[:, :, :n] = y
+                ys.append(yp)
+            out[f"est_{name}_lengths"], out[f"est_{name}_seed"] = np.array(lengths), seed
+            out[f"est_{name}_y"] = torch.cat(ys, 0).numpy()
+            print("non-causal estimator", name, out[f"est_{name}_y"].shape, float(np.abs(out[f"est_{name}_y"]).mean()))
+        np.savez_compressed(os.path.join(OUT, "est_nc_golden.npz"), **out)
+        with open(os.path.join(OUT, "est_nc_keys.json"), "w") as f:
+            import json
+            json.dump({k: list(v.shape) for k, v in est.state_dict().items()}, f, indent=0, sort_keys=True)
 
         sd = synth.dac_decoder_state_dict(DAC_TRAINED_SEED, init="trained")
         dac = R.build_reference_dac()

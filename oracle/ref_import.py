@@ -184,6 +184,14 @@ def build_reference_flow(estimator_kwargs=None):
     return cfm.eval()
 
 
+def build_reference_noncausal_estimator():
+    """The reference's non-causal ConditionalDecoder (speech/cosyvoice/flow/decoder.py:88-291) at config.yaml's geometry
+    (channels=[256]: no down/up-sampling level)."""
+    _, _, _, Dec, _ = load_flow_classes()
+    return Dec(in_channels=320, out_channels=80, channels=[256], dropout=0.0, attention_head_dim=64, n_blocks=4,
+               num_mid_blocks=12, num_heads=8, act_fn="gelu").eval()
+
+
 def build_reference_dac(cfg=None):
     dm = load_dac_module()
     return dm.DACVAE(**(cfg or DAC_CFG_X2)).eval()

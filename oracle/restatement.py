@@ -57,11 +57,30 @@ def causal_block(sd, p, x, mask):
     return h * mask
 
 
+def block1d(sd, p, x, mask):
+    """Block1D matcha decoder.py:32-43 (the non-causal ConditionalDecoder's block): Conv1d(k 3, pad 1) -> GroupNorm(8) ->
+    Mish, masked.  Restated with PER-UTTERANCE semantics (one reference call per utterance at its own length, batch 1 as
+    the reference's solve_euler requires): the GroupNorm statistics of utterance b run over its valid frames only."""
+    h = F.conv1d(x * mask, sd[p + ".block.0.weight"], sd[p + ".block.0.bias"], padding=1)
+    out = torch.zeros_like(h)
+    for b in range(h.shape[0]):
+        n = int(mask[b, 0].sum().item())
+        if n:
+            out[b:b + 1, :, :n] = F.group_norm(h[b:b + 1, :, :n], 8, sd[p + ".block.1.weight"], sd[p + ".block.1.bias"], 1e-5)
+    return F.mish(out) * mask
+
+
+def is_causal(sd):
+    """CausalConditionalDecoder keeps its LayerNorm at block.2 (after a Transpose), ConditionalDecoder its GroupNorm at block.1."""
+    return "final_block.block.2.weight" in sd
+
+
 def resnet_block(sd, p, x, mask, temb):
-    """ResnetBlock1D.forward matcha decoder.py:56-61 with causal blocks."""
-    h = causal_block(sd, p + ".block1", x, mask)
+    """ResnetBlock1D.forward matcha decoder.py:56-61 with causal (flow/decoder.py:81-85) or plain blocks."""
+    blk = causal_block if is_causal(sd) else block1d
+    h = blk(sd, p + ".block1", x, mask)
     h = h + F.linear(F.mish(temb), sd[p + ".mlp.1.weight"], sd[p + ".mlp.1.bias"]).unsqueeze(-1)
-    h = causal_block(sd, p + ".block2", h, mask)
+    h = blk(sd, p + ".block2", h, mask)
     return h + F.conv1d(x * mask, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
 
 
@@ -132,15 +151,17 @@ def estimator_forward(sd, x, mask, mu, t, spks, cond, streaming=False, heads=8, 
                 taps[f"{prefix}.1.{j}"] = u
         return u.transpose(1, 2)
 
+    causal = is_causal(sd)
+    conv3 = causal_conv if causal else (lambda xx, w, b: F.conv1d(xx, w, b, padding=1))  # decoder.py:141 / :186
     h = group(h, "down_blocks.0")
     skip = h
-    h = causal_conv(h * mask, sd["down_blocks.0.2.weight"], sd["down_blocks.0.2.bias"])
+    h = conv3(h * mask, sd["down_blocks.0.2.weight"], sd["down_blocks.0.2.bias"])
     for i in range(n_mid):
         h = group(h, f"mid_blocks.{i}")
     h = torch.cat([h, skip], dim=1)
     h = group(h, "up_blocks.0")
-    h = causal_conv(h * mask, sd["up_blocks.0.2.weight"], sd["up_blocks.0.2.bias"])
-    h = causal_block(sd, "final_block", h, mask)
+    h = conv3(h * mask, sd["up_blocks.0.2.weight"], sd["up_blocks.0.2.bias"])
+    h = (causal_block if causal else block1d)(sd, "final_block", h, mask)
     out = F.conv1d(h * mask, sd["final_proj.weight"], sd["final_proj.bias"])
     return out * mask
 

@@ -190,3 +190,23 @@ def test_dac_trained_scale_matches_reference(golden_dir, case):
     with torch.inference_mode():
         y = O.dac_decode(sd, z)
     assert O.snr_db(y, torch.from_numpy(g[f"dac_{case}_y"])) > 90.0
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_noncausal_estimator_matches_reference(golden_dir, case):
+    """ConditionalDecoder (Conv1d pad 1 + GroupNorm(8) blocks, decoder.py:88-291): the restatement, batched with per-utterance
+    GroupNorm statistics, against one reference call per utterance; and the key schema of the drop-in's synthetic weights."""
+    import json
+    g = np.load(os.path.join(golden_dir, "est_nc_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test", causal=False)
+    assert abs(synth.checksum(sd) - float(g["weights_checksum"])) < 1e-6 * abs(float(g["weights_checksum"]))
+    keys = json.load(open(os.path.join(golden_dir, "est_nc_keys.json")))
+    assert {k: list(v.shape) for k, v in sd.items()} == keys
+    lengths = [int(v) for v in g[f"est_{case}_lengths"]]
+    x, mask, mu, t, spks, cond = est_inputs(lengths, int(g[f"est_{case}_seed"]))
+    with torch.inference_mode():
+        y = O.estimator_forward(sd, x, mask, mu, t, spks, cond)
+    ref = torch.from_numpy(g[f"est_{case}_y"])
+    for b, n in enumerate(lengths):
+        assert O.rel_l2(y[b, :, :n], ref[b, :, :n]) < 2e-5
+        assert float(y[b, :, n:].abs().max() if n < y.shape[2] else 0.0) == 0.0

@@ -243,3 +243,57 @@ def test_fp16_operands_cfm_solve_vs_reference_golden(flow16, case):
         e = O.rel_l2(y[b, :, :n], ref[b, :, :n])
         print(f"cfm {case}[{b}] fp16 operands rel-L2 {e:.3e}")
         assert e < 4e-3
+
+
+# ---- the non-causal ConditionalDecoder estimator (decoder.py:88-291: Conv1d pad 1 + GroupNorm(8) blocks) ----
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_noncausal_estimator_vs_reference_golden(golden_dir, case, precision):
+    from minimax_speech_b200.flow import ConditionalDecoder
+    g = np.load(os.path.join(golden_dir, "est_nc_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test", causal=False)
+    est = ConditionalDecoder(precision=precision)
+    est.load_state_dict(sd)
+    lengths = [int(v) for v in g[f"est_{case}_lengths"]]
+    x, mask, mu, t, spks, cond = est_inputs(lengths, int(g[f"est_{case}_seed"]))
+    y = est(x.to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV), spks.to(DEV), cond.to(DEV)).cpu()
+    ref = torch.from_numpy(g[f"est_{case}_y"])
+    tol = {"fp32": 1e-4, "bf16": 1.6e-2, "fp16": 4e-3}[precision]  # single call (cf. test_estimator_vs_reference_golden)
+    for b, n in enumerate(lengths):
+        e = O.rel_l2(y[b, :, :n], ref[b, :, :n])
+        print(f"non-causal estimator {case}[{b}] ({precision}) rel-L2 {e:.3e}")
+        assert e < tol
+        assert float(y[b, :, n:].abs().max() if n < y.shape[2] else 0.0) == 0.0
+
+
+def test_noncausal_estimator_solve_and_batch_invariance(golden_dir):
+    """The non-causal estimator inside the Euler / CFG solve (ConditionalCFM.forward) against the oracle, and a padded
+    batch against one call per utterance -- including a length that is a multiple of the 128-row tile (the convolution
+    reads the first padding row after the utterance)."""
+    from minimax_speech_b200.flow import ConditionalCFM, ConditionalDecoder
+    g = np.load(os.path.join(golden_dir, "est_nc_golden.npz"))
+    sd = synth.estimator_state_dict(int(g["weights_seed"]), init="test", causal=False)
+    est = ConditionalDecoder(precision="fp16")
+    est.load_state_dict(sd)
+    cfm = ConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est)
+    mu, mask, spks, cond = synth.batch_inputs([90], first_index=33)
+    z = torch.randn(1, 80, 90, generator=torch.Generator().manual_seed(9))
+    y, _ = cfm(mu.clone().to(DEV), mask.to(DEV), 10, temperature=1.0, spks=spks.to(DEV), cond=cond.to(DEV), noise=z)
+    with torch.inference_mode():
+        ref, _ = O.cfm_forward_cached(sd, z, mu, mask, 10, 1.0, spks, cond)
+    e = O.rel_l2(y.cpu(), ref)
+    print(f"non-causal estimator, 10-step solve (fp16 operands) rel-L2 {e:.3e}")
+    assert e < LATENT_TOL
+    lengths = [300, 128, 256, 57]
+    x, mask, mu, t, spks, cond = est_inputs(lengths, 77)
+    args = [v.to(DEV) for v in (x, mask, mu, t, spks, cond)]
+    big = est(*[v.clone() for v in [torch.randn(2, 80, 400, device=DEV), torch.ones(2, 1, 400, device=DEV),
+                                    torch.randn(2, 80, 400, device=DEV), torch.rand(2, device=DEV),
+                                    torch.randn(2, 80, device=DEV), torch.randn(2, 80, 400, device=DEV)]])  # dirty the workspace
+    assert bool(torch.isfinite(big).all())
+    yb = est(*args)
+    for b, n in enumerate(lengths):
+        y1 = est(x[b:b + 1, :, :n].to(DEV), mask[b:b + 1, :, :n].to(DEV), mu[b:b + 1, :, :n].to(DEV), t[b:b + 1].to(DEV),
+                 spks[b:b + 1].to(DEV), cond[b:b + 1, :, :n].to(DEV))
+        e = O.rel_l2(yb[b, :, :n].cpu(), y1[0].cpu())
+        assert e < 1e-5, (b, n, e)
