@@ -140,6 +140,14 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
                            int64_t noise_stride, const float* t_span_host, int32_t n_timesteps, float temperature,
                            float cfg_rate, float* wav_host, int32_t B, int32_t T, void* stream);
 
+/* ---- FSQ quantizer head of the S3 speech tokenizer (second half): FSQCodebook.encode,
+ * speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:83-117 -- hidden [rows, dim] (the AudioEncoderV2 output, fp32) ->
+ * tokens [rows] in [0, 3^8): round(tanh(project_down(h)) * 0.999) + 1 per digit, base-3 packed.  All pointers are device
+ * pointers (project_down.weight [8, dim], project_down.bias [8]).  Stateless.  The encoder trunk in front of it
+ * (model_v2.py:243-351) is not built. */
+int32_t ls_fsq_encode(const float* hidden, const float* project_down_weight, const float* project_down_bias, int32_t* tokens,
+                      int64_t rows, int32_t dim, void* stream);
+
 /* lengths[b] = number of non-zero entries of mask[b,0,:] (device pointers; the glue between ls_flow_solve and
  * ls_dac_decode -- the reference builds the same information with make_pad_mask, speech/cosyvoice/flow/flow.py:478). */
 int32_t ls_mask_to_lengths(const float* mask, int32_t* lengths, int32_t B, int32_t T, void* stream);

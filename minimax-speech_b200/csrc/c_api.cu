@@ -391,6 +391,14 @@ int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, con
   });
 }
 
+int32_t ls_fsq_encode(const float* hidden, const float* project_down_weight, const float* project_down_bias, int32_t* tokens,
+                      int64_t rows, int32_t dim, void* stream) {
+  return ls::guarded([&] {
+    ls::require(hidden && project_down_weight && project_down_bias && tokens && rows >= 0 && dim > 0, "ls_fsq_encode: bad argument");
+    LS_CUDA(ls::launch_fsq_encode(hidden, project_down_weight, project_down_bias, tokens, rows, dim, (cudaStream_t)stream));
+  });
+}
+
 int32_t ls_mask_to_lengths(const float* mask, int32_t* lengths, int32_t B, int32_t T, void* stream) {
   return ls::guarded([&] {
     ls::require(mask && lengths && B > 0 && T > 0, "ls_mask_to_lengths: bad argument");

@@ -235,6 +235,39 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
   }
 }
 
+// ---- FSQ quantizer head of the S3 speech tokenizer (tools/S3Tokenizer/s3tokenizer/model_v2.py:83-117, FSQCodebook.encode):
+// h = round(tanh(project_down(x)) * 0.999) + 1 in {0, 1, 2}^8, token = sum_i h_i 3^i.  One warp per frame: eight fp32 dot
+// products over the hidden dimension, torch.round semantics (half to even).
+__global__ void __launch_bounds__(256) fsq_encode_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int* __restrict__ tokens,
+                                                         long long rows, int D) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * D;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float v = xr[k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, __ldg(w + (long long)j * D + k), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane == 0) {
+    int tok = 0, p3 = 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = tanhf(acc[j] + bias[j]) * 0.9990000128746033f;
+      tok += ((int)rintf(h) + 1) * p3;
+      p3 *= 3;
+    }
+    tokens[row] = tok;
+  }
+}
+
 // ---- timestep conditioning (matcha decoder.py:14-29 SinusoidalPosEmb, :73-117 TimestepEmbedding, :49 ResnetBlock1D.mlp)
 // Three GEMV stages over ALL time values of a solve at once, each a grid of (output rows / 8, nt) blocks of 8 warps with
 // one output row per warp -- the weights (19 MB fp32) are streamed by ~450 blocks per time value instead of by one
@@ -343,6 +376,14 @@ cudaError_t launch_unpack_nct(const float* src, float* dst, int B, int C, int T,
 cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T, int dup, cudaStream_t s, int* bad_flag) {
   ProfScope prof(s, PK_ELEMENTWISE, 0.0, (double)B * T * 4.0);
   mask_to_lengths_kernel<<<B, 256, 0, s>>>(mask, lengths, B, T, dup, bad_flag);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_fsq_encode(const float* x, const float* w, const float* bias, int* tokens, long long rows, int D,
+                              cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  ProfScope prof(s, PK_ELEMENTWISE, 16.0 * rows * D, (double)rows * D * 4.0 + 8.0 * D * 4.0 + rows * 4.0);
+  fsq_encode_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, w, bias, tokens, rows, D);
   count_launch();
   return cudaGetLastError();
 }

@@ -216,6 +216,9 @@ cudaError_t launch_mask_to_lengths(const float* mask, int* lengths, int B, int T
 cudaError_t launch_groupnorm_mish(const float* x, float2* stats, const float* gamma, const float* beta, const float* temb,
                                   long long temb_bstride, const float* addend, float* out_f32, __nv_bfloat16* out_h, int B,
                                   int C, int T, int G, const int* lengths, int fp16, cudaStream_t s);
+// FSQCodebook.encode of the S3 tokenizer: x fp32 [rows][D], w [8][D], bias [8] -> tokens int32 [rows] in [0, 3^8)
+cudaError_t launch_fsq_encode(const float* x, const float* w, const float* bias, int* tokens, long long rows, int D,
+                              cudaStream_t s);
 // timestep conditioning for nt time values: sinusoidal embedding -> MLP -> per-resnet projections
 struct TimeEmbedParams {
   const float* t;        // [nt] device, or nullptr: the values come from t_host (nt <= 64) inside the kernel parameters

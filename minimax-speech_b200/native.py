@@ -19,7 +19,7 @@ EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create
            "ls_speaker_create", "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
-           "ls_dac_decode", "ls_synthesize_host", "ls_mask_to_lengths", "ls_graph_create", "ls_graph_buffer",
+           "ls_dac_decode", "ls_synthesize_host", "ls_fsq_encode", "ls_mask_to_lengths", "ls_graph_create", "ls_graph_buffer",
            "ls_graph_launch", "ls_graph_kernel_count", "ls_graph_destroy", "ls_launch_count", "ls_debug_set_buffer", "ls_profile_begin", "ls_profile_end", "ls_test_conv_gemm", "ls_test_attention", "ls_test_tblock"]
 
 
@@ -114,6 +114,7 @@ def load():
         lib.ls_speaker_encode.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
         lib.ls_mask_to_lengths.argtypes = [vp, vp, i32, i32, vp]
+        lib.ls_fsq_encode.argtypes = [vp, vp, vp, vp, i64, i32, vp]
         lib.ls_graph_create.argtypes = [vp, vp, vp, i64, vp, i32, f32, f32, i32, i32, i32, vp, C.POINTER(vp)]
         lib.ls_graph_buffer.argtypes = [vp, i32]
         lib.ls_graph_buffer.restype = vp
@@ -337,6 +338,15 @@ def mask_to_lengths(mask):
     B, _, T = mask.shape
     out = torch.empty(B, device=mask.device, dtype=torch.int32)
     check(load().ls_mask_to_lengths(ptr(mask), ptr(out), B, T, current_stream_ptr(mask.device)), "ls_mask_to_lengths")
+    return out
+
+
+def fsq_encode(hidden, weight, bias):
+    """hidden [B, T, D] float32 (device) -> int32 tokens [B, T] (FSQCodebook.encode)."""
+    B, T, D = hidden.shape
+    out = torch.empty(B, T, device=hidden.device, dtype=torch.int32)
+    check(load().ls_fsq_encode(ptr(hidden), ptr(weight), ptr(bias), ptr(out), B * T, D, current_stream_ptr(hidden.device)),
+          "ls_fsq_encode")
     return out
 
 

@@ -77,6 +77,7 @@ def extra_golden():
                           unmodified reference: prompt_len = 20 with an empty cache, then with the returned cache
                           (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
     est_nc_golden.npz     the non-causal ConditionalDecoder estimator (decoder.py:88-291), one call per utterance.
+    fsq_golden.npz        FSQCodebook.encode of the S3 tokenizer (tools/S3Tokenizer/s3tokenizer/model_v2.py:83-117).
     dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
                           Snake alpha in [0.5, 2], activations of O(10), |alpha * x| up to ~25 rad), layers.py:18-33.
     """
@@ -122,6 +123,16 @@ def extra_golden():
         with open(os.path.join(OUT, "est_nc_keys.json"), "w") as f:
             import json
             json.dump({k: list(v.shape) for k, v in est.state_dict().items()}, f, indent=0, sort_keys=True)
+
+        # ---- FSQ quantizer head of the S3 tokenizer (model_v2.py:83-117) on synthetic hidden states
+        from minimax_speech_b200.tokenizer import FSQCodebook as OurFSQ
+        ours = OurFSQ(dim=1280, weight_seed=5)
+        ref_cb = R.load_fsq_codebook_class()(dim=1280, level=3)
+        ref_cb.load_state_dict(ours.state_dict(), strict=True)
+        hidden = torch.randn(3, 50, 1280, generator=torch.Generator().manual_seed(17)) * 3.0
+        np.savez_compressed(os.path.join(OUT, "fsq_golden.npz"), tokens=ref_cb.encode(hidden).numpy(), hidden_seed=17,
+                            weight_seed=5, keys=np.array(sorted(ref_cb.state_dict().keys())))
+        print("fsq", ref_cb.encode(hidden)[0, :8].tolist())
 
         sd = synth.dac_decoder_state_dict(DAC_TRAINED_SEED, init="trained")
         dac = R.build_reference_dac()

@@ -192,6 +192,22 @@ def build_reference_noncausal_estimator():
                num_mid_blocks=12, num_heads=8, act_fn="gelu").eval()
 
 
+def load_fsq_codebook_class():
+    """s3tokenizer.model_v2.FSQCodebook (speech/tools/S3Tokenizer); onnx / torchaudio, imported by its siblings, are stubbed."""
+    import importlib
+    import types
+    root = os.path.join(REF_ROOT, "speech", "tools", "S3Tokenizer")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    for name in ("onnx", "onnx.numpy_helper", "torchaudio", "torchaudio.compliance", "torchaudio.compliance.kaldi", "tqdm"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    return importlib.import_module("s3tokenizer.model_v2").FSQCodebook
+
+
 def build_reference_dac(cfg=None):
     dm = load_dac_module()
     return dm.DACVAE(**(cfg or DAC_CFG_X2)).eval()

@@ -478,6 +478,15 @@ def flow_inference(sd_flow, sd_est, noise, token, prompt_token, prompt_feat, emb
 # --------------------------------------------------------------------------------------
 
 
+def fsq_encode(weight, bias, x):
+    """FSQCodebook.encode tools/S3Tokenizer/s3tokenizer/model_v2.py:99-112: project_down -> tanh -> * 0.999 -> round, + 1,
+    base-3 digits.  x [B, T, D] -> int32 [B, T]."""
+    h = torch.tanh(F.linear(x.reshape(-1, x.shape[-1]), weight, bias).float()) * 0.9990000128746033
+    h = h.round() + 1
+    powers = torch.pow(3, torch.arange(8, dtype=h.dtype))
+    return torch.sum(h * powers.unsqueeze(0), dim=-1).reshape(x.shape[0], x.shape[1]).int()
+
+
 def rel_l2(y, ref):
     y, ref = y.double(), ref.double()
     return float((y - ref).norm() / ref.norm().clamp_min(1e-30))

@@ -210,3 +210,15 @@ def test_noncausal_estimator_matches_reference(golden_dir, case):
     for b, n in enumerate(lengths):
         assert O.rel_l2(y[b, :, :n], ref[b, :, :n]) < 2e-5
         assert float(y[b, :, n:].abs().max() if n < y.shape[2] else 0.0) == 0.0
+
+
+def test_fsq_codebook_matches_reference(golden_dir):
+    """FSQCodebook.encode (S3 tokenizer, model_v2.py:83-117): restatement vs the unmodified reference class."""
+    from minimax_speech_b200.tokenizer import FSQCodebook
+    g = np.load(os.path.join(golden_dir, "fsq_golden.npz"))
+    cb = FSQCodebook(dim=1280, weight_seed=int(g["weight_seed"]))
+    assert sorted(cb.state_dict().keys()) == [str(k) for k in g["keys"]]
+    hidden = torch.randn(3, 50, 1280, generator=torch.Generator().manual_seed(int(g["hidden_seed"]))) * 3.0
+    tok = O.fsq_encode(cb.project_down.weight, cb.project_down.bias, hidden)
+    assert torch.equal(tok, torch.from_numpy(g["tokens"]))
+    assert int(tok.min()) >= 0 and int(tok.max()) < 3 ** 8

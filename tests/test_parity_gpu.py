@@ -297,3 +297,17 @@ def test_noncausal_estimator_solve_and_batch_invariance(golden_dir):
                  spks[b:b + 1].to(DEV), cond[b:b + 1, :, :n].to(DEV))
         e = O.rel_l2(yb[b, :, :n].cpu(), y1[0].cpu())
         assert e < 1e-5, (b, n, e)
+
+
+def test_fsq_codebook_vs_reference_golden(golden_dir):
+    """The FSQ quantizer head of the S3 tokenizer on the GPU: integer tokens, exact."""
+    from minimax_speech_b200.tokenizer import FSQVectorQuantization
+    g = np.load(os.path.join(golden_dir, "fsq_golden.npz"))
+    vq = FSQVectorQuantization(dim=1280, weight_seed=int(g["weight_seed"]))
+    hidden = torch.randn(3, 50, 1280, generator=torch.Generator().manual_seed(int(g["hidden_seed"]))) * 3.0
+    tok = vq.encode(hidden.to(DEV)).cpu()
+    ref = torch.from_numpy(g["tokens"])
+    assert tok.dtype == torch.int32 and tok.shape == ref.shape
+    assert torch.equal(tok, ref)
+    with pytest.raises(RuntimeError):
+        vq.encode(hidden)  # CPU tensors are rejected, not emulated
