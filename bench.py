@@ -222,7 +222,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ BASELINE.json configs[2..4]
-def extra_legs(a, syn, cfm, dac, dev, world, rank, sync_all):
+def extra_legs(a, syn, cfm, dac, dev, world, rank, sync_all, esd=None):
     """Throughput of the other configurations BASELINE.json lists, next to the unchanged headline (configs[1]):
     configs[2] DAC-VAE decoder only (64 x 30 s), configs[3] 32-step solve of 32 x 30 s utterances sharded by utterance,
     configs[4] 256 mixed-length (2-30 s) utterances, length-balanced over the ranks, one waveform gather at the end --
@@ -330,6 +330,28 @@ def extra_legs(a, syn, cfm, dac, dev, world, rank, sync_all):
                                 "host wall clock per call incl. synchronise, median of 10", "kernels_per_call": g.kernels,
                     "audio_s_per_s_graph": a.seconds / (lat["cuda_graph_ms"] / 1000.0)})
         out["latency_b1"] = lat
+    # ---- the headline workload with fp16 operands (same kernels, 3 more mantissa bits: DESIGN section 2) -- speed and the
+    # distance of the two operand types' waveforms from each other
+    if rank == 0 and esd is not None:
+        from minimax_speech_b200.flow import CausalConditionalCFM, CausalConditionalDecoder
+        est16 = CausalConditionalDecoder(precision="fp16")
+        est16.load_state_dict(esd)
+        cfm16 = CausalConditionalCFM(240, dict(t_scheduler="cosine", inference_cfg_rate=0.7), 1, 80, est16)
+        T = int(round(a.seconds * FRAME_RATE))
+        inp = [t.to(dev) for t in synth.batch_inputs([T] * a.batch, first_index=0)]
+        f16 = lambda: cfm16(mu=inp[0], mask=inp[1], n_timesteps=a.n_timesteps, spks=inp[2], cond=inp[3])[0]
+        b16 = lambda: cfm(mu=inp[0], mask=inp[1], n_timesteps=a.n_timesteps, spks=inp[2], cond=inp[3])[0]
+        y16, yb = f16().clone(), b16().clone()
+        torch.cuda.synchronize()
+        ms16, msb = [], []
+        for _ in range(3):
+            e0.record(); f16(); e1.record(); torch.cuda.synchronize(); ms16.append(e0.elapsed_time(e1))
+            e0.record(); b16(); e1.record(); torch.cuda.synchronize(); msb.append(e0.elapsed_time(e1))
+        out["fp16_operands"] = {"workload": f"flow solve only, {a.batch} x {a.seconds:g} s, {a.n_timesteps} steps, same weights, interleaved",
+                                "solve_ms_fp16": statistics.median(ms16), "solve_ms_bf16": statistics.median(msb),
+                                "max_abs_diff_mel_fp16_vs_bf16": float((y16 - yb).abs().max()),
+                                "note": "parity of each against the fp32 oracle: tests/test_parity_gpu.py (bf16 <= 1e-2, fp16 ~1.5e-3)"}
+        del est16, cfm16, inp
     if world > 1:
         dist.barrier()
     return out
@@ -545,7 +567,7 @@ def run_b200(a):
 
     configs = None
     if not a.no_extra:
-        configs = extra_legs(a, syn, cfm, dac, dev, world, rank, sync_all)
+        configs = extra_legs(a, syn, cfm, dac, dev, world, rank, sync_all, esd)
 
     cb, eager = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

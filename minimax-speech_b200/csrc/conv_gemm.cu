@@ -124,8 +124,9 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 // their owner threads, global memory is accessed with consecutive lanes on consecutive 16 B pieces of a row
 // (fp32: 8 rows x 64 B per instruction, bf16: 16 rows x 32 B), i.e. whole 32 B sectors only.
 // 16 B units are XOR-swizzled so that both access patterns are bank-conflict free.
-constexpr int kStageBytesPerWarp = 3072;  // [0,2048): fp32 chunk / residual transposes, [2048,3072): bf16 chunk
+constexpr int kStageBytesPerWarp = 3072;  // [0,2048): fp32 chunk / residual transposes, [2048,3072): 16-bit out1 chunk
 constexpr int kStageB16Off = 2048;
+constexpr int kStageOut0H = 1024;  // 16-bit out0 chunk (the 16-bit residual transposes use [0,1024))
 __device__ __forceinline__ int stg_f32(int row, int unit) { return row * 64 + ((unit ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ int stg_b16(int row, int unit) { return row * 32 + ((unit ^ ((row >> 2) & 1)) << 4); }
 
@@ -151,6 +152,18 @@ struct WarpRows {
 struct AddRegs {
   uint4 v[4];
 };
+// 16-bit element kinds of out0 / addend: OUT_BF16 = this build's operand type (bf16, or fp16 in the fp16-operand build),
+// OUT_F16 = IEEE half whatever the operand type (the DAC decoder's residual stream: 11 significand bits, so 15 chained
+// residual additions cost nothing measurable, where bf16 would)
+template <int kKind>
+__device__ __forceinline__ uint32_t pack_kind(float lo, float hi) {
+  return kKind == OUT_F16 ? pack_f16x2(lo, hi) : LS_PACK_H2(lo, hi);
+}
+template <int kKind>
+__device__ __forceinline__ void unpack_kind(uint32_t w, float& lo, float& hi) {
+  if (kKind == OUT_F16) unpack_f16x2(w, lo, hi);
+  else LS_UNPACK_H2(w, lo, hi);
+}
 template <bool kF32>
 __device__ __forceinline__ void fetch_chunk(int lane, const WarpRows& wr, int n, const void* base, AddRegs& a) {
   if (kF32) {
@@ -172,9 +185,9 @@ __device__ __forceinline__ void fetch_chunk(int lane, const WarpRows& wr, int n,
   }
 }
 // v (this thread's row, 16 fp32) += the fetched chunk, transposed through the warp's staging buffer
-template <bool kF32>
+template <int kKind>
 __device__ __forceinline__ void apply_chunk(uint8_t* stg, int lane, const AddRegs& a, float (&v)[16]) {
-  if (kF32) {
+  if (kKind == OUT_F32) {
 #pragma unroll
     for (int ps = 0; ps < 4; ++ps) {
       const int rr = ps * 8 + (lane >> 2), seg = lane & 3;
@@ -200,7 +213,7 @@ __device__ __forceinline__ void apply_chunk(uint8_t* stg, int lane, const AddReg
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float lo, hi;
-        LS_UNPACK_H2(w[k], lo, hi);
+        unpack_kind<kKind>(w[k], lo, hi);
         v[8 * u + 2 * k] += lo;
         v[8 * u + 2 * k + 1] += hi;
       }
@@ -210,10 +223,10 @@ __device__ __forceinline__ void apply_chunk(uint8_t* stg, int lane, const AddReg
 }
 
 // store this thread's row chunk (16 fp32 values) coalesced, as fp32 or bf16; rows in the zero-fill range get zeros
-template <bool kF32>
+template <int kKind>
 __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRows& wr, int n, void* base,
                                             const float (&v)[16]) {
-  if (kF32) {
+  if (kKind == OUT_F32) {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       *reinterpret_cast<float4*>(stg + stg_f32(lane, u)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
@@ -233,8 +246,8 @@ __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRo
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       *reinterpret_cast<uint4*>(stg + stg_b16(lane, u)) =
-          make_uint4(LS_PACK_H2(v[8 * u], v[8 * u + 1]), LS_PACK_H2(v[8 * u + 2], v[8 * u + 3]),
-                     LS_PACK_H2(v[8 * u + 4], v[8 * u + 5]), LS_PACK_H2(v[8 * u + 6], v[8 * u + 7]));
+          make_uint4(pack_kind<kKind>(v[8 * u], v[8 * u + 1]), pack_kind<kKind>(v[8 * u + 2], v[8 * u + 3]),
+                     pack_kind<kKind>(v[8 * u + 4], v[8 * u + 5]), pack_kind<kKind>(v[8 * u + 6], v[8 * u + 7]));
     __syncwarp();
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
@@ -255,10 +268,13 @@ __device__ __forceinline__ void store_chunk(uint8_t* stg, int lane, const WarpRo
 // (fp32) / 32 B (bf16) swizzle patterns, so the warp writes its 32 rows x 16 columns once and one lane hands the
 // buffer to cp.async.bulk.tensor (box 16 x 32; rows past M are clipped by the tensor map).  Rows past the valid
 // length are written as zeros.  Before a staging region is rewritten, the bulk group that last read it must be done:
-// kPending = how many younger groups of this lane may still be in flight at that point.
-template <bool kF32, int kPending>
+// kPending = how many younger groups of this lane may still be in flight at that point.  kOff = the staging region of a
+// 16-bit chunk: kStageB16Off for out1, kStageOut0H for a 16-bit out0 (so that out0 and out1 alternate between two
+// regions like an fp32 out0 and out1 do, and neither is the region the 16-bit residual transposes use).
+template <int kKind, int kPending, int kOff = kStageB16Off>
 __device__ __forceinline__ void store_chunk_tma(uint8_t* stg, int lane, const CUtensorMap* map, int n, int t_base, int b,
                                                 bool row_valid, const float (&v)[16]) {
+  constexpr bool kF32 = kKind == OUT_F32;
   if (lane == 0) bulk_wait_read<kPending>();
   __syncwarp();
   if (kF32) {
@@ -267,27 +283,27 @@ __device__ __forceinline__ void store_chunk_tma(uint8_t* stg, int lane, const CU
       *reinterpret_cast<float4*>(stg + stg_f32(lane, u)) =
           row_valid ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
-    uint8_t* sb = stg + kStageB16Off;
+    uint8_t* sb = stg + kOff;
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       *reinterpret_cast<uint4*>(sb + stg_b16(lane, u)) =
-          row_valid ? make_uint4(LS_PACK_H2(v[8 * u], v[8 * u + 1]), LS_PACK_H2(v[8 * u + 2], v[8 * u + 3]),
-                                 LS_PACK_H2(v[8 * u + 4], v[8 * u + 5]), LS_PACK_H2(v[8 * u + 6], v[8 * u + 7]))
+          row_valid ? make_uint4(pack_kind<kKind>(v[8 * u], v[8 * u + 1]), pack_kind<kKind>(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_kind<kKind>(v[8 * u + 4], v[8 * u + 5]), pack_kind<kKind>(v[8 * u + 6], v[8 * u + 7]))
                     : make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    tma_store_3d(map, kF32 ? stg : stg + kStageB16Off, n, t_base, b);
+    tma_store_3d(map, kF32 ? stg : stg + kOff, n, t_base, b);
     bulk_commit();
   }
 }
 
-template <bool kF32>
+template <int kKind, int kOff = kStageB16Off>
 __device__ __forceinline__ void store_chunk_tma_p(bool one_pending, uint8_t* stg, int lane, const CUtensorMap* map, int n,
                                                   int t_base, int b, bool row_valid, const float (&v)[16]) {
-  if (one_pending) store_chunk_tma<kF32, 1>(stg, lane, map, n, t_base, b, row_valid, v);
-  else store_chunk_tma<kF32, 0>(stg, lane, map, n, t_base, b, row_valid, v);
+  if (one_pending) store_chunk_tma<kKind, 1, kOff>(stg, lane, map, n, t_base, b, row_valid, v);
+  else store_chunk_tma<kKind, 0, kOff>(stg, lane, map, n, t_base, b, row_valid, v);
 }
 
 // The epilogue mode (activation, outputs, residual, time embedding) is a template parameter for the combinations the
@@ -608,7 +624,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           for (int c = g; c < n_chunks; c += 4) {
             const int n = n0 + c * 16;
             if (out0_dtype == OUT_F32) st.f32(out0f, row_flat + n, n, zero);
-            else if (out0_dtype == OUT_BF16) st.bf16(out0h, row_flat + n, n, zero);
+            else if (out0_dtype != OUT_NONE) st.bf16(out0h, row_flat + n, n, zero);
             if (out1_mode != OUT1_NONE) st.bf16(out1, row_flat + n, n, zero);
           }
         }
@@ -633,7 +649,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const bool row_valid = st.row_in && row_flat + p.N <= st.valid;
       const int tma_t = tc.mt * kBlockM + q * 32;  // first row of this warp
       // fp32 out0 and a bf16 out1 alternate between two staging regions: one younger bulk group may be in flight
-      const bool one_pending = out0_dtype == OUT_F32 && (out1_mode == OUT1_COPY || out1_mode == OUT1_SNAKE);
+      const bool one_pending = out0_dtype != OUT_NONE && (out1_mode == OUT1_COPY || out1_mode == OUT1_SNAKE);
       // residual chunks of this tile: the first of this warp's chunks is fetched now (see fetch_chunk); the
       // next tile's residual rows are pulled into L2 so that its fetches do not wait for HBM
       constexpr int kPre = 1;  // (2 spills in the 96-register epilogue; later chunks hit L2 thanks to the prefetch below)
@@ -780,7 +796,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // memory for every instance that contains it
         const bool partial = (kAct == ACT_LRELU_TANH || kAct < 0) && n + 16 > p.n_store;
         if (add_dtype != OUT_NONE && !partial) {
-          if (tma_out && out0_dtype == OUT_F32) {  // the transposes below reuse the fp32 staging region
+          // the transposes below reuse the fp32 staging region (an fp32 residual also covers a 16-bit out0's region)
+          if (tma_out && (out0_dtype == OUT_F32 || (out0_dtype != OUT_NONE && add_dtype == OUT_F32))) {
             if (lane == 0) {
               if (one_pending) bulk_wait_read<1>();
               else bulk_wait_read<0>();
@@ -789,12 +806,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           }
           const int k = (c - g) >> 2;
           if (pre_ok && k < kPre) {
-            if (add_dtype == OUT_F32) apply_chunk<true>(stg, lane, pre0, x);
-            else apply_chunk<false>(stg, lane, pre0, x);
+            if (add_dtype == OUT_F32) apply_chunk<OUT_F32>(stg, lane, pre0, x);
+            else if (add_dtype == OUT_F16) apply_chunk<OUT_F16>(stg, lane, pre0, x);
+            else apply_chunk<OUT_BF16>(stg, lane, pre0, x);
           } else {
             AddRegs a;
-            if (add_dtype == OUT_F32) fetch_chunk<true>(lane, wr, n, addf, a), apply_chunk<true>(stg, lane, a, x);
-            else fetch_chunk<false>(lane, wr, n, addh, a), apply_chunk<false>(stg, lane, a, x);
+            if (add_dtype == OUT_F32) fetch_chunk<true>(lane, wr, n, addf, a), apply_chunk<OUT_F32>(stg, lane, a, x);
+            else if (add_dtype == OUT_F16) fetch_chunk<false>(lane, wr, n, addh, a), apply_chunk<OUT_F16>(stg, lane, a, x);
+            else fetch_chunk<false>(lane, wr, n, addh, a), apply_chunk<OUT_BF16>(stg, lane, a, x);
           }
         }
         if (partial) {  // scalar tail: column 0 of consecutive rows is contiguous when out_ld == n_store == 1
@@ -804,20 +823,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               const float xv = stt == 2 ? x[i] : 0.f;
               if (out0_dtype == OUT_F32) out0f[flat + i] = xv;
               else if (out0_dtype == OUT_BF16) reinterpret_cast<uint16_t*>(out0h)[flat + i] = LS_CVT_H_BITS(xv);
+              else if (out0_dtype == OUT_F16) reinterpret_cast<uint16_t*>(out0h)[flat + i] = cvt_f16_bits(xv);
               if (out1_mode == OUT1_COPY) reinterpret_cast<uint16_t*>(out1)[flat + i] = LS_CVT_H_BITS(xv);
             }
           }
         } else {
           if (tma_out) {
-            if (out0_dtype == OUT_F32) store_chunk_tma_p<true>(one_pending, stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
-            else if (out0_dtype == OUT_BF16) store_chunk_tma<false, 0>(stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
+            if (out0_dtype == OUT_F32) store_chunk_tma_p<OUT_F32>(one_pending, stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
+            else if (out0_dtype == OUT_BF16)
+              store_chunk_tma_p<OUT_BF16, kStageOut0H>(one_pending, stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
+            else if (out0_dtype == OUT_F16)
+              store_chunk_tma_p<OUT_F16, kStageOut0H>(one_pending, stg, lane, &mapOut0, n, tma_t, tc.b, row_valid, x);
           } else {
-            if (out0_dtype == OUT_F32) store_chunk<true>(stg, lane, wr, n, out0f, x);
-            else if (out0_dtype == OUT_BF16) store_chunk<false>(stg, lane, wr, n, out0h, x);
+            if (out0_dtype == OUT_F32) store_chunk<OUT_F32>(stg, lane, wr, n, out0f, x);
+            else if (out0_dtype == OUT_BF16) store_chunk<OUT_BF16>(stg, lane, wr, n, out0h, x);
+            else if (out0_dtype == OUT_F16) store_chunk<OUT_F16>(stg, lane, wr, n, out0h, x);
           }
           if (out1_mode == OUT1_COPY) {
-            if (tma_out) store_chunk_tma_p<false>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
-            else store_chunk<false>(stg, lane, wr, n, out1, x);
+            if (tma_out) store_chunk_tma_p<OUT_BF16>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
+            else store_chunk<OUT_BF16>(stg, lane, wr, n, out1, x);
           } else if (out1_mode == OUT1_SNAKE) {
             const int ch0 = n % p.chan_mod;
 #pragma unroll
@@ -829,8 +853,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               x[4 * g4 + 2] = snake_f(x[4 * g4 + 2], al.z, ia.z);
               x[4 * g4 + 3] = snake_f(x[4 * g4 + 3], al.w, ia.w);
             }
-            if (tma_out) store_chunk_tma_p<false>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
-            else store_chunk<false>(stg, lane, wr, n, out1, x);
+            if (tma_out) store_chunk_tma_p<OUT_BF16>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
+            else store_chunk<OUT_BF16>(stg, lane, wr, n, out1, x);
           } else if (out1_mode == OUT1_LN) {
             s2.add16(x);
             tmem_st16(taddr + (uint32_t)(c * 16), reinterpret_cast<const uint32_t(&)[16]>(x));
@@ -856,8 +880,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             x[4 * g4 + 2] = fmaf((x[4 * g4 + 2] - mean2) * rstd2, ga.z, be.z);
             x[4 * g4 + 3] = fmaf((x[4 * g4 + 3] - mean2) * rstd2, ga.w, be.w);
           }
-          if (tma_out) store_chunk_tma<false, 0>(stg, lane, &mapOut1, n0 + c * 16, tma_t, tc.b, row_valid, x);
-          else store_chunk<false>(stg, lane, wr, n0 + c * 16, out1, x);
+          if (tma_out) store_chunk_tma<OUT_BF16, 0>(stg, lane, &mapOut1, n0 + c * 16, tma_t, tc.b, row_valid, x);
+          else store_chunk<OUT_BF16>(stg, lane, wr, n0 + c * 16, out1, x);
         }
       }
       // every TMEM access of this tile is done: hand the accumulator stage back to the MMA warp
@@ -962,7 +986,7 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   const int grid = (int)(total < num_sms ? total : num_sms);
   const double kt = p.k_true > 0 ? p.k_true : p.kb_per_tap * kBlockK;
   const double rows = (double)p.B * p.M;
-  const double out_b = (p.out0_dtype == OUT_F32 ? 4.0 : p.out0_dtype == OUT_BF16 ? 2.0 : 0.0) +
+  const double out_b = (p.out0_dtype == OUT_F32 ? 4.0 : p.out0_dtype != OUT_NONE ? 2.0 : 0.0) +
                        (p.out1_mode != OUT1_NONE ? 2.0 : 0.0) +
                        (p.addend ? (p.addend_dtype == OUT_F32 ? 4.0 : 2.0) : 0.0);
   ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
@@ -1016,6 +1040,9 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_SNAKE, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LRELU, OUT_F32, OUT1_SNAKE, OUT_F32, 0)
   LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_F32, 0)
+  LS_CONV_CASE(ACT_NONE, OUT_F16, OUT1_SNAKE, OUT_NONE, 0)  // the same three with the residual stream kept as fp16
+  LS_CONV_CASE(ACT_LRELU, OUT_F16, OUT1_SNAKE, OUT_F16, 0)
+  LS_CONV_CASE(ACT_LRELU, OUT_NONE, OUT1_SNAKE, OUT_F16, 0)
   LS_CONV_CASE(ACT_LRELU_TANH, OUT_F32, OUT1_NONE, OUT_NONE, 0)
 #endif
 #undef LS_CONV_CASE

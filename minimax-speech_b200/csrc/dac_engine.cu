@@ -270,7 +270,14 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
   }
   long long rows = L;
   int rate = 1;
-  float* x = ws<float>(o_x_);
+  // residual stream x of the five stages: written by the transposed conv, read + rewritten by each unit's conv1.
+  // Kept as fp16 (11 significand bits; the operands the convolutions consume are bf16 anyway): the thin stages are
+  // bound by the bytes their epilogues move, and x was half of them as fp32.  -DLS_DAC_X_F32=1 keeps it fp32.
+#ifndef LS_DAC_X_F32
+#define LS_DAC_X_F32 0
+#endif
+  constexpr int kXDtype = LS_DAC_X_F32 ? OUT_F32 : OUT_F16;
+  void* x = ws<void>(o_x_);
   for (size_t i = 0; i < stages_.size(); ++i) {
     const StageW& st = stages_[i];
     const long long rows_in = rows;
@@ -286,7 +293,7 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       p.kb_per_tap = (st.cin + 63) / 64, p.kb_split = p.kb_per_tap;
       p.lengths = lengths, p.m_len_mul = rate_in, p.m_len_add = 1, p.skip_halo = 64;
       p.chan_mod = st.cout, p.bias = st.up.bias, p.act = ACT_NONE;
-      p.out0 = x, p.out0_dtype = OUT_F32;
+      p.out0 = x, p.out0_dtype = kXDtype;
       p.out1 = sA, p.out1_mode = OUT1_SNAKE, p.p1_a = f32(st.unit[0].a0), p.p1_b = f32(st.unit[0].ia0);
       p.n_store = st.up.N;
       p.out_ld = st.up.N, p.out_shift = -(long long)padT * st.cout;
@@ -304,9 +311,9 @@ void DacEngine::decode(const float* z, const int* lengths, float* wav, int B, in
       }
       {  // conv1 -> LeakyReLU -> + x ; secondary output = Snake of whatever consumes x next
         ConvGemmParams p{};
-        p.act = ACT_LRELU, p.addend = x, p.addend_dtype = OUT_F32;
+        p.act = ACT_LRELU, p.addend = x, p.addend_dtype = kXDtype;
         const bool last_unit = j == 2;
-        if (!last_unit) p.out0 = x, p.out0_dtype = OUT_F32;
+        if (!last_unit) p.out0 = x, p.out0_dtype = kXDtype;
         size_t na, nia;
         if (!last_unit) na = st.unit[j + 1].a0, nia = st.unit[j + 1].ia0;
         else if (i + 1 < stages_.size()) na = stages_[i + 1].a_in, nia = stages_[i + 1].ia_in;

@@ -60,7 +60,8 @@ inline cudaError_t smem_optin_once(std::atomic<unsigned long long>& done_mask, c
 
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4,
                  ACT_SILU = 5, ACT_LRELU001 = 6 /* F.leaky_relu's default slope 0.01 */ };
-enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 };
+enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 /* the build's 16-bit operand type */,
+                      OUT_F16 = 3 /* IEEE half whatever the operand type (conv_gemm out0 / addend only) */ };
 enum Out1Mode : int { OUT1_NONE = 0, OUT1_LN = 1, OUT1_COPY = 2, OUT1_SNAKE = 3 };
 
 // Implicit-GEMM 1-D convolution on time-major activations:
