@@ -42,6 +42,15 @@ constexpr int kMmaWarp = kProducerWarps;
 constexpr int kFirstEpiWarp = kProducerWarps + 1;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiThreads;
 constexpr int kMaxStages = 16;
+#ifndef CONV_DETAIL_TL
+#define CONV_DETAIL_TL 0  // development aid: 1 = per-tap stamps of the MMA warp, 2 = per-load stamps of weight producer 1
+#endif
+#ifndef CONV_DUAL_RESIDENT
+#define CONV_DUAL_RESIDENT 0
+#endif
+#ifndef CONV_HALO_A_STAGES
+#define CONV_HALO_A_STAGES 3  // activation stages of a streamed-weight halo launch with more than one K block
+#endif
 
 constexpr int kRedBytes = 2 * 2 * 4 * kBlockM * 8;  // [tile parity][phase][column group][row] float2
 constexpr int kSmemBudget = 157 * 1024;             // for the operand rings
@@ -340,7 +349,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float2* red_base = reinterpret_cast<float2*>(bars + 128);  // 1 KB for the barriers + TMEM slot (keeps the staging
                                                              // buffers below aligned for TMA)
-  uint8_t* stg_base = reinterpret_cast<uint8_t*>(red_base) + kRedBytes;  // per-epilogue-warp transpose buffers
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(red_base) + p.red_bytes;  // per-epilogue-warp transpose buffers
   float* svec = reinterpret_cast<float*>(stg_base + kEpiWarps * kStageBytesPerWarp);  // per-channel epilogue vectors
 
   const int warp = threadIdx.x >> 5;
@@ -370,7 +379,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], (p.dual && !p.b_resident) ? 2 : 1);  // dual mode: both MMA warps release a weight slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -405,7 +414,119 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   pdl_wait();
   if (threadIdx.x == 0) TL(2);  // everything above overlapped the previous kernel's tail; activations are read only from here on
 
-  if (warp < kProducerWarps) {
+  // next tile of this CTA that is not all padding (every role walks the same sequence)
+  auto next_tile = [&](int& cur) -> int {
+    while (cur < total_tiles) {
+      const int t = cur;
+      cur += (int)gridDim.x;
+      if (!tile_skipped(p, decode_tile(t, m_tiles, n_tiles))) return t;
+    }
+    return -1;
+  };
+  if (p.dual && warp < 2) {
+    // ------------------------------------------------------------ dual mode: TMA producers
+    // Thin layers are bound by the MMA-issuing THREAD (profiles/r02_timeline_conv_issue.log: ~600 clk of waits, descriptor
+    // arithmetic and issue per tap for 4 MMAs that execute in ~350), so two warps issue, one per accumulator, on
+    // alternating tiles (pairs).  Every weight box is fetched once per PAIR and released by both; each MMA warp has its
+    // own activation stages [m*depth, (m+1)*depth).  Warp 0: activation boxes (and, streamed weights, those of both
+    // tiles); warp 1: the weight boxes (and, once they are resident, the second tile's activation boxes).
+    if (lane == 0) {
+      const int depth = p.a_stages >> 1;
+      const uint32_t a_tx = (uint32_t)p.a_box_rows * 128u;
+      int cur = blockIdx.x, pair = 0, bs = 0;
+      uint32_t bph = 0;
+      int cnt[2] = {0, 0};
+      for (;; ++pair) {
+        int t[2];
+        t[0] = next_tile(cur);
+        if (t[0] < 0) break;
+        t[1] = next_tile(cur);
+        if (warp == 1 && (!p.b_resident || pair == 0)) {
+          for (int kb = 0; kb < p.kb_per_tap; ++kb)
+            for (int tap = 0; tap < p.taps; ++tap) {
+              if (!p.b_resident) mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
+              tma_load_2d(smem_b + (size_t)bs * b_bytes, &mapW, &b_full[bs], kb * kBlockK, tap * p.N);
+              if (++bs == p.b_stages) bs = 0, bph ^= 1;
+            }
+        }
+        for (int kb = 0; kb < p.kb_per_tap; ++kb)
+          for (int m = 0; m < 2; ++m) {
+            if (t[m] < 0 || warp != (p.b_resident ? m : 0)) continue;
+            const TileCoord tc = decode_tile(t[m], m_tiles, n_tiles);
+            const int st = m * depth + cnt[m] % depth;
+            mbar_wait(&a_empty[st], (uint32_t)(((cnt[m] / depth) & 1) ^ 1));
+            uint8_t* sa = smem_a + (size_t)st * a_bytes;
+            mbar_arrive_expect_tx(&a_full[st], a_tx);
+            if (kb < p.kb_split)
+              tma_load_3d(sa, &mapA0, &a_full[st], kb * kBlockK, tc.mt * kBlockM - p.pad, tc.b);
+            else
+              tma_load_3d(sa, &mapA1, &a_full[st], (kb - p.kb_split) * kBlockK, tc.mt * kBlockM - p.pad, tc.b);
+            ++cnt[m];
+          }
+      }
+    }
+  } else if (p.dual && (warp == 2 || warp == kMmaWarp)) {
+    // ------------------------------------------------------------ dual mode: MMA issuers (m = 0: kMmaWarp, m = 1: warp 2)
+    const int m = warp == kMmaWarp ? 0 : 1;
+    const int depth = p.a_stages >> 1;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, false, false);
+    const uint32_t d_tmem = tmem_u + (uint32_t)(m * acc_stride);
+    int cur = blockIdx.x, bs = 0, cnt = 0;
+    uint32_t bph = 0, acc_phase = 0;
+    for (int pair = 0;; ++pair) {
+      int te = next_tile(cur);
+      te = __shfl_sync(0xffffffffu, te, 0);
+      if (te < 0) break;
+      int to = next_tile(cur);
+      to = __shfl_sync(0xffffffffu, to, 0);
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      const bool lone = to < 0;  // the other warp has no tile in this pair: release the weight slots for it too
+      if ((m == 0 ? te : to) < 0) break;
+      const bool wait_b = !p.b_resident || pair == 0;
+      mbar_wait(&tempty[m], acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+        const int st = m * depth + cnt % depth;
+        mbar_wait(&a_full[st], (uint32_t)((cnt / depth) & 1));
+        tc_fence_after();
+        int nk = kBlockK / 16;
+        if (p.k_true > 0 && p.kb_split == p.kb_per_tap) nk = min(nk, (p.k_true - kb * kBlockK + 15) >> 4);
+        const uint32_t a_addr = smem_u32(smem_a + (size_t)st * a_bytes);
+        const uint32_t b_addr = smem_u32(smem_b);
+        if (elect_one()) {
+          int bl = p.b_resident ? kb * p.taps : bs;
+          uint32_t bphl = bph;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (wait_b) {
+              mbar_wait(&b_full[bl], bphl);
+              tc_fence_after();
+            }
+            const int shift = tap * p.dil;
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)shift * 128u, p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + (uint32_t)bl * (uint32_t)b_bytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (k < nk) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            if (!p.b_resident) {
+              umma_commit(&b_empty[bl]);
+              if (lone) umma_commit(&b_empty[bl]);
+            }
+            if (++bl == p.b_stages) bl = 0, bphl ^= 1;
+          }
+          umma_commit(&a_empty[st]);
+        }
+        __syncwarp();
+        for (int tap = 0; tap < p.taps; ++tap)
+          if (++bs == p.b_stages) bs = 0, bph ^= 1;
+        ++cnt;
+      }
+      if (elect_one()) umma_commit(&tfull[m]);
+      __syncwarp();
+      acc_phase ^= 1;
+    }
+  } else if (warp < kProducerWarps) {
     // ------------------------------------------------------------ TMA producers
     // A thread can start a TMA load only every ~500 clk (issue latency; profiles/micro/tma_bw3.cu) but different warps
     // overlap.  Warp 0 issues every activation box; warps 1.. share the weight boxes, warp w taking those whose sequence
@@ -419,6 +540,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t aph = 0, bph = 0;
       int b_seq = 0, p_tile = 0;
       int a_seq = 0;
+#if CONV_DETAIL_TL == 2
+      int dn = 0;
+#endif
       // Resident weights leave the weight producers idle after the first tile: the activation boxes are then shared
       // round-robin by ALL producer warps (one load per ~2 k clk and warp was what bounded the thin DAC layers once the MMA
       // issue loop had been fixed).  Safe while producers <= ring stages (see above); every producer tracks the ring.
@@ -449,9 +573,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
             if (warp != 0 && (!p.b_resident || p_tile == 1)) {  // resident weights: fetched with the CTA's first tile only
               if (b_seq == warp - 1) {
+#if CONV_DETAIL_TL == 2
+                const bool dt = tl && warp == 1 && p_tile == 4 && dn < 7;
+                if (dt) tl[8 + 3 * dn] = clock64();
+#endif
                 if (!p.b_resident) mbar_wait(&b_empty[bs], bph ^ 1);
+#if CONV_DETAIL_TL == 2
+                if (dt) tl[9 + 3 * dn] = clock64();
+#endif
                 mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
                 tma_load_2d(smem_b + (size_t)bs * b_bytes, &mapW, &b_full[bs], kb * kBlockK, tap * p.N + n0);
+#if CONV_DETAIL_TL == 2
+                if (dt) tl[10 + 3 * dn] = clock64(), ++dn;
+#endif
               }
               if (++b_seq == kWeightProducers) b_seq = 0;
               if (++bs == p.b_stages) bs = 0, bph ^= 1;
@@ -517,16 +651,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             if (p.k_true > 0 && p.kb_split == p.kb_per_tap) nk = min(nk, (p.k_true - kb * kBlockK + 15) >> 4);
             const uint32_t a_addr = smem_u32(smem_a + (size_t)as * a_bytes);
             const bool wait_b = !p.b_resident || n_tile == 0;
+#if CONV_DETAIL_TL == 0
             if (tl && n_it < 24 && lane == 0) tl[8 + n_it] = clock64();
+#endif
             n_it += p.taps;
             if (elect_one()) {
               int bl = bs;
               uint32_t bphl = bph;
               for (int tap = 0; tap < p.taps; ++tap) {
+#if CONV_DETAIL_TL == 1
+                const bool dt = tl && n_tile == 3 && kb == 0;
+                if (dt) tl[8 + 3 * tap] = clock64();
+#endif
                 if (wait_b) {
                   mbar_wait(&b_full[bl], bphl);
                   tc_fence_after();
                 }
+#if CONV_DETAIL_TL == 1
+                if (dt) tl[9 + 3 * tap] = clock64();
+#endif
                 const int shift = tap * p.dil;
                 const uint64_t adesc = make_smem_desc_sw128(a_addr + (uint32_t)shift * 128u, p.halo_mode == 1 ? ((uint32_t)shift & 7u) : 0u);
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + (size_t)bl * b_bytes));
@@ -534,6 +677,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 for (int k = 0; k < kBlockK / 16; ++k)
                   if (k < nk) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
                 if (!p.b_resident) umma_commit(&b_empty[bl]);
+#if CONV_DETAIL_TL == 1
+                if (dt) tl[10 + 3 * tap] = clock64();
+#endif
                 if (++bl == p.b_stages) bl = 0, bphl ^= 1;
               }
               umma_commit(&a_empty[as]);
@@ -951,7 +1097,10 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
     if (p.out1_mode == OUT1_SNAKE || p.out1_mode == OUT1_LN) place(pp.sv_p1a, p.p1_a, p.chan_mod), place(pp.sv_p1b, p.p1_b, p.chan_mod);
     if (p.act == ACT_LN_MISH) place(pp.sv_lng, p.ln_g, p.N), place(pp.sv_lnb, p.ln_b, p.N);
   }
-  const int budget = kSmemBudget - pp.sv_floats * 4;
+  // the LayerNorm statistics area is only there for launches that normalise: the thin DAC layers' weight rings are
+  // latency-bound (bytes in flight), so they get those 16 KB
+  pp.red_bytes = (p.act == ACT_LN_MISH || p.out1_mode == OUT1_LN || p.act < 0) ? kRedBytes : 0;
+  const int budget = kSmemBudget + (kRedBytes - pp.red_bytes) - pp.sv_floats * 4;
   const int m_tiles_ = (p.M + kBlockM - 1) / kBlockM;
   const long long tiles_per_cta = ((long long)p.B * m_tiles_ * (p.N / p.block_n) + num_sms - 1) / num_sms;
   const int w_boxes = p.taps * p.kb_per_tap;
@@ -966,17 +1115,35 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   } else if (p.halo_mode && p.taps > 1) {
     // one A box feeds `taps` B boxes: two A stages are enough, the rest of the budget goes to the weight ring
     pp.a_stages = p.kb_per_tap > 1 ? 2 : 1;
-    if (p.kb_per_tap > 1 && 3 * a_bytes + 4 * b_bytes <= budget) pp.a_stages = 3;
+    if (p.kb_per_tap > 1 && 3 * a_bytes + 4 * b_bytes <= budget) pp.a_stages = CONV_HALO_A_STAGES;
     pp.b_stages = (budget - pp.a_stages * a_bytes) / b_bytes;
   } else {
     pp.a_stages = pp.b_stages = budget / (a_bytes + b_bytes);
+  }
+  // dual-issue mode (see the kernel): halo launches with ONE N tile and enough tiles per CTA to pair
+  pp.dual = 0;
+  if (kProducerWarps == 3 && p.halo_mode && p.taps > 1 && p.N == p.block_n && tiles_per_cta >= 4 && w_boxes <= kMaxStages * 4 &&
+      conv_dual_enabled()) {
+    if (w_boxes <= kMaxStages && w_boxes * b_bytes + 4 * a_bytes <= budget && conv_resident_enabled()) {
+      // resident weights: the single-issuer lean loop with all three producer warps sharing the activation loads is
+      // faster (C = 48 conv7: 335-358 us vs 406-421 us dual) -- dual only under -DCONV_DUAL_RESIDENT=1
+      if (CONV_DUAL_RESIDENT) {
+        pp.dual = 1, pp.b_resident = 1, pp.b_stages = w_boxes;
+        pp.a_stages = (budget - w_boxes * b_bytes) / a_bytes;
+        if (pp.a_stages > 6) pp.a_stages = 6;
+        pp.a_stages &= ~1;
+      }
+    } else if (4 * a_bytes + 3 * b_bytes <= budget) {
+      pp.dual = 1, pp.b_resident = 0, pp.a_stages = 4;
+      pp.b_stages = (budget - 4 * a_bytes) / b_bytes;
+    }
   }
   if (pp.a_stages > kMaxStages) pp.a_stages = kMaxStages;
   if (pp.b_stages > kMaxStages) pp.b_stages = kMaxStages;
   if (pp.a_stages < 1 || pp.b_stages < 2 || pp.b_stages < kWeightProducers) return cudaErrorInvalidValue;
   const int acc_stride = pow2_at_least(p.block_n, 32);
   const int tmem_cols = 2 * acc_stride;
-  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + 1024 + kRedBytes +
+  size_t smem = (size_t)pp.a_stages * a_bytes + (size_t)pp.b_stages * b_bytes + 1024 + 1024 + pp.red_bytes +
                 kEpiWarps * kStageBytesPerWarp + (size_t)pp.sv_floats * 4;
   // tmem_cols == 512 must never share an SM with a second CTA of this kernel (alloc would spin):
   if (tmem_cols > 256 && smem < 120 * 1024) smem = 120 * 1024;

@@ -19,6 +19,7 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 bool pdl_enabled();
 bool conv_halo_enabled();
 int conv_halo_mode();
+bool conv_dual_enabled();  // LS_CONV_DUAL=0 switches the dual-issue mode of conv_gemm off (development aid)
 bool conv_resident_enabled();
 bool conv_tma_out_enabled();   // LS_CONV_TMA_OUT=0: epilogue stores through the LSU (development aid)  // LS_CONV_RESIDENT=0: always stream the weights through the ring (development aid)  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
 template <typename... KArgs, typename... Args>
@@ -114,6 +115,10 @@ struct ConvGemmParams {
   int tma_out;  // dense [B][M][N] outputs are stored with cp.async.bulk.tensor (filled in by launch_conv_gemm)
   // per-channel epilogue vectors staged in shared memory (float offsets into the vector area, -1 = read from global)
   int sv_bias, sv_p1a, sv_p1b, sv_lng, sv_lnb, sv_floats;
+  // dual: two MMA-issuing warps, one per accumulator, on alternating tiles; each weight box serves both (filled in by
+  // launch_conv_gemm for streamed-or-resident halo launches with one N tile, see conv_gemm.cu)
+  int dual;
+  int red_bytes;  // LayerNorm statistics exchange area (0 for launches without a LayerNorm: the operand rings get it)
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps of the first tile, or nullptr
 };
 // rows of the activation box a conv with this geometry needs in halo mode (make_act_map's box_rows)

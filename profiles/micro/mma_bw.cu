@@ -20,6 +20,9 @@ struct P {
   int mode;   // 0 SS, 1 TS
   int n;      // 128 or 256
   int iters, bg;
+  int pattern;  // 0: MMAs only; 1: tcgen05.commit after every 4 MMAs (conv_gemm frees a weight slot per tap); 2: + a wait on an
+                // already-complete mbarrier and the fence before them; 3: pattern 2 with every MMA group under its own election
+  int shift;  // A descriptor starts `shift` rows into the 128B-swizzled tile (conv_gemm's halo taps), base offset = shift & 7
 };
 
 constexpr int kTile = 16384;
@@ -57,12 +60,43 @@ __global__ void __launch_bounds__(384, 1) k_mma(const __grid_constant__ CUtensor
   const uint32_t tmem = *tmem_slot;
   if (warp == 0) {
     const uint32_t idesc = make_idesc_bf16(128, p.n, false, false);
-    const uint64_t a0 = make_smem_desc_sw128(smem_u32(smem));
+    const uint64_t a0 = make_smem_desc_sw128(smem_u32(smem) + (uint32_t)p.shift * 128u, (uint32_t)p.shift & 7u);
     const uint64_t b0 = make_smem_desc_sw128(smem_u32(smem + kOffB));
     const uint64_t b1 = make_smem_desc_sw128(smem_u32(smem + kOffB + 32768));
     const uint32_t d = tmem, at = tmem + 256;
     __syncwarp();
     const long long t0 = clock64();
+    if (p.pattern) {  // conv_gemm's per-tap shape: [wait ready barrier] 4 MMAs, commit to a slot barrier
+      uint64_t* slot = tfull;       // commit target (never waited on)
+      uint64_t* ready = tfull + 1;  // completed once below, waited on with its completed parity
+      if (lane == 0) mbar_arrive(ready);
+      __syncwarp();
+      if (p.pattern < 3) {
+        if (elect_one()) {
+          for (int it = 0; it < p.iters; it += 4) {
+            if (p.pattern >= 2) {
+              mbar_wait(ready, 0);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, 1u);
+            umma_commit(slot);
+          }
+        }
+        __syncwarp();
+      } else {
+        for (int it = 0; it < p.iters; it += 4) {
+          mbar_wait(ready, 0);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, 1u);
+            umma_commit(slot);
+          }
+          __syncwarp();
+        }
+      }
+    } else
     for (int it = 0; it < p.iters; it += 8) {
       if (elect_one()) {
 #pragma unroll
@@ -166,7 +200,7 @@ int main() {
     for (int mode = 0; mode < 2; ++mode)
       for (int n : {64, 128, 256})
         for (int bg = 0; bg < 4; ++bg) {
-          P p{mode, n, 2048, bg};
+          P p{mode, n, 2048, bg, 0, 0};
           cudaMemset(out, 0, 512 * 8);
           for (int rep = 0; rep < 2; ++rep) k_mma<<<grid, 384, kSmem>>>(map, p, out, dummy);
           cudaError_t e = cudaDeviceSynchronize();
@@ -186,5 +220,33 @@ int main() {
           (void)lsu_b;
           fflush(stdout);
         }
+  for (int n : {48, 96, 192})
+    for (int pattern = 0; pattern < 4; ++pattern) {
+      P p{0, n, 2048, 0, pattern, 0};
+      cudaMemset(out, 0, 512 * 8);
+      for (int rep = 0; rep < 2; ++rep) k_mma<<<148, 384, kSmem>>>(map, p, out, dummy);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s (n %d pattern %d)\n", cudaGetErrorString(e), n, pattern); return 1; }
+      long long h[512];
+      cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
+      double tot = 0;
+      for (int i = 0; i < 148; ++i) tot += (double)h[2 * i];
+      printf("grid 148 SS N=%3d pattern %d (0 plain, 1 commit / 4 MMAs, 2 + ready wait, 3 + election per group): %6.1f clk/MMA; floor %3d\n", n, pattern,
+             tot / 148 / p.iters, n / 2);
+    }
+  // row-shifted A descriptors (the halo taps of conv_gemm) at the DAC decoder's thin widths
+  for (int n : {48, 96, 192})
+    for (int shift : {0, 1, 4, 8, 9, 27}) {
+      P p{0, n, 2048, 0, 0, shift};
+      cudaMemset(out, 0, 512 * 8);
+      for (int rep = 0; rep < 2; ++rep) k_mma<<<148, 384, kSmem>>>(map, p, out, dummy);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s (n %d shift %d)\n", cudaGetErrorString(e), n, shift); return 1; }
+      long long h[512];
+      cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
+      double tot = 0;
+      for (int i = 0; i < 148; ++i) tot += (double)h[2 * i];
+      printf("grid 148 SS N=%3d A shifted by %2d rows: %6.1f clk/MMA; floor %3d\n", n, shift, tot / 148 / p.iters, n / 2);
+    }
   return 0;
 }

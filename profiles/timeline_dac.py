@@ -18,6 +18,8 @@ def run(name, fn):
     r = buf.view(148, 64).cpu()[77]; base = int(r[0])
     rel = lambda i: int(r[i]) - base if int(r[i]) else None
     print(f"=== {name}: {us:.0f} us\n  producer tile starts {[rel(56+i) for i in range(8)]}\n  MMA tile commits     {[rel(24+i) for i in range(8)]}\n  epilogue tile done   {[rel(48+i) for i in range(8)]}\n  MMA saw B box of k-iter 0..15 at {[rel(8+i) for i in range(16)]} setup {rel(1)} pdl {rel(2)}")
+    if os.environ.get("LS_DETAIL"):
+        print("  detail triplets (before wait, after wait, after issue) x 7:", [[rel(8 + 3 * i + j) for j in range(3)] for i in range(7)])
 g = torch.Generator(device="cpu").manual_seed(0)
 C = int(os.environ.get('LS_C', '96'))
 B, L = 16, 120000 * 96 // C   # 10 s at 12 kHz (C = 96) / 24 kHz (C = 48)
