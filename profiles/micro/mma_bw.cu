@@ -220,7 +220,7 @@ int main() {
           (void)lsu_b;
           fflush(stdout);
         }
-  for (int n : {48, 96, 192})
+  for (int n : {48, 64, 96, 128, 192, 256})
     for (int pattern = 0; pattern < 4; ++pattern) {
       P p{0, n, 2048, 0, pattern, 0};
       cudaMemset(out, 0, 512 * 8);
