@@ -133,6 +133,20 @@ void ls_speaker_destroy(ls_speaker* h);
 int32_t ls_speaker_encode(ls_speaker* h, const float* mel, float* embedding, int32_t B, int32_t T, int32_t n_refs,
                           void* stream);
 
+/* ---- S3 speech tokenizer: S3TokenizerV2.quantize for clips of at most 30 s
+ * (speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:386-415) = AudioEncoderV2.forward (:320-351: two stride-2 convs,
+ * FSMN attention blocks with rotary embedding :152-287) + FSQCodebook.encode (:97-112).  fp32 arithmetic only.
+ * mel [B,n_mels,T] (100 Hz log-mel, right-padded), mel_len [B] -> codes [B,T2] (ids < 3^8; frames past code_len[b] are
+ * undefined, as in the reference), code_len [B]; T2 = ls_s3_code_frames(T); hidden (nullable): [B,T2,n_state], the
+ * encoder output.  Weight names = the reference's state_dict keys; optional "rotary.cos" / "rotary.sin" [len][32] tables
+ * (default: precompute_freqs_cis(64, 2048), model_v2.py:37-48).  All pointers are device pointers. */
+typedef struct ls_s3 ls_s3;
+int32_t ls_s3_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_s3** out);
+void ls_s3_destroy(ls_s3* h);
+int32_t ls_s3_code_frames(int32_t T);
+int32_t ls_s3_quantize(ls_s3* h, const float* mel, const int32_t* mel_len, int32_t* codes, int32_t* code_len, float* hidden,
+                       int32_t B, int32_t T, void* stream);
+
 /* ---- end to end with HOST buffers (pinned or pageable): H2D copies, solve, decode, D2H copy, and a
  * stream synchronise all happen inside the call.  wav_host: [B,1,T*hop]. */
 int32_t ls_synthesize_host(ls_flow* flow, ls_dac* dac, const float* mu_host, const float* mask_host,

@@ -176,7 +176,36 @@ struct ls_speaker {
   std::unique_ptr<ls::SpeakerEngineF32> eng32;   // fp32 mode
 };
 
+struct ls_s3 {
+  ls::StreamSerial serial;
+  std::unique_ptr<ls::S3EngineF32> eng32;  // fp32 mode (the only one: tokens are rounding decisions)
+};
+
 extern "C" {
+
+int32_t ls_s3_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_s3** out) {
+  return ls::guarded([&] {
+    ls::require(weights && out && n_weights > 0, "ls_s3_create_fp32: null argument");
+    ls::Weights w(weights, n_weights);
+    auto h = std::make_unique<ls_s3>();
+    h->eng32 = std::make_unique<ls::S3EngineF32>(w, device);
+    *out = h.release();
+  });
+}
+void ls_s3_destroy(ls_s3* h) { delete h; }
+int32_t ls_s3_code_frames(int32_t T) {
+  int t1 = 0, t2 = 0;
+  if (T > 0) ls::S3EngineF32::code_frames(T, &t1, &t2);
+  return t2;
+}
+int32_t ls_s3_quantize(ls_s3* h, const float* mel, const int32_t* mel_len, int32_t* codes, int32_t* code_len, float* hidden,
+                       int32_t B, int32_t T, void* stream) {
+  return ls::guarded([&] {
+    ls::require(h && mel && mel_len && codes && code_len, "ls_s3_quantize: null argument");
+    ls::SerialScope scope(h->serial, h->eng32->device(), (cudaStream_t)stream);
+    h->eng32->quantize(mel, mel_len, codes, code_len, hidden, B, T, (cudaStream_t)stream);
+  });
+}
 
 int32_t ls_front_create_fp32(const ls_tensor* weights, int32_t n_weights, int32_t device, ls_front** out) {
   return ls::guarded([&] {

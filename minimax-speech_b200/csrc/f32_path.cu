@@ -95,7 +95,7 @@ __device__ __forceinline__ float mish_exact(float x) {  // F.mish: x * tanh(soft
 __global__ void __launch_bounds__(kTB) layernorm_nct_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                             const float* __restrict__ be, float* __restrict__ y, int C,
                                                             int T, int do_mish, const float* __restrict__ mask,
-                                                            const float* __restrict__ vec) {
+                                                            const float* __restrict__ vec, float eps = 1e-5f) {
   const int t = blockIdx.x * kTB + threadIdx.x;
   const int b = blockIdx.z;
   if (t >= T) return;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kTB) layernorm_nct_kernel(const float* __restr
     const float d = xb[(size_t)c * T] - mean;
     var = fmaf(d, d, var);
   }
-  const float rstd = 1.0f / sqrtf(var / (float)C + 1e-5f);
+  const float rstd = 1.0f / sqrtf(var / (float)C + eps);
   const float mv = mask ? mask[(size_t)b * T + t] : 1.f;
   float* yb = y + (size_t)b * C * T + t;
   for (int c = 0; c < C; ++c) {
@@ -536,6 +536,62 @@ __global__ void mean_stack_kernel(const float* __restrict__ x, float* __restrict
   float a = 0.f;
   for (int k = 0; k < N; ++k) a += x[(size_t)k * n + i];
   y[i] = a / (float)N;
+}
+
+// ---- S3 tokenizer trunk (tools/S3Tokenizer/s3tokenizer/model_v2.py) -------------------------------------------------
+// lengths after the two stride-2 convs (model_v2.py:330-334: (len + 2 - 2 - 1) / 2 + 1) and the float masks of
+// make_non_pad_mask (utils.py) for the input and the two conv outputs
+__global__ void s3_lens_kernel(const int* __restrict__ mel_len, int* __restrict__ l1, int* __restrict__ l2, float* __restrict__ m0,
+                               float* __restrict__ m1, float* __restrict__ m2, int T, int T1, int T2) {
+  const int b = blockIdx.x;
+  const int n0 = mel_len[b];
+  const int n1 = (n0 - 1) / 2 + 1, n2 = (n1 - 1) / 2 + 1;
+  if (threadIdx.x == 0) l1[b] = n1, l2[b] = n2;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) m0[(size_t)b * T + t] = t < n0 ? 1.f : 0.f;
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) m1[(size_t)b * T1 + t] = t < n1 ? 1.f : 0.f;
+  for (int t = threadIdx.x; t < T2; t += blockDim.x) m2[(size_t)b * T2 + t] = t < n2 ? 1.f : 0.f;
+}
+// apply_rotary_emb (model_v2.py:51-70) in place on x [B, H*64, T]: per head, x * cos + cat(-x[32:], x[:32]) * sin with the
+// table of precompute_freqs_cis(64, .) concatenated with itself (angle index d mod 32); cs / sn: [table_len][32]
+__global__ void rotary_nct_kernel(float* __restrict__ x, const float* __restrict__ cs, const float* __restrict__ sn, int H, int T,
+                                  size_t n_pairs) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int t = (int)(i % T);
+  const int d = (int)((i / T) % 32);
+  const size_t bh = i / ((size_t)T * 32);
+  float* lo = x + (bh * 64 + d) * T + t;
+  float* hi = lo + (size_t)32 * T;
+  const float c = cs[(size_t)t * 32 + d], s = sn[(size_t)t * 32 + d];
+  const float a = *lo, b = *hi;
+  *lo = a * c + (-b) * s;
+  *hi = b * c + a * s;
+}
+// FSMNMultiHeadAttention.forward_fsmn (model_v2.py:177-189): vm = v * mask; (depthwise conv over time, kernel K with
+// (K-1)/2 zeros on the left and the rest on the right, + vm) * mask.  v, y: [B, C, T]; w: [C][K]
+__global__ void __launch_bounds__(kTB) fsmn_nct_kernel(const float* __restrict__ v, const float* __restrict__ mask,
+                                                       const float* __restrict__ w, float* __restrict__ y, int C, int T, int K) {
+  const int t = blockIdx.x * kTB + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float* vb = v + ((size_t)b * C + c) * T;
+  const float* mb = mask + (size_t)b * T;
+  const int left = (K - 1) / 2;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int tt = t + k - left;
+    if (tt >= 0 && tt < T) acc = fmaf(vb[tt] * mb[tt], w[(size_t)c * K + k], acc);
+  }
+  y[((size_t)b * C + c) * T + t] = (acc + vb[t] * mb[t]) * mb[t];
+}
+// [B, C, T] -> [B, T, C] (the row layout the FSQ head reads)
+__global__ void nct_to_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int T, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % T);
+  const size_t b = i / ((size_t)C * T);
+  y[i] = x[(b * C + c) * T + t];
 }
 
 inline unsigned blocks(size_t n) { return (unsigned)((n + 255) / 256); }
@@ -1129,6 +1185,108 @@ void SpeakerEngineF32::encode(const float* mel, float* emb, int B, int T, int n_
   float* avg = scratch_.get((size_t)B * out_, s);
   F32_LAUNCH(mean_stack_kernel, blocks((size_t)B * out_), 256, s, each, avg, n_refs, (size_t)B * out_);
   F32_LAUNCH(normalize_rows_kernel, B, 128, s, avg, emb, out_);
+}
+
+// ---------------------------------------------------------------------------------------------- S3 tokenizer (f-4)
+S3EngineF32::S3EngineF32(const Weights& w, int device) : device_(device) {
+  LS_CUDA(cudaSetDevice(device));
+  upload_all(w, &w_);
+  mels_ = (int)w_.shape("encoder.conv1.weight")[1];
+  d_ = (int)w_.shape("encoder.conv1.weight")[0];
+  require(d_ % 64 == 0, "S3 tokenizer: n_audio_state must be a multiple of the 64-wide heads", LS_ERR_UNSUPPORTED);
+  heads_ = d_ / 64;
+  ksize_ = (int)w_.shape("encoder.blocks.0.attn.fsmn_block.weight")[2];
+  while (w_.has("encoder.blocks." + std::to_string(n_blocks_) + ".attn.query.weight")) ++n_blocks_;
+  require(w_.shape("quantizer._codebook.project_down.weight")[0] == 8, "S3 tokenizer: FSQ head must project to 8 dims",
+          LS_ERR_UNSUPPORTED);
+  // rotary table [len][32]: "rotary.cos" / "rotary.sin" when the caller supplies them (the Python module builds them with
+  // the reference's own torch expressions), else precompute_freqs_cis(64, 2048) restated in double precision
+  if (w_.has("rotary.cos") && w_.has("rotary.sin")) {
+    table_len_ = (int)w_.shape("rotary.cos")[0];
+    require(w_.shape("rotary.cos")[1] == 32 && w_.shape("rotary.sin")[0] == table_len_, "S3 tokenizer: rotary tables must be [len][32]");
+  } else {
+    table_len_ = 2048;
+    std::vector<float> c((size_t)table_len_ * 32), sn((size_t)table_len_ * 32);
+    for (int d = 0; d < 32; ++d) {
+      const float inv = 1.0f / (float)std::pow(10000.0, (double)(2 * d) / 64.0);
+      for (int t = 0; t < table_len_; ++t) {
+        const float ang = (float)t * inv;
+        c[(size_t)t * 32 + d] = (float)std::cos((double)ang), sn[(size_t)t * 32 + d] = (float)std::sin((double)ang);
+      }
+    }
+    w_.add("rotary.cos", c.data(), c.size(), {table_len_, 32});
+    w_.add("rotary.sin", sn.data(), sn.size(), {table_len_, 32});
+  }
+}
+
+void S3EngineF32::code_frames(int T, int* T1, int* T2) {
+  *T1 = (T - 1) / 2 + 1;
+  *T2 = (*T1 - 1) / 2 + 1;
+}
+
+// S3TokenizerV2.quantize for clips of at most 30 s (model_v2.py:386-415) = AudioEncoderV2.forward (:320-351) + FSQ head
+void S3EngineF32::quantize(const float* mel, const int* mel_len, int* codes, int* code_len, float* hidden_out, int B, int T,
+                           cudaStream_t s) {
+  require(B > 0 && T > 0, "B and T must be positive");
+  require(T <= 3000, "S3 tokenizer: clips longer than 30 s (3000 mel frames) take the reference's sliding-window path, "
+                     "which is not built", LS_ERR_UNSUPPORTED);
+  LS_CUDA(cudaSetDevice(device_));
+  scratch_.reset();
+  int T1, T2;
+  code_frames(T, &T1, &T2);
+  require(T2 <= table_len_, "S3 tokenizer: rotary table too short");
+  int* l1 = reinterpret_cast<int*>(scratch_.get((size_t)B, s));
+  float* m0 = scratch_.get((size_t)B * T, s);
+  float* m1 = scratch_.get((size_t)B * T1, s);
+  float* m2 = scratch_.get((size_t)B * T2, s);
+  F32_LAUNCH(s3_lens_kernel, B, 256, s, mel_len, l1, code_len, m0, m1, m2, T, T1, T2);
+  const size_t n1 = (size_t)B * d_ * T1, n = (size_t)B * d_ * T2;
+  float* c1 = scratch_.get(n1, s);
+  conv1d(mel, m0, w_.ptr("encoder.conv1.weight"), w_.ptr("encoder.conv1.bias"), c1, nullptr, B, mels_, T, d_, 3, 1, 1, -1.f, s, 2, T1);
+  float* g1 = scratch_.get(n1, s);
+  ew(c1, nullptr, g1, n1, EW_GELU, s);
+  float* c2 = scratch_.get(n, s);
+  conv1d(g1, m1, w_.ptr("encoder.conv2.weight"), w_.ptr("encoder.conv2.bias"), c2, nullptr, B, d_, T1, d_, 3, 1, 1, -1.f, s, 2, T2);
+  float* x = scratch_.get(n, s);
+  ew(c2, nullptr, x, n, EW_GELU, s);
+  float* nrm = scratch_.get(n, s);
+  float* q = scratch_.get(n, s);
+  float* k = scratch_.get(n, s);
+  float* v = scratch_.get(n, s);
+  float* mem = scratch_.get(n, s);
+  float* att = scratch_.get(n, s);
+  float* prj = scratch_.get(n, s);
+  float* x1 = scratch_.get(n, s);
+  float* h1 = scratch_.get(4 * n, s);
+  float* h2 = scratch_.get(4 * n, s);
+  const size_t n_pairs = (size_t)B * heads_ * 32 * T2;
+  for (int i = 0; i < n_blocks_; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i);
+    F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x, w_.ptr(p + ".attn_ln.weight"), w_.ptr(p + ".attn_ln.bias"), nrm, d_,
+               T2, 0, (const float*)nullptr, (const float*)nullptr, 1e-6f);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn.query.weight"), w_.ptr(p + ".attn.query.bias"), q, nullptr, B, d_, T2, d_, 1, 1, 0, -1.f, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn.key.weight"), nullptr, k, nullptr, B, d_, T2, d_, 1, 1, 0, -1.f, s);
+    conv1d(nrm, nullptr, w_.ptr(p + ".attn.value.weight"), w_.ptr(p + ".attn.value.bias"), v, nullptr, B, d_, T2, d_, 1, 1, 0, -1.f, s);
+    F32_LAUNCH(rotary_nct_kernel, blocks(n_pairs), 256, s, q, w_.ptr("rotary.cos"), w_.ptr("rotary.sin"), heads_, T2, n_pairs);
+    F32_LAUNCH(rotary_nct_kernel, blocks(n_pairs), 256, s, k, w_.ptr("rotary.cos"), w_.ptr("rotary.sin"), heads_, T2, n_pairs);
+    F32_LAUNCH(fsmn_nct_kernel, grid_t(T2, d_, B), kTB, s, v, m2, w_.ptr(p + ".attn.fsmn_block.weight"), mem, d_, T2, ksize_);
+    // q and k each carry 64^-1/4 in the reference (model_v2.py:198,210,213): 1/8 on the scores; keys past the clip's
+    // length get the -1e10 bias of mask_to_bias, i.e. weight exactly 0 after the softmax
+    F32_LAUNCH(attention_nct_kernel, grid_t(T2, heads_, B), kTB, s, q, k, v, att, code_len, heads_, T2, 0, 0.125f);
+    conv1d(att, nullptr, w_.ptr(p + ".attn.out.weight"), w_.ptr(p + ".attn.out.bias"), prj, nullptr, B, d_, T2, d_, 1, 1, 0, -1.f, s);
+    ew(prj, mem, att, n, EW_ADD, s);
+    ew(x, att, x1, n, EW_ADD, s);
+    F32_LAUNCH(layernorm_nct_kernel, grid_t(T2, 1, B), kTB, s, x1, w_.ptr(p + ".mlp_ln.weight"), w_.ptr(p + ".mlp_ln.bias"), nrm, d_, T2,
+               0, (const float*)nullptr, (const float*)nullptr, 1e-5f);
+    conv1d(nrm, nullptr, w_.ptr(p + ".mlp.0.weight"), w_.ptr(p + ".mlp.0.bias"), h1, nullptr, B, d_, T2, 4 * d_, 1, 1, 0, -1.f, s);
+    ew(h1, nullptr, h2, 4 * n, EW_GELU, s);
+    conv1d(h2, nullptr, w_.ptr(p + ".mlp.2.weight"), w_.ptr(p + ".mlp.2.bias"), prj, nullptr, B, 4 * d_, T2, d_, 1, 1, 0, -1.f, s);
+    ew(x1, prj, x, n, EW_ADD, s);
+  }
+  float* rows = hidden_out ? hidden_out : scratch_.get(n, s);
+  F32_LAUNCH(nct_to_rows_kernel, blocks(n), 256, s, x, rows, d_, T2, n);
+  LS_CUDA(launch_fsq_encode(rows, w_.ptr("quantizer._codebook.project_down.weight"), w_.ptr("quantizer._codebook.project_down.bias"),
+                            codes, (long long)B * T2, d_, s));
 }
 
 }  // namespace ls

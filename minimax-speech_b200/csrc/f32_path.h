@@ -133,4 +133,23 @@ class SpeakerEngineF32 {
   F32Scratch scratch_;
 };
 
+// S3TokenizerV2 (speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:290-415): 100 Hz log-mel
+// [B,n_mels,T] + lengths -> 25 Hz FSQ token ids (vocabulary 3^8) + token counts.  fp32 mode only: a token is a rounding
+// decision, and the tensor-core operand types move activations near a rounding boundary across it.
+class S3EngineF32 {
+ public:
+  S3EngineF32(const Weights& w, int device);
+  // mel [B,n_mels,T], mel_len [B] (device) -> codes [B,T2] int32, code_len [B] int32; hidden_out (nullable): [B,T2,n_state]
+  void quantize(const float* mel, const int* mel_len, int* codes, int* code_len, float* hidden_out, int B, int T, cudaStream_t s);
+  static void code_frames(int T, int* T1, int* T2);  // frames after each of the two stride-2 convs
+  int n_mels() const { return mels_; }
+  int n_state() const { return d_; }
+  int device() const { return device_; }
+
+ private:
+  int device_ = 0, mels_ = 128, d_ = 1280, heads_ = 20, ksize_ = 31, n_blocks_ = 0, table_len_ = 0;
+  F32Weights w_;
+  F32Scratch scratch_;
+};
+
 }  // namespace ls

@@ -17,6 +17,7 @@ OUT1_NONE, OUT1_LN, OUT1_COPY, OUT1_SNAKE = range(4)
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_device_check", "ls_flow_create", "ls_flow_create_fp16", "ls_flow_create_fp32", "ls_dac_create_fp32", "ls_dac_encode",
            "ls_front_create", "ls_front_create_fp32", "ls_front_destroy", "ls_front_encode",
            "ls_speaker_create", "ls_speaker_create_fp32", "ls_speaker_destroy", "ls_speaker_encode",
+           "ls_s3_create_fp32", "ls_s3_destroy", "ls_s3_code_frames", "ls_s3_quantize",
            "ls_flow_destroy",
            "ls_flow_estimator_forward", "ls_flow_solve", "ls_dac_create", "ls_dac_destroy", "ls_dac_hop_length",
            "ls_dac_decode", "ls_synthesize_host", "ls_fsq_encode", "ls_mask_to_lengths", "ls_graph_create", "ls_graph_buffer",
@@ -112,6 +113,11 @@ def load():
         lib.ls_speaker_destroy.argtypes = [vp]
         lib.ls_speaker_destroy.restype = None
         lib.ls_speaker_encode.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        lib.ls_s3_create_fp32.argtypes = [C.POINTER(LsTensor), i32, i32, C.POINTER(vp)]
+        lib.ls_s3_destroy.argtypes = [vp]
+        lib.ls_s3_destroy.restype = None
+        lib.ls_s3_code_frames.argtypes = [i32]
+        lib.ls_s3_quantize.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
         lib.ls_synthesize_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, vp, i32, i32, vp]
         lib.ls_mask_to_lengths.argtypes = [vp, vp, i32, i32, vp]
         lib.ls_fsq_encode.argtypes = [vp, vp, vp, vp, i64, i32, vp]
@@ -291,6 +297,38 @@ class SpeakerHandle:
         check(load().ls_speaker_encode(self._h, ptr(mel), ptr(emb), B, T, n_refs, current_stream_ptr(self.device)),
               "ls_speaker_encode")
         return emb
+
+
+class S3Handle:
+    """Owns an ls_s3*: S3TokenizerV2 (fp32 mode)."""
+
+    def __init__(self, state_dict, device):
+        lib = load()
+        self.device = torch.device(device)
+        arr, keep = tensor_table(state_dict)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ls_s3_create_fp32(arr, len(state_dict), self.device.index or 0, C.byref(h)), "ls_s3_create_fp32")
+        self._h = h
+        self.n_state = int(state_dict["encoder.conv1.weight"].shape[0])
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.ls_s3_destroy(h)
+
+    def quantize(self, mel, mel_len, want_hidden=False):
+        """mel [B, n_mels, T] fp32, mel_len [B] int32 (both on the handle's device) -> codes [B, T2] int32, code_len [B] int32
+        (and the encoder output [B, T2, n_state] when asked for)"""
+        B, _, T = mel.shape
+        T2 = int(load().ls_s3_code_frames(T))
+        codes = torch.empty(B, T2, device=mel.device, dtype=torch.int32)
+        code_len = torch.empty(B, device=mel.device, dtype=torch.int32)
+        hidden = torch.empty(B, T2, self.n_state, device=mel.device, dtype=torch.float32) if want_hidden else None
+        check(load().ls_s3_quantize(self._h, ptr(mel), ptr(mel_len), ptr(codes), ptr(code_len),
+                                    ptr(hidden) if hidden is not None else None, B, T, current_stream_ptr(self.device)),
+              "ls_s3_quantize")
+        return (codes, code_len, hidden) if want_hidden else (codes, code_len)
 
 
 class DacHandle:

@@ -260,6 +260,41 @@ def speaker_encoder_state_dict(seed=13, mel_dim=80, model_dim=512, output_dim=19
     return sd
 
 
+
+def s3_tokenizer_state_dict(seed=21, n_mels=128, n_state=1280, n_head=20, n_layer=6, kernel_size=31, **_):
+    """Keys/shapes of S3TokenizerV2 (tools/S3Tokenizer/s3tokenizer/model_v2.py:290-379: AudioEncoderV2 + the FSQ head).
+    Test initialisation: nn.Linear / nn.Conv1d style bounds, LayerNorm affine near (1, 0), every tensor non-trivial."""
+    assert n_state == 64 * n_head, "the reference precomputes its rotary table for 64-wide heads (model_v2.py:307)"
+    sd = {}
+
+    def lin(name, n, k, bias=True, kk=1):
+        bound = 1.0 / math.sqrt(k * kk)
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (n, k, kk) if kk > 1 else (n, k), bound)
+        if bias:
+            sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), bound)
+
+    lin("encoder.conv1", n_state, n_mels, kk=3)
+    lin("encoder.conv2", n_state, n_state, kk=3)
+    for i in range(n_layer):
+        b = f"encoder.blocks.{i}"
+        lin(b + ".attn.query", n_state, n_state)
+        lin(b + ".attn.key", n_state, n_state, bias=False)
+        lin(b + ".attn.value", n_state, n_state)
+        lin(b + ".attn.out", n_state, n_state)
+        sd[b + ".attn.fsmn_block.weight"] = _uniform(seed, b + ".fsmn", (n_state, 1, kernel_size), 1.0 / math.sqrt(kernel_size))
+        for ln in ("attn_ln", "mlp_ln"):
+            sd[f"{b}.{ln}.weight"] = _uniform(seed, f"{b}.{ln}.weight", (n_state,), 0.2).add(1.0)
+            sd[f"{b}.{ln}.bias"] = _uniform(seed, f"{b}.{ln}.bias", (n_state,), 0.1)
+        lin(b + ".mlp.0", 4 * n_state, n_state)
+        lin(b + ".mlp.2", n_state, 4 * n_state)
+    lin("quantizer._codebook.project_down", 8, n_state)
+    return sd
+
+
+def s3_mel(index, frames, n_mels=128):
+    """Synthetic log-mel input of the tokenizer (100 frames per second; whisper-style values in about [-1, 1.5])."""
+    return _normal(9000 + index, "s3mel", (1, n_mels, frames), 0.6, 0.2)
+
 def reference_mel(index, frames, mel_dim=80):
     return _normal(8000 + index, "mel", (1, mel_dim, frames), 1.0)
 

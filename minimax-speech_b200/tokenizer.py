@@ -1,11 +1,13 @@
-"""FSQ quantizer head of the S3 speech tokenizer (second half).
+"""The S3 speech tokenizer (second half): log-mel -> 25 Hz FSQ token ids.
 
-Drop-in for ``s3tokenizer.model_v2.FSQCodebook`` / ``FSQVectorQuantization``
-(speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:83-147): ``encode(hidden [B, T, dim]) -> int32 tokens [B, T]`` with the
-reference's parameter names (``project_down.weight [8, dim]``, ``project_down.bias [8]``), so a reference tokenizer
-checkpoint's ``quantizer._codebook.*`` entries load unchanged.  The tokens are the 25 Hz FSQ ids (vocabulary 3^8 = 6561)
-the flow's ``input_embedding`` consumes.  The whisper-style ``AudioEncoderV2`` trunk that produces ``hidden``
-(model_v2.py:243-351) is NOT built: this module starts from its output.
+Drop-ins for ``s3tokenizer.model_v2.S3TokenizerV2`` (speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:354-415:
+``quantize(mel [B, n_mels, T], mel_len [B]) -> (codes int32 [B, T'], code_len int32 [B])``), its ``AudioEncoderV2`` trunk
+(:290-351: two stride-2 convolutions, six FSMN-attention blocks with rotary embedding) and its quantizer head
+``FSQCodebook`` / ``FSQVectorQuantization`` (:83-147: ``encode(hidden [B, T, dim]) -> int32 tokens [B, T]``), with the
+reference's parameter names, so a reference tokenizer checkpoint loads unchanged.  The tokens are the ids (vocabulary
+3^8 = 6561) the flow's ``input_embedding`` consumes.  fp32 arithmetic only (``ls_s3_quantize``): a token is a rounding
+decision.  Not built: the sliding-window path for clips longer than 30 s (model_v2.py:417-588) and the log-mel front end
+(utils.py ``log_mel_spectrogram``: an STFT with a filter bank shipped as an asset file).
 """
 import math
 
@@ -56,3 +58,81 @@ class FSQVectorQuantization(nn.Module):
 
     def encode(self, x):
         return self._codebook.encode(x)
+
+
+def precompute_rotary(dim=64, end=2048, theta=10000.0):
+    """precompute_freqs_cis (model_v2.py:37-48) with the reference's own torch expressions -> (cos, sin) [end, dim/2]."""
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[:(dim // 2)].float() / dim))
+    ang = torch.outer(torch.arange(end), freqs).float()
+    cis = torch.polar(torch.ones_like(ang), ang)
+    real = torch.view_as_real(cis)
+    return real[..., 0].contiguous(), real[..., 1].contiguous()
+
+
+class _Block(nn.Module):
+    """Parameter container with ResidualAttentionBlock's names (model_v2.py:252-273)."""
+
+    def __init__(self, n_state, kernel_size=31):
+        super().__init__()
+        self.attn = nn.Module()
+        self.attn.query = nn.Linear(n_state, n_state)
+        self.attn.key = nn.Linear(n_state, n_state, bias=False)
+        self.attn.value = nn.Linear(n_state, n_state)
+        self.attn.out = nn.Linear(n_state, n_state)
+        self.attn.fsmn_block = nn.Conv1d(n_state, n_state, kernel_size, groups=n_state, bias=False)
+        self.attn_ln = nn.LayerNorm(n_state, eps=1e-6)
+        self.mlp = nn.Sequential(nn.Linear(n_state, 4 * n_state), nn.GELU(), nn.Linear(4 * n_state, n_state))
+        self.mlp_ln = nn.LayerNorm(n_state)
+
+
+class S3TokenizerV2(nn.Module):
+    """model_v2.py:354-415.  ``S3TokenizerV2(name, config)`` like the reference; ``config`` may be the reference's
+    ``ModelConfig`` or anything with its attribute names (n_mels, n_audio_state, n_audio_head, n_audio_layer)."""
+
+    def __init__(self, name="speech_tokenizer_v2_25hz", config=None, weight_seed=None):
+        super().__init__()
+        self.name = name
+        g = lambda k, d: getattr(config, k, d) if config is not None else d
+        self.n_mels, self.n_state = g("n_mels", 128), g("n_audio_state", 1280)
+        self.n_head, self.n_layer = g("n_audio_head", 20), g("n_audio_layer", 6)
+        if self.n_state != 64 * self.n_head:
+            raise NotImplementedError("64-wide heads: the reference precomputes its rotary table for them (model_v2.py:307)")
+        self.encoder = nn.Module()
+        self.encoder.conv1 = nn.Conv1d(self.n_mels, self.n_state, 3, stride=2, padding=1)
+        self.encoder.conv2 = nn.Conv1d(self.n_state, self.n_state, 3, stride=2, padding=1)
+        self.encoder.blocks = nn.ModuleList([_Block(self.n_state) for _ in range(self.n_layer)])
+        self.quantizer = FSQVectorQuantization(self.n_state, 3 ** 8)
+        if weight_seed is not None:
+            from . import synth
+            self.load_state_dict(synth.s3_tokenizer_state_dict(weight_seed, self.n_mels, self.n_state, self.n_head, self.n_layer))
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._handle = None
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._handle = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def handle(self, device):
+        device = torch.device(device)
+        if self._handle is None or self._handle.device != device:
+            sd = {k: v.detach().to(torch.float32).contiguous() for k, v in self.state_dict().items()}
+            sd["rotary.cos"], sd["rotary.sin"] = precompute_rotary(64, 1024 * 2)  # model_v2.py:307
+            self._handle = native.S3Handle(sd, device)
+        return self._handle
+
+    @torch.inference_mode()
+    def quantize(self, mel, mel_len, return_hidden=False):
+        if mel.dim() != 3 or mel.shape[1] != self.n_mels:
+            raise ValueError(f"mel must be [B, {self.n_mels}, T], got {tuple(mel.shape)}")
+        if mel.device.type != "cuda":
+            raise RuntimeError("the B200 path runs on CUDA tensors only (no CPU fallback)")
+        if mel.shape[2] > 3000:
+            raise NotImplementedError("clips longer than 30 s: the reference's sliding-window path (model_v2.py:417-588) is not built")
+        dev = mel.device
+        out = self.handle(dev).quantize(mel.to(torch.float32).contiguous(),
+                                        mel_len.to(device=dev, dtype=torch.int32).contiguous(), want_hidden=return_hidden)
+        return out
+
+    def forward(self, mel, mel_len):
+        return self.quantize(mel, mel_len)

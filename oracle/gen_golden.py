@@ -68,6 +68,7 @@ def pipeline_golden():
 
 NC_SEED_1, NC_SEED_2 = 501, 502   # torch.manual_seed before each non-causal forward (its z = torch.randn_like(mu))
 DAC_TRAINED_SEED = 21
+S3_SEED, S3_FRAMES, S3_LENS = 21, 203, [203, 150, 96]  # s3_golden.npz: 100 Hz mel frames per utterance (right-padded batch)
 
 
 def extra_golden():
@@ -77,6 +78,7 @@ def extra_golden():
                           unmodified reference: prompt_len = 20 with an empty cache, then with the returned cache
                           (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
     est_nc_golden.npz     the non-causal ConditionalDecoder estimator (decoder.py:88-291), one call per utterance.
+    s3_golden.npz         S3TokenizerV2 encoder trunk + quantize (model_v2.py:290-415), reduced width, ragged batch of 3.
     fsq_golden.npz        FSQCodebook.encode of the S3 tokenizer (tools/S3Tokenizer/s3tokenizer/model_v2.py:83-117).
     dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
                           Snake alpha in [0.5, 2], activations of O(10), |alpha * x| up to ~25 rad), layers.py:18-33.
@@ -133,6 +135,22 @@ def extra_golden():
         np.savez_compressed(os.path.join(OUT, "fsq_golden.npz"), tokens=ref_cb.encode(hidden).numpy(), hidden_seed=17,
                             weight_seed=5, keys=np.array(sorted(ref_cb.state_dict().keys())))
         print("fsq", ref_cb.encode(hidden)[0, :8].tolist())
+
+        # ---- S3TokenizerV2 (model_v2.py:290-415): encoder trunk + FSQ head, reduced width (2 heads of 64, 2 layers), ragged batch
+        s3cfg = dict(n_mels=128, n_state=128, n_head=2, n_layer=2)
+        s3sd = synth.s3_tokenizer_state_dict(S3_SEED, **s3cfg)
+        s3 = R.build_reference_s3_tokenizer(**s3cfg)
+        s3.load_state_dict(s3sd, strict=True)
+        mel = torch.cat([synth.s3_mel(i, S3_FRAMES) for i in range(len(S3_LENS))], 0)
+        mel_len = torch.tensor(S3_LENS)
+        hidden, code_len = s3.encoder(mel, mel_len)
+        codes, code_len2 = s3.quantize(mel, mel_len)
+        assert torch.equal(code_len, code_len2)
+        np.savez_compressed(os.path.join(OUT, "s3_golden.npz"), hidden=hidden.numpy(), codes=codes.numpy(), code_len=code_len.numpy(),
+                            mel_len=np.array(S3_LENS), frames=S3_FRAMES, weights_seed=S3_SEED,
+                            cfg=np.array([s3cfg[k] for k in ("n_mels", "n_state", "n_head", "n_layer")]),
+                            keys=np.array(sorted(s3.state_dict().keys())))
+        print("s3 tokenizer", tuple(hidden.shape), code_len.tolist(), codes[1, :6].tolist())
 
         sd = synth.dac_decoder_state_dict(DAC_TRAINED_SEED, init="trained")
         dac = R.build_reference_dac()

@@ -208,6 +208,15 @@ def load_fsq_codebook_class():
     return importlib.import_module("s3tokenizer.model_v2").FSQCodebook
 
 
+
+def build_reference_s3_tokenizer(n_mels=128, n_state=1280, n_head=20, n_layer=6):
+    """The unmodified S3TokenizerV2 (speech/tools/S3Tokenizer/s3tokenizer/model_v2.py:354-415), same stubs as above."""
+    load_fsq_codebook_class()
+    import importlib
+    m2 = importlib.import_module("s3tokenizer.model_v2")
+    cfg = m2.ModelConfig(n_mels=n_mels, n_audio_state=n_state, n_audio_head=n_head, n_audio_layer=n_layer)
+    return m2.S3TokenizerV2("speech_tokenizer_v2_25hz", cfg).eval()
+
 def build_reference_dac(cfg=None):
     dm = load_dac_module()
     return dm.DACVAE(**(cfg or DAC_CFG_X2)).eval()

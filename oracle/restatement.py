@@ -487,6 +487,66 @@ def fsq_encode(weight, bias, x):
     return torch.sum(h * powers.unsqueeze(0), dim=-1).reshape(x.shape[0], x.shape[1]).int()
 
 
+
+def s3_encode(sd, mel, mel_len):
+    """AudioEncoderV2.forward (tools/S3Tokenizer/s3tokenizer/model_v2.py:320-351) with FSMNMultiHeadAttention
+    (:152-249), ResidualAttentionBlock (:252-287), the rotary embedding (:37-70) and the masks of utils.py
+    (make_non_pad_mask, mask_to_bias).  mel [B, n_mels, T] fp32, mel_len [B] -> (hidden [B, T', n_state], code_len [B]);
+    T' = ((T - 1) // 2 + 1 - 1) // 2 + 1.  Frames past code_len carry whatever the reference computes there."""
+    def non_pad(lengths, T):
+        return (torch.arange(T).unsqueeze(0) < lengths.unsqueeze(1))
+
+    n_state = sd["encoder.conv1.weight"].shape[0]
+    H = n_state // 64
+    mel_len = mel_len.to(torch.int64)
+    x = mel.float() * non_pad(mel_len, mel.shape[2]).unsqueeze(1)
+    x = F.gelu(F.conv1d(x, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"], stride=2, padding=1))
+    l1 = (mel_len + 2 - 2 - 1) // 2 + 1
+    x = x * non_pad(l1, x.shape[2]).unsqueeze(1)
+    x = F.gelu(F.conv1d(x, sd["encoder.conv2.weight"], sd["encoder.conv2.bias"], stride=2, padding=1))
+    l2 = (l1 + 2 - 2 - 1) // 2 + 1
+    x = x.permute(0, 2, 1)  # [B, T', n_state]
+    B, T, _ = x.shape
+    mask_pad = non_pad(l2, T).unsqueeze(2).float()          # [B, T', 1]
+    bias = (1.0 - non_pad(l2, T).float()) * -1.0e10          # [B, T'] additive, per key
+    # rotary table: angle(t, d) = t * 10000^(-2 (d mod 32) / 64)  (precompute_freqs_cis(64, .) concatenated with itself)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.outer(torch.arange(T).float(), inv)
+    cos = torch.cat((ang.cos(), ang.cos()), -1)[None, :, None, :]
+    sin = torch.cat((ang.sin(), ang.sin()), -1)[None, :, None, :]
+
+    def rot(a):  # [B, T, H, 64]
+        return a * cos + torch.cat((-a[..., 32:], a[..., :32]), -1) * sin
+
+    i = 0
+    while f"encoder.blocks.{i}.attn.query.weight" in sd:
+        p = f"encoder.blocks.{i}"
+        a = F.layer_norm(x, (n_state,), sd[p + ".attn_ln.weight"], sd[p + ".attn_ln.bias"], 1e-6)
+        q = F.linear(a, sd[p + ".attn.query.weight"], sd[p + ".attn.query.bias"]).view(B, T, H, 64)
+        k = F.linear(a, sd[p + ".attn.key.weight"]).view(B, T, H, 64)
+        v = F.linear(a, sd[p + ".attn.value.weight"], sd[p + ".attn.value.bias"])
+        q, k = rot(q), rot(k)
+        vm = v * mask_pad  # forward_fsmn: depthwise conv over time (kernel 31, 15 + 15 zero padding) + its input, masked
+        w = sd[p + ".attn.fsmn_block.weight"]
+        ks = w.shape[-1]
+        mem = F.conv1d(F.pad(vm.transpose(1, 2), ((ks - 1) // 2, ks - 1 - (ks - 1) // 2)), w, groups=n_state).transpose(1, 2)
+        mem = (mem + vm) * mask_pad
+        scale = 64 ** -0.25
+        qk = torch.einsum("bthd,bshd->bhts", q * scale, k * scale) + bias[:, None, None, :]
+        o = torch.einsum("bhts,bshd->bthd", torch.softmax(qk.float(), -1), v.view(B, T, H, 64)).reshape(B, T, n_state)
+        x = x + F.linear(o, sd[p + ".attn.out.weight"], sd[p + ".attn.out.bias"]) + mem
+        m = F.layer_norm(x, (n_state,), sd[p + ".mlp_ln.weight"], sd[p + ".mlp_ln.bias"], 1e-5)
+        x = x + F.linear(F.gelu(F.linear(m, sd[p + ".mlp.0.weight"], sd[p + ".mlp.0.bias"])), sd[p + ".mlp.2.weight"],
+                         sd[p + ".mlp.2.bias"])
+        i += 1
+    return x, l2.to(torch.int32)
+
+
+def s3_quantize(sd, mel, mel_len):
+    """S3TokenizerV2.quantize for audio of at most 30 s (model_v2.py:386-415): encoder trunk, then the FSQ head."""
+    hidden, code_len = s3_encode(sd, mel, mel_len)
+    return fsq_encode(sd["quantizer._codebook.project_down.weight"], sd["quantizer._codebook.project_down.bias"], hidden), code_len
+
 def rel_l2(y, ref):
     y, ref = y.double(), ref.double()
     return float((y - ref).norm() / ref.norm().clamp_min(1e-30))

@@ -222,3 +222,30 @@ def test_fsq_codebook_matches_reference(golden_dir):
     tok = O.fsq_encode(cb.project_down.weight, cb.project_down.bias, hidden)
     assert torch.equal(tok, torch.from_numpy(g["tokens"]))
     assert int(tok.min()) >= 0 and int(tok.max()) < 3 ** 8
+
+
+def test_s3_tokenizer_matches_reference(golden_dir):
+    """S3TokenizerV2 (encoder trunk + FSQ head, model_v2.py:290-415): restatement vs the unmodified reference class on a
+    ragged batch; the drop-in module's parameter names are the reference's."""
+    from minimax_speech_b200.tokenizer import S3TokenizerV2
+
+    g = np.load(os.path.join(golden_dir, "s3_golden.npz"))
+    n_mels, n_state, n_head, n_layer = [int(v) for v in g["cfg"]]
+    sd = synth.s3_tokenizer_state_dict(int(g["weights_seed"]), n_mels, n_state, n_head, n_layer)
+    assert sorted(sd.keys()) == [str(k) for k in g["keys"]]
+
+    class Cfg:
+        n_audio_state, n_audio_head, n_audio_layer = n_state, n_head, n_layer
+    Cfg.n_mels = n_mels
+    mod = S3TokenizerV2("speech_tokenizer_v2_25hz", Cfg())
+    mod.load_state_dict(sd, strict=True)
+    lens = [int(v) for v in g["mel_len"]]
+    mel = torch.cat([synth.s3_mel(i, int(g["frames"])) for i in range(len(lens))], 0)
+    with torch.inference_mode():
+        hidden, code_len = O.s3_encode(sd, mel, torch.tensor(lens))
+        codes, _ = O.s3_quantize(sd, mel, torch.tensor(lens))
+    assert code_len.tolist() == g["code_len"].tolist()
+    ref_h, ref_c = torch.from_numpy(g["hidden"]), torch.from_numpy(g["codes"])
+    for b, n in enumerate(code_len.tolist()):
+        assert O.rel_l2(hidden[b, :n], ref_h[b, :n]) < 2e-6
+        assert torch.equal(codes[b, :n], ref_c[b, :n])

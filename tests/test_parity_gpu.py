@@ -311,3 +311,55 @@ def test_fsq_codebook_vs_reference_golden(golden_dir):
     assert torch.equal(tok, ref)
     with pytest.raises(RuntimeError):
         vq.encode(hidden)  # CPU tensors are rejected, not emulated
+
+
+def test_s3_tokenizer_vs_reference_golden(golden_dir):
+    """S3TokenizerV2.quantize on the GPU (ls_s3_quantize, fp32 arithmetic) against the unmodified reference's outputs:
+    encoder output within 1e-5 over the valid frames, token ids identical, token counts identical."""
+    from minimax_speech_b200.tokenizer import S3TokenizerV2
+    g = np.load(os.path.join(golden_dir, "s3_golden.npz"))
+    n_mels, n_state, n_head, n_layer = [int(v) for v in g["cfg"]]
+
+    class Cfg:
+        n_audio_state, n_audio_head, n_audio_layer = n_state, n_head, n_layer
+    Cfg.n_mels = n_mels
+    tok = S3TokenizerV2("speech_tokenizer_v2_25hz", Cfg(), weight_seed=int(g["weights_seed"]))
+    lens = [int(v) for v in g["mel_len"]]
+    mel = torch.cat([synth.s3_mel(i, int(g["frames"])) for i in range(len(lens))], 0)
+    codes, code_len, hidden = tok.quantize(mel.to(DEV), torch.tensor(lens), return_hidden=True)
+    assert codes.dtype == torch.int32 and code_len.tolist() == g["code_len"].tolist()
+    ref_h, ref_c = torch.from_numpy(g["hidden"]), torch.from_numpy(g["codes"])
+    for b, n in enumerate(code_len.tolist()):
+        e = O.rel_l2(hidden[b, :n].cpu(), ref_h[b, :n])
+        print(f"s3 hidden utterance {b}: rel-L2 {e:.2e}")
+        assert e < 1e-5
+        assert torch.equal(codes[b, :n].cpu(), ref_c[b, :n])
+    c2, l2 = tok(mel.to(DEV), torch.tensor(lens).to(DEV))  # forward = quantize; lengths on either device
+    assert torch.equal(c2, codes) and torch.equal(l2, code_len)
+    with pytest.raises(RuntimeError):
+        tok.quantize(mel, torch.tensor(lens))  # CPU tensors are rejected, not emulated
+
+
+def test_s3_tokenizer_full_width_vs_oracle():
+    """The shipped configuration (1280 wide, 20 heads, 6 blocks) on a ragged batch against the oracle: token agreement
+    and the encoder output."""
+    from minimax_speech_b200.tokenizer import S3TokenizerV2
+    tok = S3TokenizerV2(weight_seed=33)
+    sd = {k: v.clone() for k, v in tok.state_dict().items()}
+    lens = [400, 263]
+    mel = torch.cat([synth.s3_mel(10 + i, 400) for i in range(2)], 0)
+    codes, code_len, hidden = tok.quantize(mel.to(DEV), torch.tensor(lens), return_hidden=True)
+    with torch.inference_mode():
+        ref_h, ref_l = O.s3_encode(sd, mel, torch.tensor(lens))
+        ref_c, _ = O.s3_quantize(sd, mel, torch.tensor(lens))
+    assert code_len.tolist() == ref_l.tolist() == [100, 66]
+    agree, total = 0, 0
+    for b, n in enumerate(ref_l.tolist()):
+        e = O.rel_l2(hidden[b, :n].cpu(), ref_h[b, :n])
+        print(f"s3 full width utterance {b}: rel-L2 {e:.2e}")
+        assert e < 1e-4
+        agree += int((codes[b, :n].cpu() == ref_c[b, :n]).sum())
+        total += n
+    print(f"s3 full width: {agree} of {total} tokens identical")
+    # a token differs only where a projected value sits within fp32 noise of a rounding boundary of tanh(.) * 0.999
+    assert agree >= total - 1
