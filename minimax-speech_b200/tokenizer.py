@@ -6,8 +6,9 @@ Drop-ins for ``s3tokenizer.model_v2.S3TokenizerV2`` (speech/tools/S3Tokenizer/s3
 ``FSQCodebook`` / ``FSQVectorQuantization`` (:83-147: ``encode(hidden [B, T, dim]) -> int32 tokens [B, T]``), with the
 reference's parameter names, so a reference tokenizer checkpoint loads unchanged.  The tokens are the ids (vocabulary
 3^8 = 6561) the flow's ``input_embedding`` consumes.  fp32 arithmetic only (``ls_s3_quantize``): a token is a rounding
-decision.  Not built: the sliding-window path for clips longer than 30 s (model_v2.py:417-588) and the log-mel front end
-(utils.py ``log_mel_spectrogram``: an STFT with a filter bank shipped as an asset file).
+decision.  Clips longer than 30 s take the reference's sliding-window path (model_v2.py:417-588: host-side windowing and
+merging around one batched device call).  Not built: the log-mel front end (utils.py ``log_mel_spectrogram``: an STFT with
+a filter bank shipped as an asset file).
 """
 import math
 
@@ -127,12 +128,48 @@ class S3TokenizerV2(nn.Module):
             raise ValueError(f"mel must be [B, {self.n_mels}, T], got {tuple(mel.shape)}")
         if mel.device.type != "cuda":
             raise RuntimeError("the B200 path runs on CUDA tensors only (no CPU fallback)")
-        if mel.shape[2] > 3000:
-            raise NotImplementedError("clips longer than 30 s: the reference's sliding-window path (model_v2.py:417-588) is not built")
         dev = mel.device
-        out = self.handle(dev).quantize(mel.to(torch.float32).contiguous(),
-                                        mel_len.to(device=dev, dtype=torch.int32).contiguous(), want_hidden=return_hidden)
-        return out
+        lens = [int(v) for v in mel_len.tolist()]  # (the reference reads the lengths on the host as well: .any(), .item())
+        if max(lens) > self.MAX_FRAMES:
+            if return_hidden:
+                raise ValueError("return_hidden is only defined for batches without clips longer than 30 s")
+            return self._quantize_mixed_batch(mel.to(torch.float32), lens)
+        return self.handle(dev).quantize(mel.to(torch.float32).contiguous(),
+                                         torch.tensor(lens, dtype=torch.int32, device=dev), want_hidden=return_hidden)
+
+    MAX_FRAMES = 3000       # 30 s of 100 Hz mel frames (model_v2.py:399-401)
+    WINDOW, OVERLAP = 3000, 400  # 30 s windows overlapping by 4 s (model_v2.py:436-445)
+
+    def _quantize_mixed_batch(self, mel, lens):
+        """model_v2.py:417-588: clips longer than 30 s are cut into 30 s windows every 26 s, every window (and every short
+        clip, padded to 30 s) goes through the encoder in ONE batch, and a long clip's token lists are joined by dropping
+        half of each overlap on either side of a seam (utils.py merge_tokenized_segments).  int64 ids, like the reference's."""
+        dev = mel.device
+        stride = self.WINDOW - self.OVERLAP
+        segs, seg_lens, owner = [], [], []
+        for b, n in enumerate(lens):
+            starts = [0] if n <= self.MAX_FRAMES else list(range(0, n, stride))
+            for st in starts:
+                piece = mel[b, :, st:min(st + self.WINDOW, n)]
+                seg_lens.append(piece.shape[1])
+                segs.append(torch.nn.functional.pad(piece, (0, self.WINDOW - piece.shape[1])))
+                owner.append(b)
+        codes, code_len = self.handle(dev).quantize(torch.stack(segs).contiguous(),
+                                                    torch.tensor(seg_lens, dtype=torch.int32, device=dev))
+        codes, code_len = codes.cpu(), code_len.tolist()
+        half = (self.OVERLAP // 100 // 2) * 25  # tokens in half of the overlap: (4 s // 2) * 25 Hz
+        merged = [[] for _ in lens]
+        for b in range(len(lens)):
+            mine = [i for i, o in enumerate(owner) if o == b]
+            for j, i in enumerate(mine):
+                toks = codes[i, :code_len[i]].tolist()
+                if lens[b] > self.MAX_FRAMES:
+                    toks = toks[(0 if j == 0 else half):(len(toks) - half if j != len(mine) - 1 else len(toks))]
+                merged[b].extend(toks)
+        out = torch.zeros(len(lens), max(len(m) for m in merged), dtype=torch.long)
+        for b, m in enumerate(merged):
+            out[b, :len(m)] = torch.tensor(m, dtype=torch.long)
+        return out.to(dev), torch.tensor([len(m) for m in merged], dtype=torch.long, device=dev)
 
     def forward(self, mel, mel_len):
         return self.quantize(mel, mel_len)

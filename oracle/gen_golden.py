@@ -68,6 +68,7 @@ def pipeline_golden():
 
 NC_SEED_1, NC_SEED_2 = 501, 502   # torch.manual_seed before each non-causal forward (its z = torch.randn_like(mu))
 DAC_TRAINED_SEED = 21
+S3_LONG_LENS = [5700, 900, 3100]  # s3_long_golden.npz: 57 s (3 windows), 9 s, 31 s (2 windows)
 S3_SEED, S3_FRAMES, S3_LENS = 21, 203, [203, 150, 96]  # s3_golden.npz: 100 Hz mel frames per utterance (right-padded batch)
 
 
@@ -79,6 +80,7 @@ def extra_golden():
                           (54 frames of z | mu) reused on a longer utterance -- the CLI's streaming overlap path.
     est_nc_golden.npz     the non-causal ConditionalDecoder estimator (decoder.py:88-291), one call per utterance.
     s3_golden.npz         S3TokenizerV2 encoder trunk + quantize (model_v2.py:290-415), reduced width, ragged batch of 3.
+    s3_long_golden.npz    the same tokenizer on a batch with clips longer than 30 s (sliding windows, model_v2.py:417-588).
     fsq_golden.npz        FSQCodebook.encode of the S3 tokenizer (tools/S3Tokenizer/s3tokenizer/model_v2.py:83-117).
     dac_trained_golden.npz  DACVAE.decode with weights in the regime of a TRAINED checkpoint (synth init="trained":
                           Snake alpha in [0.5, 2], activations of O(10), |alpha * x| up to ~25 rad), layers.py:18-33.
@@ -151,6 +153,15 @@ def extra_golden():
                             cfg=np.array([s3cfg[k] for k in ("n_mels", "n_state", "n_head", "n_layer")]),
                             keys=np.array(sorted(s3.state_dict().keys())))
         print("s3 tokenizer", tuple(hidden.shape), code_len.tolist(), codes[1, :6].tolist())
+        # clips longer than 30 s: the sliding-window path (_quantize_mixed_batch, model_v2.py:417-588), mixed with a short one
+        long_mel = torch.zeros(len(S3_LONG_LENS), s3cfg["n_mels"], max(S3_LONG_LENS))
+        for i, n in enumerate(S3_LONG_LENS):
+            long_mel[i, :, :n] = synth.s3_mel(40 + i, n)[0]
+        lcodes, llen = s3.quantize(long_mel, torch.tensor(S3_LONG_LENS))
+        np.savez_compressed(os.path.join(OUT, "s3_long_golden.npz"), codes=lcodes.numpy(), code_len=llen.numpy(),
+                            mel_len=np.array(S3_LONG_LENS), weights_seed=S3_SEED,
+                            cfg=np.array([s3cfg[k] for k in ("n_mels", "n_state", "n_head", "n_layer")]))
+        print("s3 tokenizer, long clips", tuple(lcodes.shape), llen.tolist())
 
         sd = synth.dac_decoder_state_dict(DAC_TRAINED_SEED, init="trained")
         dac = R.build_reference_dac()

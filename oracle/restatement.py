@@ -543,9 +543,43 @@ def s3_encode(sd, mel, mel_len):
 
 
 def s3_quantize(sd, mel, mel_len):
-    """S3TokenizerV2.quantize for audio of at most 30 s (model_v2.py:386-415): encoder trunk, then the FSQ head."""
-    hidden, code_len = s3_encode(sd, mel, mel_len)
-    return fsq_encode(sd["quantizer._codebook.project_down.weight"], sd["quantizer._codebook.project_down.bias"], hidden), code_len
+    """S3TokenizerV2.quantize (model_v2.py:386-415): encoder trunk, then the FSQ head; batches holding a clip longer than
+    30 s (3000 mel frames) go through _quantize_mixed_batch (:417-588) with merge_tokenized_segments (utils.py:367-390)."""
+    w, b = sd["quantizer._codebook.project_down.weight"], sd["quantizer._codebook.project_down.bias"]
+    lens = [int(v) for v in mel_len]
+    if max(lens) <= 3000:
+        hidden, code_len = s3_encode(sd, mel, mel_len)
+        return fsq_encode(w, b, hidden), code_len
+    window, overlap_s = 3000, 4
+    stride = window - overlap_s * 100
+    pieces, piece_len, of = [], [], []
+    for i, n in enumerate(lens):
+        start = 0
+        while True:  # one pass for a short clip; windows every `stride` frames for a long one
+            seg = mel[i, :, start:min(start + window, n)]
+            piece_len.append(seg.shape[1])
+            pieces.append(F.pad(seg, (0, window - seg.shape[1])))
+            of.append(i)
+            start += stride
+            if n <= 3000 or start >= n:
+                break
+    hidden, code_len = s3_encode(sd, torch.stack(pieces), torch.tensor(piece_len))
+    codes = fsq_encode(w, b, hidden)
+    drop = (overlap_s // 2) * 25
+    out = []
+    for i, n in enumerate(lens):
+        idx = [j for j, o in enumerate(of) if o == i]
+        toks = []
+        for pos, j in enumerate(idx):
+            t = codes[j, :int(code_len[j])].tolist()
+            if n > 3000:
+                t = t[(0 if pos == 0 else drop):(len(t) if pos == len(idx) - 1 else len(t) - drop)]
+            toks += t
+        out.append(toks)
+    res = torch.zeros(len(lens), max(len(t) for t in out), dtype=torch.long)
+    for i, t in enumerate(out):
+        res[i, :len(t)] = torch.tensor(t, dtype=torch.long)
+    return res, torch.tensor([len(t) for t in out], dtype=torch.long)
 
 def rel_l2(y, ref):
     y, ref = y.double(), ref.double()

@@ -249,3 +249,18 @@ def test_s3_tokenizer_matches_reference(golden_dir):
     for b, n in enumerate(code_len.tolist()):
         assert O.rel_l2(hidden[b, :n], ref_h[b, :n]) < 2e-6
         assert torch.equal(codes[b, :n], ref_c[b, :n])
+
+
+def test_s3_tokenizer_long_clips_match_reference(golden_dir):
+    """Batches with clips longer than 30 s: windowing + merging (model_v2.py:417-588, utils.py:367-390) restated."""
+    g = np.load(os.path.join(golden_dir, "s3_long_golden.npz"))
+    n_mels, n_state, n_head, n_layer = [int(v) for v in g["cfg"]]
+    sd = synth.s3_tokenizer_state_dict(int(g["weights_seed"]), n_mels, n_state, n_head, n_layer)
+    lens = [int(v) for v in g["mel_len"]]
+    mel = torch.zeros(len(lens), n_mels, max(lens))
+    for i, n in enumerate(lens):
+        mel[i, :, :n] = synth.s3_mel(40 + i, n)[0]
+    with torch.inference_mode():
+        codes, code_len = O.s3_quantize(sd, mel, torch.tensor(lens))
+    assert code_len.tolist() == g["code_len"].tolist() and codes.dtype == torch.long
+    assert torch.equal(codes, torch.from_numpy(g["codes"]))
