@@ -32,6 +32,13 @@ int conv_halo_mode() {  // 0: per-tap boxes; 1: halo box, descriptor base offset
   return mode;
 }
 bool conv_halo_enabled() { return conv_halo_mode() != 0; }
+bool conv_fuse_res_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LS_CONV_FUSE_RES");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 bool conv_dual_enabled() {
   static const bool on = [] {
     const char* e = getenv("LS_CONV_DUAL");

@@ -328,7 +328,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int act = kAct >= 0 ? kAct : p.act;
   const int out0_dtype = kOut0 >= 0 ? kOut0 : p.out0_dtype;
   const int out1_mode = kOut1 >= 0 ? kOut1 : p.out1_mode;
-  const int add_dtype = kAdd >= 0 ? kAdd : (p.addend ? p.addend_dtype : OUT_NONE);  // OUT_NONE: no residual
+  const int add_dtype = kAdd >= 0 ? kAdd : (p.addend_dtype == ADD_GEMM ? (int)ADD_GEMM : p.addend ? p.addend_dtype : (int)OUT_NONE);  // OUT_NONE: no residual
   const bool has_temb = kTemb >= 0 ? kTemb != 0 : p.temb != nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -369,6 +369,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapA1);
     prefetch_tmap(&mapW);
+    if (p.res_kb > 0) {
+      prefetch_tmap(&p.res_a0);
+      prefetch_tmap(&p.res_a1);
+      prefetch_tmap(&p.res_w);
+    }
     if (p.tma_out) {
       prefetch_tmap(&mapOut0);
       prefetch_tmap(&mapOut1);
@@ -592,6 +597,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
           }
         }
+        // fused residual GEMM: its 128-row activation boxes and weight boxes follow in the same rings
+        for (int kb2 = 0; kb2 < p.res_kb; ++kb2) {
+          if (warp == 0) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_arrive_expect_tx(&a_full[as], (uint32_t)(kBlockM * 128));
+            if (kb2 < p.res_split) tma_load_3d(smem_a + (size_t)as * a_bytes, &p.res_a0, &a_full[as], kb2 * kBlockK, t0, tc.b);
+            else tma_load_3d(smem_a + (size_t)as * a_bytes, &p.res_a1, &a_full[as], (kb2 - p.res_split) * kBlockK, t0, tc.b);
+          }
+          if (++as == p.a_stages) as = 0, aph ^= 1;
+          if (warp != 0) {
+            if (b_seq == warp - 1) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
+              tma_load_2d(smem_b + (size_t)bs * b_bytes, &p.res_w, &b_full[bs], kb2 * kBlockK, n0);
+            }
+            if (++b_seq == kWeightProducers) b_seq = 0;
+            if (++bs == p.b_stages) bs = 0, bph ^= 1;
+          }
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -729,6 +753,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
+        if (p.res_kb > 0) {
+          // fused residual GEMM into the other accumulator (single-tile launches: it is free); the epilogue's LayerNorm
+          // statistics pass over the main accumulator runs under these MMAs
+          const uint32_t d2 = tmem_u + (uint32_t)((acc ^ 1) * acc_stride);
+          for (int kb2 = 0; kb2 < p.res_kb; ++kb2) {
+            mbar_wait(&a_full[as], aph);
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const int nk2 = min(kBlockK / 16, (p.res_k_true - kb2 * kBlockK + 15) >> 4);
+            const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + (size_t)as * a_bytes));
+            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + (size_t)bs * b_bytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                if (k < nk2) umma_bf16(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (kb2 | k) != 0 ? 1u : 0u);
+              umma_commit(&b_empty[bs]);
+              umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
+            if (++as == p.a_stages) as = 0, aph ^= 1;
+            if (++bs == p.b_stages) bs = 0, bph ^= 1;
+          }
+          if (elect_one()) umma_commit(&tfull[acc ^ 1]);
+          __syncwarp();
+        }
         if (tl && lane == 0 && n_it <= p.taps * p.kb_per_tap) tl[32] = clock64();
         if (tl && lane == 0 && n_tile < 8) tl[24 + n_tile] = clock64();  // (overlaps the late k-iteration stamps: fine for multi-tile runs)
         ++n_tile;
@@ -802,7 +851,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #ifndef CONV_PRE
 #define CONV_PRE 0  // measured: the 16 extra live registers spill, and the spills cost more than the L2 hit they hide
 #endif
-      const bool pre_ok = CONV_PRE && add_dtype != OUT_NONE && act != ACT_LN_MISH;  // (LayerNorm epilogues: registers are scarce)
+      const bool pre_ok = CONV_PRE && add_dtype != OUT_NONE && add_dtype != ADD_GEMM && act != ACT_LN_MISH;  // (LayerNorm epilogues: registers are scarce)
       AddRegs pre0;
       if (pre_ok) {
         auto fetch = [&](int k, AddRegs& a) {
@@ -815,7 +864,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         };
         fetch(0, pre0);
       }
-      if (add_dtype != OUT_NONE) {
+      if (add_dtype != OUT_NONE && add_dtype != ADD_GEMM) {
         const int nxt = tile + (int)gridDim.x;
         if (nxt < total_tiles) {
           const TileCoord nc = decode_tile(nxt, m_tiles, n_tiles);
@@ -913,11 +962,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (tle) tle[45] = clock64();
 
       Stats s2;
+      if (add_dtype == ADD_GEMM) {  // the fused residual GEMM (second accumulator) has retired
+        mbar_wait(&tfull[acc ^ 1], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t taddr_res = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc ^ 1) * acc_stride);
       // pass B: finish the values, store the primary / copy / snake outputs
 #pragma unroll 1
       for (int c = g; c < n_chunks; c += 4) {
         float x[16];
+#if CONV_DETAIL_TL == 3
+        const int dk = (c - g) >> 2;
+        long long* dt = (tle && dk < 4) ? tle + 8 + 6 * dk : nullptr;
+        if (dt) dt[0] = clock64();
+#endif
         load_x(c, x);
+#if CONV_DETAIL_TL == 3
+        if (dt) dt[1] = clock64();
+#endif
         const int n = n0 + c * 16;
         if (act == ACT_LN_MISH) {
 #pragma unroll
@@ -937,11 +999,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             x[4 * g4] += tv.x, x[4 * g4 + 1] += tv.y, x[4 * g4 + 2] += tv.z, x[4 * g4 + 3] += tv.w;
           }
         }
+#if CONV_DETAIL_TL == 3
+        if (dt) dt[2] = clock64();
+#endif
         const long long flat = row_flat + n;
         // only the padded final conv (n_store = 1): the scalar tail indexes x dynamically, which would put x in local
         // memory for every instance that contains it
         const bool partial = (kAct == ACT_LRELU_TANH || kAct < 0) && n + 16 > p.n_store;
-        if (add_dtype != OUT_NONE && !partial) {
+        if (add_dtype == ADD_GEMM) {  // residual = the second accumulator's chunk + its bias
+          float r[16];
+          tmem_ld16(taddr_res + (uint32_t)(c * 16), reinterpret_cast<uint32_t(&)[16]>(r));
+          tmem_ld_wait();
+          const float4* rb = reinterpret_cast<const float4*>(p.res_bias + n);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 bv = __ldg(rb + g4);
+            x[4 * g4] += r[4 * g4] + bv.x, x[4 * g4 + 1] += r[4 * g4 + 1] + bv.y;
+            x[4 * g4 + 2] += r[4 * g4 + 2] + bv.z, x[4 * g4 + 3] += r[4 * g4 + 3] + bv.w;
+          }
+        } else if (add_dtype != OUT_NONE && !partial) {
           // the transposes below reuse the fp32 staging region (an fp32 residual also covers a 16-bit out0's region)
           if (tma_out && (out0_dtype == OUT_F32 || (out0_dtype != OUT_NONE && add_dtype == OUT_F32))) {
             if (lane == 0) {
@@ -962,6 +1038,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             else fetch_chunk<false>(lane, wr, n, addh, a), apply_chunk<OUT_BF16>(stg, lane, a, x);
           }
         }
+#if CONV_DETAIL_TL == 3
+        if (dt) dt[3] = clock64();
+#endif
         if (partial) {  // scalar tail: column 0 of consecutive rows is contiguous when out_ld == n_store == 1
           const int stt = st.state(flat, max(p.n_store - n, 1));
           if (stt != 0 && n < p.n_store) {
@@ -985,6 +1064,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             else if (out0_dtype == OUT_BF16) store_chunk<OUT_BF16>(stg, lane, wr, n, out0h, x);
             else if (out0_dtype == OUT_F16) store_chunk<OUT_F16>(stg, lane, wr, n, out0h, x);
           }
+#if CONV_DETAIL_TL == 3
+          if (dt) dt[4] = clock64();
+#endif
           if (out1_mode == OUT1_COPY) {
             if (tma_out) store_chunk_tma_p<OUT_BF16>(one_pending, stg, lane, &mapOut1, n, tma_t, tc.b, row_valid, x);
             else store_chunk<OUT_BF16>(stg, lane, wr, n, out1, x);
@@ -1080,6 +1162,12 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   if ((p.act == ACT_LN_MISH || p.out1_mode == OUT1_LN) && p.block_n != p.N) return cudaErrorInvalidValue;
   if (p.out1_mode == OUT1_LN && p.out0_dtype != OUT_F32) return cudaErrorInvalidValue;
   if (p.out1_mode != OUT1_NONE && p.out1 == nullptr) return cudaErrorInvalidValue;
+  if (p.addend_dtype == ADD_GEMM) {  // fused residual GEMM: one tile per CTA, one N tile, a bias and at least one K block
+    const long long tiles = (long long)p.B * ((p.M + kBlockM - 1) / kBlockM);
+    if (p.res_kb <= 0 || p.res_bias == nullptr || p.N != p.block_n || tiles > num_sms) return cudaErrorInvalidValue;
+  } else if (p.res_kb != 0) {
+    return cudaErrorInvalidValue;
+  }
   ConvGemmParams pp = p;
   pp.timeline = (g_debug_buffer && g_debug_bytes >= 148 * 64 * 8) ? g_debug_buffer : nullptr;
   pp.a_box_rows = p.halo_mode ? conv_halo_box_rows(p.taps, p.dil) : kBlockM;
@@ -1156,7 +1244,7 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   const double out_b = (p.out0_dtype == OUT_F32 ? 4.0 : p.out0_dtype != OUT_NONE ? 2.0 : 0.0) +
                        (p.out1_mode != OUT1_NONE ? 2.0 : 0.0) +
                        (p.addend ? (p.addend_dtype == OUT_F32 ? 4.0 : 2.0) : 0.0);
-  ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * kt * p.taps,
+  ProfScope prof(stream, p.tag == 1 ? PK_CONV_DAC : PK_CONV_FLOW, 2.0 * rows * p.N * (kt * p.taps + (p.res_kb > 0 ? p.res_k_true : 0)),
                  rows * kt * 2.0 + (double)p.taps * p.N * kt * 2.0 + rows * (p.n_store < p.N ? p.n_store : p.N) * out_b);
   count_launch();
   // dense outputs go out through TMA stores (see store_chunk_tma); tensor maps cached per (buffer, shape).  The cache
@@ -1188,7 +1276,7 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   }
   const CUtensorMap* mo0 = &mo0v;
   const CUtensorMap* mo1 = &mo1v;
-  const int add = p.addend ? p.addend_dtype : OUT_NONE;
+  const int add = p.addend_dtype == ADD_GEMM ? (int)ADD_GEMM : p.addend ? p.addend_dtype : (int)OUT_NONE;
   const int temb = p.temb ? 1 : 0;
 #define LS_CONV_CASE(A, O0, O1, AD, TE)                                                                          \
   if (p.act == (A) && p.out0_dtype == (O0) && p.out1_mode == (O1) && add == (AD) && temb == (TE))               \
@@ -1198,6 +1286,8 @@ cudaError_t LS_FN(launch_conv_gemm)(const CUtensorMap& mapA0, const CUtensorMap&
   LS_CONV_CASE(ACT_NONE, OUT_F32, OUT1_NONE, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_LN, OUT_F32, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_NONE, OUT_F32, 0)
+  LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_NONE, ADD_GEMM, 0)  // resnet conv2 with res_conv fused in (single-tile launches)
+  LS_CONV_CASE(ACT_LN_MISH, OUT_F32, OUT1_LN, ADD_GEMM, 0)
   LS_CONV_CASE(ACT_NONE, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
   LS_CONV_CASE(ACT_LN_MISH, OUT_NONE, OUT1_COPY, OUT_NONE, 0)
 #if !LS_HALF_FP16  // (the fp16-operand build serves the flow estimator only)

@@ -19,6 +19,7 @@ inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relax
 bool pdl_enabled();
 bool conv_halo_enabled();
 int conv_halo_mode();
+bool conv_fuse_res_enabled();  // LS_CONV_FUSE_RES=0: the resnet's res_conv keeps its own launch (development aid)
 bool conv_dual_enabled();  // LS_CONV_DUAL=0 switches the dual-issue mode of conv_gemm off (development aid)
 bool conv_resident_enabled();
 bool conv_tma_out_enabled();   // LS_CONV_TMA_OUT=0: epilogue stores through the LSU (development aid)  // LS_CONV_RESIDENT=0: always stream the weights through the ring (development aid)  // LS_CONV_HALO=0: fetch the activation box per tap instead of once with a halo
@@ -62,7 +63,8 @@ inline cudaError_t smem_optin_once(std::atomic<unsigned long long>& done_mask, c
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_LN_MISH = 3, ACT_LRELU_TANH = 4,
                  ACT_SILU = 5, ACT_LRELU001 = 6 /* F.leaky_relu's default slope 0.01 */ };
 enum OutDtype : int { OUT_NONE = 0, OUT_F32 = 1, OUT_BF16 = 2 /* the build's 16-bit operand type */,
-                      OUT_F16 = 3 /* IEEE half whatever the operand type (conv_gemm out0 / addend only) */ };
+                      OUT_F16 = 3 /* IEEE half whatever the operand type (conv_gemm out0 / addend only) */,
+                      ADD_GEMM = 4 /* addend only: the residual is a second GEMM of this launch (ConvGemmParams::res_*) */ };
 enum Out1Mode : int { OUT1_NONE = 0, OUT1_LN = 1, OUT1_COPY = 2, OUT1_SNAKE = 3 };
 
 // Implicit-GEMM 1-D convolution on time-major activations:
@@ -118,6 +120,14 @@ struct ConvGemmParams {
   // dual: two MMA-issuing warps, one per accumulator, on alternating tiles; each weight box serves both (filled in by
   // launch_conv_gemm for streamed-or-resident halo launches with one N tile, see conv_gemm.cu)
   int dual;
+  // Fused residual GEMM (addend_dtype == ADD_GEMM; single-tile launches only: B * ceil(M/128) <= SMs, N == block_n): after
+  // the main GEMM the same CTA computes R[t, n] = sum_c A2[t, c] W2[n][c] + res_bias[n] (a 1x1 convolution of a second
+  // input: the resnet's res_conv, decoder.py:84 / matcha decoder.py:60) into the SECOND TMEM accumulator, and the
+  // epilogue adds it where it would have added a residual read from global memory.  res_kb 64-wide K blocks, the first
+  // res_split of them from res_a0, the rest from res_a1 (128-row activation boxes).
+  alignas(64) CUtensorMap res_a0, res_a1, res_w;
+  int res_kb, res_split, res_k_true;
+  const float* res_bias;
   int red_bytes;  // LayerNorm statistics exchange area (0 for launches without a LayerNorm: the operand rings get it)
   long long* timeline;  // development aid (ls_debug_set_buffer): [CTA][64] clock64 stamps of the first tile, or nullptr
 };

@@ -32,6 +32,11 @@ def run(name, fn):
         print(f"  CTA {cta}: setup {rel(1)} pdl_wait {rel(2)} | MMA saw k-iter data at {[rel(8+i) for i in range(24) if int(r[8+i])]} | tile committed {rel(32)}"
               f" | EPI: acc ready {rel(40)} regs loaded {rel(41)} bias/act done {rel(45)} LN done {rel(46)} chunk starts {[rel(47+i) for i in range(4)]} main stores done {rel(42)} epilogue done {rel(43)} exit {rel(44)}")
 
+    if os.environ.get("LS_DETAIL") == "3":
+        r = t[0]; base = int(r[0])
+        print("  pass B, chunks 0..3 of one epilogue thread: [start, acc loaded, LN+Mish(+temb) done, residual added, out0 store issued]:",
+              [[int(r[8 + 6 * k + j]) - base if int(r[8 + 6 * k + j]) else None for j in range(5)] for k in range(4)])
+
 g = torch.Generator(device="cpu").manual_seed(0)
 B, T = 32, 500
 def mk(*s, scale=1.0): return (torch.randn(*s, generator=g) * scale)
