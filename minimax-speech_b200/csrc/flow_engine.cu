@@ -57,6 +57,17 @@ void finalize_linear(const Arena& a, PackedLinear& pl) {
 
 bool fused_blocks_check(int C, int inner) { return C == 256 && inner == 512; }
 
+// LS_HEAD_VIA_CONV=1 (development aid): the first block's QKV as a conv_gemm launch over the LayerNorm output of block2's
+// epilogue instead of the fused kernel's head launch.  Measured: tblock -4.5 ms, conv_gemm +5.0 ms per step (70.3 -> 71.3 ms,
+// profiles/r02_ab_head_via_conv.log), so it is off.
+bool head_via_conv_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LS_HEAD_VIA_CONV");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 int count_prefix(const Weights& w, const char* fmt) {
   int n = 0;
   char buf[160];
@@ -418,6 +429,7 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
   // `a0`(+`a1`) = masked bf16 input; `tail` = bf16 buffer that receives the masked group output.
   auto group = [&](int gi, const ActMaps& a0, const ActMaps* a1, int a0_ch, void* tail) {
     const GroupW& g = groups_[gi];
+    const bool head_via_conv = fused_blocks_ && causal_ && head_via_conv_enabled();
     if (!causal_) {
       // matcha Block1D (decoder.py:32-43): conv3 (pad 1) -> GroupNorm(8) over the utterance's frames -> Mish -> mask.  The
       // statistics span the whole utterance, so the convolution writes its raw fp32 output and two bandwidth kernels
@@ -471,7 +483,8 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
         e.addend = r, e.addend_dtype = OUT_F32;
       }
       e.out0 = u, e.out0_dtype = OUT_F32;
-      if (!fused_blocks_)  // the fused path computes LayerNorm(norm1) + QKV of the first block from u (head launch)
+      // LayerNorm(norm1 of the first block) rides in this epilogue unless the fused kernel's head launch computes it from u
+      if (!fused_blocks_ || head_via_conv)
         e.out1 = ws<void>(o_nrm_), e.out1_mode = OUT1_LN, e.p1_a = f32(g.tb[0].n1g), e.p1_b = f32(g.tb[0].n1b);
       gemm(pl.hA, nullptr, 0, g.res.conv2, e);
     }
@@ -484,9 +497,15 @@ void FlowEngine::run_estimator(int B2, int T, const float* temb, long long temb_
       LS_CUDA(launch_attention(pl.qkv_attn, ap, s));
     };
     if (fused_blocks_) {
-      // QKV of the first block: LayerNorm(norm1) + projection straight from u (head mode of the fused kernel);
+      // QKV of the first block: LayerNorm(norm1) + projection straight from u (head mode of the fused kernel), or -- causal
+      // estimator -- the projection alone as a conv_gemm launch over the LayerNorm output block2's epilogue wrote (750
+      // tiles pipelined over persistent CTAs instead of 125 single-tile CTAs that each stream the whole weight);
       // every later QKV comes out of the previous block's launch
-      {
+      if (head_via_conv) {
+        Epi e;
+        e.out1 = ws<void>(o_qkv_), e.out1_mode = OUT1_COPY;
+        gemm(pl.nrm, nullptr, 0, g.tb[0].qkv, e);
+      } else {
         TBlockParams tp{};
         tp.R = B2 * T, tp.T = T, tp.lengths = lengths, tp.vec = arena_.ptr<float>(g.head_vec), tp.tail_mode = 2, tp.fp16 = fp16_, tp.no_skip = causal_ ? 0 : 1;
         TBlockMaps tm;
