@@ -71,38 +71,86 @@ def config_of(a):
 
 
 # ------------------------------------------------------------------------------------------ CPU / reference arm
-def oracle_sample(seconds, n_timesteps, esd, dsd):
-    """One utterance through the CPU oracle (fp32, all host threads): the reference algorithm's CPU path."""
+class ReferenceModules:
+    """The reference's OWN modules through its own call surface -- ``CausalConditionalCFM.forward``
+    (speech/cosyvoice/flow/flow_matching.py:323-348, batch 1 like its solve_euler) then ``DACVAE.decode``
+    (dac-vae/model.py:236-257) -- imported unmodified from /root/reference in the build container or from the copy
+    oracle/stage_ref.py staged under baseline/_ref (git-ignored, travels to the GPU box); third-party packages absent
+    from the image are the stubs of oracle/ref_import.py.  None of this repo's kernels or modules are on this path."""
+
+    def __init__(self, esd, dsd, dev="cpu"):
+        from oracle import ref_import as R
+        self.root = R.REF_ROOT
+        self.cfm = R.build_reference_flow()
+        self.cfm.estimator.load_state_dict(esd, strict=True)
+        self.dac = R.build_reference_dac()
+        missing, unexpected = self.dac.load_state_dict(dsd, strict=False)
+        assert not unexpected and all(k.startswith(("encoder.", "en_conv_post.")) for k in missing), (missing[:3], unexpected[:3])
+        self.cfm.to(dev).eval()
+        self.dac.to(dev).eval()
+
+    def __call__(self, mu, mask, spks, cond, n_timesteps):
+        lat, _ = self.cfm(mu=mu, mask=mask, n_timesteps=n_timesteps, temperature=1.0, spks=spks, cond=cond)
+        return self.dac.decode(lat.float())
+
+
+def reference_modules(esd, dsd, dev="cpu"):
+    """-> ReferenceModules, or None when no copy of the reference is importable here (then the oracle port is timed)."""
+    try:
+        from oracle import ref_import as R
+        if not R.reference_available():
+            return None
+        return ReferenceModules(esd, dsd, dev)
+    except Exception as e:  # a reference that does not import is reported, not fatal: the port stands in
+        sys.stderr.write(f"bench: reference modules not importable ({type(e).__name__}: {e}); timing the oracle port\n")
+        return None
+
+
+def oracle_sample(seconds, n_timesteps, esd, dsd, ref=None):
+    """One utterance through the reference's CPU path (fp32, all host threads): the reference's own modules when a copy
+    is importable (``ref``), else the oracle restatement."""
     import minimax_speech_b200.synth as synth
     from oracle import restatement as O
     T = int(round(seconds * FRAME_RATE))
     mu, mask, spks, cond = synth.batch_inputs([T])
     t0 = time.perf_counter()
     with torch.inference_mode():
-        lat = O.cfm_forward(esd, synth.fixed_noise(), mu, mask, n_timesteps, 1.0, spks, cond)
-        wav = O.dac_decode(dsd, lat)
+        if ref is not None:
+            wav = ref(mu, mask, spks, cond, n_timesteps)
+        else:
+            lat = O.cfm_forward(esd, synth.fixed_noise(), mu, mask, n_timesteps, 1.0, spks, cond)
+            wav = O.dac_decode(dsd, lat)
     dt = time.perf_counter() - t0
     return dt, float(wav.abs().max())
+
+
+def _ref_kind(ref):
+    if ref is None:
+        return "port", "oracle/restatement.py (restatement of the reference's PyTorch CPU path; no copy of the reference is importable on this box)"
+    return "reference", (f"the reference's own CausalConditionalCFM.forward -> DACVAE.decode, unmodified modules from {ref.root} "
+                         f"(third-party imports stubbed by oracle/ref_import.py)")
 
 
 def cpu_baseline(a, esd, dsd):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    oracle_sample(0.32, 1, esd, dsd)  # thread-pool / allocator warm-up
+    ref = reference_modules(esd, dsd)
+    kind, what = _ref_kind(ref)
+    oracle_sample(0.32, 1, esd, dsd, ref)  # thread-pool / allocator warm-up
     n, total = 0, 0.0
     while n < a.batch and (n == 0 or total < 12.0):  # about 10-30 s of CPU work
-        dt, _ = oracle_sample(a.seconds, a.n_timesteps, esd, dsd)
+        dt, _ = oracle_sample(a.seconds, a.n_timesteps, esd, dsd, ref)
         n, total = n + 1, total + dt
-    return {"value": n * a.seconds / total, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": n * a.seconds / total, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{n} of {a.batch} utterances ({a.seconds:g} s, {a.n_timesteps} steps CFG + DAC decode), one at a "
-                      f"time (the reference's solve_euler is batch-1), oracle/restatement.py fp32 torch-CPU, "
+                      f"time (the reference's solve_euler is batch-1), {what}, fp32 torch-CPU, "
                       f"{torch.get_num_threads()} threads, {total:.2f} s"}
 
 
 def gpu_eager_baseline(a, esd, dsd, dev):
-    """The denominator north_star names: the reference algorithm as eager PyTorch ON THE GPU (fp32 and bf16 autocast),
-    one utterance at a time like the reference's solve_euler.  The reference itself is Python + absent third-party
-    packages and cannot travel to this box, so this runs the oracle restatement (plain torch ops) on cuda."""
+    """The denominator north_star names: the reference as eager PyTorch ON THE GPU (fp32 and bf16 autocast), one
+    utterance at a time like the reference's solve_euler -- the reference's own modules when a copy is importable
+    (baseline/_ref, staged by oracle/stage_ref.py), else the oracle restatement (plain torch ops) on cuda."""
     import minimax_speech_b200.synth as synth
     from oracle import restatement as O
     T = int(round(a.seconds * FRAME_RATE))
@@ -110,7 +158,9 @@ def gpu_eager_baseline(a, esd, dsd, dev):
     d_gpu = {k: v.to(dev) for k, v in dsd.items()}
     noise = synth.fixed_noise().to(dev)
     inputs = [[t.to(dev) for t in synth.batch_inputs([T], first_index=i)] for i in range(2)]
-    out = {"unit": UNIT, "kind": "port", "sample": f"2 of {a.batch} utterances, batch 1 each, oracle/restatement.py as eager "
+    ref = reference_modules(esd, dsd, dev)
+    kind, what = _ref_kind(ref)
+    out = {"unit": UNIT, "kind": kind, "sample": f"2 of {a.batch} utterances, batch 1 each, {what} as eager "
            f"PyTorch on cuda ({a.n_timesteps} steps CFG + DAC decode), best of 2 passes"}
     for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
         best = None
@@ -119,13 +169,17 @@ def gpu_eager_baseline(a, esd, dsd, dev):
             e0.record()
             with torch.inference_mode(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
                 for mu, mask, spks, cond in inputs:
-                    lat = O.cfm_forward(e_gpu, noise, mu, mask, a.n_timesteps, 1.0, spks, cond)
-                    O.dac_decode(d_gpu, lat.float())
+                    if ref is not None:
+                        ref(mu, mask, spks, cond, a.n_timesteps)
+                    else:
+                        lat = O.cfm_forward(e_gpu, noise, mu, mask, a.n_timesteps, 1.0, spks, cond)
+                        O.dac_decode(d_gpu, lat.float())
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             best = ms if best is None or _ == 1 else min(best, ms)
         out[name] = len(inputs) * a.seconds / (best / 1000.0)
+    del ref
     # fairness figure (SURVEY section 8d ii): the same eager algorithm with the whole batch in one call (the estimator
     # itself is batch-agnostic; the reference's solve_euler is not)
     mu, mask, spks, cond = [t.to(dev) for t in synth.batch_inputs([T] * a.batch)]
@@ -143,7 +197,8 @@ def gpu_eager_baseline(a, esd, dsd, dev):
             ms = e0.elapsed_time(e1)
             best = ms if it == 0 else min(best, ms)
         out[name] = a.batch * a.seconds / (best / 1000.0)
-    out["sample"] += f"; batched_*: all {a.batch} utterances in one call (DAC decode in groups of 4)"
+    out["sample"] += (f"; batched_*: all {a.batch} utterances in one call (DAC decode in groups of 4) through "
+                      f"oracle/restatement.py (kind port: the reference's solve_euler cannot batch)")
     return out
 
 
@@ -156,21 +211,22 @@ def run_reference(a):
     torch.set_num_threads(cores)
     esd = synth.estimator_state_dict(1986, "reference")
     dsd = synth.dac_decoder_state_dict(0, "reference")
-    oracle_sample(0.32, 1, esd, dsd)
+    ref = reference_modules(esd, dsd)
+    kind, what = _ref_kind(ref)
+    oracle_sample(0.32, 1, esd, dsd, ref)
     seconds = a.seconds
-    probe, _ = oracle_sample(seconds, a.n_timesteps, esd, dsd)
+    probe, _ = oracle_sample(seconds, a.n_timesteps, esd, dsd, ref)
     note = ""
     if probe * (a.steps + a.warmup) > 240.0 and seconds > 2.0:
         seconds, note = 2.0, " (sample shortened to 2 s utterances to bound the run)"
     for _ in range(max(a.warmup - 1, 0)):
-        oracle_sample(seconds, a.n_timesteps, esd, dsd)
-    times = [oracle_sample(seconds, a.n_timesteps, esd, dsd)[0] for _ in range(a.steps)]
+        oracle_sample(seconds, a.n_timesteps, esd, dsd, ref)
+    times = [oracle_sample(seconds, a.n_timesteps, esd, dsd, ref)[0] for _ in range(a.steps)]
     total = sum(times)
     value = seconds * a.steps / total
-    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
           "sample": f"each step = 1 utterance ({seconds:g} s, {a.n_timesteps} steps CFG + DAC decode) of the "
-                    f"{a.batch}-utterance batch, oracle/restatement.py (restatement of the reference's PyTorch "
-                    f"CPU path; the reference itself is Python and is not on this box), fp32, {cores} threads{note}"}
+                    f"{a.batch}-utterance batch, {what}, fp32, {cores} threads{note}"}
     emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
           "warmup": a.warmup, "ms_per_step": 1000.0 * total / a.steps, "higher_is_better": True,
           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -586,7 +642,8 @@ def run_b200(a):
                "kernels": kernels, "from_tokens": from_tokens, "cpu_baseline": cb, "gpu_eager_baseline": eager,
                "configs": configs, "hbm": hbm, "audio_seconds_per_step": audio_per_step,
                "weights": "synthetic numpy draws with the reference initialisers' distributions and the reference state_dict "
-                          "schema (synth.py), not the reference constructors' tensors: the reference does not import on this box"}
+                          "schema (synth.py), loaded into both arms (strict load into the reference's own modules when they are "
+                          "timed), not the reference constructors' own random tensors"}
         emit(rec)
     if world > 1:
         dist.destroy_process_group()

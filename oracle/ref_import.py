@@ -25,7 +25,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("LS_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# /root/reference in the build container; on the GPU box the unmodified hot-path modules staged by oracle/stage_ref.py
+REF_ROOT = os.environ.get("LS_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/speech/cosyvoice") else _STAGED)
 
 
 def reference_available():
