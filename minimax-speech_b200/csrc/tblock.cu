@@ -87,6 +87,18 @@ constexpr bool kDetailTl = TBLOCK_DETAIL_TL != 0;
 #define TBLOCK_MERGE_ELECT 0  // measured: 58.3 vs 57.3 us per launch (profiles/r02_ab_tblock_merge_elect.log)
 #endif
 constexpr bool kMergeElect = TBLOCK_MERGE_ELECT != 0;
+// TBLOCK_ATT_DIRECT: the out-proj's A operand (the 128 x 512 attention-output tile, 8 boxes) does not travel through the
+// weight ring.  It is loaded at the start of the tile straight into the 8 boxes of A3 + AH that used to hold the fp32 u
+// tile from the start (all 8 loads in flight at once, on top of the ring's), and u box j follows into the same place as
+// soon as the MMAs of K block j have retired (the u tile is only read by the out-proj EPILOGUE).  The ring then carries
+// the 16 Wo boxes alone, in groups of two -- with three boxes per K block in five slots the third box of every K block
+// could only be requested after the previous block had retired, one TMA round trip per K block
+// (profiles/r02_timeline_tblock_detail.log).
+#ifndef TBLOCK_ATT_DIRECT
+#define TBLOCK_ATT_DIRECT 1
+#endif
+constexpr bool kAttDirect = TBLOCK_ATT_DIRECT != 0 && !kPair && kCS == 1 && !kRingB;
+constexpr int kOutLoads = kAttDirect ? 16 : 24;  // ring loads of the out-proj phase (single-CTA form)
 static_assert(!kRingB || kFf2Ts, "the second ring lives in the AH region: it needs the TS form of FF2");
 constexpr int kSlotsB = 4;
 constexpr int kEpiWarps = 16;
@@ -194,6 +206,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint8_t* sA3 = smem + kOffA3;
   uint8_t* sAH = smem + kOffAH;
   uint8_t* sRing = smem + kOffRing;
+  // place j of the 8 boxes of A3 + AH that hold the tile's fp32 u (u box j = columns 32 j .. 32 j + 31: even j in the AH
+  // region, odd j in A3, which is how the out-proj epilogue reads them) and, before that, att box j (kAttDirect)
+  auto att_place = [&](int j) -> uint8_t* { return ((j & 1) ? sA3 : sAH) + (j >> 1) * kSlotBytes; };
   float* sVec = reinterpret_cast<float*>(smem + kOffVec);
   float2* sRed = reinterpret_cast<float2*>(smem + kOffRed);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -208,7 +223,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint64_t* full_b = u_full + 1;       // [kSlotsB] TMA -> MMA: W2 box r of the current FF chunk
   uint64_t* empty_b = full_b + kSlotsB;  // [kSlotsB] MMA -> TMA
   uint64_t* stage_free = empty_b + kSlotsB;  // epilogue -> TMA: the staging region may take this tile's W2 boxes
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  uint64_t* full_c = stage_free + 1;         // [8] TMA -> MMA: att box kb of this tile has landed in its A3 / AH place
+  uint64_t* empty_c = full_c + 8;            // [8] MMA -> epilogue leader: K block kb retired, u box kb may take the place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_c + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,6 +275,10 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       mbar_init(&empty_b[i], 1);
     }
     mbar_init(stage_free, 1);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full_c[i], 1);
+      mbar_init(&empty_c[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -294,7 +315,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     constexpr bool kWarpIssue = kProducerLanes == 1;
     if (kWarpIssue || lane < kProducerLanes) {
       const int issuer = warp * kProducerLanes + (kWarpIssue ? 0 : lane);
-      const int per_tile = kPair ? (head ? 24 : (do_qkv ? 72 : 48)) : (head ? 48 : (do_qkv ? 136 : 88));
+      const int per_tile = kPair ? (head ? 24 : (do_qkv ? 72 : 48)) : (head ? 48 : (do_qkv ? kOutLoads + 112 : kOutLoads + 64));
       long long seq0 = 0;  // sequence number of the tile's first ring-A load (slot = seq % kSlots, use = seq / kSlots)
       uint32_t tile_n = 0;  // tiles processed by this CTA (ring B: eight uses of every slot per tile)
       for (int g = group0; g < n_groups; g += group_step) {
@@ -339,15 +360,17 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             }
           } else if (head) {  // QKV weight only
             m = &mapWqkv, c0 = (i & 3) * 64, c1 = (i >> 2) * 128;
-          } else if (i < 24) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
+          } else if (kAttDirect && i < kOutLoads) {  // out-proj: per 64-wide K block Wo rows 0-127 and 128-255
+            m = &mapWo, c0 = (i >> 1) * 64, c1 = (i & 1) * 128;
+          } else if (i < kOutLoads) {  // out-proj: per 64-wide K block the att box, then Wo rows 0-127 and 128-255
             const int kb = i / 3, r = i - kb * 3;
             if (r == 0) m = &mapAtt, c0 = kb * 64, c1 = row0, own_rows = true;
             else m = &mapWo, c0 = kb * 64, c1 = (r - 1) * 128;
-          } else if (i < 32) {  // FF1 chunks 0 and 1
-            const int j = i - 24;
+          } else if (i < kOutLoads + 8) {  // FF1 chunks 0 and 1
+            const int j = i - kOutLoads;
             m = &mapW1, c0 = (j & 3) * 64, c1 = (j >> 2) * 128;
-          } else if (i < 88) {  // per FF chunk c: W2 (2 K blocks x 2 row halves), then FF1 chunk c+2
-            const int j = i - 32;
+          } else if (i < kOutLoads + 64) {  // per FF chunk c: W2 (2 K blocks x 2 row halves), then FF1 chunk c+2
+            const int j = i - (kOutLoads + 8);
             int c, r;
             if (j < 48) c = j >> 3, r = j & 7;
             else c = 6 + ((j - 48) >> 2), r = (j - 48) & 3;
@@ -359,7 +382,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             }
             if (kRingB) a_idx = i - (4 * c + (r < 4 ? r : 4));  // W2 boxes before this load travel in ring B
           } else {  // next block's QKV weight, 12 chunks of 128 rows
-            const int j = i - 88;
+            const int j = i - (kOutLoads + 64);
             m = &mapWqkv, c0 = (j & 3) * 64, c1 = (j >> 2) * 128;
             if (kRingB) a_idx = i - 32;
           }
@@ -528,6 +551,27 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         if (!head) {
         // ---- out-proj: D = att . Wo^T.  D is free: the previous tile's second a3_ready was waited below.
         for (int kb = 0; kb < kInner / 64; ++kb) {
+          if (kAttDirect) {
+            // A = att box kb in its own place (A3 / AH, see att_place); the ring holds the two Wo boxes of the K block
+            mbar_wait(&full_c[kb], tile_n & 1);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc_sw128(smem_u32(att_place(kb)));
+            const uint64_t b0 = slot_desc(0);
+            const uint64_t b1 = slot_desc(1);
+            if (kb == 0) TLM(1);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                mma(dD, adesc + 2 * k, b0 + 2 * k, acc);
+                mma(dD + 128, adesc + 2 * k, b1 + 2 * k, acc);
+              }
+              release_elected(2);
+              umma_commit(&empty_c[kb]);  // K block kb has retired: u box kb may take the att box's place
+            }
+            advance(2);
+            continue;
+          }
           const uint64_t adesc = slot_desc(0);
           const uint64_t b0 = slot_desc(1);
           if (kPair) {  // b0 = this CTA's 128 rows of Wo: the pair's operand is all 256
@@ -686,10 +730,23 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           mbar_arrive_expect_tx(u_full, 8 * kSlotBytes);
         }
         __syncwarp();
-        if (lane < 8) {  // one box per lane: the issue latencies overlap
-          const int k = lane >> 1;
-          if (lane & 1) tma_load_2d(sA3 + k * kSlotBytes, &mapU, u_full, k * 64 + 32, row0);
-          else tma_load_2d(stage + k * kSlotBytes, &mapU, u_full, k * 64, row0);
+        if (kAttDirect && !head) {
+          // att boxes first (all eight in flight at once), each followed into the same place by its u box once the
+          // MMAs of that K block have retired; the last u box lands one TMA round trip after the out-proj
+          if (lane < 8) {
+            mbar_arrive_expect_tx(&full_c[lane], kSlotBytes);
+            tma_load_2d(att_place(lane), &mapAtt, &full_c[lane], lane * 64, row0);
+          }
+          __syncwarp();
+          if (lane == 0) {
+            for (int j = 0; j < 8; ++j) {
+              mbar_wait(&empty_c[j], u_cnt & 1);
+              tma_load_2d(att_place(j), &mapU, u_full, j * 32, row0);
+            }
+          }
+          __syncwarp();
+        } else if (lane < 8) {  // one box per lane: the issue latencies overlap
+          tma_load_2d(att_place(lane), &mapU, u_full, lane * 32, row0);
         }
       }
 
