@@ -69,11 +69,28 @@ constexpr uint16_t kCtaMask = (uint16_t)((1u << kCS) - 1);
 #endif
 constexpr bool kRingB = TBLOCK_RING_B != 0 && !kPair && kCS == 1;
 // FF2 with its A operand (the GELU output) in tensor memory -- the tcgen05 "TS" form: 73 instead of 102 clk per N = 128
-// MMA (profiles/micro/mma_bw.cu), no AH staging, no ah_free barrier.  Parity-green; in the same-box A/B of the whole
-// bench step it measured 38.5 against 37.8 ms of fused-block time, so it is off by default (the FF phase is bound by the
-// arrival of the weight boxes, not by the MMAs; the second ring above needs it).
+// MMA (profiles/micro/mma_bw.cu), no AH staging, no ah_free barrier.  With the att tile still in the weight ring it
+// measured 38.5 against 37.8 ms of fused-block time per bench step; with TBLOCK_ATT_DIRECT it is the faster form (52.9
+// against 54.5 us per launch, 34.7 against 36.1 ms per step: profiles/r02_ab_tblock_att_direct.log) and the default.
+// TBLOCK_WIDE_FF: in the FF phase the weight ring is NINE slots -- the four boxes of the AH region, idle there once the
+// GELU output lives in tensor memory (TS form of FF2), join the five ring slots.  A slot takes ~1.9 k clk from "MMAs
+// issued" through "retired -> producer woken -> TMA issued -> landed" (profiles/r02_timeline_tblock_*.log), so five 16 KB
+// slots feed ~35-43 B/clk where the MMAs of a box want 64.  Ring slots 4..8 and AH slots 0..3 are two cyclic sub-rings with
+// running counters: out-proj, FF1 chunks 0 / 1, the QKV phase and head mode use the ring alone, the 56 loads of the FF chunk
+// loop follow the pattern 4 x AH, 5 x ring.  Slot and use number are closed forms of (tile, load) for the producers and
+// incremental uniform-register state for the MMA warp (a first version looked them up in a shared-memory table: the look-ups
+// sat on the slot-turnaround path and cost 500 clk per K block, 73 instead of 53 us).  Each slot has TWO release barriers,
+// for its even and odd uses, so that a producer warp that runs ahead of the consumer across a phase boundary cannot mistake
+// an older phase for its own (profiles/ring_protocol_sim.py checks the invariant and simulates the protocol); the first
+// four AH loads of a tile wait for the epilogue to be done with the u tile (stage_free).
+// Measured (profiles/r02_ab_tblock_wide_ff.log): 56.1 us against 52.7 us for the five-slot ring with the same TS form -- the
+// FF chunk period goes UP (4.3 k from 3.9 k clk) and the ring-only phases pay ~150 clk per K block for the extra slot
+// bookkeeping: ring depth is not what bounds the weight stream, the per-box handling chain is.  Off.
+#ifndef TBLOCK_WIDE_FF
+#define TBLOCK_WIDE_FF 0
+#endif
 #ifndef TBLOCK_FF2_TS
-#define TBLOCK_FF2_TS TBLOCK_RING_B
+#define TBLOCK_FF2_TS 1
 #endif
 constexpr bool kFf2Ts = TBLOCK_FF2_TS != 0 && !kPair;
 // TBLOCK_DETAIL_TL=1 adds per-sub-step clock64 stamps of FF chunk 4 / QKV chunk 6 (profiles/timeline_tblock.py); they cost
@@ -99,6 +116,9 @@ constexpr bool kMergeElect = TBLOCK_MERGE_ELECT != 0;
 #endif
 constexpr bool kAttDirect = TBLOCK_ATT_DIRECT != 0 && !kPair && kCS == 1 && !kRingB;
 constexpr int kOutLoads = kAttDirect ? 16 : 24;  // ring loads of the out-proj phase (single-CTA form)
+constexpr bool kWide = TBLOCK_WIDE_FF != 0 && kAttDirect && kFf2Ts && kSlots == 5 && !kMergeElect;
+constexpr int kWideSlots = 9;       // AH boxes 0..3 + ring slots 4..8 (contiguous in shared memory)
+constexpr int kWideAhPerTile = 26;  // AH-slot loads of one tile's FF chunk loop: 6 patterns of (4 AH + 5 ring) + 2
 static_assert(!kRingB || kFf2Ts, "the second ring lives in the AH region: it needs the TS form of FF2");
 constexpr int kSlotsB = 4;
 constexpr int kEpiWarps = 16;
@@ -112,7 +132,8 @@ constexpr int kOffRing = kOffAH + 4 * kSlotBytes;
 constexpr int kOffVec = kOffRing + kSlots * kRingSlotBytes;
 constexpr int kOffRed = kOffVec + TBLOCK_VEC_FLOATS * 4;
 constexpr int kOffBars = kOffRed + 4 * kTileM * 8;  // [column group][row] float2
-constexpr int kSmemBytes = kOffBars + 256 + 1024;
+constexpr int kBarBytes = 1024;  // ~60 mbarriers, the TMEM slot
+constexpr int kSmemBytes = kOffBars + kBarBytes + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "tblock shared memory budget");
 
 // offsets (floats) inside the per-block vector pack
@@ -212,9 +233,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   float* sVec = reinterpret_cast<float*>(smem + kOffVec);
   float2* sRed = reinterpret_cast<float2*>(smem + kOffRed);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* full = bars;             // [kSlots]  TMA -> MMA
-  uint64_t* empty = bars + kSlots;   // [kSlots]  MMA -> TMA
-  uint64_t* d_full = bars + 2 * kSlots;  // MMA -> epilogue: D holds out-proj / FF2 result
+  uint64_t* full = bars;                  // [kWideSlots]  TMA -> MMA (the first kSlots of them without the wide ring)
+  uint64_t* empty = bars + kWideSlots;    // [2][kWideSlots]  MMA -> TMA (wide ring: [use & 1][slot]; else the first kSlots)
+  uint64_t* d_full = bars + 3 * kWideSlots;  // MMA -> epilogue: D holds out-proj / FF2 result
   uint64_t* a3_ready = d_full + 1;   // epilogue -> MMA: A3 written (and D read / rewritten)
   uint64_t* h_full = a3_ready + 1;   // [2] MMA -> epilogue: H[i] holds an FF1 / QKV chunk
   uint64_t* ah_ready = h_full + 2;   // [2] epilogue -> MMA: H[i] drained (and AH[i] written in the FF phase)
@@ -226,6 +247,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
   uint64_t* full_c = stage_free + 1;         // [8] TMA -> MMA: att box kb of this tile has landed in its A3 / AH place
   uint64_t* empty_c = full_c + 8;            // [8] MMA -> epilogue leader: K block kb retired, u box kb may take the place
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_c + 8);
+  static_assert((3 * kWideSlots + 10 + 2 * kSlotsB + 1 + 16) * 8 + 8 <= kBarBytes, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,9 +280,10 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
     prefetch_tmap(&mapU);
     prefetch_tmap(&mapQkvOut);
     prefetch_tmap(&mapTail);
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < kWideSlots; ++i) {
       mbar_init(&full[i], kPair ? 2 : 1);        // pair: one arrive.expect_tx per CTA, on the leader's barrier
       mbar_init(&empty[i], kPair ? 1 : kCS);     // multicast: released by the MMA warp of every CTA of the cluster
+      mbar_init(&empty[kWideSlots + i], 1);
     }
     mbar_init(d_full, 1);
     mbar_init(a3_ready, kPair ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogue warps arrive at the leader
@@ -389,7 +412,31 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (two_rings && (ring_b >= 0 ? !b_warp : (b_warp || a_idx % n_a != issuer))) continue;  // another warp's load
           uint64_t* full_bar;
           uint8_t* dst;
-          if (ring_b >= 0) {
+          if (kWide) {
+            int sl, rc = i, hc = -1;
+            uint32_t use;
+            if (!head && i >= kOutLoads + 8) {
+              if (i < kOutLoads + 64) {  // FF chunk loop: 4 x AH, 5 x ring
+                const int f = i - (kOutLoads + 8), q9 = f / 9, m9 = f - q9 * 9;
+                if (m9 < 4) hc = q9 * 4 + m9;
+                else rc = 24 + q9 * 5 + (m9 - 4);
+              } else {
+                rc = i - kWideAhPerTile;
+              }
+            }
+            if (hc >= 0) {
+              const uint32_t cnt = tile_n * (uint32_t)kWideAhPerTile + (uint32_t)hc;
+              sl = (int)(cnt & 3u), use = cnt >> 2;
+              if (hc < 4) mbar_wait(stage_free, tile_n & 1);  // the u tile has been read out of the AH boxes
+            } else {
+              const uint32_t cnt = tile_n * (uint32_t)(per_tile - (head ? 0 : kWideAhPerTile)) + (uint32_t)rc;
+              sl = 4 + (int)(cnt % 5u), use = cnt / 5u;
+            }
+            if (use > 0) mbar_wait(&empty[((use - 1) & 1) * kWideSlots + sl], ((use - 1) >> 1) & 1);
+            if (tl && i < 48 && tile_n == 0 && (!kWarpIssue || lane == 0)) tl[64 + i] = clock64();
+            full_bar = &full[sl];
+            dst = sAH + sl * kSlotBytes;
+          } else if (ring_b >= 0) {
             // second ring: slot r holds W2 box r of one chunk at a time; the first box of a tile waits for the epilogue to
             // hand the staging region over, the others for the MMAs that read the slot's previous box
             if (chunk_b == 0) mbar_wait(stage_free, tile_n & 1);
@@ -458,7 +505,48 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       uint32_t drained0 = 0, drained1 = 0;  // fills of H[i] known to be consumed by the epilogue
       // wait for the ring slot `ahead` positions after the current one; returns its descriptor
       int n_full = 0;  // timeline aid: arrival of the first slots as seen by this thread
+      uint32_t tile_n = 0;  // tiles processed (second ring / wide ring parities)
+      // wide ring: the two sub-rings' next slot and its use number, and the position in the FF loop's 4 x AH, 5 x ring pattern
+      int r_slot = 0, h_slot = 0, f_pos = 0;
+      uint32_t r_use = 0, h_use = 0;
+      bool in_f = false;
+      auto wide_peek = [&](int ahead, uint32_t& use) -> int {  // slot (and use number) of the box `ahead` after the next one
+        int rs = r_slot, hs = h_slot, fp = f_pos;
+        uint32_t ru = r_use, hu = h_use;
+        for (int a = 0;; ++a) {
+          const bool ah = in_f && fp < 4;
+          if (a == ahead) {
+            use = ah ? hu : ru;
+            return ah ? hs : 4 + rs;
+          }
+          if (ah) {
+            if (++hs == 4) hs = 0, ++hu;
+          } else {
+            if (++rs == 5) rs = 0, ++ru;
+          }
+          if (in_f && ++fp == 9) fp = 0;
+        }
+      };
+      auto wide_advance = [&](int n) {
+        for (int a = 0; a < n; ++a) {
+          if (in_f && f_pos < 4) {
+            if (++h_slot == 4) h_slot = 0, ++h_use;
+          } else {
+            if (++r_slot == 5) r_slot = 0, ++r_use;
+          }
+          if (in_f && ++f_pos == 9) f_pos = 0;
+        }
+      };
       auto slot_desc = [&](int ahead) -> uint64_t {
+        if (kWide) {
+          uint32_t use;
+          const int sl = wide_peek(ahead, use);
+          mbar_wait(&full[sl], use & 1);
+          tc_fence_after();
+          if (tl && lane == 0 && n_full < 16) tl[112 + n_full] = clock64();
+          n_full += (ahead == 0);
+          return make_smem_desc_sw128(smem_u32(sAH + sl * kSlotBytes));
+        }
         int s = slot + ahead;
         uint32_t ph = phase;
         if (s >= kSlots) s -= kSlots, ph ^= 1;
@@ -470,6 +558,18 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         return make_smem_desc_sw128(smem_u32(sRing + s * kRingSlotBytes));
       };
       auto release = [&](int n) {  // hand the next n slots back once the MMAs issued so far retire
+        if (kWide) {
+          if (elect_one()) {
+            for (int j = 0; j < n; ++j) {
+              uint32_t use;
+              const int sl = wide_peek(j, use);
+              umma_commit(&empty[(use & 1) * kWideSlots + sl]);
+            }
+          }
+          __syncwarp();
+          wide_advance(n);
+          return;
+        }
         if (elect_one()) {
           int sl = slot;
           for (int j = 0; j < n; ++j) {
@@ -540,7 +640,6 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         else fills0 += 1;
       };
       const uint32_t dD = tmem_u + kTmemD;
-      uint32_t tile_n = 0;  // tiles processed (second ring parities)
       TLM(0);
       for (int g = group0; g < n_groups; g += group_step, ++tile_n) {
         if (__shfl_sync(0xffffffffu, (int)group_skipped(g), 0)) {
@@ -566,10 +665,11 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
                 mma(dD, adesc + 2 * k, b0 + 2 * k, acc);
                 mma(dD + 128, adesc + 2 * k, b1 + 2 * k, acc);
               }
-              release_elected(2);
+              if (!kWide) release_elected(2);
               umma_commit(&empty_c[kb]);  // K block kb has retired: u box kb may take the att box's place
             }
-            advance(2);
+            if (kWide) release(2);
+            else advance(2);
             continue;
           }
           const uint64_t adesc = slot_desc(0);
@@ -606,6 +706,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         TLM(3);
         gemm_from_a3(0);
         gemm_from_a3(1);
+        in_f = true, f_pos = 0;  // (wide ring) the loads of the chunk loop alternate between the AH boxes and the ring
         for (int c = 0; c < kFF / 128; ++c) {
           const int i = c & 1;
           if (kDetailTl && c == 4) TLM(128);
@@ -666,6 +767,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           if (kDetailTl && c == 4) TLM(133);
           if (c + 2 < kFF / 128) gemm_from_a3(i, kDetailTl && c == 4 ? 134 : -1);
         }
+        in_f = false;
         commit(d_full);
         TLM(12);
         }  // !head
@@ -796,7 +898,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         const float nmr = -mean * rstd;                 // before the A3 writes below (A3 held half of the u tile)
         // every thread is done with the u tile and the previous tile's stores have left the staging region (the leader
         // waited for them before loading u): it may take this tile's W2 boxes
-        if (kRingB && leader && !head) mbar_arrive(stage_free);
+        if ((kRingB || kWide) && leader && !head) mbar_arrive(stage_free);
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int col = cg * 64 + ch * 32;

@@ -167,3 +167,13 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), lib, "-o", str(exe),
                     "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_tblock_wide_ring_protocol():
+    """The table-driven weight ring of csrc/tblock.cu (TBLOCK_WIDE_FF): no producer warp can alias a parity wait, and a
+    randomised simulation of the real wait conditions neither overwrites an unconsumed box nor deadlocks."""
+    import profiles.ring_protocol_sim as sim
+    for mode in ("head", "tail0", "tail1"):
+        assert sim.static_invariant(mode) == 0
+        for seed in range(4):
+            assert sim.simulate(mode, tiles=3, seed=seed) == "ok"
