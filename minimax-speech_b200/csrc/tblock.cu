@@ -11,16 +11,19 @@
 // `att` is the flash kernel's output (bf16 [R][512]); `u` the fp32 residual stream (read once, written once).
 // The 1024-wide FF intermediate and both LayerNorm outputs never leave the SM.
 //
-// Structure (one CTA per SM, persistent over tiles, 10 warps):
-//   warp 0      TMA producer: streams the att tile and every weight tile (128 rows x 64 K, 16 KB, 128B swizzle)
-//               through a 5-slot mbarrier ring in exactly the order the MMA warp consumes them
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane); M=128 x N=128 x K=16 bf16 MMAs, fp32 accumulate
-//   warps 2-9   epilogue: warp w owns TMEM lanes 32*(w%4).. (= 32 rows) and column half (w-2)/4
+// Structure (one CTA per SM, persistent over tiles, 20 warps):
+//   warps 0-2   TMA producers: stream every weight tile (128 rows x 64 K, 16 KB, 128B swizzle) through a 5-slot mbarrier
+//               ring in exactly the order the MMA warp consumes them (load i is issued by warp i % 3)
+//   warp 3      TMEM allocator + tcgen05.mma issuer (one elected lane); M=128 x N=128 x K=16 MMAs, fp32 accumulate
+//   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4).. (= 32 rows) and column group (w-4)/4; its first warp also
+//               issues the tile's att boxes, the u boxes that follow them, and every TMA store
 // TMEM (512 columns): D = [0,256) holds u' then u''; H0/H1 = [256,384) / [384,512) double-buffer the 128-wide
 // FF1 chunks (and later the 128-wide QKV chunks).  FF2 accumulates straight onto u' in D (the epilogue writes
-// u' back with tcgen05.st), so the residual add costs nothing.
-// Shared memory: A3 (64 KB) = LayerNorm output as the K-major A operand of FF1 / QKV; AH (2 x 32 KB) = GELU
-// output chunks as the A operand of FF2; ring (80 KB); per-block vectors (10 KB).
+// u' back with tcgen05.st), so the residual add costs nothing; its A operand, the GELU output, is written back over
+// its own H columns as packed 16-bit pairs and read from there (tcgen05.mma TS form).
+// Shared memory: A3 (64 KB) = LayerNorm output as the K-major A operand of FF1 / QKV; AH (64 KB) = staging boxes of the
+// TMA stores (u'', qkv, tail); A3 + AH together hold the att tile, then the fp32 u tile, while the out-proj runs;
+// ring (80 KB); per-block vectors (10 KB).
 #include "kernels.h"
 #include "profiler.h"
 #include "ptx.cuh"
@@ -452,6 +455,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             full_bar = &full[slot];
             dst = sRing + slot * kRingSlotBytes;
           }
+          const int qk6 = kOutLoads + 64 + 24;  // first load of QKV chunk 6 (detailed timeline)
+          const bool stamp_q6 = kDetailTl && tl && !kWide && do_qkv && !head && i >= qk6 && i < qk6 + 4 && seq0 == 0;
+          if (stamp_q6 && (!kWarpIssue || lane == 0)) tl[216 + 2 * (i - qk6)] = clock64();  // slot free seen by the producer
           if (kWarpIssue && !elect_one()) {
             // (the other lanes only keep the warp's control flow uniform)
           } else if (kPair) {
@@ -466,6 +472,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
             else tma_load_2d(dst, m, full_bar, c0, c1);
           }
           if (kWarpIssue) __syncwarp();
+          if (stamp_q6 && (!kWarpIssue || lane == 0)) tl[217 + 2 * (i - qk6)] = clock64();  // load issued
         }
         seq0 += (kRingB && !head) ? per_tile - 32 : per_tile;
         tile_n += 1;
@@ -632,7 +639,9 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma(d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
           }
+          if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 56 + 2 * kb] = clock64();  // MMAs issued
           if (!kPair || (kb & 1)) release(1);
+          if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 57 + 2 * kb] = clock64();  // slot handed back (commit issued)
         }
         commit(&h_full[i]);
         if (kDetailTl && tl && tlb >= 0 && lane == 0) tl[tlb + 6] = clock64();
