@@ -873,6 +873,11 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
         TLE(32);
         // Only 32 values are live at a time: u' goes back to TMEM (FF2 accumulates onto it anyway) and is re-read
         // for the LayerNorm pass.  Registers are scarce here -- a spill costs an L2 round trip, the L1 is all smem.
+        // (Measured, profiles/r02_timeline_tblock_ln_detail.log: pass 1 costs 1.5-2.0 k clk per 32-column chunk, pass 2
+        // 1.4 k; keeping columns 32..63 in registers across the barrier instead of re-reading them takes pass 2 from
+        // 2.85 k to 2.8 k -- the chunk time is the per-column constants (48 LDS.128 per thread and LayerNorm), the
+        // FMAs / conversions and the swizzled stores of 16 warps, not the tcgen05.ld -- and four accumulator chains in
+        // the statistics change nothing; neither is kept.)
         RowStats st;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
@@ -900,11 +905,14 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           }
           st.add32(x);
           tmem_st32(trow + kTmemD + col, reinterpret_cast<const uint32_t(&)[32]>(x));
+          if (kDetailTl) TLE(56 + ch);
         }
         tmem_st_wait();
+        if (kDetailTl) TLE(58);
         float mean, rstd;
         combine_groups(st, sRed, cg, row, mean, rstd);  // the barrier inside also orders every thread's u reads
         const float nmr = -mean * rstd;                 // before the A3 writes below (A3 held half of the u tile)
+        if (kDetailTl) TLE(59);
         // every thread is done with the u tile and the previous tile's stores have left the staging region (the leader
         // waited for them before loading u): it may take this tile's W2 boxes
         if ((kRingB || kWide) && leader && !head) mbar_arrive(stage_free);
@@ -916,6 +924,7 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
           tmem_ld_wait();
           normalize32(x, rstd, nmr, sVec + (head ? V_G1N : V_G3) + col, sVec + (head ? V_BE1N : V_BE3) + col, x);
           store_row_chunks(sA3 + cg * kSlotBytes + row * 128, sw, ch * 4, x);
+          if (kDetailTl) TLE(60 + ch);
         }
         tmem_st_wait();
         warp_arrive(a3_ready);

@@ -31,6 +31,7 @@ for cta in (0, 60, 124):
     print("MMA FF1(6): before drained wait, after, kb0..3 slot seen, committed:", d(134, 141))
     print("MMA QKV chunk 6: before drained wait, after, kb0..3 slot seen, committed:", d(144, 151))
     print("EPI FF chunk 4: before h_full, after, ld done, gelu done, ah_free ok, arrived:", d(160, 166))
+    print("EPI out-proj LayerNorm (leader thread): pass 1 chunk 0 / 1 done, tmem_st drained, statistics combined, pass 2 chunk 0 / 1 done:", d(56, 62))
     print("LOAD QKV chunk 6, boxes 0..3: (slot free seen by the producer, TMA issued):", d(216, 224))
     print("MMA QKV chunk 6, kb0..3: (MMAs issued, commit issued):", d(200, 208))
     print("EPI QKV chunk 6: before h_full, after, ld+arrive, staged, bulk_wait_read, barrier, stores issued:", d(170, 177))
