@@ -379,6 +379,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       prefetch_tmap(&mapOut1);
     }
   }
+#ifndef CONV_L2_PREFETCH
+#define CONV_L2_PREFETCH 1
+#endif
+  if (CONV_L2_PREFETCH && p.tag == 0 && warp == 1 && lane == 0) {
+    // Flow-estimator launches: ask for the launch's weight boxes, spread over the CTAs of the grid, to be brought into L2
+    // before the PDL wait (weights do not depend on the previous kernel).  Inside a solve they are cold (the estimator's
+    // 212 MB of weights and > 1 GB of activations pass through the 126 MB L2 between two uses) and every CTA streams them
+    // in the same order at about the same time: without this each box is a DRAM miss the whole grid waits for.
+    const int per_tile = p.taps * p.kb_per_tap;
+    const int n_boxes = per_tile * n_tiles;
+    for (int j = blockIdx.x; j < n_boxes; j += gridDim.x) {
+      const int nt = j / per_tile, r = j - nt * per_tile;
+      const int tap = r / p.kb_per_tap, kb = r - tap * p.kb_per_tap;
+      tma_prefetch_l2_2d(&mapW, kb * kBlockK, tap * p.N + nt * p.block_n);
+    }
+    for (int j = blockIdx.x; j < p.res_kb; j += gridDim.x) tma_prefetch_l2_2d(&p.res_w, j * kBlockK, 0);
+  }
   if (warp == kMmaWarp && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&a_full[i], 1);

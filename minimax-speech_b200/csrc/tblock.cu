@@ -107,6 +107,16 @@ constexpr bool kDetailTl = TBLOCK_DETAIL_TL != 0;
 #define TBLOCK_MERGE_ELECT 0  // measured: 58.3 vs 57.3 us per launch (profiles/r02_ab_tblock_merge_elect.log)
 #endif
 constexpr bool kMergeElect = TBLOCK_MERGE_ELECT != 0;
+// TBLOCK_L2_PREFETCH: in the prologue (before the PDL wait: weights do not depend on the previous kernel) the CTAs of the
+// grid ask for the launch's weight boxes, one or two each, to be brought into L2.  Inside a bench step the 2.2 MB of a
+// block's weights are cold (112 MB of block weights and > 1 GB of activations pass through the 126 MB L2 per step), every
+// CTA streams them in the same order at about the same time, so without this each box is a DRAM miss that all 125 CTAs
+// wait for, on the ring's critical path (ncu launch list with flushed caches: 56.9 / 37.8 / 27.8 us per tail-0 / tail-1 /
+// head launch against 52.7 / 32.6 / 23.5 us with L2-warm operands).
+#ifndef TBLOCK_L2_PREFETCH
+#define TBLOCK_L2_PREFETCH 1
+#endif
+constexpr bool kL2Prefetch = TBLOCK_L2_PREFETCH != 0 && !kPair && kCS == 1;
 // TBLOCK_ATT_DIRECT: the out-proj's A operand (the 128 x 512 attention-output tile, 8 boxes) does not travel through the
 // weight ring.  It is loaded at the start of the tile straight into the 8 boxes of A3 + AH that used to hold the fp32 u
 // tile from the start (all 8 loads in flight at once, on top of the ring's), and u box j follows into the same place as
@@ -306,6 +316,24 @@ tblock_kernel(const __grid_constant__ CUtensorMap mapAtt, const __grid_constant_
       mbar_init(&empty_c[i], 1);
     }
     fence_barrier_init();
+  }
+  if (kL2Prefetch && warp == 1 && lane == 0) {
+    const int n_boxes = head ? 48 : (do_qkv ? 128 : 80);  // 16 Wo + 32 W1 + 32 W2 (+ 48 Wqkv), 16 KB each
+    for (int j = blockIdx.x; j < n_boxes; j += gridDim.x) {
+      int q = j;
+      if (head || q >= 80) {
+        if (!head) q -= 80;
+        tma_prefetch_l2_2d(&mapWqkv, (q & 3) * 64, (q >> 2) * 128);
+      } else if (q < 16) {
+        tma_prefetch_l2_2d(&mapWo, (q >> 1) * 64, (q & 1) * 128);
+      } else if (q < 48) {
+        q -= 16;
+        tma_prefetch_l2_2d(&mapW1, (q & 3) * 64, (q >> 2) * 128);
+      } else {
+        q -= 48;
+        tma_prefetch_l2_2d(&mapW2, (q >> 1) * 64, (q & 1) * 128);
+      }
+    }
   }
   if (warp == kMmaWarp) {
     __syncwarp();
